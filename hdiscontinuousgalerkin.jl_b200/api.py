@@ -1,0 +1,553 @@
+"""Host-side mirror of the reference's Julia API for the HDG Poisson path.
+
+Julia is not available in this image, so the host layer above the C ABI is Python; names,
+argument meaning and error behaviour follow the reference (src/HDiscontinuousGalerkin.jl:38-108
+exports and the script-level functions of examples/poisson2D_HDG.jl) so that
+`examples/poisson2D_hdg.py` and the parity tests read like the reference's own driver/tests.
+All numerical work happens in libhdg_b200.so on the GPU - the objects here are thin handles
+around one `hdg_context`.  The same calls expressed as Julia `ccall`s are in
+julia/HDGB200.jl / INTEGRATION.md.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import re
+
+import numpy as np
+
+from . import _lib
+from ._lib import HDGError, Params, Sizes, SolveInfo, check, f64p, i64p
+
+# ----------------------------------------------------------------------------------------------
+# element / basis descriptors (src/basis.jl, src/FiniteElement.jl) - tables are built by the library
+# ----------------------------------------------------------------------------------------------
+TriangleCell = "TriangleCell"      # Cell{2,3,3}, src/mesh.jl:24
+RefTetrahedron = "RefTetrahedron"  # src/shapes.jl:4
+
+
+class Dubiner:
+    """Dubiner{dim,RefTetrahedron,order}, src/basis.jl:52."""
+
+    def __init__(self, dim=2, shape=RefTetrahedron, order=1):
+        if dim != 2:
+            raise ValueError("Dubiner basis is defined on the triangle (dim = 2)")
+        self.dim, self.shape, self.order = dim, shape, int(order)
+
+    def getnbasefunctions(self):
+        return (self.order + 1) * (self.order + 2) // 2
+
+
+class Legendre:
+    """Legendre{dim,RefTetrahedron,order}, src/basis.jl:339."""
+
+    def __init__(self, dim=1, shape=RefTetrahedron, order=1):
+        self.dim, self.shape, self.order = dim, shape, int(order)
+
+    def getnbasefunctions(self):
+        return self.order + 1
+
+
+class GenericFiniteElement:
+    """GenericFiniteElement(func_basis), src/FiniteElement.jl:8-27 (order-1 Lagrange geometry)."""
+
+    def __init__(self, basis):
+        self.basis = basis
+        self.order = basis.order
+
+
+# ----------------------------------------------------------------------------------------------
+# mesh (src/mesh.jl, src/generate_mesh.jl, src/triangle_mesh.jl)
+# ----------------------------------------------------------------------------------------------
+class PolygonalMesh:
+    """PolygonalMesh{2,3,3,2,Float64}, src/mesh.jl:43-49, in the Julia memory layouts the C ABI takes.
+
+    cells : (ncell,6) int64 C-order  = Vector{Cell{2,3,3}} (3 node ids then 3 face ids, 1-based)
+    nodes : (nnode,2) float64        = Vector{Node{2,Float64}}
+    faces : (nface,4) int64 F-order  = Matrix{Int}  (v1 v2 cell1 cell2|0)
+    """
+
+    def __init__(self, cells, nodes, faces, facesets, rect=None):
+        self.cells = np.ascontiguousarray(cells, dtype=np.int64)
+        self.nodes = np.ascontiguousarray(nodes, dtype=np.float64)
+        self.faces = np.asfortranarray(faces, dtype=np.int64)
+        self.facesets = facesets
+        self._rect = rect   # (nx, ny, LL, UR) when produced by rectangle_mesh
+
+    # queries, src/mesh.jl:70-76
+    def getncells(self):
+        return self.cells.shape[0]
+
+    def getnfaces(self):
+        return self.faces.shape[0]
+
+    def getnnodes(self):
+        return self.nodes.shape[0]
+
+    def getfaceset(self, name):
+        return self.facesets[name]
+
+    def getcells_matrix(self):      # src/mesh.jl:63-69
+        return self.cells[:, :3].copy()
+
+    def get_vertices_matrix(self):  # src/mesh.jl:56-62
+        return self.nodes.copy()
+
+
+def getncells(mesh):
+    return mesh.getncells()
+
+
+def getnfaces(mesh):
+    return mesh.getnfaces()
+
+
+def getnnodes(mesh):
+    return mesh.getnnodes()
+
+
+def getfaceset(mesh, name):
+    return mesh.getfaceset(name)
+
+
+def face_orientation(mesh, cell_idx, face_idx):
+    """src/mesh.jl:51-54 (1-based cell / local face)."""
+    k1, k2 = ((2, 3), (3, 1), (1, 2))[face_idx - 1]
+    nd = mesh.cells[cell_idx - 1]
+    return bool(nd[k2 - 1] > nd[k1 - 1])
+
+
+def rectangle_mesh(celltype, nel, LL, UR):
+    """rectangle_mesh(TriangleCell,(nx,ny),LL,UR), src/generate_mesh.jl:101-143.
+
+    Generated on the GPU (node coordinates with the reference's arithmetic, first-encounter face
+    numbering in closed form) and downloaded into the Julia layouts."""
+    if celltype != TriangleCell:
+        raise NotImplementedError("only TriangleCell meshes are on the HDG path (RectangleCell is VEM-only)")
+    nx, ny = int(nel[0]), int(nel[1])
+    ctx = _Context(order=1)
+    try:
+        check(_lib.load().hdg_set_rectangle_mesh(ctx.h, nx, ny, float(LL[0]), float(LL[1]), float(UR[0]), float(UR[1])), ctx.h)
+        mesh = ctx.download_mesh()
+    finally:
+        ctx.close()
+    mesh._rect = (nx, ny, (float(LL[0]), float(LL[1])), (float(UR[0]), float(UR[1])))
+    # named edge sets by exact coordinate compare, src/generate_mesh.jl:60-89
+    b = np.array(sorted(mesh.facesets["boundary"]), dtype=np.int64) - 1
+    a, c = mesh.nodes[mesh.faces[b, 0] - 1], mesh.nodes[mesh.faces[b, 1] - 1]
+    sets = {"bottom": (a[:, 1] == LL[1]) & (c[:, 1] == LL[1])}
+    sets["right"] = ~sets["bottom"] & (a[:, 0] == UR[0]) & (c[:, 0] == UR[0])
+    sets["top"] = ~sets["bottom"] & ~sets["right"] & (a[:, 1] == UR[1]) & (c[:, 1] == UR[1])
+    sets["left"] = ~sets["bottom"] & ~sets["right"] & ~sets["top"] & (a[:, 0] == LL[0]) & (c[:, 0] == LL[0])
+    for k, msk in sets.items():
+        mesh.facesets[k] = set((b[msk] + 1).tolist())
+    return mesh
+
+
+_NUM = re.compile(r"\b((\d*\.)?\d+)\b")
+
+
+def _triangle_rows(path):
+    rows, first = [], True
+    with open(path) as fh:
+        for ln in fh:
+            if re.match(r"^\s*(?:#|$)", ln):
+                continue
+            if first:           # header row
+                first = False
+                continue
+            rows.append([m.group(0) for m in _NUM.finditer(ln)])
+    return rows
+
+
+def number_faces(tri_nodes):
+    """First-encounter face numbering of a triangle list (src/generate_mesh.jl:20-46,
+    src/triangle_mesh.jl:66-101) without the sequential hash table: sort the 3*ncell edge keys,
+    take the first encounter position of every distinct edge, rank the distinct edges by that
+    position.  tri_nodes: (ncell,3) 1-based CCW.  Returns (cell_faces (ncell,3), faces (nface,4))."""
+    tri = np.asarray(tri_nodes, dtype=np.int64)
+    nc = tri.shape[0]
+    k1 = np.array([1, 2, 0])
+    k2 = np.array([2, 0, 1])
+    v1 = tri[:, k1].reshape(-1)          # encounter position p = 3*cell + local face
+    v2 = tri[:, k2].reshape(-1)
+    lo, hi = np.minimum(v1, v2), np.maximum(v1, v2)
+    key = lo * (tri.max() + 1) + hi
+    order = np.argsort(key, kind="stable")          # stable: encounter positions ascend inside a group
+    sk = key[order]
+    start = np.ones(sk.size, bool)
+    start[1:] = sk[1:] != sk[:-1]
+    end = np.ones(sk.size, bool)
+    end[:-1] = start[1:]
+    grp = np.cumsum(start) - 1                       # group (distinct edge) of every sorted slot
+    first_pos, last_pos = order[start], order[end]   # first / last encounter of every distinct edge
+    if np.any(np.bincount(grp) > 2):
+        raise ValueError("non-manifold mesh: an edge is shared by more than two cells")
+    by_first = np.argsort(first_pos, kind="stable")  # face id = rank of the first encounter
+    rank = np.empty(first_pos.size, np.int64)
+    rank[by_first] = np.arange(first_pos.size)
+    face_of_pos = np.empty(sk.size, np.int64)
+    face_of_pos[order] = rank[grp]
+    cell_faces = (face_of_pos + 1).reshape(nc, 3)
+    fp, lp = first_pos[by_first], last_pos[by_first]
+    faces = np.zeros((fp.size, 4), dtype=np.int64)
+    faces[:, 0] = v1[fp]                             # (v1,v2) in the first cell's local direction
+    faces[:, 1] = v2[fp]
+    faces[:, 2] = fp // 3 + 1
+    faces[:, 3] = np.where(lp != fp, lp // 3 + 1, 0)
+    return cell_faces, faces
+
+
+def parse_mesh_triangle(root_file):
+    """parse_mesh_triangle(root_file), src/triangle_mesh.jl:115-126 (.node/.edge/.ele reader)."""
+    nodes = np.array([[float(r[1]), float(r[2])] for r in _triangle_rows(root_file + ".node")])
+    marks = {}
+    for r in _triangle_rows(root_file + ".edge"):
+        a, b, mk = int(r[1]), int(r[2]), int(r[3])
+        marks.setdefault((min(a, b), max(a, b)), mk)
+    tri = np.array([[int(r[1]), int(r[2]), int(r[3])] for r in _triangle_rows(root_file + ".ele")], dtype=np.int64)
+    # _check_node_data (src/generate_mesh.jl:49-57): make every cell counter-clockwise
+    p = nodes[tri - 1]
+    a, b = p[:, 1] - p[:, 0], p[:, 2] - p[:, 0]
+    flip = (a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]) < 0
+    tri[flip] = tri[flip][:, [0, 2, 1]]
+    cell_faces, faces = number_faces(tri)
+    boundary = {f + 1 for f in range(faces.shape[0])
+                if marks.get((min(faces[f, 0], faces[f, 1]), max(faces[f, 0], faces[f, 1])), -1) > 0}
+    return PolygonalMesh(np.hstack([tri, cell_faces]), nodes, faces, {"boundary": boundary})
+
+
+def ref_table(order, quad_degree, name):
+    """Reference table from the library's host-side builder (no device needed)."""
+    lib = _lib.load()
+    cnt = C.c_int64()
+    check(lib.hdg_ref_table(int(order), int(quad_degree or 0), name.encode(), None, C.byref(cnt)), None)
+    buf = np.empty(cnt.value)
+    check(lib.hdg_ref_table(int(order), int(quad_degree or 0), name.encode(), f64p(buf), C.byref(cnt)), None)
+    return buf
+
+
+# ----------------------------------------------------------------------------------------------
+# context handle
+# ----------------------------------------------------------------------------------------------
+class _Context:
+    def __init__(self, order, quad_degree=0, tau=1.0, source_id=1, device=-1, local_solver=0):
+        lib = _lib.load()
+        prm = Params(int(order), int(quad_degree or 0), float(tau), int(source_id), int(device), int(local_solver), 0)
+        h = C.c_void_p()
+        check(lib.hdg_create(C.byref(prm), C.byref(h)), None)
+        self.h = h
+        self.lib = lib
+        self.mesh = None
+
+    def close(self):
+        if self.h:
+            self.lib.hdg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sizes(self):
+        s = Sizes()
+        check(self.lib.hdg_get_sizes(self.h, C.byref(s)), self.h)
+        return s
+
+    def set_mesh(self, mesh):
+        if mesh._rect is not None and not getattr(mesh, "_modified", False):
+            nx, ny, LL, UR = mesh._rect
+            check(self.lib.hdg_set_rectangle_mesh(self.h, nx, ny, LL[0], LL[1], UR[0], UR[1]), self.h)
+        else:
+            bf = np.array(sorted(mesh.facesets["boundary"]), dtype=np.int64)
+            check(self.lib.hdg_set_mesh(self.h, i64p(mesh.cells), mesh.cells.shape[0], f64p(mesh.nodes),
+                                        mesh.nodes.shape[0], i64p(mesh.faces), mesh.faces.shape[0],
+                                        i64p(bf), bf.size), self.h)
+        self.mesh = mesh
+
+    def download_mesh(self):
+        s = self.sizes()
+        cells = np.empty((s.ncell, 6), np.int64)
+        nodes = np.empty((s.nnode, 2), np.float64)
+        faces = np.empty((s.nface, 4), np.int64, order="F")
+        bf = np.empty(s.nbface, np.int64)
+        check(self.lib.hdg_get_mesh(self.h, i64p(cells), f64p(nodes), i64p(faces), i64p(bf)), self.h)
+        return PolygonalMesh(cells, nodes, faces, {"boundary": set(bf.tolist())})
+
+    def table(self, name):
+        cnt = C.c_int64()
+        check(self.lib.hdg_get_table(self.h, name.encode(), None, C.byref(cnt)), self.h)
+        buf = np.empty(cnt.value)
+        check(self.lib.hdg_get_table(self.h, name.encode(), f64p(buf), C.byref(cnt)), self.h)
+        return buf
+
+
+# ----------------------------------------------------------------------------------------------
+# function spaces (src/ScalarFunctionSpaces.jl, src/VectorFunctionSpaces.jl, src/TraceFunctionSpaces.jl)
+# ----------------------------------------------------------------------------------------------
+class ScalarFunctionSpace:
+    """ScalarFunctionSpace(mesh, fe; quad_degree = order+1), src/ScalarFunctionSpaces.jl:24-29."""
+    components = 1
+
+    def __init__(self, mesh, felem, quad_degree=None):
+        self.mesh, self.fe = mesh, felem
+        self.quad_degree = felem.order + 1 if quad_degree is None else int(quad_degree)
+        self._tabs = None
+
+    def getnbasefunctions(self):
+        return self.fe.basis.getnbasefunctions()
+
+    getnlocaldofs = getnbasefunctions
+
+    def _tables(self):
+        if self._tabs is None:   # raises UnsupportedRuleError like src/quadrature.jl:24
+            self._tabs = {k: ref_table(self.fe.order, self.quad_degree, k)
+                          for k in ("qpoints", "qweights", "fpoints", "fweights", "N", "dNdxi", "E", "T")}
+        return self._tabs
+
+    def getnquadpoints(self):
+        return self._tables()["qweights"].size
+
+
+class VectorFunctionSpace(ScalarFunctionSpace):
+    """VectorFunctionSpace(mesh, fe; quad_degree), src/VectorFunctionSpaces.jl:10-18."""
+    components = 2
+
+    def getnbasefunctions(self):
+        return 2 * self.fe.basis.getnbasefunctions()
+
+    getnlocaldofs = getnbasefunctions
+
+
+class ScalarTraceFunctionSpace:
+    """ScalarTraceFunctionSpace(Wh, fe), src/TraceFunctionSpaces.jl:11-28."""
+    components = 1
+
+    def __init__(self, psp, felem):
+        self.fs, self.fe, self.mesh = psp, felem, psp.mesh
+
+    def getnbasefunctions(self):
+        return self.fe.basis.getnbasefunctions()
+
+    def getnlocaldofs(self):
+        return 3 * self.getnbasefunctions()
+
+
+def getnbasefunctions(x):
+    return x.getnbasefunctions()
+
+
+def getnlocaldofs(x):
+    return x.getnlocaldofs()
+
+
+class TrialFunction:
+    """TrialFunction(fs) with NaN-filled m_values, src/DiscreteFunctions.jl:27-54."""
+
+    def __init__(self, fs):
+        self.fs = fs
+        nc = fs.mesh.getncells()
+        if isinstance(fs, ScalarTraceFunctionSpace):
+            self.m_values = np.full((nc, fs.getnbasefunctions(), 3), np.nan, order="F")
+        else:
+            self.m_values = np.full((nc, fs.getnbasefunctions()), np.nan, order="F")
+        self.components = fs.components
+        self._ctx = None
+
+    def getnbasefunctions(self):
+        return self.fs.getnbasefunctions()
+
+
+class Dirichlet:
+    """Dirichlet(u_hat, mesh, faceset, f) for trace spaces, src/boundary.jl:7-42: prescribed dofs
+    face*nt-nt+i over the set in ascending face order.  Only g == 0 is on the hot path (the
+    reference's projection of non-zero data is inconsistent, SURVEY.md section 0 trap 4), so
+    `f` is sampled at the face end points only to verify that it vanishes."""
+
+    def __init__(self, u, mesh, faceset, f):
+        fs = u.fs
+        if not isinstance(fs, ScalarTraceFunctionSpace):
+            raise NotImplementedError("only trace-space Dirichlet conditions are on the HDG path")
+        nt = fs.getnbasefunctions()
+        faces = sorted(mesh.getfaceset(faceset)) if isinstance(faceset, str) else sorted(faceset)
+        for fi in faces:
+            if mesh.faces[fi - 1, 3] != 0:
+                raise AssertionError(f"Face {fi} is not in boundary")   # src/boundary.jl:22
+        self.faces = np.array(faces, dtype=np.int64)
+        self.prescribed_dofs = (self.faces[:, None] * nt - nt + np.arange(1, nt + 1)[None, :]).reshape(-1)
+        vals = np.zeros(self.prescribed_dofs.size)
+        if faces:
+            ends = mesh.nodes[mesh.faces[self.faces - 1, :2].reshape(-1) - 1]
+            g = np.array([float(f(p)) for p in ends[: min(len(ends), 64)]])
+            if np.any(g != 0.0):
+                raise NotImplementedError("non-homogeneous Dirichlet data is not on the HDG hot path (g must be 0)")
+        self.values = vals
+
+
+# ----------------------------------------------------------------------------------------------
+# the hot path: doassemble / apply! / solve / get_uσ! / errornorm
+# ----------------------------------------------------------------------------------------------
+def poisson_source(x):
+    """f of examples/poisson2D_HDG.jl:55; passing this exact function selects the built-in
+    device evaluation (source_id = 1) instead of sampling on the host."""
+    return 2 * np.pi ** 2 * np.sin(np.pi * x[0]) * np.sin(np.pi * x[1])
+
+
+def poisson_exact(x):
+    """u_ex of examples/poisson2D_HDG.jl:216."""
+    return np.sin(np.pi * x[0]) * np.sin(np.pi * x[1])
+
+
+class TraceMatrix:
+    """Handle of the assembled trace matrix K (SparseMatrixCSC in the reference)."""
+
+    def __init__(self, ctx):
+        self._ctx = ctx
+
+    @property
+    def shape(self):
+        s = self._ctx.sizes()
+        return (s.ndof, s.ndof)
+
+    def pattern(self):
+        """(colptr, rowval) of sparse(I,J,V), Int64 1-based (src/assembler.jl:47-49)."""
+        s = self._ctx.sizes()
+        colptr = np.empty(s.ndof + 1, np.int64)
+        rowval = np.empty(s.nnz, np.int64)
+        check(self._ctx.lib.hdg_get_pattern(self._ctx.h, i64p(colptr), i64p(rowval)), self._ctx.h)
+        return colptr, rowval
+
+    def nzval(self):
+        s = self._ctx.sizes()
+        v = np.empty(s.nnz)
+        check(self._ctx.lib.hdg_get_values(self._ctx.h, f64p(v)), self._ctx.h)
+        return v
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        colptr, rowval = self.pattern()
+        n = colptr.size - 1
+        return sp.csc_matrix((self.nzval(), rowval - 1, colptr - 1), shape=(n, n))
+
+
+class DeviceVector:
+    def __init__(self, ctx, getter):
+        self._ctx, self._getter = ctx, getter
+
+    def to_numpy(self):
+        s = self._ctx.sizes()
+        v = np.empty(s.ndof)
+        check(getattr(self._ctx.lib, self._getter)(self._ctx.h, f64p(v)), self._ctx.h)
+        return v
+
+    def __array__(self, dtype=None, copy=None):
+        return self.to_numpy()
+
+
+class LocalSolvers:
+    """K_element / b_element (examples/poisson2D_HDG.jl:74-75), resident on the device."""
+
+    def __init__(self, ctx, which):
+        self._ctx, self._which = ctx, which
+
+    def __len__(self):
+        return self._ctx.sizes().ncell
+
+    def __getitem__(self, cell0):
+        s = self._ctx.sizes()
+        Ke = np.empty((s.m, s.t), order="F")
+        be = np.empty(s.m)
+        check(self._ctx.lib.hdg_get_local(self._ctx.h, int(cell0) + 1, f64p(Ke), f64p(be)), self._ctx.h)
+        return Ke if self._which == "K" else be
+
+
+def doassemble(Vh, Wh, Mh, tau=1.0, f=poisson_source, device=-1, local_solver=0):
+    """doassemble(Vh,Wh,Mh,tau) of examples/poisson2D_HDG.jl:58-186 -> (K, rhs, K_element, b_element)."""
+    if Vh.quad_degree != Wh.quad_degree or Vh.fe.order != Wh.fe.order or Mh.fe.order != Wh.fe.order:
+        raise ValueError("Vh, Wh, Mh must share order and quad_degree")
+    mesh = Wh.mesh
+    builtin = f is poisson_source
+    ctx = _Context(Wh.fe.order, Wh.quad_degree, tau, 1 if builtin else 0, device, local_solver)
+    ctx.set_mesh(mesh)
+    if not builtin:
+        # function_value(f, Wh, cell, q) sampled on the host: x_q = sum_g M[g,q] x_g  (src/DiscreteFunctions.jl:6-24)
+        qp = Wh._tables()["qpoints"].reshape(-1, 2)
+        M = np.stack([1 - qp[:, 0] - qp[:, 1], qp[:, 0], qp[:, 1]], axis=0)          # (3,nq)
+        xc = mesh.nodes[mesh.cells[:, :3] - 1]                                        # (ncell,3,2)
+        xq = np.einsum("gq,cgd->cqd", M, xc)
+        fq = np.ascontiguousarray(np.vectorize(lambda a, b: f((a, b)))(xq[..., 0], xq[..., 1]), dtype=np.float64)
+        check(ctx.lib.hdg_set_source_values(ctx.h, f64p(fq)), ctx.h)
+    check(ctx.lib.hdg_assemble(ctx.h), ctx.h)
+    return TraceMatrix(ctx), DeviceVector(ctx, "hdg_get_rhs"), LocalSolvers(ctx, "K"), LocalSolvers(ctx, "b")
+
+
+def apply_(K, b, dbc):
+    """apply!(K, b, dbc), src/boundary.jl:121-158 (in place on the device)."""
+    ctx = K._ctx
+    s = ctx.sizes()
+    mine = np.array(sorted(ctx.mesh.facesets["boundary"]), dtype=np.int64)
+    if dbc.faces.size != s.nbface or not np.array_equal(dbc.faces, mine):
+        raise NotImplementedError("the Dirichlet set must be the mesh's \"boundary\" face set")
+    vals = dbc.values if np.any(dbc.values != 0) else None
+    check(ctx.lib.hdg_apply_dirichlet(ctx.h, f64p(vals)), ctx.h)
+
+
+def meandiag(K):
+    m = C.c_double()
+    check(K._ctx.lib.hdg_get_meandiag(K._ctx.h, C.byref(m)), K._ctx.h)
+    return m.value
+
+
+def solve(K, b, rtol=1e-13, maxit=200000):
+    """u_hat = K \\ b (examples/poisson2D_HDG.jl:195) by Jacobi-PCG on the sign-fixed system.
+    Returns (DeviceVector, info dict)."""
+    ctx = K._ctx
+    info = SolveInfo()
+    check(ctx.lib.hdg_solve(ctx.h, float(rtol), int(maxit), C.byref(info)), ctx.h)
+    d = dict(iterations=info.iterations, converged=bool(info.converged), relres=info.relres,
+             bnorm=info.bnorm, solve_ms=info.solve_ms)
+    return DeviceVector(ctx, "hdg_get_trace"), d
+
+
+def get_usigma_(sigma_h, u_h, uhat_h, uhat, K_e, b_e, mesh):
+    """get_uσ!(σ_h,u_h,û_h,û,K_e,b_e,mesh), examples/poisson2D_HDG.jl:197-212."""
+    ctx = K_e._ctx
+    if isinstance(uhat, np.ndarray):
+        check(ctx.lib.hdg_set_trace(ctx.h, f64p(np.ascontiguousarray(uhat, dtype=np.float64))), ctx.h)
+    check(ctx.lib.hdg_recover(ctx.h), ctx.h)
+    check(ctx.lib.hdg_get_mvalues(ctx.h, f64p(sigma_h.m_values), f64p(u_h.m_values), f64p(uhat_h.m_values)), ctx.h)
+    u_h._ctx = sigma_h._ctx = uhat_h._ctx = ctx
+
+
+def errornorm(u_h, u_ex=poisson_exact, norm_type="L2"):
+    """errornorm(u_h,u_ex): squared L2 error, src/DiscreteFunctions.jl:97-120."""
+    if norm_type != "L2":
+        raise ValueError(f"Norm {norm_type} not available")
+    if u_ex is not poisson_exact:
+        raise NotImplementedError("only the manufactured solution sin(pi x) sin(pi y) is built in")
+    ctx = u_h._ctx
+    if ctx is None:
+        raise HDGError(1, "errornorm before get_usigma_")
+    e = C.c_double()
+    check(ctx.lib.hdg_errornorm(ctx.h, 1, C.byref(e)), ctx.h)
+    return e.value
+
+
+def poisson2D_HDG(mesh=None, order=1, quad_degree=None, tau=1.0, rtol=1e-13, maxit=200000):
+    """The driver examples/poisson2D_HDG.jl:37-218 end to end.  Returns a dict of results."""
+    if mesh is None:
+        mesh = rectangle_mesh(TriangleCell, (10, 10), (0.0, 0.0), (1.0, 1.0))
+    fe = GenericFiniteElement(Dubiner(2, RefTetrahedron, order))
+    Wh = ScalarFunctionSpace(mesh, fe, quad_degree)
+    Vh = VectorFunctionSpace(mesh, fe, quad_degree)
+    Mh = ScalarTraceFunctionSpace(Wh, GenericFiniteElement(Legendre(1, RefTetrahedron, order)))
+    uhat_h, sigma_h, u_h = TrialFunction(Mh), TrialFunction(Vh), TrialFunction(Wh)
+    dbc = Dirichlet(uhat_h, mesh, "boundary", lambda x: 0)
+    K, b, K_e, b_e = doassemble(Vh, Wh, Mh, tau)
+    apply_(K, b, dbc)
+    uhat, info = solve(K, b, rtol, maxit)
+    get_usigma_(sigma_h, u_h, uhat_h, uhat, K_e, b_e, mesh)
+    err2 = errornorm(u_h, poisson_exact)
+    return dict(K=K, b=b, K_e=K_e, b_e=b_e, uhat=uhat, sigma_h=sigma_h, u_h=u_h, uhat_h=uhat_h,
+                err2=err2, info=info, dbc=dbc, mesh=mesh)

@@ -1,0 +1,379 @@
+// C ABI of libhdg_b200 (include/hdg_b200.h): argument checking, call-order state machine, error
+// reporting.  No compute lives here and there is no CPU fallback: every compute entry point ends
+// in a CUDA kernel launch or fails with HDG_ERR_CUDA.
+#include <cmath>
+#include <cstring>
+
+#include "hdg_internal.h"
+
+namespace hdg {
+
+static thread_local std::string g_create_error;
+
+hdg_status set_err(hdg_context* c, hdg_status s, const std::string& msg) {
+    if (c) c->err = msg;
+    else g_create_error = msg;
+    return s;
+}
+
+void timer_start(hdg_context* c, Timer& t) {
+    if (!t.a) { cudaEventCreate(&t.a); cudaEventCreate(&t.b); }
+    cudaEventRecord(t.a, c->stream);
+}
+void timer_stop(hdg_context* c, Timer& t) {
+    cudaEventRecord(t.b, c->stream);
+    t.pending = true;
+}
+float timer_ms(Timer& t) {
+    if (t.pending) {
+        cudaEventSynchronize(t.b);
+        cudaEventElapsedTime(&t.last_ms, t.a, t.b);
+        t.pending = false;
+    }
+    return t.last_ms;
+}
+
+static hdg_status check_flags(hdg_context* c) {
+    HDG_CUDA(c, cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int32_t) * NFLAGS, cudaMemcpyDeviceToHost, c->stream));
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->h_flags[FLAG_BAD_GEOM])
+        return set_err(c, HDG_ERR_BAD_GEOMETRY, "det(J) is not positive in cell " + std::to_string(c->h_flags[FLAG_BAD_GEOM]));
+    if (c->h_flags[FLAG_SINGULAR])
+        return set_err(c, HDG_ERR_SINGULAR_LOCAL, "singular local matrix in cell " + std::to_string(c->h_flags[FLAG_SINGULAR]));
+    return HDG_OK;
+}
+
+}  // namespace hdg
+
+using namespace hdg;
+
+extern "C" {
+
+const char* hdg_version(void) { return "hdg_b200 0.1 (sm_100a)"; }
+
+const char* hdg_last_error(const hdg_context* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+hdg_status hdg_create(const hdg_params* prm, hdg_context** out) {
+    if (!prm || !out) return set_err(nullptr, HDG_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (prm->source_id < 0 || prm->source_id > 1) return set_err(nullptr, HDG_ERR_INVALID, "unknown source_id");
+    if (prm->local_solver < 0 || prm->local_solver > 1) return set_err(nullptr, HDG_ERR_INVALID, "unknown local_solver");
+    RefTables tab;
+    try {
+        tab = build_ref_tables(prm->order, prm->quad_degree);
+    } catch (const std::string& e) {
+        bool rule = e.find("not available") != std::string::npos;
+        return set_err(nullptr, rule ? HDG_ERR_UNSUPPORTED_RULE : HDG_ERR_INVALID, e);
+    }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return set_err(nullptr, HDG_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(ce));
+    hdg_context* c = new hdg_context();
+    c->prm = *prm;
+    c->tab = tab;
+    if (prm->device >= 0) {
+        if (cudaSetDevice(prm->device) != cudaSuccess) {
+            delete c;
+            return set_err(nullptr, HDG_ERR_CUDA, "cudaSetDevice failed");
+        }
+    }
+    cudaGetDevice(&c->device);
+    auto fail = [&](const char* what) {
+        std::string msg = std::string(what) + ": " + cudaGetErrorString(cudaGetLastError());
+        hdg_destroy(c);
+        return set_err(nullptr, HDG_ERR_CUDA, msg);
+    };
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate");
+    if (cudaMalloc(&c->d_flags, sizeof(int32_t) * NFLAGS) != cudaSuccess) return fail("cudaMalloc");
+    if (cudaMalloc(&c->d_scal, sizeof(double) * 8) != cudaSuccess) return fail("cudaMalloc");
+    if (cudaMalloc(&c->d_partials, sizeof(double) * 5 * 2048) != cudaSuccess) return fail("cudaMalloc");
+    if (cudaMallocHost(&c->h_flags, sizeof(int32_t) * NFLAGS) != cudaSuccess) return fail("cudaMallocHost");
+    if (cudaMallocHost(&c->h_scal, sizeof(double) * 8) != cudaSuccess) return fail("cudaMallocHost");
+    cudaMemset(c->d_flags, 0, sizeof(int32_t) * NFLAGS);
+    // Block elimination needs the mass matrix of the chosen cell rule to be invertible; it is
+    // the identity exactly when the rule integrates degree 2k (Dubiner is orthonormal).  Rules that
+    // under-integrate it (e.g. the reference default quad_degree = k+1 for k = 2) go through the
+    // literal quadrature + LU path, as the reference does.
+    double dev = 0.0;
+    for (int i = 0; i < tab.n; ++i)
+        for (int j = 0; j < tab.n; ++j) dev = std::fmax(dev, std::fabs(tab.Mhat[size_t(i) * tab.n + j] - (i == j ? 1.0 : 0.0)));
+    c->use_lu = prm->local_solver == 1 || !(dev < 1e-9);
+    hdg_status st = upload_tables(c);
+    if (st) {
+        std::string msg = c->err;
+        hdg_destroy(c);
+        return set_err(nullptr, st, msg);
+    }
+    *out = c;
+    return HDG_OK;
+}
+
+void hdg_destroy(hdg_context* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_mesh(c);
+    if (c->d_rawtab) cudaFree(c->d_rawtab);
+    if (c->d_flags) cudaFree(c->d_flags);
+    if (c->d_scal) cudaFree(c->d_scal);
+    if (c->d_partials) cudaFree(c->d_partials);
+    if (c->h_flags) cudaFreeHost(c->h_flags);
+    if (c->h_scal) cudaFreeHost(c->h_scal);
+    for (Timer* t : {&c->t_assemble, &c->t_apply, &c->t_solve, &c->t_recover, &c->t_err}) {
+        if (t->a) cudaEventDestroy(t->a);
+        if (t->b) cudaEventDestroy(t->b);
+    }
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+hdg_status hdg_set_mesh(hdg_context* c, const int64_t* cells, int64_t ncell, const double* nodes, int64_t nnode,
+                        const int64_t* faces, int64_t nface, const int64_t* bfaces, int64_t nbface) {
+    if (!c) return HDG_ERR_INVALID;
+    if (!cells || !nodes || !faces || (nbface > 0 && !bfaces)) return set_err(c, HDG_ERR_INVALID, "null mesh array");
+    cudaSetDevice(c->device);
+    return mesh_from_host(c, cells, ncell, nodes, nnode, faces, nface, bfaces, nbface);
+}
+
+hdg_status hdg_set_rectangle_mesh(hdg_context* c, int64_t nx, int64_t ny, double llx, double lly, double urx, double ury) {
+    if (!c) return HDG_ERR_INVALID;
+    cudaSetDevice(c->device);
+    return mesh_rectangle(c, nx, ny, llx, lly, urx, ury);
+}
+
+hdg_status hdg_perturb_nodes(hdg_context* c, double fraction, uint64_t seed) {
+    if (!c) return HDG_ERR_INVALID;
+    cudaSetDevice(c->device);
+    return mesh_perturb(c, fraction, seed);
+}
+
+hdg_status hdg_get_sizes(const hdg_context* c, hdg_sizes* s) {
+    if (!c || !s) return HDG_ERR_INVALID;
+    std::memset(s, 0, sizeof(*s));
+    s->n = c->tab.n; s->nt = c->tab.nt; s->m = c->tab.m; s->t = c->tab.t; s->nq = c->tab.nq; s->nfq = c->tab.nfq;
+    if (c->have_mesh) {
+        s->ncell = c->ncell; s->nnode = c->nnode; s->nface = c->nface; s->nbface = c->nbface;
+        s->ndof = c->nface * c->tab.nt;
+        s->nnz = pattern_nnz(const_cast<hdg_context*>(c));
+    }
+    return HDG_OK;
+}
+
+hdg_status hdg_get_mesh(hdg_context* c, int64_t* cells, double* nodes, int64_t* faces, int64_t* bf) {
+    if (!c) return HDG_ERR_INVALID;
+    cudaSetDevice(c->device);
+    return mesh_download(c, cells, nodes, faces, bf);
+}
+
+static const std::vector<double>* table_by_name(const RefTables& T, const std::string& s) {
+    if (s == "qpoints") return &T.qpts;
+    if (s == "qweights") return &T.qw;
+    if (s == "fpoints") return &T.fpts;
+    if (s == "fweights") return &T.fw;
+    if (s == "N") return &T.N;
+    if (s == "dNdxi") return &T.dN;
+    if (s == "E") return &T.E;
+    if (s == "T") return &T.T;
+    if (s == "Mhat") return &T.Mhat;
+    return nullptr;
+}
+
+hdg_status hdg_get_table(const hdg_context* c, const char* name, double* buf, int64_t* count) {
+    if (!c || !name || !count) return HDG_ERR_INVALID;
+    const std::vector<double>* v = table_by_name(c->tab, name);
+    if (!v) return set_err(const_cast<hdg_context*>(c), HDG_ERR_INVALID, "unknown table name");
+    *count = int64_t(v->size());
+    if (buf) std::memcpy(buf, v->data(), sizeof(double) * v->size());
+    return HDG_OK;
+}
+
+hdg_status hdg_ref_table(int32_t order, int32_t quad_degree, const char* name, double* buf, int64_t* count) {
+    if (!name || !count) return HDG_ERR_INVALID;
+    RefTables tab;
+    try {
+        tab = build_ref_tables(order, quad_degree);
+    } catch (const std::string& e) {
+        bool rule = e.find("not available") != std::string::npos;
+        return set_err(nullptr, rule ? HDG_ERR_UNSUPPORTED_RULE : HDG_ERR_INVALID, e);
+    }
+    const std::vector<double>* v = table_by_name(tab, name);
+    if (!v) return set_err(nullptr, HDG_ERR_INVALID, "unknown table name");
+    *count = int64_t(v->size());
+    if (buf) std::memcpy(buf, v->data(), sizeof(double) * v->size());
+    return HDG_OK;
+}
+
+hdg_status hdg_set_source_values(hdg_context* c, const double* fq) {
+    if (!c || !fq) return HDG_ERR_INVALID;
+    if (!c->have_mesh) return set_err(c, HDG_ERR_INVALID, "hdg_set_source_values before a mesh is set");
+    cudaSetDevice(c->device);
+    size_t bytes = sizeof(double) * c->ncell * c->tab.nq;
+    if (!c->d_fq) HDG_CUDA(c, cudaMalloc(&c->d_fq, bytes));
+    HDG_CUDA(c, cudaMemcpyAsync(c->d_fq, fq, bytes, cudaMemcpyHostToDevice, c->stream));
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HDG_OK;
+}
+
+hdg_status hdg_assemble_async(hdg_context* c) {
+    if (!c) return HDG_ERR_INVALID;
+    if (!c->have_mesh) return set_err(c, HDG_ERR_INVALID, "hdg_assemble before a mesh is set");
+    if (c->prm.source_id == 0 && !c->d_fq) return set_err(c, HDG_ERR_INVALID, "source_id 0 needs hdg_set_source_values");
+    cudaSetDevice(c->device);
+    timer_start(c, c->t_assemble);
+    hdg_status st = launch_element_kernels(c);
+    timer_stop(c, c->t_assemble);
+    if (st) return st;
+    c->assembled = true;
+    c->applied = c->solved = c->recovered = false;
+    return HDG_OK;
+}
+
+hdg_status hdg_sync(hdg_context* c) {
+    if (!c) return HDG_ERR_INVALID;
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HDG_OK;
+}
+
+uint64_t hdg_stream(const hdg_context* c) { return c ? uint64_t(reinterpret_cast<uintptr_t>(c->stream)) : 0; }
+
+hdg_status hdg_assemble(hdg_context* c) {
+    if (!c) return HDG_ERR_INVALID;
+    HDG_CUDA(c, cudaMemsetAsync(c->d_flags, 0, sizeof(int32_t) * NFLAGS, c->stream));
+    hdg_status st = hdg_assemble_async(c);
+    if (st) return st;
+    st = check_flags(c);
+    if (st) c->assembled = false;
+    return st;
+}
+
+hdg_status hdg_apply_dirichlet(hdg_context* c, const double* values) {
+    if (!c) return HDG_ERR_INVALID;
+    if (!c->assembled) return set_err(c, HDG_ERR_INVALID, "hdg_apply_dirichlet before hdg_assemble");
+    if (c->applied) return set_err(c, HDG_ERR_INVALID, "hdg_apply_dirichlet called twice on the same assembly");
+    cudaSetDevice(c->device);
+    timer_start(c, c->t_apply);
+    hdg_status st = apply_dirichlet(c, values);
+    timer_stop(c, c->t_apply);
+    if (st) return st;
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->applied = true;
+    return HDG_OK;
+}
+
+hdg_status hdg_solve(hdg_context* c, double rtol, int32_t maxit, hdg_solve_info* info) {
+    if (!c) return HDG_ERR_INVALID;
+    if (!c->assembled) return set_err(c, HDG_ERR_INVALID, "hdg_solve before hdg_assemble");
+    if (!c->applied) return set_err(c, HDG_ERR_INVALID, "hdg_solve before hdg_apply_dirichlet (the raw condensed matrix is singular)");
+    if (!(rtol > 0.0) || maxit < 1) return set_err(c, HDG_ERR_INVALID, "need rtol > 0 and maxit >= 1");
+    cudaSetDevice(c->device);
+    return pcg_solve(c, rtol, maxit, info);
+}
+
+hdg_status hdg_recover(hdg_context* c) {
+    if (!c) return HDG_ERR_INVALID;
+    if (!c->assembled || !c->d_x) return set_err(c, HDG_ERR_INVALID, "hdg_recover needs hdg_assemble and a trace solution (hdg_solve / hdg_set_trace)");
+    cudaSetDevice(c->device);
+    return recover(c);
+}
+
+hdg_status hdg_errornorm(hdg_context* c, int32_t exact_id, double* err2) {
+    if (!c || !err2) return HDG_ERR_INVALID;
+    if (!c->recovered) return set_err(c, HDG_ERR_INVALID, "hdg_errornorm before hdg_recover");
+    if (exact_id != 1) return set_err(c, HDG_ERR_INVALID, "unknown exact_id");
+    cudaSetDevice(c->device);
+    return errornorm(c, exact_id, err2);
+}
+
+hdg_status hdg_get_pattern(hdg_context* c, int64_t* colptr, int64_t* rowval) {
+    if (!c) return HDG_ERR_INVALID;
+    cudaSetDevice(c->device);
+    return pattern_download(c, colptr, rowval);
+}
+
+hdg_status hdg_get_values(hdg_context* c, double* nzval) {
+    if (!c || !nzval) return HDG_ERR_INVALID;
+    cudaSetDevice(c->device);
+    return values_download(c, nzval);
+}
+
+hdg_status hdg_get_rhs(hdg_context* c, double* rhs) {
+    if (!c || !rhs) return HDG_ERR_INVALID;
+    if (!c->assembled) return set_err(c, HDG_ERR_INVALID, "hdg_get_rhs before hdg_assemble");
+    HDG_CUDA(c, cudaMemcpyAsync(rhs, c->d_rhs, sizeof(double) * c->nface * c->tab.nt, cudaMemcpyDeviceToHost, c->stream));
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HDG_OK;
+}
+
+hdg_status hdg_get_trace(hdg_context* c, double* uhat) {
+    if (!c || !uhat) return HDG_ERR_INVALID;
+    if (!c->d_x) return set_err(c, HDG_ERR_INVALID, "no trace solution yet");
+    HDG_CUDA(c, cudaMemcpyAsync(uhat, c->d_x, sizeof(double) * c->nface * c->tab.nt, cudaMemcpyDeviceToHost, c->stream));
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HDG_OK;
+}
+
+hdg_status hdg_set_trace(hdg_context* c, const double* uhat) {
+    if (!c || !uhat) return HDG_ERR_INVALID;
+    if (!c->have_mesh) return set_err(c, HDG_ERR_INVALID, "no mesh");
+    cudaSetDevice(c->device);
+    if (!c->d_x) HDG_CUDA(c, cudaMalloc(&c->d_x, sizeof(double) * c->nface * c->tab.nt));
+    HDG_CUDA(c, cudaMemcpyAsync(c->d_x, uhat, sizeof(double) * c->nface * c->tab.nt, cudaMemcpyHostToDevice, c->stream));
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HDG_OK;
+}
+
+hdg_status hdg_get_meandiag(const hdg_context* c, double* m) {
+    if (!c || !m) return HDG_ERR_INVALID;
+    if (!c->applied) return set_err(const_cast<hdg_context*>(c), HDG_ERR_INVALID, "meandiag is computed by hdg_apply_dirichlet");
+    *m = c->meandiag;
+    return HDG_OK;
+}
+
+hdg_status hdg_get_local(hdg_context* c, int64_t cell, double* Ke, double* be) {
+    if (!c) return HDG_ERR_INVALID;
+    if (!c->assembled) return set_err(c, HDG_ERR_INVALID, "hdg_get_local before hdg_assemble");
+    if (cell < 1 || cell > c->ncell) return set_err(c, HDG_ERR_INVALID, "cell out of range");
+    cudaSetDevice(c->device);
+    return local_download(c, cell - 1, Ke, be);
+}
+
+hdg_status hdg_get_condensed(hdg_context* c, int64_t cell, double* Ate, double* bte) {
+    if (!c || !Ate || !bte) return HDG_ERR_INVALID;
+    if (!c->have_mesh) return set_err(c, HDG_ERR_INVALID, "no mesh");
+    if (cell < 1 || cell > c->ncell) return set_err(c, HDG_ERR_INVALID, "cell out of range");
+    if (c->prm.source_id == 0 && !c->d_fq) return set_err(c, HDG_ERR_INVALID, "source_id 0 needs hdg_set_source_values");
+    cudaSetDevice(c->device);
+    return condensed_of_cell(c, cell - 1, Ate, bte);
+}
+
+hdg_status hdg_get_mvalues(hdg_context* c, double* sigma, double* u, double* uhat_h) {
+    if (!c) return HDG_ERR_INVALID;
+    if (!c->recovered) return set_err(c, HDG_ERR_INVALID, "hdg_get_mvalues before hdg_recover");
+    const int n = c->tab.n, nt = c->tab.nt;
+    if (sigma) HDG_CUDA(c, cudaMemcpyAsync(sigma, c->d_sigma, sizeof(double) * c->ncell * 2 * n, cudaMemcpyDeviceToHost, c->stream));
+    if (u) HDG_CUDA(c, cudaMemcpyAsync(u, c->d_u, sizeof(double) * c->ncell * n, cudaMemcpyDeviceToHost, c->stream));
+    if (uhat_h) HDG_CUDA(c, cudaMemcpyAsync(uhat_h, c->d_uhat_h, sizeof(double) * c->ncell * nt * 3, cudaMemcpyDeviceToHost, c->stream));
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return HDG_OK;
+}
+
+hdg_status hdg_last_phase_ms(const hdg_context* cc, const char* phase, double* ms) {
+    if (!cc || !phase || !ms) return HDG_ERR_INVALID;
+    hdg_context* c = const_cast<hdg_context*>(cc);
+    std::string s(phase);
+    Timer* t = nullptr;
+    if (s == "assemble") t = &c->t_assemble;
+    else if (s == "apply") t = &c->t_apply;
+    else if (s == "solve") t = &c->t_solve;
+    else if (s == "recover") t = &c->t_recover;
+    else if (s == "errornorm") t = &c->t_err;
+    else return set_err(c, HDG_ERR_INVALID, "unknown phase");
+    if (!t->a) { *ms = 0.0; return HDG_OK; }
+    *ms = double(timer_ms(*t));
+    return HDG_OK;
+}
+
+int64_t hdg_launch_count(const hdg_context* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,626 @@
+// K1+K2+K3: fused local-block formation, static condensation and scatter, one pass per element.
+//
+// Replaces the per-element body of doassemble (examples/poisson2D_HDG.jl:77-184): reinit!
+// (src/ScalarFunctionSpaces.jl:101-132), the quadrature loops (:88-153), the block solve
+// Me \ [-E;F], Ate = [E;F]'K_e - He, b_e, bte (:155-174) and the scatter assemble!(...)
+// (:176-183, src/assembler.jl:31-60).
+//
+// Two device paths, both FP64:
+//  * element_schur_kernel<K>  (default when the cell rule integrates the mass matrix exactly):
+//    one thread per element.  On an affine triangle every block is a geometry scalar times a
+//    reference matrix, so Me is eliminated block-wise:
+//      S = C + B' A^-1 B = tau*sum_l |wn_l| Chat_l + detJ (alpha Prr + beta Prs + gamma Pss)   (n x n, SPD)
+//    factored LDL' per element; the t+1 right-hand sides ([-E;F] columns and [0;be]) are then
+//    solved one column at a time, each column immediately contracted into its column of
+//    Ate / bte and scattered.  Reference matrices live in __constant__ memory so the operand of
+//    most DFMAs comes straight from the constant bank.
+//  * element_lu_kernel (any quad_degree; literal quadrature + dense partial-pivot LU, one warp
+//    per element in shared memory) - the reference's formulation, used when the mass matrix of
+//    the chosen rule is not the identity (e.g. the reference default quad_degree = 3 for k = 2).
+//
+// Scatter: the trace matrix is stored block-wise (hdg_internal.h): every (row face, column
+// face) block of Ate is nt*nt contiguous doubles.  Off-diagonal blocks have exactly one
+// contributing cell -> plain stores.  Face-diagonal blocks and rhs entries have at most two
+// contributions -> RED.ADD.F64 onto zeroed storage, which is bitwise deterministic because a
+// two-term IEEE sum is commutative.
+#include "hdg_internal.h"
+
+namespace hdg {
+
+__constant__ DevTables<1> c_tab1;
+__constant__ DevTables<2> c_tab2;
+__constant__ DevTables<3> c_tab3;
+__constant__ DevTables<4> c_tab4;
+
+template <int K> __device__ __forceinline__ const DevTables<K>& ctab();
+template <> __device__ __forceinline__ const DevTables<1>& ctab<1>() { return c_tab1; }
+template <> __device__ __forceinline__ const DevTables<2>& ctab<2>() { return c_tab2; }
+template <> __device__ __forceinline__ const DevTables<3>& ctab<3>() { return c_tab3; }
+template <> __device__ __forceinline__ const DevTables<4>& ctab<4>() { return c_tab4; }
+
+struct ElemArgs {
+    const int32_t* cellinfo;
+    const double* nodes;
+    const double* fq;      // ncell x nq (source_id == 0)
+    double* Ke;            // [K_e | b_e], KE_TILE32 layout
+    double* Kd;
+    double* Ko;
+    double* rhs;
+    int32_t* flags;
+    int64_t cell_begin, cell_end;
+    double tau;
+    int nq;
+    int source_id;
+    double* dbg_At;        // when non-null: write Ate (t x t column-major) / bte here instead of scattering
+    double* dbg_bt;
+};
+
+struct CellGeom {
+    double detJ, G00, G01, G10, G11;   // G = J^-1
+    double wn[3][2];                   // weighted normals, src/shapes.jl:80-87
+    double dJf[3];
+    double x[3][2];
+    int32_t v[3];
+    uint32_t f[3];                     // face id | sec<<31
+    bool ok;
+};
+
+__device__ __forceinline__ void load_geometry(const ElemArgs& a, int64_t c, CellGeom& g) {
+    const int2* ci = reinterpret_cast<const int2*>(a.cellinfo + 6 * c);
+    int2 p0 = __ldg(ci), p1 = __ldg(ci + 1), p2 = __ldg(ci + 2);
+    g.v[0] = p0.x; g.v[1] = p0.y; g.v[2] = p1.x;
+    g.f[0] = uint32_t(p1.y); g.f[1] = uint32_t(p2.x); g.f[2] = uint32_t(p2.y);
+    const double2* nd = reinterpret_cast<const double2*>(a.nodes);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double2 xy = __ldg(nd + g.v[k]);
+        g.x[k][0] = xy.x; g.x[k][1] = xy.y;
+    }
+    // J = [x2-x1 | x3-x1]  (reinit!, src/ScalarFunctionSpaces.jl:105-112)
+    double J00 = g.x[1][0] - g.x[0][0], J01 = g.x[2][0] - g.x[0][0];
+    double J10 = g.x[1][1] - g.x[0][1], J11 = g.x[2][1] - g.x[0][1];
+    g.detJ = J00 * J11 - J01 * J10;
+    g.ok = g.detJ > 0.0;
+    double id = 1.0 / g.detJ;
+    g.G00 = J11 * id; g.G01 = -J01 * id; g.G10 = -J10 * id; g.G11 = J00 * id;
+    g.wn[0][0] = -(J10 - J11); g.wn[0][1] = J00 - J01;
+    g.wn[1][0] = -J11;         g.wn[1][1] = J01;
+    g.wn[2][0] = J10;          g.wn[2][1] = -J00;
+#pragma unroll
+    for (int l = 0; l < 3; ++l) g.dJf[l] = sqrt(g.wn[l][0] * g.wn[l][0] + g.wn[l][1] * g.wn[l][1]);
+}
+
+__device__ __forceinline__ double source_value(int source_id, double x, double y) {
+    // f of examples/poisson2D_HDG.jl:55
+    const double pi = 3.141592653589793;
+    return 2.0 * (pi * pi) * sin(pi * x) * sin(pi * y);
+}
+
+// strict lower triangle index
+__device__ __forceinline__ constexpr int tri(int i, int j) { return i * (i - 1) / 2 + j; }
+
+template <int K, bool L_SMEM>
+__global__ void __launch_bounds__(128) element_schur_kernel(const ElemArgs a) {
+    constexpr int n = Ord<K>::n, nt = Ord<K>::nt, t = Ord<K>::t, ke = Ord<K>::ke;
+    constexpr int nL = n * (n - 1) / 2;
+    const DevTables<K>& T = ctab<K>();
+    extern __shared__ double smem_L[];   // L_SMEM: [nL][blockDim.x]
+
+    const int64_t c = a.cell_begin + int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= a.cell_end) return;
+    CellGeom g;
+    load_geometry(a, c, g);
+    if (!g.ok) {
+        atomicCAS(&a.flags[FLAG_BAD_GEOM], 0, int32_t(c + 1));
+        return;
+    }
+    const double tau = a.tau;
+    // orientation bits, face_orientation src/mesh.jl:51-54: local edge l joins local nodes ((1,2),(2,0),(0,1))
+    const bool o0 = g.v[2] > g.v[1], o1 = g.v[0] > g.v[2], o2 = g.v[1] > g.v[0];
+
+    // ---- S = C + B'A^-1 B, LDL' factorisation ------------------------------------------------
+    double Lr[L_SMEM ? 1 : (nL > 0 ? nL : 1)];
+    double dinv[n], dd[n];
+    auto Lget = [&](int i, int j) -> double {
+        if constexpr (L_SMEM) return smem_L[tri(i, j) * blockDim.x + threadIdx.x];
+        else return Lr[tri(i, j)];
+    };
+    auto Lset = [&](int i, int j, double v) {
+        if constexpr (L_SMEM) smem_L[tri(i, j) * blockDim.x + threadIdx.x] = v;
+        else Lr[tri(i, j)] = v;
+    };
+    {
+        const double al = g.detJ * (g.G00 * g.G00 + g.G01 * g.G01);
+        const double be = g.detJ * (g.G00 * g.G10 + g.G01 * g.G11);
+        const double ga = g.detJ * (g.G10 * g.G10 + g.G11 * g.G11);
+        const double c0 = tau * g.dJf[0], c1 = tau * g.dJf[1], c2 = tau * g.dJf[2];
+        bool spd = true;
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+            // column j of S below the diagonal, eliminated against columns < j
+            double col[n];
+#pragma unroll
+            for (int i = j; i < n; ++i) {
+                double s = c0 * T.Chat[(0 * n + i) * n + j];
+                s = fma(c1, T.Chat[(1 * n + i) * n + j], s);
+                s = fma(c2, T.Chat[(2 * n + i) * n + j], s);
+                s = fma(al, T.Prr[i * n + j], s);
+                s = fma(be, T.Prs[i * n + j], s);
+                s = fma(ga, T.Pss[i * n + j], s);
+                col[i] = s;
+            }
+#pragma unroll
+            for (int k = 0; k < j; ++k) {
+                const double ljk_dk = Lget(j, k) * dd[k];   // L[j][k] * d_k
+#pragma unroll
+                for (int i = j; i < n; ++i) col[i] = fma(-Lget(i, k), ljk_dk, col[i]);
+            }
+            spd = spd && (col[j] > 0.0);
+            dd[j] = col[j];
+            dinv[j] = 1.0 / col[j];
+#pragma unroll
+            for (int i = j + 1; i < n; ++i) Lset(i, j, col[i] * dinv[j]);
+        }
+        if (!spd) {
+            atomicCAS(&a.flags[FLAG_SINGULAR], 0, int32_t(c + 1));
+            return;
+        }
+    }
+
+    // ---- rhs vector be[i] = detJ sum_q w_q f(x_q) N[i,q]  (poisson2D_HDG.jl:106-114) -------------
+    double bev[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) bev[i] = 0.0;
+    for (int q = 0; q < a.nq; ++q) {
+        double fv;
+        if (a.source_id == 0) fv = a.fq[c * a.nq + q];
+        else {
+            double xq = T.Mgeo[3 * q] * g.x[0][0] + T.Mgeo[3 * q + 1] * g.x[1][0] + T.Mgeo[3 * q + 2] * g.x[2][0];
+            double yq = T.Mgeo[3 * q] * g.x[0][1] + T.Mgeo[3 * q + 1] * g.x[1][1] + T.Mgeo[3 * q + 2] * g.x[2][1];
+            fv = source_value(a.source_id, xq, yq);
+        }
+#pragma unroll
+        for (int i = 0; i < n; ++i) bev[i] = fma(T.WN[q * n + i], fv, bev[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < n; ++i) bev[i] *= g.detJ;
+
+    // per-face coefficients of the E-columns:  B'A^-1 E_l = a_l Qr_l + b_l Qs_l
+    double ca[3], cb[3];
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        ca[l] = g.G00 * g.wn[l][0] + g.G01 * g.wn[l][1];
+        cb[l] = g.G10 * g.wn[l][0] + g.G11 * g.wn[l][1];
+    }
+    const double idet = 1.0 / g.detJ;
+    const int lane = threadIdx.x & 31;
+    double* __restrict__ Ke_tile = a.Ke + ((c >> 5) * ke) * 32 + (c & 31);
+    (void)lane;
+    const int64_t nt2 = nt * nt;
+
+    // ---- one column of [K_e | b_e] at a time ----------------------------------------------------
+#pragma unroll 1
+    for (int col = 0; col <= t; ++col) {
+        const bool isb = col == t;
+        const int l = isb ? 0 : col / nt;
+        const int j = isb ? 0 : col - l * nt;
+        const double dJf_l = l == 0 ? g.dJf[0] : (l == 1 ? g.dJf[1] : g.dJf[2]);
+        const double wnx = l == 0 ? g.wn[0][0] : (l == 1 ? g.wn[1][0] : g.wn[2][0]);
+        const double wny = l == 0 ? g.wn[0][1] : (l == 1 ? g.wn[1][1] : g.wn[2][1]);
+        const double ca_l = l == 0 ? ca[0] : (l == 1 ? ca[1] : ca[2]);
+        const double cb_l = l == 0 ? cb[0] : (l == 1 ? cb[1] : cb[2]);
+        const bool o_l = l == 0 ? o0 : (l == 1 ? o1 : o2);
+        const double scol = (isb || o_l || !(j & 1)) ? 1.0 : -1.0;   // Legendre parity of a reversed face
+
+        double u[n];
+        if (isb) {
+#pragma unroll
+            for (int i = 0; i < n; ++i) u[i] = bev[i];
+        } else {
+            const double cf = tau * dJf_l;
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+                double r = cf * T.Fhat[i * t + col];
+                r = fma(ca_l, T.Qr[i * t + col], r);
+                u[i] = fma(cb_l, T.Qs[i * t + col], r);
+            }
+        }
+        // S u = r  by L D L'
+#pragma unroll
+        for (int i = 1; i < n; ++i)
+#pragma unroll
+            for (int k = 0; k < i; ++k) u[i] = fma(-Lget(i, k), u[k], u[i]);
+#pragma unroll
+        for (int i = 0; i < n; ++i) u[i] *= dinv[i];
+#pragma unroll
+        for (int i = n - 2; i >= 0; --i)
+#pragma unroll
+            for (int k = i + 1; k < n; ++k) u[i] = fma(-Lget(k, i), u[k], u[i]);
+
+        // sigma = A^-1 (r1 + B u)
+        double sx[n], sy[n];
+        const double ex = isb ? 0.0 : wnx * idet, ey = isb ? 0.0 : wny * idet;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            double p = 0.0, q = 0.0;
+#pragma unroll
+            for (int k = 0; k < n; ++k) {
+                p = fma(T.Tr[i * n + k], u[k], p);
+                q = fma(T.Ts[i * n + k], u[k], q);
+            }
+            double mf = isb ? 0.0 : T.MF[i * t + col];
+            sx[i] = fma(g.G00, p, fma(g.G10, q, -ex * mf));
+            sy[i] = fma(g.G01, p, fma(g.G11, q, -ey * mf));
+        }
+        // store column of [K_e | b_e]   (rows: sigma_x, sigma_y, u)
+        if (a.dbg_At == nullptr) {
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+                Ke_tile[int64_t((i) * (t + 1) + col) * 32] = scol * sx[i];
+                Ke_tile[int64_t((n + i) * (t + 1) + col) * 32] = scol * sy[i];
+                Ke_tile[int64_t((2 * n + i) * (t + 1) + col) * 32] = scol * u[i];
+            }
+        }
+        // column of Ate = [E;F]' K_e - He  /  bte = -[E;F]' b_e
+#pragma unroll
+        for (int lp = 0; lp < 3; ++lp) {
+            const bool o_lp = lp == 0 ? o0 : (lp == 1 ? o1 : o2);
+            const double cf = tau * g.dJf[lp];
+            double w[n];
+#pragma unroll
+            for (int i = 0; i < n; ++i) w[i] = fma(g.wn[lp][0], sx[i], fma(g.wn[lp][1], sy[i], cf * u[i]));
+            double val[nt];
+#pragma unroll
+            for (int ip = 0; ip < nt; ++ip) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < n; ++k) s = fma(T.Fhat[k * t + lp * nt + ip], w[k], s);
+                const double srow = (o_lp || !(ip & 1)) ? 1.0 : -1.0;
+                val[ip] = s * (srow * scol);
+            }
+            const int64_t f_lp = g.f[lp] & 0x7fffffffu;
+            if (isb) {
+                if (a.dbg_At) {
+#pragma unroll
+                    for (int ip = 0; ip < nt; ++ip) a.dbg_bt[lp * nt + ip] = -val[ip];
+                } else {
+#pragma unroll
+                    for (int ip = 0; ip < nt; ++ip) atomicAdd(&a.rhs[f_lp * nt + ip], -val[ip]);
+                }
+            } else {
+                if (lp == l) {
+#pragma unroll
+                    for (int ip = 0; ip < nt; ++ip) val[ip] = fma(-dJf_l, T.Hhat[ip * nt + j], val[ip]);
+                }
+                if (a.dbg_At) {
+#pragma unroll
+                    for (int ip = 0; ip < nt; ++ip) a.dbg_At[col * t + lp * nt + ip] = val[ip];
+                } else if (lp == l) {
+                    double* dst = a.Kd + f_lp * nt2 + j * nt;
+#pragma unroll
+                    for (int ip = 0; ip < nt; ++ip) atomicAdd(dst + ip, val[ip]);
+                } else {
+                    const int slot = int(g.f[lp] >> 31) * 2 + ((l - lp + 3) % 3 - 1);
+                    double* dst = a.Ko + (f_lp * 4 + slot) * nt2 + j * nt;
+                    if constexpr (nt % 2 == 0) {
+#pragma unroll
+                        for (int ip = 0; ip < nt; ip += 2)
+                            *reinterpret_cast<double2*>(dst + ip) = make_double2(val[ip], val[ip + 1]);
+                    } else {
+#pragma unroll
+                        for (int ip = 0; ip < nt; ++ip) dst[ip] = val[ip];
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// General path: literal quadrature + dense LU with partial pivoting, one warp per element.
+// Follows examples/poisson2D_HDG.jl:88-174 term by term.
+// ---------------------------------------------------------------------------------------------
+struct LuArgs {
+    ElemArgs e;
+    RawTablesDev raw;
+    int n, nt;
+};
+
+__global__ void __launch_bounds__(128) element_lu_kernel(const LuArgs A) {
+    const ElemArgs& a = A.e;
+    const RawTablesDev& R = A.raw;
+    const int n = A.n, nt = A.nt, nv = 2 * n, m = 3 * n, t = 3 * nt, nc = t + 1;   // rhs columns
+    const int ld = (m + nc) | 1;   // row length of [Me | rhs], odd so that lane-strided rows hit distinct banks
+    extern __shared__ double sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    // per warp: aug[m][ld], G[m][t] ( = [E;F] ), be[n], perm scratch
+    const int per_warp = m * ld + m * t + n + 8;
+    double* aug = sm + size_t(warp) * per_warp;
+    double* Gm = aug + m * ld;
+    double* bev = Gm + m * t;
+
+    const int64_t c = a.cell_begin + int64_t(blockIdx.x) * wpb + warp;
+    if (c >= a.cell_end) return;
+    CellGeom g;
+    load_geometry(a, c, g);
+    if (!g.ok) {
+        if (lane == 0) atomicCAS(&a.flags[FLAG_BAD_GEOM], 0, int32_t(c + 1));
+        return;
+    }
+    const double tau = a.tau;
+    const bool ori[3] = {g.v[2] > g.v[1], g.v[0] > g.v[2], g.v[1] > g.v[0]};
+    for (int k = lane; k < m * ld + m * t + n; k += 32) aug[k] = 0.0;
+    __syncwarp();
+
+    // cell integrals: A (block diagonal mass) and B  (:88-104).  One (i,j) pair per lane-iteration.
+    for (int idx = lane; idx < n * n; idx += 32) {
+        int i = idx / n, j = idx - i * n;
+        double mass = 0.0, bx = 0.0, by = 0.0;
+        for (int q = 0; q < R.nq; ++q) {
+            double dO = g.detJ * R.qw[q];
+            double Ni = R.N[i + n * q], Nj = R.N[j + n * q];
+            double dr = R.dN[(i + n * q) * 2], ds = R.dN[(i + n * q) * 2 + 1];
+            double gx = dr * g.G00 + ds * g.G10, gy = dr * g.G01 + ds * g.G11;   // dNdxi . Jinv
+            mass += (Nj * Ni) * dO;
+            bx += (Nj * gx) * dO;
+            by += (Nj * gy) * dO;
+        }
+        aug[i * ld + j] = mass;                     // A, x component
+        aug[(n + i) * ld + n + j] = mass;           // A, y component
+        aug[i * ld + nv + j] = -bx;                 // -B
+        aug[(n + i) * ld + nv + j] = -by;
+        aug[(nv + j) * ld + i] = bx;                // B'
+        aug[(nv + j) * ld + n + i] = by;
+    }
+    // rhs be (:106-114)
+    for (int i = lane; i < n; i += 32) {
+        double s = 0.0;
+        for (int q = 0; q < R.nq; ++q) {
+            double fv;
+            if (a.source_id == 0) fv = a.fq[c * R.nq + q];
+            else {
+                double xq = R.Mgeo[3 * q] * g.x[0][0] + R.Mgeo[3 * q + 1] * g.x[1][0] + R.Mgeo[3 * q + 2] * g.x[2][0];
+                double yq = R.Mgeo[3 * q] * g.x[0][1] + R.Mgeo[3 * q + 1] * g.x[1][1] + R.Mgeo[3 * q + 2] * g.x[2][1];
+                fv = source_value(a.source_id, xq, yq);
+            }
+            s += fv * R.N[i + n * q] * (g.detJ * R.qw[q]);
+        }
+        bev[i] = s;
+    }
+    // face integrals C (:120-126)
+    for (int idx = lane; idx < n * n; idx += 32) {
+        int i = idx / n, j = idx - i * n;
+        double s = 0.0;
+        for (int l = 0; l < 3; ++l)
+            for (int p = 0; p < R.nfq; ++p) {
+                double dS = g.dJf[l] * R.fw[p];
+                s += tau * (R.E[j + n * (p + R.nfq * l)] * R.E[i + n * (p + R.nfq * l)]) * dS;
+            }
+        aug[(nv + i) * ld + nv + j] = s;
+    }
+    // F, E (:127-143): G = [E;F]
+    for (int idx = lane; idx < n * t; idx += 32) {
+        int i = idx / t, cj = idx - i * t, l = cj / nt, j = cj - l * nt;
+        double f = 0.0;
+        for (int p = 0; p < R.nfq; ++p) {
+            int po = ori[l] ? p : R.nfq - 1 - p;
+            double dS = g.dJf[l] * R.fw[p];
+            f += (R.T[j + nt * p] * R.E[i + n * (po + R.nfq * l)]) * dS;
+        }
+        double nx = g.wn[l][0] / g.dJf[l], ny = g.wn[l][1] / g.dJf[l];
+        Gm[i * t + cj] = f * nx;
+        Gm[(n + i) * t + cj] = f * ny;
+        Gm[(nv + i) * t + cj] = tau * f;
+    }
+    __syncwarp();
+    // right-hand sides [-E;F | 0;be]
+    for (int idx = lane; idx < m * nc; idx += 32) {
+        int i = idx / nc, cj = idx - i * nc;
+        double v;
+        if (cj < t) v = i < nv ? -Gm[i * t + cj] : Gm[i * t + cj];
+        else v = i < nv ? 0.0 : bev[i - nv];
+        aug[i * ld + m + cj] = v;
+    }
+    __syncwarp();
+
+    // LU with partial pivoting (LAPACK getrf semantics) on [Me | rhs], rows distributed over lanes
+    bool singular = false;
+    for (int k = 0; k < m; ++k) {
+        // pivot search
+        double best = -1.0;
+        int bi = k;
+        for (int i = k + lane; i < m; i += 32) {
+            double v = fabs(aug[i * ld + k]);
+            if (v > best) { best = v; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (!(best > 0.0)) { singular = true; break; }
+        if (bi != k)
+            for (int j2 = lane; j2 < ld; j2 += 32) {
+                double tmp = aug[k * ld + j2];
+                aug[k * ld + j2] = aug[bi * ld + j2];
+                aug[bi * ld + j2] = tmp;
+            }
+        __syncwarp();
+        double ip = 1.0 / aug[k * ld + k];
+        for (int i = k + 1 + lane; i < m; i += 32) {
+            double lik = aug[i * ld + k] * ip;
+            for (int j2 = k + 1; j2 < ld; ++j2) aug[i * ld + j2] = fma(-lik, aug[k * ld + j2], aug[i * ld + j2]);
+        }
+        __syncwarp();
+    }
+    if (singular) {
+        if (lane == 0) atomicCAS(&a.flags[FLAG_SINGULAR], 0, int32_t(c + 1));
+        return;
+    }
+    // back substitution, one rhs column per lane
+    for (int cj = lane; cj < nc; cj += 32) {
+        for (int i = m - 1; i >= 0; --i) {
+            double s = aug[i * ld + m + cj];
+            for (int k = i + 1; k < m; ++k) s = fma(-aug[i * ld + k], aug[k * ld + m + cj], s);
+            aug[i * ld + m + cj] = s / aug[i * ld + i];
+        }
+    }
+    __syncwarp();
+    // store [K_e | b_e]
+    if (a.dbg_At == nullptr) {
+        double* Ke_tile = a.Ke + ((c >> 5) * int64_t(m * nc)) * 32 + (c & 31);
+        for (int idx = lane; idx < m * nc; idx += 32) {
+            int i = idx / nc, cj = idx - i * nc;
+            Ke_tile[int64_t(idx) * 32] = aug[i * ld + m + cj];
+        }
+    }
+    // Ate = G' K_e - He ; bte = -G' b_e ; scatter
+    const int nt2 = nt * nt;
+    for (int idx = lane; idx < t * nc; idx += 32) {
+        int col = idx / t, row = idx - col * t;        // (row, col) of Ate, col == t -> bte
+        double s = 0.0;
+        for (int i = 0; i < m; ++i) s = fma(Gm[i * t + row], aug[i * ld + m + col], s);
+        int lp = row / nt, ip = row - lp * nt;
+        int64_t f_lp = g.f[lp] & 0x7fffffffu;
+        if (col == t) {
+            if (a.dbg_At) a.dbg_bt[row] = -s;
+            else atomicAdd(&a.rhs[f_lp * nt + ip], -s);
+            continue;
+        }
+        int l = col / nt, j = col - l * nt;
+        if (l == lp) {   // He (:144-151)
+            double h = 0.0;
+            for (int p = 0; p < R.nfq; ++p) h += (R.T[j + nt * p] * R.T[ip + nt * p]) * (g.dJf[l] * R.fw[p]);
+            s -= h;
+        }
+        if (a.dbg_At) a.dbg_At[col * t + row] = s;
+        else if (l == lp) atomicAdd(&a.Kd[f_lp * nt2 + j * nt + ip], s);
+        else {
+            int slot = int(g.f[lp] >> 31) * 2 + ((l - lp + 3) % 3 - 1);
+            a.Ko[(f_lp * 4 + slot) * nt2 + j * nt + ip] = s;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int K> static void fill_dev_tables(const RefTables& R, DevTables<K>& D) {
+    auto cp = [](const std::vector<double>& src, double* dst, size_t cap) {
+        for (size_t i = 0; i < cap; ++i) dst[i] = i < src.size() ? src[i] : 0.0;
+    };
+    constexpr int n = Ord<K>::n, t = Ord<K>::t, nt = Ord<K>::nt;
+    cp(R.Tr, D.Tr, n * n); cp(R.Ts, D.Ts, n * n);
+    cp(R.Prr, D.Prr, n * n); cp(R.Prs, D.Prs, n * n); cp(R.Pss, D.Pss, n * n);
+    cp(R.Chat, D.Chat, 3 * n * n);
+    cp(R.Fhat, D.Fhat, n * t); cp(R.MF, D.MF, n * t); cp(R.Qr, D.Qr, n * t); cp(R.Qs, D.Qs, n * t);
+    cp(R.Hhat, D.Hhat, nt * nt);
+    cp(R.WN, D.WN, MAX_NQ * n);
+    cp(R.Mgeo, D.Mgeo, MAX_NQ * 3);
+    cp(R.qw, D.qw, MAX_NQ);
+    D.nq = R.nq;
+    D.pad = 0;
+}
+
+hdg_status upload_tables(hdg_context* c) {
+    const RefTables& R = c->tab;
+    if (R.nq > MAX_NQ || R.nfq > MAX_NFQ) return set_err(c, HDG_ERR_UNSUPPORTED_RULE, "quadrature rule too large for the device tables");
+    if (!c->use_lu) {
+        switch (R.order) {
+            case 1: { static DevTables<1> D; fill_dev_tables<1>(R, D); HDG_CUDA(c, cudaMemcpyToSymbol(c_tab1, &D, sizeof(D))); break; }
+            case 2: { static DevTables<2> D; fill_dev_tables<2>(R, D); HDG_CUDA(c, cudaMemcpyToSymbol(c_tab2, &D, sizeof(D))); break; }
+            case 3: { static DevTables<3> D; fill_dev_tables<3>(R, D); HDG_CUDA(c, cudaMemcpyToSymbol(c_tab3, &D, sizeof(D))); break; }
+            case 4: { static DevTables<4> D; fill_dev_tables<4>(R, D); HDG_CUDA(c, cudaMemcpyToSymbol(c_tab4, &D, sizeof(D))); break; }
+        }
+    }
+    // raw tables in global memory (LU path, error norm)
+    std::vector<double> buf;
+    auto push = [&](const std::vector<double>& v) { size_t o = buf.size(); buf.insert(buf.end(), v.begin(), v.end()); return o; };
+    size_t oN = push(R.N), odN = push(R.dN), oE = push(R.E), oT = push(R.T), oqw = push(R.qw), ofw = push(R.fw), oM = push(R.Mgeo);
+    if (c->d_rawtab) cudaFree(c->d_rawtab);
+    HDG_CUDA(c, cudaMalloc(&c->d_rawtab, sizeof(double) * buf.size()));
+    HDG_CUDA(c, cudaMemcpy(c->d_rawtab, buf.data(), sizeof(double) * buf.size(), cudaMemcpyHostToDevice));
+    c->raw.N = c->d_rawtab + oN; c->raw.dN = c->d_rawtab + odN; c->raw.E = c->d_rawtab + oE; c->raw.T = c->d_rawtab + oT;
+    c->raw.qw = c->d_rawtab + oqw; c->raw.fw = c->d_rawtab + ofw; c->raw.Mgeo = c->d_rawtab + oM;
+    c->raw.n = R.n; c->raw.nt = R.nt; c->raw.nq = R.nq; c->raw.nfq = R.nfq;
+    return HDG_OK;
+}
+
+// The constant tables are per order, shared by every context of that order in the process.
+// Re-upload when another context (different quad_degree) used them last.
+static const hdg_context* g_table_owner[MAX_ORDER + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+
+template <int K> static hdg_status launch_schur(hdg_context* c, const ElemArgs& a) {
+    constexpr bool LS = K >= 3;
+    constexpr int nL = Ord<K>::n * (Ord<K>::n - 1) / 2;
+    const int B = K >= 4 ? 64 : 128;
+    size_t smem = LS ? sizeof(double) * nL * B : 0;
+    auto kern = element_schur_kernel<K, LS>;
+    if (smem > 48 * 1024) HDG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int64_t ncell = a.cell_end - a.cell_begin;
+    kern<<<(unsigned)ceil_div(ncell, B), B, smem, c->stream>>>(a);
+    c->launches += 1;
+    HDG_CUDA(c, cudaGetLastError());
+    return HDG_OK;
+}
+
+static hdg_status launch_elements(hdg_context* c, ElemArgs a) {
+    if (c->use_lu) {
+        LuArgs A{a, c->raw, c->tab.n, c->tab.nt};
+        const int m = c->tab.m, t = c->tab.t, ld = (m + t + 1) | 1;
+        const int wpb = 4;
+        size_t smem = sizeof(double) * size_t(wpb) * (m * ld + m * t + c->tab.n + 8);
+        if (smem > 48 * 1024) HDG_CUDA(c, cudaFuncSetAttribute(element_lu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        int64_t ncell = a.cell_end - a.cell_begin;
+        element_lu_kernel<<<(unsigned)ceil_div(ncell, wpb), wpb * 32, smem, c->stream>>>(A);
+        c->launches += 1;
+        HDG_CUDA(c, cudaGetLastError());
+        return HDG_OK;
+    }
+    if (g_table_owner[c->tab.order] != c) {
+        HDG_CUDA(c, cudaDeviceSynchronize());
+        hdg_status st = upload_tables(c);
+        if (st) return st;
+        g_table_owner[c->tab.order] = c;
+    }
+    switch (c->tab.order) {
+        case 1: return launch_schur<1>(c, a);
+        case 2: return launch_schur<2>(c, a);
+        case 3: return launch_schur<3>(c, a);
+        case 4: return launch_schur<4>(c, a);
+    }
+    return set_err(c, HDG_ERR_INVALID, "unsupported order");
+}
+
+hdg_status launch_element_kernels(hdg_context* c) {
+    const int nt = c->tab.nt;
+    HDG_CUDA(c, cudaMemsetAsync(c->d_Kd, 0, sizeof(double) * c->nface * nt * nt, c->stream));
+    HDG_CUDA(c, cudaMemsetAsync(c->d_rhs, 0, sizeof(double) * c->nface * nt, c->stream));
+    ElemArgs a{};
+    a.cellinfo = c->d_cellinfo; a.nodes = c->d_nodes; a.fq = c->d_fq;
+    a.Ke = c->d_Ke; a.Kd = c->d_Kd; a.Ko = c->d_Ko; a.rhs = c->d_rhs; a.flags = c->d_flags;
+    a.cell_begin = 0; a.cell_end = c->ncell; a.tau = c->prm.tau; a.nq = c->tab.nq; a.source_id = c->prm.source_id;
+    a.dbg_At = nullptr; a.dbg_bt = nullptr;
+    return launch_elements(c, a);
+}
+
+hdg_status condensed_of_cell(hdg_context* c, int64_t cell, double* At, double* bt) {
+    const int t = c->tab.t;
+    double* d = nullptr;
+    HDG_CUDA(c, cudaMalloc(&d, sizeof(double) * (t * t + t)));
+    ElemArgs a{};
+    a.cellinfo = c->d_cellinfo; a.nodes = c->d_nodes; a.fq = c->d_fq;
+    a.Ke = c->d_Ke; a.Kd = c->d_Kd; a.Ko = c->d_Ko; a.rhs = c->d_rhs; a.flags = c->d_flags;
+    a.cell_begin = cell; a.cell_end = cell + 1; a.tau = c->prm.tau; a.nq = c->tab.nq; a.source_id = c->prm.source_id;
+    a.dbg_At = d; a.dbg_bt = d + t * t;
+    hdg_status st = launch_elements(c, a);
+    if (st) { cudaFree(d); return st; }
+    std::vector<double> h(t * t + t);
+    HDG_CUDA(c, cudaMemcpyAsync(h.data(), d, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, c->stream));
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d);
+    for (int i = 0; i < t * t; ++i) At[i] = h[i];
+    for (int i = 0; i < t; ++i) bt[i] = h[t * t + i];
+    return HDG_OK;
+}
+
+}  // namespace hdg

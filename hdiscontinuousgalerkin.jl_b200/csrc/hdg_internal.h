@@ -1,0 +1,172 @@
+// Internal declarations shared by the translation units of libhdg_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/hdg_b200.h"
+#include "hdg_tables.h"
+
+namespace hdg {
+
+// ---- compile-time sizes per order ---------------------------------------------------------
+template <int K> struct Ord {
+    static constexpr int n = (K + 1) * (K + 2) / 2;   // scalar dofs per cell
+    static constexpr int nt = K + 1;                  // trace dofs per face
+    static constexpr int m = 3 * n;                   // local system
+    static constexpr int t = 3 * nt;                  // local trace dofs
+    static constexpr int ke = m * (t + 1);            // doubles of [K_e | b_e] per cell
+};
+
+constexpr int MAX_NQ = 40;    // largest supported cell rule: Grundmann-Moeller s=4 has 35 points
+constexpr int MAX_NFQ = 12;
+
+// Reference matrices in __constant__ memory, one instance per order (uniform-index reads fold
+// into the DFMA operand).  Layouts: row-major.
+template <int K> struct DevTables {
+    double Tr[Ord<K>::n * Ord<K>::n], Ts[Ord<K>::n * Ord<K>::n];
+    double Prr[Ord<K>::n * Ord<K>::n], Prs[Ord<K>::n * Ord<K>::n], Pss[Ord<K>::n * Ord<K>::n];
+    double Chat[3 * Ord<K>::n * Ord<K>::n];
+    double Fhat[Ord<K>::n * Ord<K>::t], MF[Ord<K>::n * Ord<K>::t];
+    double Qr[Ord<K>::n * Ord<K>::t], Qs[Ord<K>::n * Ord<K>::t];
+    double Hhat[Ord<K>::nt * Ord<K>::nt];
+    double WN[MAX_NQ * Ord<K>::n];        // w_q N[i,q] at [q*n + i]
+    double Mgeo[MAX_NQ * 3];
+    double qw[MAX_NQ];
+    int nq;
+    int pad;
+};
+
+// Raw tables for the literal-quadrature + LU kernel (global memory, small, L1/L2 resident).
+struct RawTablesDev {
+    const double* N;    // n*nq
+    const double* dN;   // n*nq*2
+    const double* E;    // n*nfq*3
+    const double* T;    // nt*nfq
+    const double* qw;   // nq
+    const double* fw;   // nfq
+    const double* Mgeo; // nq*3
+    int n, nt, nq, nfq;
+};
+
+// Storage layout of [K_e | b_e]
+enum KeLayout : int {
+    KE_TILE32 = 0,   // tiles of 32 cells, entry-major inside: ((c/32)*ke + e)*32 + c%32 ; e = i*(t+1)+j
+    KE_CELL = 1      // per cell contiguous, row-major m x (t+1): c*ke + i*(t+1) + j
+};
+
+struct Timer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    float last_ms = 0.f;
+    bool pending = false;
+};
+
+struct Comm;  // multi-GPU state (hdg_comm.cu)
+
+}  // namespace hdg
+
+struct hdg_context {
+    hdg_params prm{};
+    hdg::RefTables tab;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    bool use_lu = false;          // literal quadrature + LU path (mass matrix not identity / requested)
+    int ke_layout = hdg::KE_TILE32;
+
+    // mesh (device)
+    int64_t ncell = 0, nnode = 0, nface = 0, nbface = 0;
+    int32_t* d_cellinfo = nullptr;   // ncell x 6 int32: v0 v1 v2 (0-based), f0 f1 f2 (0-based, bit31 = this cell is the face's second cell)
+    double* d_nodes = nullptr;       // nnode x 2
+    int32_t* d_facecell = nullptr;   // nface x 2 : cell1, cell2 (0-based, -1 = none)
+    int32_t* d_facenode = nullptr;   // nface x 2 : v1, v2 (0-based)
+    int32_t* d_bfaces = nullptr;     // nbface sorted ascending (0-based)
+    uint8_t* d_isbc = nullptr;       // nface
+    int32_t* d_kcol = nullptr;       // nface x 4 neighbour faces of the block-ELL rows (-1 = none)
+    bool have_mesh = false;
+    // structured-mesh parameters (0 when the mesh came from hdg_set_mesh)
+    int64_t nx = 0, ny = 0;
+
+    // source
+    double* d_fq = nullptr;          // ncell x nq when source_id == 0
+
+    // raw tables on device (LU path + error norm)
+    double* d_rawtab = nullptr;
+    hdg::RawTablesDev raw{};
+
+    // trace system, block-ELL: diagonal blocks + 4 off-diagonal blocks per face, blocks column-major nt x nt
+    double* d_Kd = nullptr;          // nface * nt*nt
+    double* d_Ko = nullptr;          // nface * 4 * nt*nt
+    double* d_rhs = nullptr;         // ndof
+    double* d_Ke = nullptr;          // ncell * ke  ([K_e | b_e])
+    bool assembled = false, applied = false;
+    double meandiag = 0.0;
+    double* d_bcval = nullptr;       // nbface*nt prescribed values (NULL = 0)
+
+    // solver vectors
+    double* d_x = nullptr;           // trace solution u_hat
+    double *d_r = nullptr, *d_p = nullptr, *d_Ap = nullptr, *d_dinv = nullptr;
+    double* d_partials = nullptr;    // reduction partials
+    double* d_scal = nullptr;        // device scalars
+    int32_t* d_flags = nullptr;      // error / convergence flags
+    int32_t* h_flags = nullptr;      // pinned mirror
+    double* h_scal = nullptr;        // pinned mirror
+    bool solved = false;
+
+    // recovered values, column-major ncell x nb
+    double *d_sigma = nullptr, *d_u = nullptr, *d_uhat_h = nullptr;
+    bool recovered = false;
+
+    hdg::Timer t_assemble, t_apply, t_solve, t_recover, t_err;
+    hdg::Comm* comm = nullptr;
+};
+
+namespace hdg {
+
+// error helpers -------------------------------------------------------------------------------
+hdg_status set_err(hdg_context* c, hdg_status s, const std::string& msg);
+#define HDG_CUDA(c, call)                                                                        \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return hdg::set_err((c), HDG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+void timer_start(hdg_context* c, Timer& t);
+void timer_stop(hdg_context* c, Timer& t);
+float timer_ms(Timer& t);
+
+// flag words in d_flags
+enum Flag : int { FLAG_BAD_GEOM = 0, FLAG_SINGULAR = 1, FLAG_DONE = 2, FLAG_ITERS = 3, FLAG_NOT_BOUNDARY = 4, NFLAGS = 8 };
+
+// ---- per-translation-unit entry points ------------------------------------------------------
+hdg_status upload_tables(hdg_context* c);                       // hdg_element.cu
+hdg_status launch_element_kernels(hdg_context* c);              // hdg_element.cu
+hdg_status condensed_of_cell(hdg_context* c, int64_t cell, double* At, double* bt);  // hdg_element.cu
+
+hdg_status mesh_from_host(hdg_context* c, const int64_t* cells, int64_t ncell, const double* nodes,
+                          int64_t nnode, const int64_t* faces, int64_t nface, const int64_t* bfaces,
+                          int64_t nbface);                      // hdg_mesh.cu
+hdg_status mesh_rectangle(hdg_context* c, int64_t nx, int64_t ny, double llx, double lly, double urx,
+                          double ury);                          // hdg_mesh.cu
+hdg_status mesh_perturb(hdg_context* c, double fraction, uint64_t seed);
+hdg_status mesh_download(hdg_context* c, int64_t* cells, double* nodes, int64_t* faces, int64_t* bf);
+hdg_status pattern_download(hdg_context* c, int64_t* colptr, int64_t* rowval);
+hdg_status values_download(hdg_context* c, double* nzval);
+int64_t pattern_nnz(hdg_context* c);
+hdg_status alloc_system(hdg_context* c);                        // hdg_mesh.cu (after mesh known)
+void free_mesh(hdg_context* c);
+
+hdg_status apply_dirichlet(hdg_context* c, const double* values);   // hdg_solve.cu
+hdg_status pcg_solve(hdg_context* c, double rtol, int maxit, hdg_solve_info* info);
+
+hdg_status recover(hdg_context* c);                             // hdg_recover.cu
+hdg_status errornorm(hdg_context* c, int exact_id, double* err2);
+hdg_status local_download(hdg_context* c, int64_t cell, double* Ke, double* be);
+
+}  // namespace hdg

@@ -1,0 +1,603 @@
+// K0: mesh ingestion / generation, adjacency and sparsity pattern - integer work on the device.
+//
+// Replaces: rectangle_mesh + _build_cells + _generate_2d_nodes! + boundary sets
+// (src/generate_mesh.jl:1-143), the CellIterator gathers (src/iterator.jl:48-57), the dof map
+// gdof = face*nt-(nt-j) (examples/poisson2D_HDG.jl:176-181) and the pattern of sparse(I,J,V)
+// (src/assembler.jl:47-49).
+#include <algorithm>
+
+#include "hdg_internal.h"
+
+namespace hdg {
+
+// ------------------------------------------------------------------------------------------
+// small device scan (exclusive, int32 -> int64), three phases, deterministic
+// ------------------------------------------------------------------------------------------
+constexpr int SCAN_BLOCK = 256;
+constexpr int SCAN_ITEMS = 8;   // per thread
+constexpr int SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
+
+__device__ inline int64_t block_exclusive_scan(int64_t v, int64_t* total) {
+    __shared__ int64_t warp_sums[SCAN_BLOCK / 32];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int64_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        int64_t s = lane < SCAN_BLOCK / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int64_t y = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += y;
+        }
+        if (lane < SCAN_BLOCK / 32) warp_sums[lane] = s;
+    }
+    __syncthreads();
+    int64_t base = wid > 0 ? warp_sums[wid - 1] : 0;
+    if (total) *total = warp_sums[SCAN_BLOCK / 32 - 1];
+    int64_t r = base + x - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void scan_tile_sums(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ tile_sums) {
+    int64_t base = int64_t(blockIdx.x) * SCAN_TILE + int64_t(threadIdx.x) * SCAN_ITEMS;
+    int64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < n) s += in[base + k];
+    int64_t tot;
+    block_exclusive_scan(s, &tot);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+__global__ void scan_tile_offsets(int64_t* tile_sums, int64_t ntiles, int64_t* grand_total) {
+    // single block; serial over chunks of SCAN_BLOCK
+    __shared__ int64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t c = 0; c < ntiles; c += SCAN_BLOCK) {
+        int64_t i = c + threadIdx.x;
+        int64_t v = i < ntiles ? tile_sums[i] : 0;
+        int64_t tot;
+        int64_t ex = block_exclusive_scan(v, &tot);
+        int64_t cr = carry;
+        if (i < ntiles) tile_sums[i] = cr + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = cr + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *grand_total = carry;
+}
+
+__global__ void scan_apply(const int32_t* __restrict__ in, int64_t n, const int64_t* __restrict__ tile_offs,
+                           int64_t* __restrict__ out) {
+    int64_t base = int64_t(blockIdx.x) * SCAN_TILE + int64_t(threadIdx.x) * SCAN_ITEMS;
+    int32_t v[SCAN_ITEMS];
+    int64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = base + k < n ? in[base + k] : 0;
+        s += v[k];
+    }
+    int64_t ex = block_exclusive_scan(s, nullptr) + tile_offs[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) out[base + k] = ex;
+        ex += v[k];
+    }
+}
+
+// out[i] = sum_{j<i} in[j]; *d_total = sum of all. d_total is a device pointer.
+static hdg_status exclusive_scan(hdg_context* c, const int32_t* in, int64_t n, int64_t* out, int64_t* d_total) {
+    int64_t ntiles = ceil_div(n, SCAN_TILE);
+    int64_t* tile_sums = nullptr;
+    HDG_CUDA(c, cudaMalloc(&tile_sums, sizeof(int64_t) * std::max<int64_t>(ntiles, 1)));
+    scan_tile_sums<<<(unsigned)ntiles, SCAN_BLOCK, 0, c->stream>>>(in, n, tile_sums);
+    scan_tile_offsets<<<1, SCAN_BLOCK, 0, c->stream>>>(tile_sums, ntiles, d_total);
+    scan_apply<<<(unsigned)ntiles, SCAN_BLOCK, 0, c->stream>>>(in, n, tile_sums, out);
+    c->launches += 3;
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    HDG_CUDA(c, cudaFree(tile_sums));
+    return HDG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// mesh from host arrays (Julia layouts, 1-based int64)
+// ------------------------------------------------------------------------------------------
+__global__ void convert_faces(const int64_t* __restrict__ faces, int64_t nface, int32_t* __restrict__ facecell,
+                              int32_t* __restrict__ facenode) {
+    int64_t f = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (f >= nface) return;
+    facenode[2 * f + 0] = int32_t(faces[f] - 1);
+    facenode[2 * f + 1] = int32_t(faces[f + nface] - 1);
+    facecell[2 * f + 0] = int32_t(faces[f + 2 * nface] - 1);
+    facecell[2 * f + 1] = int32_t(faces[f + 3 * nface] - 1);   // 0 -> -1 (no second cell)
+}
+
+__global__ void convert_cells(const int64_t* __restrict__ cells, int64_t ncell, const int32_t* __restrict__ facecell,
+                              int32_t* __restrict__ cellinfo) {
+    int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cellinfo[6 * c + k] = int32_t(cells[6 * c + k] - 1);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int32_t f = int32_t(cells[6 * c + 3 + k] - 1);
+        uint32_t sec = facecell[2 * f + 1] == int32_t(c) ? 0x80000000u : 0u;
+        cellinfo[6 * c + 3 + k] = int32_t(uint32_t(f) | sec);
+    }
+}
+
+__global__ void build_kcol(const int32_t* __restrict__ cellinfo, int64_t ncell, int32_t* __restrict__ kcol) {
+    int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    uint32_t fr[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) fr[k] = uint32_t(cellinfo[6 * c + 3 + k]);
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        int64_t f = fr[l] & 0x7fffffffu;
+        int sec = fr[l] >> 31;
+        kcol[4 * f + 2 * sec + 0] = int32_t(fr[(l + 1) % 3] & 0x7fffffffu);
+        kcol[4 * f + 2 * sec + 1] = int32_t(fr[(l + 2) % 3] & 0x7fffffffu);
+    }
+}
+
+__global__ void mark_bfaces(const int32_t* __restrict__ bfaces, int64_t nb, const int32_t* __restrict__ facecell,
+                            uint8_t* __restrict__ isbc, int32_t* __restrict__ flags) {
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    int32_t f = bfaces[i];
+    if (facecell[2 * f + 1] >= 0) atomicExch(&flags[FLAG_NOT_BOUNDARY], f + 1);  // src/boundary.jl:22
+    isbc[f] = 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// structured mesh on the device: closed forms of the first-encounter numbering
+// ------------------------------------------------------------------------------------------
+__global__ void rect_nodes(double* __restrict__ nodes, int64_t nnx, int64_t nny, double llx, double lly,
+                           double urx, double ury) {
+    int64_t id = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (id >= nnx * nny) return;
+    int64_t i = id / nnx, j = id % nnx;   // row i, column j (src/generate_mesh.jl:1-18)
+    // every product / sum rounded separately, as the Julia expression does (no FMA contraction)
+    double rb = double(i) / double(nny - 1);
+    double omr = __dsub_rn(1.0, rb);
+    // LL=(llx,lly) UL=(llx,ury) LR=(urx,lly) UR=(urx,ury)
+    double x0 = __dadd_rn(__dmul_rn(llx, omr), __dmul_rn(rb, llx));
+    double x1 = __dadd_rn(__dmul_rn(urx, omr), __dmul_rn(rb, urx));
+    double y0 = __dadd_rn(__dmul_rn(lly, omr), __dmul_rn(rb, ury));
+    double y1 = __dadd_rn(__dmul_rn(lly, omr), __dmul_rn(rb, ury));
+    double r = double(j) / double(nnx - 1);
+    double om = __dsub_rn(1.0, r);
+    nodes[2 * id + 0] = __dadd_rn(__dmul_rn(x0, om), __dmul_rn(r, x1));
+    nodes[2 * id + 1] = __dadd_rn(__dmul_rn(y0, om), __dmul_rn(r, y1));
+}
+
+// 0-based face ids of quad (i,j), i in [0,nx), j in [0,ny)
+struct QuadFaces { int64_t diag, left, bottom, top, right; };
+__host__ __device__ inline int64_t quad_base(int64_t i, int64_t j, int64_t nx) {
+    // number of faces created before quad (i,j) (0-based i,j)
+    if (j == 0) return 4 * i + (i > 0 ? 1 : 0);
+    return 4 * nx + 1 + (j - 1) * (3 * nx + 1) + 3 * i + (i > 0 ? 1 : 0);
+}
+__host__ __device__ inline QuadFaces quad_faces(int64_t i, int64_t j, int64_t nx) {
+    QuadFaces q;
+    int64_t b = quad_base(i, j, nx);
+    int i0 = i == 0, j0 = j == 0;
+    q.diag = b;
+    q.top = b + 1 + i0 + j0;
+    q.right = b + 2 + i0 + j0;
+    if (i0) q.left = b + 1;
+    else {
+        int64_t bl = quad_base(i - 1, j, nx);
+        q.left = bl + 2 + (i - 1 == 0) + j0;
+    }
+    if (j0) q.bottom = b + 1 + i0;
+    else {
+        int64_t bb = quad_base(i, j - 1, nx);
+        q.bottom = bb + 1 + i0 + (j - 1 == 0);
+    }
+    return q;
+}
+
+__global__ void rect_cells(int64_t nx, int64_t ny, int32_t* __restrict__ cellinfo, int32_t* __restrict__ facecell,
+                           int32_t* __restrict__ facenode) {
+    int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (q >= nx * ny) return;
+    int64_t i = q % nx, j = q / nx, nnx = nx + 1;
+    auto na = [&](int64_t a, int64_t b) { return int32_t(a + b * nnx); };
+    QuadFaces F = quad_faces(i, j, nx);
+    const uint32_t SEC = 0x80000000u;
+    int64_t c0 = 2 * q, c1 = 2 * q + 1;
+    // lower-left triangle: nodes (na(i,j), na(i+1,j), na(i,j+1)), faces (diag, left, bottom)
+    cellinfo[6 * c0 + 0] = na(i, j);
+    cellinfo[6 * c0 + 1] = na(i + 1, j);
+    cellinfo[6 * c0 + 2] = na(i, j + 1);
+    cellinfo[6 * c0 + 3] = int32_t(F.diag);
+    cellinfo[6 * c0 + 4] = int32_t(uint32_t(F.left) | (i > 0 ? SEC : 0u));
+    cellinfo[6 * c0 + 5] = int32_t(uint32_t(F.bottom) | (j > 0 ? SEC : 0u));
+    // upper-right triangle: nodes (na(i+1,j), na(i+1,j+1), na(i,j+1)), faces (top, diag, right)
+    cellinfo[6 * c1 + 0] = na(i + 1, j);
+    cellinfo[6 * c1 + 1] = na(i + 1, j + 1);
+    cellinfo[6 * c1 + 2] = na(i, j + 1);
+    cellinfo[6 * c1 + 3] = int32_t(F.top);
+    cellinfo[6 * c1 + 4] = int32_t(uint32_t(F.diag) | SEC);
+    cellinfo[6 * c1 + 5] = int32_t(F.right);
+    // faces created by this quad, (v1,v2) in the creating cell's local direction
+    auto setf = [&](int64_t f, int32_t v1, int32_t v2, int64_t ca, int64_t cb) {
+        facenode[2 * f] = v1; facenode[2 * f + 1] = v2;
+        facecell[2 * f] = int32_t(ca); facecell[2 * f + 1] = int32_t(cb);
+    };
+    setf(F.diag, na(i + 1, j), na(i, j + 1), c0, c1);
+    if (i == 0) setf(F.left, na(i, j + 1), na(i, j), c0, -1);
+    if (j == 0) setf(F.bottom, na(i, j), na(i + 1, j), c0, -1);
+    setf(F.top, na(i + 1, j + 1), na(i, j + 1), c1, j + 1 < ny ? 2 * (q + nx) : -1);
+    setf(F.right, na(i + 1, j), na(i + 1, j + 1), c1, i + 1 < nx ? 2 * (q + 1) : -1);
+}
+
+__global__ void flag_boundary(const int32_t* __restrict__ facecell, int64_t nface, int32_t* __restrict__ flag) {
+    int64_t f = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (f < nface) flag[f] = facecell[2 * f + 1] < 0 ? 1 : 0;
+}
+__global__ void compact_boundary(const int32_t* __restrict__ flag, const int64_t* __restrict__ offs, int64_t nface,
+                                 int32_t* __restrict__ bfaces, uint8_t* __restrict__ isbc) {
+    int64_t f = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (f >= nface) return;
+    isbc[f] = uint8_t(flag[f]);
+    if (flag[f]) bfaces[offs[f]] = int32_t(f);
+}
+
+__global__ void perturb_nodes_k(double* __restrict__ nodes, int64_t nnx, int64_t nny, double hx, double hy,
+                                double frac, uint64_t seed) {
+    int64_t id = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (id >= nnx * nny) return;
+    int64_t i = id / nnx, j = id % nnx;
+    if (i == 0 || j == 0 || i == nny - 1 || j == nnx - 1) return;   // boundary nodes stay
+    uint64_t z = uint64_t(id) * 0x9E3779B97F4A7C15ull + seed;        // splitmix64
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    double a = double(z & 0xffffffffu) / 4294967296.0 - 0.5;
+    double b = double(z >> 32) / 4294967296.0 - 0.5;
+    nodes[2 * id + 0] += 2.0 * frac * hx * a;
+    nodes[2 * id + 1] += 2.0 * frac * hy * b;
+}
+
+// ------------------------------------------------------------------------------------------
+void free_mesh(hdg_context* c) {
+    auto F = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
+    F(c->d_cellinfo); F(c->d_nodes); F(c->d_facecell); F(c->d_facenode); F(c->d_bfaces); F(c->d_isbc);
+    F(c->d_kcol); F(c->d_fq); F(c->d_Kd); F(c->d_Ko); F(c->d_rhs); F(c->d_Ke); F(c->d_bcval);
+    F(c->d_x); F(c->d_r); F(c->d_p); F(c->d_Ap); F(c->d_dinv);
+    F(c->d_sigma); F(c->d_u); F(c->d_uhat_h);
+    c->have_mesh = c->assembled = c->applied = c->solved = c->recovered = false;
+}
+
+static hdg_status alloc_mesh(hdg_context* c) {
+    if (c->ncell <= 0 || c->nface <= 0 || c->nnode <= 0) return set_err(c, HDG_ERR_INVALID, "empty mesh");
+    if (c->nface >= (int64_t(1) << 31) || c->ncell >= (int64_t(1) << 31) || c->nnode >= (int64_t(1) << 31))
+        return set_err(c, HDG_ERR_INVALID, "mesh too large for 32-bit device ids");
+    HDG_CUDA(c, cudaMalloc(&c->d_cellinfo, sizeof(int32_t) * 6 * c->ncell));
+    HDG_CUDA(c, cudaMalloc(&c->d_nodes, sizeof(double) * 2 * c->nnode));
+    HDG_CUDA(c, cudaMalloc(&c->d_facecell, sizeof(int32_t) * 2 * c->nface));
+    HDG_CUDA(c, cudaMalloc(&c->d_facenode, sizeof(int32_t) * 2 * c->nface));
+    HDG_CUDA(c, cudaMalloc(&c->d_isbc, c->nface));
+    HDG_CUDA(c, cudaMalloc(&c->d_kcol, sizeof(int32_t) * 4 * c->nface));
+    HDG_CUDA(c, cudaMemsetAsync(c->d_isbc, 0, c->nface, c->stream));
+    HDG_CUDA(c, cudaMemsetAsync(c->d_kcol, 0xFF, sizeof(int32_t) * 4 * c->nface, c->stream));
+    return HDG_OK;
+}
+
+hdg_status alloc_system(hdg_context* c) {
+    const int nt = c->tab.nt, ke = c->tab.m * (c->tab.t + 1);
+    int64_t ncell_pad = ceil_div(c->ncell, 32) * 32;
+    HDG_CUDA(c, cudaMalloc(&c->d_Kd, sizeof(double) * c->nface * nt * nt));
+    HDG_CUDA(c, cudaMalloc(&c->d_Ko, sizeof(double) * c->nface * 4 * nt * nt));
+    HDG_CUDA(c, cudaMalloc(&c->d_rhs, sizeof(double) * c->nface * nt));
+    HDG_CUDA(c, cudaMalloc(&c->d_Ke, sizeof(double) * ncell_pad * ke));
+    HDG_CUDA(c, cudaMemsetAsync(c->d_Ko, 0, sizeof(double) * c->nface * 4 * nt * nt, c->stream));
+    return HDG_OK;
+}
+
+hdg_status mesh_from_host(hdg_context* c, const int64_t* cells, int64_t ncell, const double* nodes, int64_t nnode,
+                          const int64_t* faces, int64_t nface, const int64_t* bfaces, int64_t nbface) {
+    free_mesh(c);
+    c->ncell = ncell; c->nnode = nnode; c->nface = nface; c->nbface = nbface; c->nx = c->ny = 0;
+    hdg_status st = alloc_mesh(c);
+    if (st) return st;
+    int64_t *d_cells = nullptr, *d_faces = nullptr;
+    HDG_CUDA(c, cudaMalloc(&d_cells, sizeof(int64_t) * 6 * ncell));
+    HDG_CUDA(c, cudaMalloc(&d_faces, sizeof(int64_t) * 4 * nface));
+    HDG_CUDA(c, cudaMemcpyAsync(d_cells, cells, sizeof(int64_t) * 6 * ncell, cudaMemcpyHostToDevice, c->stream));
+    HDG_CUDA(c, cudaMemcpyAsync(d_faces, faces, sizeof(int64_t) * 4 * nface, cudaMemcpyHostToDevice, c->stream));
+    HDG_CUDA(c, cudaMemcpyAsync(c->d_nodes, nodes, sizeof(double) * 2 * nnode, cudaMemcpyHostToDevice, c->stream));
+    const int B = 256;
+    convert_faces<<<(unsigned)ceil_div(nface, B), B, 0, c->stream>>>(d_faces, nface, c->d_facecell, c->d_facenode);
+    convert_cells<<<(unsigned)ceil_div(ncell, B), B, 0, c->stream>>>(d_cells, ncell, c->d_facecell, c->d_cellinfo);
+    build_kcol<<<(unsigned)ceil_div(ncell, B), B, 0, c->stream>>>(c->d_cellinfo, ncell, c->d_kcol);
+    c->launches += 3;
+    // Dirichlet face set: sort ascending on the host (the reference iterates faces 1..nface and
+    // tests membership, src/boundary.jl:19-21, so the dof order is ascending face id)
+    std::vector<int32_t> bf(nbface);
+    for (int64_t i = 0; i < nbface; ++i) {
+        if (bfaces[i] < 1 || bfaces[i] > nface) {
+            cudaFree(d_cells); cudaFree(d_faces);
+            return set_err(c, HDG_ERR_INVALID, "boundary face id out of range");
+        }
+        bf[i] = int32_t(bfaces[i] - 1);
+    }
+    std::sort(bf.begin(), bf.end());
+    bf.erase(std::unique(bf.begin(), bf.end()), bf.end());
+    c->nbface = int64_t(bf.size());
+    HDG_CUDA(c, cudaMalloc(&c->d_bfaces, sizeof(int32_t) * std::max<int64_t>(c->nbface, 1)));
+    if (c->nbface) {
+        HDG_CUDA(c, cudaMemcpyAsync(c->d_bfaces, bf.data(), sizeof(int32_t) * c->nbface, cudaMemcpyHostToDevice, c->stream));
+        HDG_CUDA(c, cudaMemsetAsync(c->d_flags, 0, sizeof(int32_t) * NFLAGS, c->stream));
+        mark_bfaces<<<(unsigned)ceil_div(c->nbface, B), B, 0, c->stream>>>(c->d_bfaces, c->nbface, c->d_facecell, c->d_isbc, c->d_flags);
+        c->launches += 1;
+        HDG_CUDA(c, cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int32_t) * NFLAGS, cudaMemcpyDeviceToHost, c->stream));
+    }
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    HDG_CUDA(c, cudaFree(d_cells));
+    HDG_CUDA(c, cudaFree(d_faces));
+    if (c->nbface && c->h_flags[FLAG_NOT_BOUNDARY])
+        return set_err(c, HDG_ERR_NOT_BOUNDARY, "Face " + std::to_string(c->h_flags[FLAG_NOT_BOUNDARY]) + " is not in boundary");
+    st = alloc_system(c);
+    if (st) return st;
+    c->have_mesh = true;
+    return HDG_OK;
+}
+
+hdg_status mesh_rectangle(hdg_context* c, int64_t nx, int64_t ny, double llx, double lly, double urx, double ury) {
+    if (nx < 1 || ny < 1 || !(urx > llx) || !(ury > lly)) return set_err(c, HDG_ERR_INVALID, "rectangle_mesh: need nx,ny >= 1 and UR > LL");
+    free_mesh(c);
+    c->nx = nx; c->ny = ny;
+    c->ncell = 2 * nx * ny;
+    c->nnode = (nx + 1) * (ny + 1);
+    c->nface = 3 * nx * ny + nx + ny;   // src/generate_mesh.jl:121
+    c->nbface = 2 * (nx + ny);
+    hdg_status st = alloc_mesh(c);
+    if (st) return st;
+    const int B = 256;
+    rect_nodes<<<(unsigned)ceil_div(c->nnode, B), B, 0, c->stream>>>(c->d_nodes, nx + 1, ny + 1, llx, lly, urx, ury);
+    rect_cells<<<(unsigned)ceil_div(nx * ny, B), B, 0, c->stream>>>(nx, ny, c->d_cellinfo, c->d_facecell, c->d_facenode);
+    build_kcol<<<(unsigned)ceil_div(c->ncell, B), B, 0, c->stream>>>(c->d_cellinfo, c->ncell, c->d_kcol);
+    c->launches += 3;
+    // boundary = faces with one cell (src/generate_mesh.jl:60-89), ascending
+    int32_t* flag = nullptr;
+    int64_t *offs = nullptr, *d_tot = nullptr;
+    HDG_CUDA(c, cudaMalloc(&flag, sizeof(int32_t) * c->nface));
+    HDG_CUDA(c, cudaMalloc(&offs, sizeof(int64_t) * c->nface));
+    HDG_CUDA(c, cudaMalloc(&d_tot, sizeof(int64_t)));
+    HDG_CUDA(c, cudaMalloc(&c->d_bfaces, sizeof(int32_t) * c->nbface));
+    flag_boundary<<<(unsigned)ceil_div(c->nface, B), B, 0, c->stream>>>(c->d_facecell, c->nface, flag);
+    c->launches += 1;
+    st = exclusive_scan(c, flag, c->nface, offs, d_tot);
+    if (st) return st;
+    int64_t tot = 0;
+    HDG_CUDA(c, cudaMemcpy(&tot, d_tot, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (tot != c->nbface) return set_err(c, HDG_ERR_INVALID, "internal: boundary face count mismatch");
+    compact_boundary<<<(unsigned)ceil_div(c->nface, B), B, 0, c->stream>>>(flag, offs, c->nface, c->d_bfaces, c->d_isbc);
+    c->launches += 1;
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(flag); cudaFree(offs); cudaFree(d_tot);
+    st = alloc_system(c);
+    if (st) return st;
+    c->have_mesh = true;
+    return HDG_OK;
+}
+
+hdg_status mesh_perturb(hdg_context* c, double fraction, uint64_t seed) {
+    if (!c->have_mesh || c->nx == 0) return set_err(c, HDG_ERR_INVALID, "hdg_perturb_nodes needs a rectangle mesh");
+    if (!(fraction >= 0.0 && fraction < 0.5)) return set_err(c, HDG_ERR_INVALID, "perturbation fraction must be in [0,0.5)");
+    double h_nodes[4];
+    // mesh extents from the first and last node
+    HDG_CUDA(c, cudaMemcpy(h_nodes, c->d_nodes, 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    HDG_CUDA(c, cudaMemcpy(h_nodes + 2, c->d_nodes + 2 * (c->nnode - 1), 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    double hx = (h_nodes[2] - h_nodes[0]) / double(c->nx), hy = (h_nodes[3] - h_nodes[1]) / double(c->ny);
+    perturb_nodes_k<<<(unsigned)ceil_div(c->nnode, 256), 256, 0, c->stream>>>(c->d_nodes, c->nx + 1, c->ny + 1, hx, hy, fraction, seed);
+    c->launches += 1;
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->assembled = c->applied = c->solved = c->recovered = false;
+    return HDG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// downloads in the Julia layouts
+// ------------------------------------------------------------------------------------------
+__global__ void export_cells(const int32_t* __restrict__ cellinfo, int64_t ncell, int64_t* __restrict__ cells) {
+    int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cells[6 * c + k] = int64_t(cellinfo[6 * c + k]) + 1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cells[6 * c + 3 + k] = int64_t(uint32_t(cellinfo[6 * c + 3 + k]) & 0x7fffffffu) + 1;
+}
+__global__ void export_faces(const int32_t* __restrict__ facecell, const int32_t* __restrict__ facenode, int64_t nface,
+                             int64_t* __restrict__ faces) {
+    int64_t f = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (f >= nface) return;
+    faces[f] = int64_t(facenode[2 * f]) + 1;
+    faces[f + nface] = int64_t(facenode[2 * f + 1]) + 1;
+    faces[f + 2 * nface] = int64_t(facecell[2 * f]) + 1;
+    faces[f + 3 * nface] = int64_t(facecell[2 * f + 1]) + 1;
+}
+__global__ void export_i32_plus1(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = int64_t(in[i]) + 1;
+}
+
+hdg_status mesh_download(hdg_context* c, int64_t* cells, double* nodes, int64_t* faces, int64_t* bf) {
+    if (!c->have_mesh) return set_err(c, HDG_ERR_INVALID, "no mesh");
+    const int B = 256;
+    int64_t nmax = std::max({6 * c->ncell, 4 * c->nface, c->nbface});
+    int64_t* tmp = nullptr;
+    HDG_CUDA(c, cudaMalloc(&tmp, sizeof(int64_t) * nmax));
+    if (cells) {
+        export_cells<<<(unsigned)ceil_div(c->ncell, B), B, 0, c->stream>>>(c->d_cellinfo, c->ncell, tmp);
+        HDG_CUDA(c, cudaMemcpyAsync(cells, tmp, sizeof(int64_t) * 6 * c->ncell, cudaMemcpyDeviceToHost, c->stream));
+        HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    if (faces) {
+        export_faces<<<(unsigned)ceil_div(c->nface, B), B, 0, c->stream>>>(c->d_facecell, c->d_facenode, c->nface, tmp);
+        HDG_CUDA(c, cudaMemcpyAsync(faces, tmp, sizeof(int64_t) * 4 * c->nface, cudaMemcpyDeviceToHost, c->stream));
+        HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    if (bf && c->nbface) {
+        export_i32_plus1<<<(unsigned)ceil_div(c->nbface, B), B, 0, c->stream>>>(c->d_bfaces, c->nbface, tmp);
+        HDG_CUDA(c, cudaMemcpyAsync(bf, tmp, sizeof(int64_t) * c->nbface, cudaMemcpyDeviceToHost, c->stream));
+        HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    c->launches += 3;
+    if (nodes) HDG_CUDA(c, cudaMemcpy(nodes, c->d_nodes, sizeof(double) * 2 * c->nnode, cudaMemcpyDeviceToHost));
+    HDG_CUDA(c, cudaFree(tmp));
+    return HDG_OK;
+}
+
+// ---- CSC pattern of sparse(I,J,V) ------------------------------------------------------------
+// Column (f,b) holds rows (f',a) for every face f' of the cells adjacent to f, ascending.
+__device__ inline int sorted_neighbours(const int32_t* __restrict__ kcol, int64_t f, int32_t nb[5]) {
+    int cnt = 0;
+    nb[cnt++] = int32_t(f);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        int32_t g = kcol[4 * f + s];
+        if (g < 0) continue;
+        bool dup = false;
+        for (int k = 0; k < cnt; ++k) dup |= nb[k] == g;
+        if (!dup) nb[cnt++] = g;
+    }
+    for (int a = 1; a < cnt; ++a) {   // insertion sort, <= 5 entries
+        int32_t v = nb[a];
+        int b = a - 1;
+        while (b >= 0 && nb[b] > v) { nb[b + 1] = nb[b]; --b; }
+        nb[b + 1] = v;
+    }
+    return cnt;
+}
+
+__global__ void count_neighbours(const int32_t* __restrict__ kcol, int64_t nface, int32_t* __restrict__ cnt) {
+    int64_t f = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (f >= nface) return;
+    int32_t nb[5];
+    cnt[f] = sorted_neighbours(kcol, f, nb);
+}
+
+__global__ void fill_pattern(const int32_t* __restrict__ kcol, const int64_t* __restrict__ offs, int64_t nface, int nt,
+                             int64_t* __restrict__ colptr, int64_t* __restrict__ rowval) {
+    int64_t f = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (f >= nface) return;
+    int32_t nb[5];
+    int cnt = sorted_neighbours(kcol, f, nb);
+    int64_t base = int64_t(nt) * nt * offs[f];
+    for (int b = 0; b < nt; ++b) {
+        int64_t p = base + int64_t(b) * cnt * nt;
+        colptr[f * nt + b] = p + 1;
+        if (rowval)
+            for (int k = 0; k < cnt; ++k)
+                for (int a = 0; a < nt; ++a) rowval[p++] = int64_t(nb[k]) * nt + a + 1;
+    }
+    if (f == nface - 1) colptr[nface * nt] = base + int64_t(nt) * cnt * nt + 1;
+}
+
+__global__ void fill_values(const int32_t* __restrict__ kcol, const int64_t* __restrict__ offs, int64_t nface, int nt,
+                            const double* __restrict__ Kd, const double* __restrict__ Ko, double* __restrict__ nzval) {
+    // one thread per face column block; value of entry (row (f',a), col (f,b)) = block(f',f)(a,b)
+    int64_t f = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (f >= nface) return;
+    int32_t nb[5];
+    int cnt = sorted_neighbours(kcol, f, nb);
+    int64_t base = int64_t(nt) * nt * offs[f];
+    const int nt2 = nt * nt;
+    for (int b = 0; b < nt; ++b) {
+        int64_t p = base + int64_t(b) * cnt * nt;
+        for (int k = 0; k < cnt; ++k) {
+            int64_t fr = nb[k];   // row face
+            for (int a = 0; a < nt; ++a) {
+                double v = 0.0;
+                if (fr == f) v = Kd[f * nt2 + b * nt + a];
+                else
+                    for (int s = 0; s < 4; ++s)
+                        if (kcol[4 * fr + s] == int32_t(f)) v += Ko[(fr * 4 + s) * nt2 + b * nt + a];
+                nzval[p++] = v;
+            }
+        }
+    }
+}
+
+struct PatternTmp {
+    int32_t* cnt = nullptr;
+    int64_t* offs = nullptr;
+    int64_t* d_tot = nullptr;
+    int64_t total = 0;
+};
+static hdg_status pattern_offsets(hdg_context* c, PatternTmp& P) {
+    HDG_CUDA(c, cudaMalloc(&P.cnt, sizeof(int32_t) * c->nface));
+    HDG_CUDA(c, cudaMalloc(&P.offs, sizeof(int64_t) * c->nface));
+    HDG_CUDA(c, cudaMalloc(&P.d_tot, sizeof(int64_t)));
+    count_neighbours<<<(unsigned)ceil_div(c->nface, 256), 256, 0, c->stream>>>(c->d_kcol, c->nface, P.cnt);
+    c->launches += 1;
+    hdg_status st = exclusive_scan(c, P.cnt, c->nface, P.offs, P.d_tot);
+    if (st) return st;
+    HDG_CUDA(c, cudaMemcpy(&P.total, P.d_tot, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    return HDG_OK;
+}
+static void pattern_free(PatternTmp& P) {
+    cudaFree(P.cnt); cudaFree(P.offs); cudaFree(P.d_tot);
+}
+
+int64_t pattern_nnz(hdg_context* c) {
+    if (!c->have_mesh) return 0;
+    PatternTmp P;
+    if (pattern_offsets(c, P) != HDG_OK) { pattern_free(P); return -1; }
+    pattern_free(P);
+    return P.total * c->tab.nt * c->tab.nt;
+}
+
+hdg_status pattern_download(hdg_context* c, int64_t* colptr, int64_t* rowval) {
+    if (!c->have_mesh) return set_err(c, HDG_ERR_INVALID, "no mesh");
+    PatternTmp P;
+    hdg_status st = pattern_offsets(c, P);
+    if (st) { pattern_free(P); return st; }
+    const int nt = c->tab.nt;
+    int64_t ndof = c->nface * nt, nnz = P.total * nt * nt;
+    int64_t *d_cp = nullptr, *d_rv = nullptr;
+    HDG_CUDA(c, cudaMalloc(&d_cp, sizeof(int64_t) * (ndof + 1)));
+    if (rowval) HDG_CUDA(c, cudaMalloc(&d_rv, sizeof(int64_t) * nnz));
+    fill_pattern<<<(unsigned)ceil_div(c->nface, 256), 256, 0, c->stream>>>(c->d_kcol, P.offs, c->nface, nt, d_cp, d_rv);
+    c->launches += 1;
+    if (colptr) HDG_CUDA(c, cudaMemcpyAsync(colptr, d_cp, sizeof(int64_t) * (ndof + 1), cudaMemcpyDeviceToHost, c->stream));
+    if (rowval) HDG_CUDA(c, cudaMemcpyAsync(rowval, d_rv, sizeof(int64_t) * nnz, cudaMemcpyDeviceToHost, c->stream));
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d_cp);
+    if (d_rv) cudaFree(d_rv);
+    pattern_free(P);
+    return HDG_OK;
+}
+
+hdg_status values_download(hdg_context* c, double* nzval) {
+    if (!c->assembled) return set_err(c, HDG_ERR_INVALID, "hdg_get_values before hdg_assemble");
+    PatternTmp P;
+    hdg_status st = pattern_offsets(c, P);
+    if (st) { pattern_free(P); return st; }
+    const int nt = c->tab.nt;
+    int64_t nnz = P.total * nt * nt;
+    double* d_v = nullptr;
+    HDG_CUDA(c, cudaMalloc(&d_v, sizeof(double) * nnz));
+    fill_values<<<(unsigned)ceil_div(c->nface, 256), 256, 0, c->stream>>>(c->d_kcol, P.offs, c->nface, nt, c->d_Kd, c->d_Ko, d_v);
+    c->launches += 1;
+    HDG_CUDA(c, cudaMemcpyAsync(nzval, d_v, sizeof(double) * nnz, cudaMemcpyDeviceToHost, c->stream));
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d_v);
+    pattern_free(P);
+    return HDG_OK;
+}
+
+}  // namespace hdg

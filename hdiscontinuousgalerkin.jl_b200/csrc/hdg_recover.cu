@@ -1,0 +1,150 @@
+// K5 + K6: element-wise recovery of (sigma, u) from the trace solution, and the squared L2 error.
+//
+// Replaces get_uσ! (examples/poisson2D_HDG.jl:197-212, with the hard-coded nt = 2 slice at
+// :205-206 generalised to nt) and errornorm (src/DiscreteFunctions.jl:97-120).
+// Both are streaming kernels, one thread per element: [K_e | b_e] is stored in tiles of 32 cells
+// (entry-major inside a tile) so every load of a warp is one contiguous 256-byte segment, and the
+// TrialFunction.m_values outputs are column-major ncell x nb (src/DiscreteFunctions.jl:38-54),
+// i.e. unit stride across the cells of a warp.
+#include <algorithm>
+
+#include "hdg_internal.h"
+#include "hdg_reduce.cuh"
+
+namespace hdg {
+
+template <int K>
+__global__ void __launch_bounds__(128) recover_kernel(const double* __restrict__ Ke, const double* __restrict__ x,
+                                                     const int32_t* __restrict__ cellinfo, int64_t ncell,
+                                                     double* __restrict__ sigma, double* __restrict__ u,
+                                                     double* __restrict__ uhat_h) {
+    constexpr int n = Ord<K>::n, nt = Ord<K>::nt, t = Ord<K>::t, m = Ord<K>::m, ke = Ord<K>::ke;
+    const int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    const int2* ci = reinterpret_cast<const int2*>(cellinfo + 6 * c);
+    int2 p1 = __ldg(ci + 1), p2 = __ldg(ci + 2);
+    const int64_t f[3] = {int64_t(uint32_t(p1.y) & 0x7fffffffu), int64_t(uint32_t(p2.x) & 0x7fffffffu),
+                          int64_t(uint32_t(p2.y) & 0x7fffffffu)};
+    double ue[t];
+#pragma unroll
+    for (int l = 0; l < 3; ++l)
+#pragma unroll
+        for (int j = 0; j < nt; ++j) {
+            ue[l * nt + j] = x[f[l] * nt + j];
+            uhat_h[c + ncell * (j + nt * l)] = ue[l * nt + j];   // m_values[cell, :, k]
+        }
+    const double* __restrict__ tile = Ke + ((c >> 5) * ke) * 32 + (c & 31);
+#pragma unroll
+    for (int i = 0; i < m; ++i) {
+        double d = tile[int64_t(i * (t + 1) + t) * 32];   // b_e[i]
+#pragma unroll
+        for (int j = 0; j < t; ++j) d = fma(tile[int64_t(i * (t + 1) + j) * 32], ue[j], d);
+        if (i < 2 * n) sigma[c + ncell * i] = d;
+        else u[c + ncell * (i - 2 * n)] = d;
+    }
+}
+
+template <int K> static hdg_status recover_t(hdg_context* c) {
+    const int B = 128;
+    recover_kernel<K><<<(unsigned)ceil_div(c->ncell, B), B, 0, c->stream>>>(c->d_Ke, c->d_x, c->d_cellinfo, c->ncell,
+                                                                           c->d_sigma, c->d_u, c->d_uhat_h);
+    c->launches += 1;
+    HDG_CUDA(c, cudaGetLastError());
+    return HDG_OK;
+}
+
+hdg_status recover(hdg_context* c) {
+    const int n = c->tab.n, nt = c->tab.nt;
+    if (!c->d_sigma) {
+        HDG_CUDA(c, cudaMalloc(&c->d_sigma, sizeof(double) * c->ncell * 2 * n));
+        HDG_CUDA(c, cudaMalloc(&c->d_u, sizeof(double) * c->ncell * n));
+        HDG_CUDA(c, cudaMalloc(&c->d_uhat_h, sizeof(double) * c->ncell * nt * 3));
+    }
+    timer_start(c, c->t_recover);
+    hdg_status st = HDG_ERR_INVALID;
+    switch (c->tab.order) {
+        case 1: st = recover_t<1>(c); break;
+        case 2: st = recover_t<2>(c); break;
+        case 3: st = recover_t<3>(c); break;
+        case 4: st = recover_t<4>(c); break;
+    }
+    timer_stop(c, c->t_recover);
+    if (st) return st;
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->recovered = true;
+    return HDG_OK;
+}
+
+// ---- squared L2 error ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(RB) errornorm_kernel(const double* __restrict__ u, const int32_t* __restrict__ cellinfo,
+                                                       const double* __restrict__ nodes, RawTablesDev R, int64_t ncell,
+                                                       int exact_id, double* __restrict__ part) {
+    const double pi = 3.141592653589793;
+    double acc = 0.0;
+    for (int64_t c = int64_t(blockIdx.x) * RB + threadIdx.x; c < ncell; c += int64_t(gridDim.x) * RB) {
+        const int32_t* ci = cellinfo + 6 * c;
+        double x[3][2];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            x[k][0] = nodes[2 * int64_t(ci[k])];
+            x[k][1] = nodes[2 * int64_t(ci[k]) + 1];
+        }
+        double detJ = (x[1][0] - x[0][0]) * (x[2][1] - x[0][1]) - (x[2][0] - x[0][0]) * (x[1][1] - x[0][1]);
+        double el = 0.0;
+        for (int q = 0; q < R.nq; ++q) {
+            double uq = 0.0;
+            for (int i = 0; i < R.n; ++i) uq += u[c + ncell * i] * R.N[i + R.n * q];
+            double xq = R.Mgeo[3 * q] * x[0][0] + R.Mgeo[3 * q + 1] * x[1][0] + R.Mgeo[3 * q + 2] * x[2][0];
+            double yq = R.Mgeo[3 * q] * x[0][1] + R.Mgeo[3 * q + 1] * x[1][1] + R.Mgeo[3 * q + 2] * x[2][1];
+            double ex = exact_id == 1 ? sin(pi * xq) * sin(pi * yq) : 0.0;   // u_ex, poisson2D_HDG.jl:216
+            double d = uq - ex;
+            el += d * d * (detJ * R.qw[q]);
+        }
+        acc += el;
+    }
+    double tot = block_sum(acc);
+    if (threadIdx.x == 0) part[blockIdx.x] = tot;
+}
+
+hdg_status errornorm(hdg_context* c, int exact_id, double* err2) {
+    int np = int(std::min<int64_t>(ceil_div(c->ncell, RB), 1024));
+    timer_start(c, c->t_err);
+    errornorm_kernel<<<np, RB, 0, c->stream>>>(c->d_u, c->d_cellinfo, c->d_nodes, c->raw, c->ncell, exact_id, c->d_partials);
+    final_sum<<<1, RB, 0, c->stream>>>(c->d_partials, np, c->d_scal + 3);
+    c->launches += 2;
+    timer_stop(c, c->t_err);
+    HDG_CUDA(c, cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(double) * 8, cudaMemcpyDeviceToHost, c->stream));
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    *err2 = c->h_scal[3];
+    return HDG_OK;
+}
+
+// ---- K_element[cell], b_element[cell] ----------------------------------------------------------------
+__global__ void gather_local(const double* __restrict__ Ke, int64_t c, int m, int t, double* __restrict__ out) {
+    // out: K_e column-major m x t, then b_e (m)
+    int ke = m * (t + 1);
+    const double* tile = Ke + ((c >> 5) * int64_t(ke)) * 32 + (c & 31);
+    for (int e = threadIdx.x; e < ke; e += blockDim.x) {
+        int i = e / (t + 1), j = e - i * (t + 1);
+        double v = tile[int64_t(e) * 32];
+        if (j < t) out[j * m + i] = v;
+        else out[m * t + i] = v;
+    }
+}
+
+hdg_status local_download(hdg_context* c, int64_t cell, double* Ke, double* be) {
+    const int m = c->tab.m, t = c->tab.t;
+    double* d = nullptr;
+    HDG_CUDA(c, cudaMalloc(&d, sizeof(double) * m * (t + 1)));
+    gather_local<<<1, 128, 0, c->stream>>>(c->d_Ke, cell, m, t, d);
+    c->launches += 1;
+    std::vector<double> h(size_t(m) * (t + 1));
+    HDG_CUDA(c, cudaMemcpyAsync(h.data(), d, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, c->stream));
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d);
+    if (Ke) std::copy(h.begin(), h.begin() + size_t(m) * t, Ke);
+    if (be) std::copy(h.begin() + size_t(m) * t, h.end(), be);
+    return HDG_OK;
+}
+
+}  // namespace hdg

@@ -1,0 +1,342 @@
+// K3b + K4: Dirichlet apply! and the Jacobi-PCG trace solve.
+//
+// Replaces apply!(K,b,dbc) (src/boundary.jl:121-175) and u_hat = K \ b
+// (examples/poisson2D_HDG.jl:195; UMFPACK LU in the reference).  The condensed matrix is
+// symmetric NEGATIVE semi-definite and apply! puts +meandiag on the Dirichlet rows, so PCG runs
+// on D*K*u = D*b with D = -1 on free rows, +1 on Dirichlet rows (trap 3);
+// Dirichlet rows/columns are decoupled after apply!, hence D*K is SPD and the solution is the
+// solution of K u = b.
+//
+// Matrix storage (hdg_internal.h): per face row-block one diagonal block and four off-diagonal
+// blocks (the two other faces of each adjacent cell), every block nt x nt column-major.  No row
+// pointers, 16 B of column indices per face.
+//
+// PCG iteration = 3 kernels, no host synchronisation:
+//   pcg_spmv    Ap = D K p            + partial sums of p.Ap
+//   pcg_update  alpha = rz/pAp; x += alpha p; r -= alpha Ap; partial sums of r.Dinv r and r.r
+//   pcg_dir     beta = rz'/rz; convergence test; p = Dinv r + beta p
+// Dot products are reduced deterministically: every block writes one partial, and every block
+// of the next kernel re-reduces the (<= 1184) partials in a fixed order.  Iterations are
+// launched in CUDA-graph chunks; kernels turn into no-ops once the device-side flag says
+// converged, and the host polls that flag once per chunk.
+#include <algorithm>
+#include <cmath>
+
+#include "hdg_internal.h"
+#include "hdg_reduce.cuh"
+
+namespace hdg {
+
+constexpr int MAX_PARTIALS = 2048;
+
+// d_scal layout
+enum Scal : int { S_BNORM2 = 0, S_RELRES = 1, S_MEANSUM = 2, NSCAL = 8 };
+// d_partials layout: 5 arrays of MAX_PARTIALS
+enum Part : int { P_PAP = 0, P_RZ0 = 1, P_RZ1 = 2, P_RR = 3, P_BB = 4, NPART = 5 };
+
+// ---- apply! ----------------------------------------------------------------------------------
+template <int NT>
+__global__ void diag_abs_partial(const double* __restrict__ Kd, int64_t nface, double* __restrict__ part) {
+    double s = 0.0;
+    for (int64_t f = int64_t(blockIdx.x) * RB + threadIdx.x; f < nface; f += int64_t(gridDim.x) * RB) {
+#pragma unroll
+        for (int a = 0; a < NT; ++a) s += fabs(Kd[f * NT * NT + a * NT + a]);
+    }
+    double tot = block_sum(s);
+    if (threadIdx.x == 0) part[blockIdx.x] = tot;
+}
+
+__device__ inline int64_t bc_index(const int32_t* __restrict__ bfaces, int64_t nb, int32_t f) {
+    int64_t lo = 0, hi = nb - 1;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (bfaces[mid] < f) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+template <int NT>
+__global__ void apply_bc_kernel(double* __restrict__ Kd, double* __restrict__ Ko, double* __restrict__ rhs,
+                                const int32_t* __restrict__ kcol, const uint8_t* __restrict__ isbc,
+                                const int32_t* __restrict__ bfaces, int64_t nb, const double* __restrict__ bcval,
+                                double m, int64_t nface) {
+    constexpr int NT2 = NT * NT;
+    int64_t f = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (f >= nface) return;
+    if (isbc[f]) {
+        // zero row, K[d,d] = m, f[d] = v*m   (src/boundary.jl:139-157)
+        int64_t bi = bcval ? bc_index(bfaces, nb, int32_t(f)) : 0;
+#pragma unroll
+        for (int e = 0; e < NT2; ++e) Kd[f * NT2 + e] = (e % NT == e / NT) ? m : 0.0;
+#pragma unroll
+        for (int e = 0; e < 4 * NT2; ++e) Ko[f * 4 * NT2 + e] = 0.0;
+#pragma unroll
+        for (int a = 0; a < NT; ++a) rhs[f * NT + a] = bcval ? bcval[bi * NT + a] * m : 0.0;
+        return;
+    }
+    for (int s = 0; s < 4; ++s) {
+        int32_t g = kcol[4 * f + s];
+        if (g < 0 || !isbc[g]) continue;
+        double* blk = Ko + (f * 4 + s) * NT2;
+        if (bcval) {   // rhs lift f -= v * K[:,d]  (:129-138)
+            int64_t bi = bc_index(bfaces, nb, g);
+#pragma unroll
+            for (int b = 0; b < NT; ++b) {
+                double v = bcval[bi * NT + b];
+                if (v != 0.0)
+#pragma unroll
+                    for (int a = 0; a < NT; ++a) rhs[f * NT + a] -= v * blk[b * NT + a];
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < NT2; ++e) blk[e] = 0.0;   // zero_out_columns!
+    }
+}
+
+template <int NT> static hdg_status apply_t(hdg_context* c) {
+    int np = int(std::min<int64_t>(ceil_div(c->nface, RB), 1024));
+    diag_abs_partial<NT><<<np, RB, 0, c->stream>>>(c->d_Kd, c->nface, c->d_partials);
+    final_sum<<<1, RB, 0, c->stream>>>(c->d_partials, np, c->d_scal + S_MEANSUM);
+    c->launches += 2;
+    HDG_CUDA(c, cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(double) * NSCAL, cudaMemcpyDeviceToHost, c->stream));
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->meandiag = c->h_scal[S_MEANSUM] / double(c->nface * NT);   // meandiag, src/boundary.jl:169-175
+    apply_bc_kernel<NT><<<(unsigned)ceil_div(c->nface, 128), 128, 0, c->stream>>>(
+        c->d_Kd, c->d_Ko, c->d_rhs, c->d_kcol, c->d_isbc, c->d_bfaces, c->nbface, c->d_bcval, c->meandiag, c->nface);
+    c->launches += 1;
+    HDG_CUDA(c, cudaGetLastError());
+    return HDG_OK;
+}
+
+hdg_status apply_dirichlet(hdg_context* c, const double* values) {
+    const int nt = c->tab.nt;
+    if (c->d_bcval) { cudaFree(c->d_bcval); c->d_bcval = nullptr; }
+    if (values && c->nbface) {
+        HDG_CUDA(c, cudaMalloc(&c->d_bcval, sizeof(double) * c->nbface * nt));
+        HDG_CUDA(c, cudaMemcpyAsync(c->d_bcval, values, sizeof(double) * c->nbface * nt, cudaMemcpyHostToDevice, c->stream));
+    }
+    switch (nt) {
+        case 2: return apply_t<2>(c);
+        case 3: return apply_t<3>(c);
+        case 4: return apply_t<4>(c);
+        case 5: return apply_t<5>(c);
+    }
+    return set_err(c, HDG_ERR_INVALID, "unsupported order");
+}
+
+// ---- PCG ---------------------------------------------------------------------------------------
+struct PcgArgs {
+    const double* Kd;
+    const double* Ko;
+    const int32_t* kcol;
+    const uint8_t* isbc;
+    const double* rhs;
+    double *x, *r, *p, *Ap, *dinv;
+    double* part;      // NPART x MAX_PARTIALS
+    double* scal;
+    int32_t* flags;
+    int64_t nface;
+    int np;            // number of partials == gridDim of the vector kernels
+    double rtol;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(RB) pcg_init(const PcgArgs a) {
+    // r = D b ; dinv = 1/diag(D K) ; p = z = dinv r ; x = 0 ; partials of r.z and b.b
+    constexpr int NT2 = NT * NT;
+    const int64_t N = a.nface * NT;
+    double rz = 0.0, bb = 0.0;
+    for (int64_t row = int64_t(blockIdx.x) * RB + threadIdx.x; row < N; row += int64_t(gridDim.x) * RB) {
+        int64_t f = row / NT;
+        int aa = int(row - f * NT);
+        double sgn = a.isbc[f] ? 1.0 : -1.0;
+        double d = sgn * a.Kd[f * NT2 + aa * NT + aa];
+        double di = 1.0 / d;
+        double r = sgn * a.rhs[row];
+        double z = di * r;
+        a.dinv[row] = di;
+        a.r[row] = r;
+        a.p[row] = z;
+        a.x[row] = 0.0;
+        rz += r * z;
+        bb += r * r;
+    }
+    double t1 = block_sum(rz), t2 = block_sum(bb);
+    if (threadIdx.x == 0) {
+        a.part[P_RZ0 * MAX_PARTIALS + blockIdx.x] = t1;
+        a.part[P_BB * MAX_PARTIALS + blockIdx.x] = t2;
+    }
+}
+
+__global__ void pcg_init_final(const PcgArgs a) {
+    double bb = reduce_partials(a.part + P_BB * MAX_PARTIALS, a.np);
+    if (threadIdx.x == 0) {
+        a.scal[S_BNORM2] = bb;
+        a.scal[S_RELRES] = bb > 0.0 ? 1.0 : 0.0;
+        a.flags[FLAG_DONE] = bb > 0.0 ? 0 : 1;   // b == 0 -> x = 0 is the solution
+        a.flags[FLAG_ITERS] = 0;
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(RB) pcg_spmv(const PcgArgs a) {
+    if (*reinterpret_cast<volatile int32_t*>(a.flags + FLAG_DONE)) return;
+    constexpr int NT2 = NT * NT;
+    const int64_t N = a.nface * NT;
+    double pap = 0.0;
+    for (int64_t row = int64_t(blockIdx.x) * RB + threadIdx.x; row < N; row += int64_t(gridDim.x) * RB) {
+        int64_t f = row / NT;
+        int aa = int(row - f * NT);
+        double y = 0.0;
+        const double* kd = a.Kd + f * NT2 + aa;
+        const double* pf = a.p + f * NT;
+#pragma unroll
+        for (int b = 0; b < NT; ++b) y = fma(kd[b * NT], pf[b], y);
+        const int4 cols = *reinterpret_cast<const int4*>(a.kcol + 4 * f);
+        const int cc[4] = {cols.x, cols.y, cols.z, cols.w};
+        const double* ko = a.Ko + f * 4 * NT2 + aa;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            if (cc[s] < 0) continue;
+            const double* pg = a.p + int64_t(cc[s]) * NT;
+#pragma unroll
+            for (int b = 0; b < NT; ++b) y = fma(ko[s * NT2 + b * NT], pg[b], y);
+        }
+        y = a.isbc[f] ? y : -y;
+        a.Ap[row] = y;
+        pap = fma(pf[aa], y, pap);
+    }
+    double tot = block_sum(pap);
+    if (threadIdx.x == 0) a.part[P_PAP * MAX_PARTIALS + blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(RB) pcg_update(const PcgArgs a, int64_t N, int parity) {
+    if (*reinterpret_cast<volatile int32_t*>(a.flags + FLAG_DONE)) return;
+    const double pap = reduce_partials(a.part + P_PAP * MAX_PARTIALS, a.np);
+    const double rz = reduce_partials(a.part + (parity ? P_RZ1 : P_RZ0) * MAX_PARTIALS, a.np);
+    const double alpha = rz / pap;
+    double rz_new = 0.0, rr = 0.0;
+    for (int64_t row = int64_t(blockIdx.x) * RB + threadIdx.x; row < N; row += int64_t(gridDim.x) * RB) {
+        double p = a.p[row], r = a.r[row];
+        a.x[row] = fma(alpha, p, a.x[row]);
+        r = fma(-alpha, a.Ap[row], r);
+        a.r[row] = r;
+        rz_new = fma(r * a.dinv[row], r, rz_new);
+        rr = fma(r, r, rr);
+    }
+    double t1 = block_sum(rz_new), t2 = block_sum(rr);
+    if (threadIdx.x == 0) {
+        a.part[(parity ? P_RZ0 : P_RZ1) * MAX_PARTIALS + blockIdx.x] = t1;
+        a.part[P_RR * MAX_PARTIALS + blockIdx.x] = t2;
+    }
+}
+
+__global__ void __launch_bounds__(RB) pcg_dir(const PcgArgs a, int64_t N, int parity, int iter) {
+    if (*reinterpret_cast<volatile int32_t*>(a.flags + FLAG_DONE)) return;
+    const double rz_old = reduce_partials(a.part + (parity ? P_RZ1 : P_RZ0) * MAX_PARTIALS, a.np);
+    const double rz_new = reduce_partials(a.part + (parity ? P_RZ0 : P_RZ1) * MAX_PARTIALS, a.np);
+    const double rr = reduce_partials(a.part + P_RR * MAX_PARTIALS, a.np);
+    const double bb = a.scal[S_BNORM2];
+    const bool conv = rr <= a.rtol * a.rtol * bb;
+    // the decision is recomputed identically by every block; a block that starts after block 0
+    // has already raised FLAG_DONE returns at the top, which is the same outcome.
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.scal[S_RELRES] = sqrt(rr / bb);
+        a.flags[FLAG_ITERS] = iter;
+    }
+    if (conv) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.flags[FLAG_DONE] = 1;
+        return;
+    }
+    const double beta = rz_new / rz_old;
+    for (int64_t row = int64_t(blockIdx.x) * RB + threadIdx.x; row < N; row += int64_t(gridDim.x) * RB)
+        a.p[row] = fma(beta, a.p[row], a.dinv[row] * a.r[row]);
+}
+
+template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit, hdg_solve_info* info) {
+    const int64_t N = c->nface * NT;
+    if (!c->d_x) {
+        HDG_CUDA(c, cudaMalloc(&c->d_x, sizeof(double) * N));
+        HDG_CUDA(c, cudaMalloc(&c->d_r, sizeof(double) * N));
+        HDG_CUDA(c, cudaMalloc(&c->d_p, sizeof(double) * N));
+        HDG_CUDA(c, cudaMalloc(&c->d_Ap, sizeof(double) * N));
+        HDG_CUDA(c, cudaMalloc(&c->d_dinv, sizeof(double) * N));
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    PcgArgs a{};
+    a.Kd = c->d_Kd; a.Ko = c->d_Ko; a.kcol = c->d_kcol; a.isbc = c->d_isbc; a.rhs = c->d_rhs;
+    a.x = c->d_x; a.r = c->d_r; a.p = c->d_p; a.Ap = c->d_Ap; a.dinv = c->d_dinv;
+    a.part = c->d_partials; a.scal = c->d_scal; a.flags = c->d_flags; a.nface = c->nface;
+    a.np = int(std::min<int64_t>(ceil_div(N, RB), std::min<int64_t>(int64_t(sms) * 8, MAX_PARTIALS)));
+    a.rtol = rtol;
+    const int G = a.np;
+
+    timer_start(c, c->t_solve);
+    HDG_CUDA(c, cudaMemsetAsync(c->d_flags, 0, sizeof(int32_t) * NFLAGS, c->stream));
+    pcg_init<NT><<<G, RB, 0, c->stream>>>(a);
+    pcg_init_final<<<1, RB, 0, c->stream>>>(a);
+    c->launches += 2;
+
+    // one CUDA graph = CHUNK iterations (even, so the rz double-buffer parity restarts at 0)
+    const int CHUNK = 32;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    auto enqueue_iter = [&](int it) {
+        int parity = it & 1;
+        pcg_spmv<NT><<<G, RB, 0, c->stream>>>(a);
+        pcg_update<<<G, RB, 0, c->stream>>>(a, N, parity);
+        pcg_dir<<<G, RB, 0, c->stream>>>(a, N, parity, it + 1);
+    };
+    int it = 0;
+    bool done = false;
+    while (it < maxit && !done) {
+        int chunk = std::min(CHUNK, maxit - it);
+        if (chunk == CHUNK) {
+            // the iteration number baked into pcg_dir is relative; FLAG_ITERS is fixed up below
+            if (!gexec) {
+                HDG_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                for (int k = 0; k < CHUNK; ++k) enqueue_iter(k);
+                HDG_CUDA(c, cudaStreamEndCapture(c->stream, &graph));
+                HDG_CUDA(c, cudaGraphInstantiate(&gexec, graph, 0));
+            }
+            HDG_CUDA(c, cudaGraphLaunch(gexec, c->stream));
+        } else {
+            for (int k = 0; k < chunk; ++k) enqueue_iter(k);
+        }
+        c->launches += 3 * chunk;
+        HDG_CUDA(c, cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int32_t) * NFLAGS, cudaMemcpyDeviceToHost, c->stream));
+        HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+        done = c->h_flags[FLAG_DONE] != 0;
+        if (done) it += c->h_flags[FLAG_ITERS];
+        else it += chunk;
+    }
+    timer_stop(c, c->t_solve);
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
+    HDG_CUDA(c, cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(double) * NSCAL, cudaMemcpyDeviceToHost, c->stream));
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (info) {
+        info->iterations = it;
+        info->converged = done ? 1 : 0;
+        info->relres = c->h_scal[S_RELRES];
+        info->bnorm = std::sqrt(c->h_scal[S_BNORM2]);
+        info->solve_ms = timer_ms(c->t_solve);
+    }
+    c->solved = true;
+    if (!done) return set_err(c, HDG_ERR_NOT_CONVERGED, "PCG did not converge in " + std::to_string(maxit) + " iterations");
+    return HDG_OK;
+}
+
+hdg_status pcg_solve(hdg_context* c, double rtol, int maxit, hdg_solve_info* info) {
+    switch (c->tab.nt) {
+        case 2: return pcg_t<2>(c, rtol, maxit, info);
+        case 3: return pcg_t<3>(c, rtol, maxit, info);
+        case 4: return pcg_t<4>(c, rtol, maxit, info);
+        case 5: return pcg_t<5>(c, rtol, maxit, info);
+    }
+    return set_err(c, HDG_ERR_INVALID, "unsupported order");
+}
+
+}  // namespace hdg

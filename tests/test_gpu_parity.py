@@ -1,0 +1,258 @@
+"""GPU parity tests: the CUDA path through the C ABI against the CPU oracle on the same inputs.
+
+Bar (BASELINE.json north_star): integer numbering / pattern bit-exact; condensed matrices, trace
+solution and recovered u, sigma within 1e-10 relative in FP64; identical L2 error.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import hdg_b200 as hdg
+import hdg_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CONFIGS = [(1, 2), (2, 4), (3, 6), (4, 9), (2, 3), (1, 3)]   # (order, quad_degree); (2,3) is the reference default -> LU path
+
+
+def relerr(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def host_mesh_from_oracle(mo):
+    return hdg.PolygonalMesh(np.hstack([mo.cells, mo.cell_faces]), mo.nodes, mo.faces,
+                             {k: set(v) for k, v in mo.facesets.items()})
+
+
+# ---------------------------------------------------------------------------------- integer work
+@pytest.mark.parametrize("nx,ny", [(1, 1), (2, 2), (3, 2), (1, 5), (5, 1), (10, 10), (17, 9)])
+def test_rectangle_mesh_bit_exact(nx, ny):
+    LL, UR = (0.0, 0.0), (1.0, 1.0) if nx != 17 else (2.0, 1.0)
+    m = hdg.rectangle_mesh(hdg.TriangleCell, (nx, ny), LL, UR)
+    mo = orc.rectangle_mesh(nx, ny, LL, UR)
+    assert np.array_equal(m.cells[:, :3], mo.cells)
+    assert np.array_equal(m.cells[:, 3:], mo.cell_faces)
+    assert np.array_equal(m.faces, mo.faces)
+    assert np.array_equal(m.nodes, mo.nodes)          # coordinates bit for bit
+    for k in ("boundary", "bottom", "right", "top", "left"):
+        assert m.facesets[k] == mo.facesets[k]
+
+
+def test_reference_mesh_goldens_through_abi():
+    # test/test_mesh.jl:31-44
+    m = hdg.rectangle_mesh(hdg.TriangleCell, (2, 2), (0.0, 0.0), (1.0, 1.0))
+    assert m.getncells() == 8 and m.getnnodes() == 9
+    assert m.getcells_matrix().tolist() == [[1, 2, 4], [2, 5, 4], [2, 3, 5], [3, 6, 5], [4, 5, 7], [5, 8, 7], [5, 6, 8], [6, 9, 8]]
+    assert m.get_vertices_matrix().tolist() == [[0, 0], [.5, 0], [1, 0], [0, .5], [.5, .5], [1, .5], [0, 1], [.5, 1], [1, 1]]
+    assert tuple(m.cells[0, 3:]) == (1, 2, 3)
+    assert [hdg.face_orientation(m, 1, i) for i in (1, 2, 3)] == [True, False, True]
+    assert m.getfaceset("boundary") == {3, 7, 9, 16, 2, 11, 12, 15}
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_pattern_bit_exact(order):
+    mo = orc.rectangle_mesh(5, 4)
+    tab = orc.build_tables(order, 2 * order)
+    asm = orc.doassemble(mo, tab)
+    r = _assemble(mo, order, 2 * order, rect=(5, 4, (0., 0.), (1., 1.)))
+    colptr, rowval = r["K"].pattern()
+    assert np.array_equal(colptr, asm.K.indptr.astype(np.int64) + 1)
+    assert np.array_equal(rowval, asm.K.indices.astype(np.int64) + 1)
+
+
+# ---------------------------------------------------------------------------------- assembly
+def _spaces(mesh, order, qd):
+    fe = hdg.GenericFiniteElement(hdg.Dubiner(2, hdg.RefTetrahedron, order))
+    Wh = hdg.ScalarFunctionSpace(mesh, fe, qd)
+    Vh = hdg.VectorFunctionSpace(mesh, fe, qd)
+    Mh = hdg.ScalarTraceFunctionSpace(Wh, hdg.GenericFiniteElement(hdg.Legendre(1, hdg.RefTetrahedron, order)))
+    return Vh, Wh, Mh
+
+
+def _assemble(mo, order, qd, rect=None, f=hdg.poisson_source, local_solver=0):
+    mesh = host_mesh_from_oracle(mo)
+    mesh._rect = rect
+    Vh, Wh, Mh = _spaces(mesh, order, qd)
+    K, b, K_e, b_e = hdg.doassemble(Vh, Wh, Mh, 1.0, f, local_solver=local_solver)
+    return dict(mesh=mesh, Vh=Vh, Wh=Wh, Mh=Mh, K=K, b=b, K_e=K_e, b_e=b_e)
+
+
+def _check_assembly(mo, order, qd, rect=None, local_solver=0, f=hdg.poisson_source, fo=orc.source_poisson):
+    tab = orc.build_tables(order, qd)
+    asm = orc.doassemble(mo, tab, fo)
+    r = _assemble(mo, order, qd, rect, f, local_solver)
+    ctx = r["K"]._ctx
+    s = ctx.sizes()
+    assert (s.n, s.nt, s.m, s.t, s.nq, s.nfq) == (tab.n, tab.nt, 3 * tab.n, 3 * tab.nt, tab.nq, tab.nfq)
+    assert s.ndof == asm.K.shape[0] and s.nnz == asm.K.nnz
+    # local solvers K_e, b_e and condensed blocks Ate, bte, cell by cell
+    worst = 0.0
+    At = np.empty((s.t, s.t), order="F")
+    bt = np.empty(s.t)
+    for c in range(mo.ncells):
+        worst = max(worst, relerr(r["K_e"][c], asm.K_e[c]), relerr(r["b_e"][c], asm.b_e[c]))
+        hdg.check(ctx.lib.hdg_get_condensed(ctx.h, c + 1, hdg.api.f64p(At), hdg.api.f64p(bt)), ctx.h)
+        worst = max(worst, relerr(At, asm.At[c]), relerr(bt, asm.bt[c]))
+    assert worst < RTOL, worst
+    # global matrix in the CSC order of sparse(I,J,V), and rhs
+    colptr, rowval = r["K"].pattern()
+    assert np.array_equal(colptr, asm.K.indptr + 1) and np.array_equal(rowval, asm.K.indices + 1)
+    assert relerr(r["K"].nzval(), asm.K.data) < RTOL
+    assert relerr(r["b"].to_numpy(), asm.rhs) < RTOL
+    return r, asm, tab
+
+
+@pytest.mark.parametrize("order,qd", CONFIGS)
+def test_assembly_rectangle(order, qd):
+    mo = orc.rectangle_mesh(4, 3, (0.0, 0.0), (2.0, 1.0))
+    _check_assembly(mo, order, qd, rect=(4, 3, (0.0, 0.0), (2.0, 1.0)))
+
+
+@pytest.mark.parametrize("order,qd", CONFIGS)
+def test_assembly_triangle_fixture(order, qd):
+    mo = orc.parse_mesh_triangle(os.path.join(GOLDEN, "figure2.1"))
+    _check_assembly(mo, order, qd)
+
+
+@pytest.mark.parametrize("order,qd", [(1, 2), (3, 6)])
+def test_assembly_unstructured_62(order, qd):
+    mo = orc.parse_mesh_triangle(os.path.join(GOLDEN, "figure.1"))
+    _check_assembly(mo, order, qd)
+
+
+@pytest.mark.parametrize("order,qd", [(1, 2), (2, 4), (3, 6)])
+def test_lu_path_equals_schur_path(order, qd):
+    mo = orc.rectangle_mesh(3, 3)
+    _check_assembly(mo, order, qd, local_solver=1)
+
+
+def test_user_source_values():
+    f = lambda x: 1.0 + x[0] * x[1]
+    mo = orc.rectangle_mesh(3, 2)
+    _check_assembly(mo, 2, 4, f=f, fo=f)
+
+
+def test_perturbed_mesh():
+    rng = np.random.default_rng(7)
+    mo = orc.rectangle_mesh(6, 5)
+    interior = np.ones(mo.nnodes, bool)
+    interior[np.unique(mo.faces[mo.faces[:, 3] == 0, :2]) - 1] = False
+    mo.nodes[interior] += rng.uniform(-0.03, 0.03, size=(interior.sum(), 2))
+    _check_assembly(mo, 3, 6)
+
+
+# ---------------------------------------------------------------------------------- full driver
+@pytest.mark.parametrize("order,qd,nx", [(1, 2, 10), (2, 4, 8), (2, 3, 6), (3, 6, 6), (4, 9, 4)])
+def test_full_driver_vs_oracle(order, qd, nx):
+    mo = orc.rectangle_mesh(nx, nx)
+    ro = orc.run_poisson(mo, order, qd)
+    mesh = hdg.rectangle_mesh(hdg.TriangleCell, (nx, nx), (0.0, 0.0), (1.0, 1.0))
+    r = hdg.poisson2D_HDG(mesh, order, qd, rtol=1e-14)
+    assert np.array_equal(r["dbc"].prescribed_dofs, ro["dofs"])
+    assert abs(hdg.meandiag(r["K"]) - ro["meandiag"]) <= 1e-13 * ro["meandiag"]
+    Kb = r["K"].to_scipy()
+    assert relerr(Kb.data, ro["K_bc"].data) < RTOL                 # apply! output, stored zeros included
+    assert relerr(r["b"].to_numpy(), ro["rhs_bc"]) < RTOL
+    assert r["info"]["converged"]
+    assert relerr(r["uhat"].to_numpy(), ro["uhat"]) < RTOL
+    assert relerr(r["u_h"].m_values, ro["u"]) < RTOL
+    assert relerr(r["sigma_h"].m_values, ro["sigma"]) < RTOL
+    assert relerr(r["uhat_h"].m_values, ro["uhat_h"]) < RTOL
+    assert abs(r["err2"] - ro["err2"]) <= 1e-9 * ro["err2"] + 1e-18
+
+
+def test_reference_error_bounds():
+    # examples/poisson2D_HDG.jl:218 and test/test_FunctionSpace.jl:243
+    r = hdg.poisson2D_HDG()                      # as shipped: 10x10, k=1
+    assert r["err2"] <= 0.00006
+    assert abs(r["err2"] - 5.364546646411725e-05) < 1e-14
+    m = hdg.parse_mesh_triangle(os.path.join(GOLDEN, "figure2.1"))
+    r = hdg.poisson2D_HDG(m, 1)
+    assert r["err2"] <= 0.12
+    assert abs(r["err2"] - 0.11019700386004985) < 1e-12
+    assert np.allclose(r["uhat"].to_numpy()[:2], [0.525025534481746, 0.469960493473947], rtol=1e-12)
+
+
+# ---------------------------------------------------------------------------------- error behaviour
+def test_bad_geometry_raises():
+    mo = orc.rectangle_mesh(2, 2)
+    cells = np.hstack([mo.cells, mo.cell_faces])
+    cells[3, [1, 2]] = cells[3, [2, 1]]          # clockwise cell -> det(J) < 0  (src/ScalarFunctionSpaces.jl:110)
+    mesh = hdg.PolygonalMesh(cells, mo.nodes, mo.faces, {"boundary": set(mo.facesets["boundary"])})
+    Vh, Wh, Mh = _spaces(mesh, 1, 2)
+    with pytest.raises(hdg.BadGeometryError):
+        hdg.doassemble(Vh, Wh, Mh)
+
+
+def test_singular_local_matrix_raises():
+    # k=3 with the reference default quad_degree=4: local matrix singular (trap 1)
+    mesh = hdg.rectangle_mesh(hdg.TriangleCell, (2, 2), (0.0, 0.0), (1.0, 1.0))
+    Vh, Wh, Mh = _spaces(mesh, 3, 5)
+    try:
+        K, b, _, _ = hdg.doassemble(Vh, Wh, Mh)
+    except hdg.SingularLocalError:
+        return
+    # LAPACK only raises on an exactly zero pivot; otherwise the result is garbage, like the reference
+    assert not np.all(np.isfinite(K.nzval())) or np.abs(K.nzval()).max() > 1e6
+
+
+def test_not_boundary_face_raises():
+    mo = orc.rectangle_mesh(2, 2)
+    mesh = host_mesh_from_oracle(mo)
+    mesh.facesets["boundary"] = set(mesh.facesets["boundary"]) | {1}     # face 1 is interior
+    Vh, Wh, Mh = _spaces(mesh, 1, 2)
+    with pytest.raises(AssertionError):
+        hdg.Dirichlet(hdg.TrialFunction(Mh), mesh, "boundary", lambda x: 0)
+    with pytest.raises(hdg.NotBoundaryError):
+        hdg.doassemble(Vh, Wh, Mh)
+
+
+def test_call_order_errors():
+    ctx = hdg._Context(1)
+    with pytest.raises(hdg.HDGError):
+        hdg.check(ctx.lib.hdg_assemble(ctx.h), ctx.h)        # no mesh yet
+    ctx.close()
+
+
+# ---------------------------------------------------------------------------------- full-size properties
+def test_c2_size_properties():
+    """BASELINE config C2 (k=1, 1000x500 = 1M elements): size-independent properties."""
+    nx, ny = 1000, 500
+    ctx = hdg._Context(1, 2)
+    lib = ctx.lib
+    hdg.check(lib.hdg_set_rectangle_mesh(ctx.h, nx, ny, 0.0, 0.0, 2.0, 1.0), ctx.h)
+    s = ctx.sizes()
+    assert (s.ncell, s.nface, s.ndof, s.nnz) == (1_000_000, 1_501_500, 3_003_000, 30_006_000)
+    hdg.check(lib.hdg_assemble(ctx.h), ctx.h)
+    K = hdg.TraceMatrix(ctx).to_scipy()
+    # symmetric to rounding, and the constant trace (Legendre mode 0 on every face) spans the null space
+    asym = abs(K - K.T).max()
+    assert asym < 1e-12 * abs(K).max()
+    ones = np.zeros(s.ndof)
+    ones[0::2] = 1.0
+    assert np.abs(K @ ones).max() < 1e-10 * abs(K).max()
+    # deterministic: a second assembly gives bit-identical values
+    v1 = hdg.TraceMatrix(ctx).nzval()
+    hdg.check(lib.hdg_assemble(ctx.h), ctx.h)
+    assert np.array_equal(v1, hdg.TraceMatrix(ctx).nzval())
+    rhs = hdg.DeviceVector(ctx, "hdg_get_rhs").to_numpy()
+    hdg.check(lib.hdg_apply_dirichlet(ctx.h, None), ctx.h)
+    Kb = hdg.TraceMatrix(ctx).to_scipy()
+    bb = hdg.DeviceVector(ctx, "hdg_get_rhs").to_numpy()
+    info = hdg.api.SolveInfo()
+    import ctypes as C
+    hdg.check(lib.hdg_solve(ctx.h, 1e-10, 20000, C.byref(info)), ctx.h)
+    x = hdg.DeviceVector(ctx, "hdg_get_trace").to_numpy()
+    res = np.linalg.norm(Kb @ x - bb) / np.linalg.norm(bb)          # residual checked independently (scipy)
+    assert res < 5e-10, res
+    hdg.check(lib.hdg_recover(ctx.h), ctx.h)
+    e = C.c_double()
+    hdg.check(lib.hdg_errornorm(ctx.h, 1, C.byref(e)), ctx.h)
+    # k=1: err^2 ~ C h^4; 10x10 on the unit square gives 5.36e-5 at h=0.1  ->  h=0.002 gives ~8.6e-12
+    assert 1e-12 < e.value < 5e-11, e.value
+    assert rhs.shape == bb.shape
+    ctx.close()
