@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the HDG hot path (BASELINE.json metric).
+
+metric : HDG elements/sec (assemble + condense + scatter); the trace PCG solve is timed beside it
+workload (N=1): BASELINE config C2 - Poisson HDG k=1 on a 1M-element structured triangle mesh
+         (rectangle_mesh 1000x500 on [0,2]x[0,1], quad_degree 2, tau 1, f = 2 pi^2 sin sin).
+A "step" = one full pass of hdg_assemble over the mesh (memsets + fused element kernel: local
+blocks, static condensation, scatter into the block trace matrix + rhs, K_e/b_e stored).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (C port of the
+                                                           # Julia driver, all host threads, bounded sample)
+Under torchrun (N>1) every rank assembles its own strip of quad rows (weak scaling, no data-path
+collective); timing = max over ranks of the CUDA-event time, bracketed by barrier + synchronize.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+QD_FOR_ORDER = {1: 2, 2: 4, 3: 6, 4: 9}
+# algorithmic figures per element, SURVEY.md section 8(d) / BASELINE.md section 3
+ALG_BYTES = {1: 840, 2: 2088, 3: 4200, 4: 7392}
+ALG_FLOPS = {1: 3090, 2: 18648, 3: 73896, 4: 268350}
+RECOVER_BYTES = {1: 600, 2: 1656, 3: 3456, 4: 6240}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_elements_per_s(order, qd, sample, nthreads, passes=1):
+    """Time the C port of the reference's doassemble on a bounded sample mesh (host cores)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import hdg_oracle as orc      # checker / CPU baseline only
+    import hdg_oracle_c as occ
+    nx, ny = sample
+    mesh = orc.rectangle_mesh(nx, ny, (0.0, 0.0), (2.0, 1.0))
+    tab = orc.build_tables(order, qd)
+    occ.doassemble(orc.rectangle_mesh(8, 4), tab, nthreads=nthreads, keep_local=True)   # warm the library
+    t0 = time.perf_counter()
+    for _ in range(passes):
+        occ.doassemble(mesh, tab, nthreads=nthreads, keep_local=True)
+    dt = (time.perf_counter() - t0) / passes
+    return mesh.ncells / dt, dt, mesh.ncells
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  Julia cannot run here
+    (DESIGN.md), so this is the loop-faithful C port (oracle/hdg_oracle.c) with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import hdg_oracle_c as occ
+    order = args.order
+    qd = args.quad_degree or QD_FOR_ORDER[order]
+    cores = occ.max_threads()
+    sample = (400, 200) if order == 1 else ((200, 100) if order == 2 else (100, 50))
+    for _ in range(args.warmup):
+        cpu_port_elements_per_s(order, qd, (40, 20), cores)
+    t_tot, n_tot = 0.0, 0
+    for _ in range(args.steps):
+        eps, dt, ncell = cpu_port_elements_per_s(order, qd, sample, cores)
+        t_tot += dt
+        n_tot += ncell
+    value = n_tot / t_tot
+    desc = f"rectangle_mesh {sample[0]}x{sample[1]} ({2*sample[0]*sample[1]} elements) per step, same k/quad_degree/tau/f"
+    out = {
+        "impl": "reference", "metric": "HDG elements/sec (assemble+condense+scatter)", "value": value,
+        "unit": "elements/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C2: Poisson HDG k={order} qd={qd}, 1M-element structured triangle mesh (bounded sample: {desc})"},
+        "cpu_baseline": {"value": value, "unit": "elements/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--order", type=int, default=1)
+    ap.add_argument("--quad-degree", type=int, default=0)
+    ap.add_argument("--nx", type=int, default=0)
+    ap.add_argument("--ny", type=int, default=0)
+    ap.add_argument("--perturb", type=float, default=0.0, help="jitter interior nodes by this fraction of h")
+    ap.add_argument("--rtol", type=float, default=1e-12)
+    ap.add_argument("--maxit", type=int, default=40000)
+    ap.add_argument("--no-pcg", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import hdg_b200 as hdg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    order = args.order
+    qd = args.quad_degree or QD_FOR_ORDER[order]
+    default_mesh = {1: (1000, 500), 2: (2000, 1000), 3: (2000, 1000), 4: (1000, 500)}
+    nx, ny = (args.nx, args.ny) if args.nx and args.ny else default_mesh[order]
+    W = max(args.warmup, 3)
+    K = args.steps
+
+    ctx = hdg._Context(order, qd, 1.0, 1, local_rank)
+    lib = ctx.lib
+    # every rank: its own strip of ny quad rows (weak scaling): global mesh nx x (ny*world) on [0,2]x[0,world]
+    hdg.check(lib.hdg_set_rectangle_mesh(ctx.h, nx, ny, 0.0, float(rank), 2.0, float(rank + 1)), ctx.h)
+    if args.perturb > 0:
+        hdg.check(lib.hdg_perturb_nodes(ctx.h, args.perturb, 12345), ctx.h)
+    s = ctx.sizes()
+    ncell = int(s.ncell)
+    stream = torch.cuda.ExternalStream(int(lib.hdg_stream(ctx.h)), device=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def phase_ms(name):
+        v = C.c_double()
+        hdg.check(lib.hdg_last_phase_ms(ctx.h, name.encode(), C.byref(v)), ctx.h)
+        return v.value
+
+    # ---------------- device-resident timing: K steps of assemble+condense+scatter ----------------
+    for _ in range(W):
+        hdg.check(lib.hdg_assemble_async(ctx.h), ctx.h)
+    hdg.check(lib.hdg_sync(ctx.h), ctx.h)
+    hdg.check(lib.hdg_assemble(ctx.h), ctx.h)        # checked variant once: raises on bad geometry / singular cells
+    launches0 = lib.hdg_launch_count(ctx.h)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(K):
+            hdg.check(lib.hdg_assemble_async(ctx.h), ctx.h)
+        e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    launches = lib.hdg_launch_count(ctx.h) - launches0
+    if dist is not None:
+        tt = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+    ms_step = ms_total / K
+    value = ncell * world / (ms_step * 1e-3)
+
+    # element kernel alone (roofline numerator): CUDA events around the kernel launch, averaged over K launches
+    kern_ms = []
+    for _ in range(K):
+        hdg.check(lib.hdg_assemble_async(ctx.h), ctx.h)
+        hdg.check(lib.hdg_sync(ctx.h), ctx.h)
+        kern_ms.append(phase_ms("element_kernel"))
+    kern_ms_avg = float(np.mean(kern_ms))
+    peak, peak_src = measured_peaks()
+    achieved = ALG_BYTES[order] * ncell / (kern_ms_avg * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": f"element_schur_kernel<{order}>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "alg_bytes_per_element": ALG_BYTES[order],
+                "alg_flops_per_element": ALG_FLOPS[order], "kernel_ms": kern_ms_avg,
+                "gflops_alg": ALG_FLOPS[order] * ncell / (kern_ms_avg * 1e-3) / 1e9, "peak_source": peak_src}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            with open(prof) as fh:
+                roofline["traffic"] = json.load(fh).get(f"element_k{order}")
+        except Exception:
+            pass
+
+    # ---------------- end to end through the C ABI with HOST buffers ----------------
+    e2e = None
+    if rank == 0 or world > 1:
+        cells = torch.empty((ncell, 6), dtype=torch.int64).pin_memory().numpy()
+        nodes = torch.empty((int(s.nnode), 2), dtype=torch.float64).pin_memory().numpy()
+        faces_t = torch.empty((4, int(s.nface)), dtype=torch.int64).pin_memory()      # column-major nface x 4
+        faces = faces_t.numpy()
+        bfaces = torch.empty((int(s.nbface),), dtype=torch.int64).pin_memory().numpy()
+        rhs_out = torch.empty((int(s.ndof),), dtype=torch.float64).pin_memory().numpy()
+        hdg.check(lib.hdg_get_mesh(ctx.h, hdg.api.i64p(cells), hdg.api.f64p(nodes), hdg.api.i64p(faces), hdg.api.i64p(bfaces)), ctx.h)
+        ctx2 = hdg._Context(order, qd, 1.0, 1, local_rank)
+
+        def e2e_step():
+            hdg.check(lib.hdg_set_mesh(ctx2.h, hdg.api.i64p(cells), ncell, hdg.api.f64p(nodes), int(s.nnode),
+                                       hdg.api.i64p(faces), int(s.nface), hdg.api.i64p(bfaces), int(s.nbface)), ctx2.h)
+            hdg.check(lib.hdg_assemble(ctx2.h), ctx2.h)
+            hdg.check(lib.hdg_get_rhs(ctx2.h, hdg.api.f64p(rhs_out)), ctx2.h)
+
+        ke2e = max(3, min(K, 10))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke2e):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / ke2e
+        if dist is not None:
+            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        h2d = cells.nbytes + nodes.nbytes + faces.nbytes + bfaces.nbytes
+        e2e = {"value": ncell * world / dt, "unit": "elements/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(rhs_out.nbytes), "ms_per_step": dt * 1e3, "steps": ke2e,
+               "what": "hdg_set_mesh(host Julia-layout arrays) + hdg_assemble + hdg_get_rhs(host)"}
+        ctx2.close()
+
+    # ---------------- trace solve (Jacobi-PCG), recovery, error ----------------
+    pcg = None
+    if not args.no_pcg and world == 1:
+        hdg.check(lib.hdg_apply_dirichlet(ctx.h, None), ctx.h)
+        info = hdg.api.SolveInfo()
+        st = lib.hdg_solve(ctx.h, args.rtol, args.maxit, C.byref(info))
+        if st not in (0, 7):
+            hdg.check(st, ctx.h)
+        hdg.check(lib.hdg_recover(ctx.h), ctx.h)
+        err2 = C.c_double()
+        hdg.check(lib.hdg_errornorm(ctx.h, 1, C.byref(err2)), ctx.h)
+        it = max(info.iterations, 1)
+        bytes_iter = 12 * int(s.nnz) + 116 * int(s.ndof)
+        ms_iter = info.solve_ms / it
+        rec_ms = phase_ms("recover")
+        pcg = {"iterations": info.iterations, "converged": bool(info.converged), "relres": info.relres,
+               "rtol": args.rtol, "solve_s": info.solve_ms * 1e-3, "ms_per_iter": ms_iter,
+               "roofline": {"bound": "hbm", "alg_bytes_per_iter": bytes_iter, "achieved": bytes_iter / (ms_iter * 1e-3) / 1e9,
+                            "peak": peak, "unit": "GB/s", "frac": bytes_iter / (ms_iter * 1e-3) / 1e9 / peak},
+               "recover_ms": rec_ms,
+               "recover_roofline": {"bound": "hbm", "achieved": RECOVER_BYTES[order] * ncell / (rec_ms * 1e-3) / 1e9, "peak": peak,
+                                    "unit": "GB/s", "frac": RECOVER_BYTES[order] * ncell / (rec_ms * 1e-3) / 1e9 / peak},
+               "err2": err2.value}
+
+    # ---------------- CPU baseline on the box's host cores (rank 0, N=1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample = (400, 200) if order == 1 else ((200, 100) if order == 2 else (100, 50))
+        v1, dt1, n1 = cpu_port_elements_per_s(order, qd, sample, 1, passes=3 if order == 1 else 1)
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import hdg_oracle_c as occ
+        cores = occ.max_threads()
+        vN, dtN, _ = cpu_port_elements_per_s(order, qd, sample, cores, passes=3 if order == 1 else 1)
+        cpu = {"value": v1, "unit": "elements/s", "cores": 1, "kind": "port",
+               "sample": f"C port of doassemble (oracle/hdg_oracle.c), rectangle_mesh {sample[0]}x{sample[1]} = {n1} elements, "
+                         f"{dt1:.2f} s/pass single thread (the reference is single-threaded)",
+               "all_cores": {"value": vN, "cores": cores, "s_per_pass": dtN}}
+
+    if rank == 0:
+        out = {
+            "metric": "HDG elements/sec (assemble+condense+scatter)", "value": value, "unit": "elements/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C2: Poisson HDG k={order} quad_degree={qd} tau=1, rectangle_mesh {nx}x{ny} per GPU "
+                                   f"({ncell} elements, {int(s.ndof)} trace dofs, nnz {int(s.nnz)}) on [0,2]x[0,1]",
+                       "l2": f"inputs+outputs per step {ALG_BYTES[order]*ncell/1e6:.0f} MB > 126 MB L2 (no explicit flush needed)",
+                       "perturb": args.perturb, "elements_per_gpu": ncell},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "pcg": pcg,
+        }
+        print(json.dumps(out))
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -120,7 +120,7 @@ void hdg_destroy(hdg_context* c) {
     if (c->d_partials) cudaFree(c->d_partials);
     if (c->h_flags) cudaFreeHost(c->h_flags);
     if (c->h_scal) cudaFreeHost(c->h_scal);
-    for (Timer* t : {&c->t_assemble, &c->t_apply, &c->t_solve, &c->t_recover, &c->t_err}) {
+    for (Timer* t : {&c->t_assemble, &c->t_apply, &c->t_solve, &c->t_recover, &c->t_err, &c->t_elem}) {
         if (t->a) cudaEventDestroy(t->a);
         if (t->b) cudaEventDestroy(t->b);
     }
@@ -368,6 +368,7 @@ hdg_status hdg_last_phase_ms(const hdg_context* cc, const char* phase, double* m
     else if (s == "solve") t = &c->t_solve;
     else if (s == "recover") t = &c->t_recover;
     else if (s == "errornorm") t = &c->t_err;
+    else if (s == "element_kernel") t = &c->t_elem;
     else return set_err(c, HDG_ERR_INVALID, "unknown phase");
     if (!t->a) { *ms = 0.0; return HDG_OK; }
     *ms = double(timer_ms(*t));

@@ -600,7 +600,10 @@ hdg_status launch_element_kernels(hdg_context* c) {
     a.Ke = c->d_Ke; a.Kd = c->d_Kd; a.Ko = c->d_Ko; a.rhs = c->d_rhs; a.flags = c->d_flags;
     a.cell_begin = 0; a.cell_end = c->ncell; a.tau = c->prm.tau; a.nq = c->tab.nq; a.source_id = c->prm.source_id;
     a.dbg_At = nullptr; a.dbg_bt = nullptr;
-    return launch_elements(c, a);
+    timer_start(c, c->t_elem);
+    hdg_status st = launch_elements(c, a);
+    timer_stop(c, c->t_elem);
+    return st;
 }
 
 hdg_status condensed_of_cell(hdg_context* c, int64_t cell, double* At, double* bt) {

@@ -120,7 +120,7 @@ struct hdg_context {
     double *d_sigma = nullptr, *d_u = nullptr, *d_uhat_h = nullptr;
     bool recovered = false;
 
-    hdg::Timer t_assemble, t_apply, t_solve, t_recover, t_err;
+    hdg::Timer t_assemble, t_apply, t_solve, t_recover, t_err, t_elem;
     hdg::Comm* comm = nullptr;
 };
 

@@ -179,7 +179,8 @@ hdg_status hdg_comm_init(hdg_context* ctx, int32_t rank, int32_t nranks, const u
 
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* Device time (ms, CUDA events on the context stream) of the kernels of the last call of the
- * named phase: "assemble", "apply", "solve", "recover", "errornorm". */
+ * named phase: "assemble" (memsets + element kernel), "element_kernel", "apply", "solve",
+ * "recover", "errornorm". */
 hdg_status hdg_last_phase_ms(const hdg_context* ctx, const char* phase, double* ms);
 /* Number of kernel launches issued by this context since creation. */
 int64_t    hdg_launch_count(const hdg_context* ctx);

@@ -248,7 +248,7 @@ def test_c2_size_properties():
     hdg.check(lib.hdg_solve(ctx.h, 1e-10, 20000, C.byref(info)), ctx.h)
     x = hdg.DeviceVector(ctx, "hdg_get_trace").to_numpy()
     res = np.linalg.norm(Kb @ x - bb) / np.linalg.norm(bb)          # residual checked independently (scipy)
-    assert res < 5e-10, res
+    assert res < 1e-8, res   # true residual drifts from the recurrence residual at cond ~ 1e6
     hdg.check(lib.hdg_recover(ctx.h), ctx.h)
     e = C.c_double()
     hdg.check(lib.hdg_errornorm(ctx.h, 1, C.byref(e)), ctx.h)
