@@ -62,14 +62,16 @@ struct CellGeom {
     double x[3][2];
     int32_t v[3];
     uint32_t f[3];                     // face id | sec<<31
+    int32_t partner, bflags;           // in-warp neighbour per local face (8 bits each); boundary-face bits
     bool ok;
 };
 
 __device__ __forceinline__ void load_geometry(const ElemArgs& a, int64_t c, CellGeom& g) {
-    const int2* ci = reinterpret_cast<const int2*>(a.cellinfo + 6 * c);
-    int2 p0 = __ldg(ci), p1 = __ldg(ci + 1), p2 = __ldg(ci + 2);
-    g.v[0] = p0.x; g.v[1] = p0.y; g.v[2] = p1.x;
-    g.f[0] = uint32_t(p1.y); g.f[1] = uint32_t(p2.x); g.f[2] = uint32_t(p2.y);
+    const int4* ci = reinterpret_cast<const int4*>(a.cellinfo + CI * c);
+    int4 p0 = __ldg(ci), p1 = __ldg(ci + 1);
+    g.v[0] = p0.x; g.v[1] = p0.y; g.v[2] = p0.z;
+    g.f[0] = uint32_t(p0.w); g.f[1] = uint32_t(p1.x); g.f[2] = uint32_t(p1.y);
+    g.partner = p1.z; g.bflags = p1.w;
     const double2* nd = reinterpret_cast<const double2*>(a.nodes);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -99,20 +101,69 @@ __device__ __forceinline__ double source_value(int source_id, double x, double y
 // strict lower triangle index
 __device__ __forceinline__ constexpr int tri(int i, int j) { return i * (i - 1) / 2 + j; }
 
-template <int K, bool L_SMEM>
-__global__ void __launch_bounds__(128) element_schur_kernel(const ElemArgs a) {
-    constexpr int n = Ord<K>::n, nt = Ord<K>::nt, t = Ord<K>::t, ke = Ord<K>::ke;
-    constexpr int nL = n * (n - 1) / 2;
-    const DevTables<K>& T = ctab<K>();
-    extern __shared__ double smem_L[];   // L_SMEM: [nL][blockDim.x]
+// widest aligned vector store of N doubles (256-bit STG on sm_100a where the block is 32-byte aligned)
+template <int N> __device__ __forceinline__ void store_vec(double* __restrict__ dst, const double* v) {
+    if constexpr (N % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i += 4)
+            asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(dst + i), "d"(v[i]), "d"(v[i + 1]), "d"(v[i + 2]), "d"(v[i + 3]) : "memory");
+    } else if constexpr (N % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i += 2) *reinterpret_cast<double2*>(dst + i) = make_double2(v[i], v[i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) dst[i] = v[i];
+    }
+}
 
-    const int64_t c = a.cell_begin + int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (c >= a.cell_end) return;
+// Staging area in shared memory, entry-major ([entry][thread]) so that every access is conflict free.
+template <int K> struct Stage {
+    static constexpr int nt = Ord<K>::nt;
+    __host__ __device__ static constexpr int diag(int l, int j, int ip) { return (l * nt + j) * nt + ip; }          // face-diagonal blocks
+    __host__ __device__ static constexpr int rhs(int l, int ip) { return 3 * nt * nt + l * nt + ip; }              // bte
+    __host__ __device__ static constexpr int off(int lp, int s, int j, int ip) { return 3 * nt * nt + 3 * nt + ((lp * 2 + s) * nt + j) * nt + ip; }
+    static constexpr int n_base = 3 * nt * nt + 3 * nt;
+    static constexpr int n_off = 6 * nt * nt;
+};
+
+#ifndef MINB1
+#define MINB1 5
+#endif
+#ifndef MINB2
+#define MINB2 3
+#endif
+template <int K> struct SchurCfg {
+    static constexpr int threads = K >= 4 ? 64 : 128;
+    static constexpr int min_blocks = K == 1 ? MINB1 : (K == 2 ? MINB2 : 1);
+    static constexpr bool stage_diag = K <= 3;      // face-diagonal blocks + rhs staged in shared memory (in-warp pairing)
+    static constexpr bool l_smem = K >= 3;          // LDL' factor in shared memory (register pressure)
+    static constexpr bool stage_off = K == 1;       // off-diagonal blocks staged too -> one 256-bit store per block
+    static constexpr int nL = Ord<K>::n * (Ord<K>::n - 1) / 2;
+    static constexpr int smem_doubles = (l_smem ? nL : 0) + (stage_diag ? Stage<K>::n_base : 0) + (stage_off ? Stage<K>::n_off : 0);
+};
+
+template <int K>
+__global__ void __launch_bounds__(SchurCfg<K>::threads, SchurCfg<K>::min_blocks) element_schur_kernel(const ElemArgs a) {
+    constexpr int n = Ord<K>::n, nt = Ord<K>::nt, t = Ord<K>::t, ke = Ord<K>::ke;
+    constexpr int nL = SchurCfg<K>::nL;
+    constexpr bool L_SMEM = SchurCfg<K>::l_smem, STAGE_OFF = SchurCfg<K>::stage_off, STAGE_DIAG = SchurCfg<K>::stage_diag;
+    constexpr int B = SchurCfg<K>::threads;
+    using St = Stage<K>;
+    const DevTables<K>& T = ctab<K>();
+    extern __shared__ double smem[];
+    double* const smem_L = smem + threadIdx.x;                                   // [nL][B]
+    double* const stg = smem + (L_SMEM ? nL * B : 0) + threadIdx.x;              // [entries][B]
+
+    const int64_t c = a.cell_begin + int64_t(blockIdx.x) * B + threadIdx.x;
+    bool active = c < a.cell_end;
+    const bool dbg = a.dbg_At != nullptr;
     CellGeom g;
-    load_geometry(a, c, g);
-    if (!g.ok) {
-        atomicCAS(&a.flags[FLAG_BAD_GEOM], 0, int32_t(c + 1));
-        return;
+    if (active) {
+        load_geometry(a, c, g);
+        if (!g.ok) {
+            atomicCAS(&a.flags[FLAG_BAD_GEOM], 0, int32_t(c + 1));
+            active = false;
+        }
     }
     const double tau = a.tau;
     // orientation bits, face_orientation src/mesh.jl:51-54: local edge l joins local nodes ((1,2),(2,0),(0,1))
@@ -120,16 +171,17 @@ __global__ void __launch_bounds__(128) element_schur_kernel(const ElemArgs a) {
 
     // ---- S = C + B'A^-1 B, LDL' factorisation ------------------------------------------------
     double Lr[L_SMEM ? 1 : (nL > 0 ? nL : 1)];
-    double dinv[n], dd[n];
+    double dinv[n];
     auto Lget = [&](int i, int j) -> double {
-        if constexpr (L_SMEM) return smem_L[tri(i, j) * blockDim.x + threadIdx.x];
+        if constexpr (L_SMEM) return smem_L[tri(i, j) * B];
         else return Lr[tri(i, j)];
     };
     auto Lset = [&](int i, int j, double v) {
-        if constexpr (L_SMEM) smem_L[tri(i, j) * blockDim.x + threadIdx.x] = v;
+        if constexpr (L_SMEM) smem_L[tri(i, j) * B] = v;
         else Lr[tri(i, j)] = v;
     };
-    {
+    if (active) {
+        double dd[n];
         const double al = g.detJ * (g.G00 * g.G00 + g.G01 * g.G01);
         const double be = g.detJ * (g.G00 * g.G10 + g.G01 * g.G11);
         const double ga = g.detJ * (g.G10 * g.G10 + g.G11 * g.G11);
@@ -163,154 +215,210 @@ __global__ void __launch_bounds__(128) element_schur_kernel(const ElemArgs a) {
         }
         if (!spd) {
             atomicCAS(&a.flags[FLAG_SINGULAR], 0, int32_t(c + 1));
-            return;
+            active = false;
         }
     }
 
-    // ---- rhs vector be[i] = detJ sum_q w_q f(x_q) N[i,q]  (poisson2D_HDG.jl:106-114) -------------
-    double bev[n];
+    if (active) {
+        // ---- rhs vector be[i] = detJ sum_q w_q f(x_q) N[i,q]  (poisson2D_HDG.jl:106-114) ---------
+        double bev[n];
 #pragma unroll
-    for (int i = 0; i < n; ++i) bev[i] = 0.0;
-    for (int q = 0; q < a.nq; ++q) {
-        double fv;
-        if (a.source_id == 0) fv = a.fq[c * a.nq + q];
-        else {
-            double xq = T.Mgeo[3 * q] * g.x[0][0] + T.Mgeo[3 * q + 1] * g.x[1][0] + T.Mgeo[3 * q + 2] * g.x[2][0];
-            double yq = T.Mgeo[3 * q] * g.x[0][1] + T.Mgeo[3 * q + 1] * g.x[1][1] + T.Mgeo[3 * q + 2] * g.x[2][1];
-            fv = source_value(a.source_id, xq, yq);
+        for (int i = 0; i < n; ++i) bev[i] = 0.0;
+        for (int q = 0; q < a.nq; ++q) {
+            double fv;
+            if (a.source_id == 0) fv = a.fq[c * a.nq + q];
+            else {
+                double xq = T.Mgeo[3 * q] * g.x[0][0] + T.Mgeo[3 * q + 1] * g.x[1][0] + T.Mgeo[3 * q + 2] * g.x[2][0];
+                double yq = T.Mgeo[3 * q] * g.x[0][1] + T.Mgeo[3 * q + 1] * g.x[1][1] + T.Mgeo[3 * q + 2] * g.x[2][1];
+                fv = source_value(a.source_id, xq, yq);
+            }
+#pragma unroll
+            for (int i = 0; i < n; ++i) bev[i] = fma(T.WN[q * n + i], fv, bev[i]);
         }
 #pragma unroll
-        for (int i = 0; i < n; ++i) bev[i] = fma(T.WN[q * n + i], fv, bev[i]);
-    }
-#pragma unroll
-    for (int i = 0; i < n; ++i) bev[i] *= g.detJ;
+        for (int i = 0; i < n; ++i) bev[i] *= g.detJ;
 
-    // per-face coefficients of the E-columns:  B'A^-1 E_l = a_l Qr_l + b_l Qs_l
-    double ca[3], cb[3];
+        // per-face coefficients of the E-columns:  B'A^-1 E_l = a_l Qr_l + b_l Qs_l
+        double ca[3], cb[3];
 #pragma unroll
-    for (int l = 0; l < 3; ++l) {
-        ca[l] = g.G00 * g.wn[l][0] + g.G01 * g.wn[l][1];
-        cb[l] = g.G10 * g.wn[l][0] + g.G11 * g.wn[l][1];
-    }
-    const double idet = 1.0 / g.detJ;
-    const int lane = threadIdx.x & 31;
-    double* __restrict__ Ke_tile = a.Ke + ((c >> 5) * ke) * 32 + (c & 31);
-    (void)lane;
-    const int64_t nt2 = nt * nt;
+        for (int l = 0; l < 3; ++l) {
+            ca[l] = g.G00 * g.wn[l][0] + g.G01 * g.wn[l][1];
+            cb[l] = g.G10 * g.wn[l][0] + g.G11 * g.wn[l][1];
+        }
+        const double idet = 1.0 / g.detJ;
+        double* __restrict__ Ke_tile = a.Ke + ((c >> 5) * ke) * 32 + (c & 31);
+        constexpr int64_t nt2 = nt * nt;
 
-    // ---- one column of [K_e | b_e] at a time ----------------------------------------------------
+        // ---- one column of [K_e | b_e] at a time ------------------------------------------------
 #pragma unroll 1
-    for (int col = 0; col <= t; ++col) {
-        const bool isb = col == t;
-        const int l = isb ? 0 : col / nt;
-        const int j = isb ? 0 : col - l * nt;
-        const double dJf_l = l == 0 ? g.dJf[0] : (l == 1 ? g.dJf[1] : g.dJf[2]);
-        const double wnx = l == 0 ? g.wn[0][0] : (l == 1 ? g.wn[1][0] : g.wn[2][0]);
-        const double wny = l == 0 ? g.wn[0][1] : (l == 1 ? g.wn[1][1] : g.wn[2][1]);
-        const double ca_l = l == 0 ? ca[0] : (l == 1 ? ca[1] : ca[2]);
-        const double cb_l = l == 0 ? cb[0] : (l == 1 ? cb[1] : cb[2]);
-        const bool o_l = l == 0 ? o0 : (l == 1 ? o1 : o2);
-        const double scol = (isb || o_l || !(j & 1)) ? 1.0 : -1.0;   // Legendre parity of a reversed face
+        for (int col = 0; col <= t; ++col) {
+            const bool isb = col == t;
+            const int l = isb ? 0 : col / nt;
+            const int j = isb ? 0 : col - l * nt;
+            const double dJf_l = l == 0 ? g.dJf[0] : (l == 1 ? g.dJf[1] : g.dJf[2]);
+            const double wnx = l == 0 ? g.wn[0][0] : (l == 1 ? g.wn[1][0] : g.wn[2][0]);
+            const double wny = l == 0 ? g.wn[0][1] : (l == 1 ? g.wn[1][1] : g.wn[2][1]);
+            const double ca_l = l == 0 ? ca[0] : (l == 1 ? ca[1] : ca[2]);
+            const double cb_l = l == 0 ? cb[0] : (l == 1 ? cb[1] : cb[2]);
+            const bool o_l = l == 0 ? o0 : (l == 1 ? o1 : o2);
+            const double scol = (isb || o_l || !(j & 1)) ? 1.0 : -1.0;   // Legendre parity of a reversed face
 
-        double u[n];
-        if (isb) {
-#pragma unroll
-            for (int i = 0; i < n; ++i) u[i] = bev[i];
-        } else {
-            const double cf = tau * dJf_l;
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-                double r = cf * T.Fhat[i * t + col];
-                r = fma(ca_l, T.Qr[i * t + col], r);
-                u[i] = fma(cb_l, T.Qs[i * t + col], r);
-            }
-        }
-        // S u = r  by L D L'
-#pragma unroll
-        for (int i = 1; i < n; ++i)
-#pragma unroll
-            for (int k = 0; k < i; ++k) u[i] = fma(-Lget(i, k), u[k], u[i]);
-#pragma unroll
-        for (int i = 0; i < n; ++i) u[i] *= dinv[i];
-#pragma unroll
-        for (int i = n - 2; i >= 0; --i)
-#pragma unroll
-            for (int k = i + 1; k < n; ++k) u[i] = fma(-Lget(k, i), u[k], u[i]);
-
-        // sigma = A^-1 (r1 + B u)
-        double sx[n], sy[n];
-        const double ex = isb ? 0.0 : wnx * idet, ey = isb ? 0.0 : wny * idet;
-#pragma unroll
-        for (int i = 0; i < n; ++i) {
-            double p = 0.0, q = 0.0;
-#pragma unroll
-            for (int k = 0; k < n; ++k) {
-                p = fma(T.Tr[i * n + k], u[k], p);
-                q = fma(T.Ts[i * n + k], u[k], q);
-            }
-            double mf = isb ? 0.0 : T.MF[i * t + col];
-            sx[i] = fma(g.G00, p, fma(g.G10, q, -ex * mf));
-            sy[i] = fma(g.G01, p, fma(g.G11, q, -ey * mf));
-        }
-        // store column of [K_e | b_e]   (rows: sigma_x, sigma_y, u)
-        if (a.dbg_At == nullptr) {
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-                Ke_tile[int64_t((i) * (t + 1) + col) * 32] = scol * sx[i];
-                Ke_tile[int64_t((n + i) * (t + 1) + col) * 32] = scol * sy[i];
-                Ke_tile[int64_t((2 * n + i) * (t + 1) + col) * 32] = scol * u[i];
-            }
-        }
-        // column of Ate = [E;F]' K_e - He  /  bte = -[E;F]' b_e
-#pragma unroll
-        for (int lp = 0; lp < 3; ++lp) {
-            const bool o_lp = lp == 0 ? o0 : (lp == 1 ? o1 : o2);
-            const double cf = tau * g.dJf[lp];
-            double w[n];
-#pragma unroll
-            for (int i = 0; i < n; ++i) w[i] = fma(g.wn[lp][0], sx[i], fma(g.wn[lp][1], sy[i], cf * u[i]));
-            double val[nt];
-#pragma unroll
-            for (int ip = 0; ip < nt; ++ip) {
-                double s = 0.0;
-#pragma unroll
-                for (int k = 0; k < n; ++k) s = fma(T.Fhat[k * t + lp * nt + ip], w[k], s);
-                const double srow = (o_lp || !(ip & 1)) ? 1.0 : -1.0;
-                val[ip] = s * (srow * scol);
-            }
-            const int64_t f_lp = g.f[lp] & 0x7fffffffu;
+            double u[n];
             if (isb) {
-                if (a.dbg_At) {
 #pragma unroll
-                    for (int ip = 0; ip < nt; ++ip) a.dbg_bt[lp * nt + ip] = -val[ip];
-                } else {
-#pragma unroll
-                    for (int ip = 0; ip < nt; ++ip) atomicAdd(&a.rhs[f_lp * nt + ip], -val[ip]);
-                }
+                for (int i = 0; i < n; ++i) u[i] = bev[i];
             } else {
-                if (lp == l) {
+                const double cf = tau * dJf_l;
 #pragma unroll
-                    for (int ip = 0; ip < nt; ++ip) val[ip] = fma(-dJf_l, T.Hhat[ip * nt + j], val[ip]);
+                for (int i = 0; i < n; ++i) {
+                    double r = cf * T.Fhat[i * t + col];
+                    r = fma(ca_l, T.Qr[i * t + col], r);
+                    u[i] = fma(cb_l, T.Qs[i * t + col], r);
                 }
-                if (a.dbg_At) {
+            }
+            // S u = r  by L D L'
 #pragma unroll
-                    for (int ip = 0; ip < nt; ++ip) a.dbg_At[col * t + lp * nt + ip] = val[ip];
-                } else if (lp == l) {
-                    double* dst = a.Kd + f_lp * nt2 + j * nt;
+            for (int i = 1; i < n; ++i)
 #pragma unroll
-                    for (int ip = 0; ip < nt; ++ip) atomicAdd(dst + ip, val[ip]);
+                for (int k = 0; k < i; ++k) u[i] = fma(-Lget(i, k), u[k], u[i]);
+#pragma unroll
+            for (int i = 0; i < n; ++i) u[i] *= dinv[i];
+#pragma unroll
+            for (int i = n - 2; i >= 0; --i)
+#pragma unroll
+                for (int k = i + 1; k < n; ++k) u[i] = fma(-Lget(k, i), u[k], u[i]);
+
+            // sigma = A^-1 (r1 + B u)
+            double sx[n], sy[n];
+            const double ex = isb ? 0.0 : wnx * idet, ey = isb ? 0.0 : wny * idet;
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+                double p = 0.0, q = 0.0;
+#pragma unroll
+                for (int k = 0; k < n; ++k) {
+                    p = fma(T.Tr[i * n + k], u[k], p);
+                    q = fma(T.Ts[i * n + k], u[k], q);
+                }
+                double mf = isb ? 0.0 : T.MF[i * t + col];
+                sx[i] = fma(g.G00, p, fma(g.G10, q, -ex * mf));
+                sy[i] = fma(g.G01, p, fma(g.G11, q, -ey * mf));
+            }
+            // store column of [K_e | b_e]   (rows: sigma_x, sigma_y, u); 256-byte segments per warp
+            if (!dbg) {
+#pragma unroll
+                for (int i = 0; i < n; ++i) {
+                    Ke_tile[int64_t((i) * (t + 1) + col) * 32] = scol * sx[i];
+                    Ke_tile[int64_t((n + i) * (t + 1) + col) * 32] = scol * sy[i];
+                    Ke_tile[int64_t((2 * n + i) * (t + 1) + col) * 32] = scol * u[i];
+                }
+            }
+            // column of Ate = [E;F]' K_e - He  /  bte = -[E;F]' b_e
+#pragma unroll
+            for (int lp = 0; lp < 3; ++lp) {
+                const bool o_lp = lp == 0 ? o0 : (lp == 1 ? o1 : o2);
+                const double cf = tau * g.dJf[lp];
+                double w[n];
+#pragma unroll
+                for (int i = 0; i < n; ++i) w[i] = fma(g.wn[lp][0], sx[i], fma(g.wn[lp][1], sy[i], cf * u[i]));
+                double val[nt];
+#pragma unroll
+                for (int ip = 0; ip < nt; ++ip) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < n; ++k) s = fma(T.Fhat[k * t + lp * nt + ip], w[k], s);
+                    const double srow = (o_lp || !(ip & 1)) ? 1.0 : -1.0;
+                    val[ip] = s * (srow * scol);
+                }
+                if (isb) {
+#pragma unroll
+                    for (int ip = 0; ip < nt; ++ip) {
+                        if (dbg) a.dbg_bt[lp * nt + ip] = -val[ip];
+                        else if constexpr (STAGE_DIAG) stg[St::rhs(lp, ip) * B] = -val[ip];
+                        else atomicAdd(&a.rhs[int64_t(g.f[lp] & 0x7fffffffu) * nt + ip], -val[ip]);
+                    }
                 } else {
-                    const int slot = int(g.f[lp] >> 31) * 2 + ((l - lp + 3) % 3 - 1);
-                    double* dst = a.Ko + (f_lp * 4 + slot) * nt2 + j * nt;
-                    if constexpr (nt % 2 == 0) {
+                    if (lp == l) {
 #pragma unroll
-                        for (int ip = 0; ip < nt; ip += 2)
-                            *reinterpret_cast<double2*>(dst + ip) = make_double2(val[ip], val[ip + 1]);
+                        for (int ip = 0; ip < nt; ++ip) val[ip] = fma(-dJf_l, T.Hhat[ip * nt + j], val[ip]);
+                    }
+                    if (dbg) {
+#pragma unroll
+                        for (int ip = 0; ip < nt; ++ip) a.dbg_At[col * t + lp * nt + ip] = val[ip];
+                    } else if (lp == l) {
+                        if constexpr (STAGE_DIAG) {
+#pragma unroll
+                            for (int ip = 0; ip < nt; ++ip) stg[(St::diag(lp, 0, ip) + j * nt) * B] = val[ip];
+                        } else {
+                            double* dst = a.Kd + int64_t(g.f[lp] & 0x7fffffffu) * nt2 + j * nt;
+#pragma unroll
+                            for (int ip = 0; ip < nt; ++ip) atomicAdd(dst + ip, val[ip]);
+                        }
                     } else {
+                        const int s = (l - lp + 3) % 3 - 1;
+                        if constexpr (STAGE_OFF) {
 #pragma unroll
-                        for (int ip = 0; ip < nt; ++ip) dst[ip] = val[ip];
+                            for (int ip = 0; ip < nt; ++ip) stg[(St::off(lp, 0, 0, ip) + (s * nt + j) * nt) * B] = val[ip];
+                        } else {
+                            const int64_t f_lp = g.f[lp] & 0x7fffffffu;
+                            const int slot = int(g.f[lp] >> 31) * 2 + s;
+                            store_vec<nt>(a.Ko + (f_lp * 4 + slot) * nt2 + j * nt, val);
+                        }
                     }
                 }
+            }
+        }
+    }
+    if (dbg || !STAGE_DIAG) return;
+    // ---- scatter of the staged blocks ------------------------------------------------------------
+    // Every trace-matrix entry has one or two contributing cells.  If the neighbour across a face
+    // sits in the same warp its contribution is read from shared memory and the first cell stores
+    // the two-term sum; boundary faces are stored directly; only faces whose neighbour lives in
+    // another warp use RED.ADD.F64 onto the zeroed array (two-term sums are commutative, so the
+    // result is bitwise independent of the order in every case).
+    __syncwarp();
+    if (!active) return;
+    constexpr int64_t nt2 = nt * nt;
+    const uint32_t pinfo = uint32_t(g.partner), binfo = uint32_t(g.bflags);
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        const int64_t f = g.f[l] & 0x7fffffffu;
+        const uint32_t sec = g.f[l] >> 31;
+        const uint32_t pb = (pinfo >> (8 * l)) & 0xffu;
+        double* const kd = a.Kd + f * nt2;
+        double* const rh = a.rhs + f * nt;
+        if (pb & 0x80u) {
+            if (!sec) {
+                const int pl = int(pb & 31u), plf = int((pb >> 5) & 3u);
+                const double* ps = stg + (pl - int(threadIdx.x & 31));           // partner's column of the staging area
+                double v[nt2], r[nt];
+#pragma unroll
+                for (int e = 0; e < nt2; ++e) v[e] = stg[(St::diag(l, 0, 0) + e) * B] + ps[(plf * nt2 + e) * B];
+#pragma unroll
+                for (int e = 0; e < nt; ++e) r[e] = stg[St::rhs(l, e) * B] + ps[(3 * nt2 + plf * nt + e) * B];
+                store_vec<nt2>(kd, v);
+                store_vec<nt>(rh, r);
+            }
+        } else if ((binfo >> l) & 1u) {
+            double v[nt2], r[nt];
+#pragma unroll
+            for (int e = 0; e < nt2; ++e) v[e] = stg[(St::diag(l, 0, 0) + e) * B];
+#pragma unroll
+            for (int e = 0; e < nt; ++e) r[e] = stg[St::rhs(l, e) * B];
+            store_vec<nt2>(kd, v);
+            store_vec<nt>(rh, r);
+        } else {
+#pragma unroll
+            for (int e = 0; e < nt2; ++e) atomicAdd(kd + e, stg[(St::diag(l, 0, 0) + e) * B]);
+#pragma unroll
+            for (int e = 0; e < nt; ++e) atomicAdd(rh + e, stg[St::rhs(l, e) * B]);
+        }
+        if constexpr (STAGE_OFF) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                double v[nt2];
+#pragma unroll
+                for (int e = 0; e < nt2; ++e) v[e] = stg[(St::off(l, s, 0, 0) + e) * B];
+                store_vec<nt2>(a.Ko + (f * 4 + sec * 2 + s) * nt2, v);
             }
         }
     }
@@ -550,11 +658,9 @@ hdg_status upload_tables(hdg_context* c) {
 static const hdg_context* g_table_owner[MAX_ORDER + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 
 template <int K> static hdg_status launch_schur(hdg_context* c, const ElemArgs& a) {
-    constexpr bool LS = K >= 3;
-    constexpr int nL = Ord<K>::n * (Ord<K>::n - 1) / 2;
-    const int B = K >= 4 ? 64 : 128;
-    size_t smem = LS ? sizeof(double) * nL * B : 0;
-    auto kern = element_schur_kernel<K, LS>;
+    constexpr int B = SchurCfg<K>::threads;
+    constexpr size_t smem = sizeof(double) * SchurCfg<K>::smem_doubles * B;
+    auto kern = element_schur_kernel<K>;
     if (smem > 48 * 1024) HDG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int64_t ncell = a.cell_end - a.cell_begin;
     kern<<<(unsigned)ceil_div(ncell, B), B, smem, c->stream>>>(a);

@@ -20,6 +20,7 @@ template <int K> struct Ord {
     static constexpr int ke = m * (t + 1);            // doubles of [K_e | b_e] per cell
 };
 
+constexpr int CI = 8;        // int32 words per cell record (32 bytes)
 constexpr int MAX_NQ = 40;    // largest supported cell rule: Grundmann-Moeller s=4 has 35 points
 constexpr int MAX_NFQ = 12;
 
@@ -79,7 +80,10 @@ struct hdg_context {
 
     // mesh (device)
     int64_t ncell = 0, nnode = 0, nface = 0, nbface = 0;
-    int32_t* d_cellinfo = nullptr;   // ncell x 6 int32: v0 v1 v2 (0-based), f0 f1 f2 (0-based, bit31 = this cell is the face's second cell)
+    // ncell x CI int32 records: v0 v1 v2 (0-based node ids), f0 f1 f2 (0-based face ids, bit31 = this cell is
+    // the face's second cell), partner word (per local face 8 bits: bit7 = neighbour cell lies in the same
+    // 32-cell tile, bits0-4 its index in the tile, bits5-6 its local face index), boundary-face bits
+    int32_t* d_cellinfo = nullptr;
     double* d_nodes = nullptr;       // nnode x 2
     int32_t* d_facecell = nullptr;   // nface x 2 : cell1, cell2 (0-based, -1 = none)
     int32_t* d_facenode = nullptr;   // nface x 2 : v1, v2 (0-based)
@@ -87,6 +91,8 @@ struct hdg_context {
     uint8_t* d_isbc = nullptr;       // nface
     int32_t* d_kcol = nullptr;       // nface x 4 neighbour faces of the block-ELL rows (-1 = none)
     bool have_mesh = false;
+    int64_t cap_ncell = 0, cap_nnode = 0, cap_nface = 0, cap_nbface = 0;   // sizes the device buffers were allocated for
+    int64_t *d_stage_cells = nullptr, *d_stage_faces = nullptr;           // int64 staging of hdg_set_mesh inputs
     // structured-mesh parameters (0 when the mesh came from hdg_set_mesh)
     int64_t nx = 0, ny = 0;
 

@@ -125,12 +125,12 @@ __global__ void convert_cells(const int64_t* __restrict__ cells, int64_t ncell, 
     int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (c >= ncell) return;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) cellinfo[6 * c + k] = int32_t(cells[6 * c + k] - 1);
+    for (int k = 0; k < 3; ++k) cellinfo[CI * c + k] = int32_t(cells[6 * c + k] - 1);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         int32_t f = int32_t(cells[6 * c + 3 + k] - 1);
         uint32_t sec = facecell[2 * f + 1] == int32_t(c) ? 0x80000000u : 0u;
-        cellinfo[6 * c + 3 + k] = int32_t(uint32_t(f) | sec);
+        cellinfo[CI * c + 3 + k] = int32_t(uint32_t(f) | sec);
     }
 }
 
@@ -139,7 +139,7 @@ __global__ void build_kcol(const int32_t* __restrict__ cellinfo, int64_t ncell, 
     if (c >= ncell) return;
     uint32_t fr[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) fr[k] = uint32_t(cellinfo[6 * c + 3 + k]);
+    for (int k = 0; k < 3; ++k) fr[k] = uint32_t(cellinfo[CI * c + 3 + k]);
 #pragma unroll
     for (int l = 0; l < 3; ++l) {
         int64_t f = fr[l] & 0x7fffffffu;
@@ -147,6 +147,28 @@ __global__ void build_kcol(const int32_t* __restrict__ cellinfo, int64_t ncell, 
         kcol[4 * f + 2 * sec + 0] = int32_t(fr[(l + 1) % 3] & 0x7fffffffu);
         kcol[4 * f + 2 * sec + 1] = int32_t(fr[(l + 2) % 3] & 0x7fffffffu);
     }
+}
+
+// In-warp pairing hints for the element kernel: for every local face, is the neighbour cell in the same
+// 32-cell tile (= warp of the element kernel), at which lane, and which of its local faces is the shared one.
+__global__ void build_partner(int32_t* __restrict__ cellinfo, int64_t ncell, const int32_t* __restrict__ facecell) {
+    int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    uint32_t pw = 0, bw = 0;
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        int32_t f = int32_t(uint32_t(cellinfo[CI * c + 3 + l]) & 0x7fffffffu);
+        int32_t c1 = facecell[2 * f], c2 = facecell[2 * f + 1];
+        if (c2 < 0) { bw |= 1u << l; continue; }
+        int64_t o = c1 == int32_t(c) ? c2 : c1;
+        if ((o >> 5) != (c >> 5)) continue;
+        int lo = 0;
+        for (int k = 0; k < 3; ++k)
+            if (int32_t(uint32_t(cellinfo[CI * o + 3 + k]) & 0x7fffffffu) == f) lo = k;
+        pw |= (0x80u | uint32_t(o & 31) | (uint32_t(lo) << 5)) << (8 * l);
+    }
+    cellinfo[CI * c + 6] = int32_t(pw);
+    cellinfo[CI * c + 7] = int32_t(bw);
 }
 
 __global__ void mark_bfaces(const int32_t* __restrict__ bfaces, int64_t nb, const int32_t* __restrict__ facecell,
@@ -217,19 +239,19 @@ __global__ void rect_cells(int64_t nx, int64_t ny, int32_t* __restrict__ cellinf
     const uint32_t SEC = 0x80000000u;
     int64_t c0 = 2 * q, c1 = 2 * q + 1;
     // lower-left triangle: nodes (na(i,j), na(i+1,j), na(i,j+1)), faces (diag, left, bottom)
-    cellinfo[6 * c0 + 0] = na(i, j);
-    cellinfo[6 * c0 + 1] = na(i + 1, j);
-    cellinfo[6 * c0 + 2] = na(i, j + 1);
-    cellinfo[6 * c0 + 3] = int32_t(F.diag);
-    cellinfo[6 * c0 + 4] = int32_t(uint32_t(F.left) | (i > 0 ? SEC : 0u));
-    cellinfo[6 * c0 + 5] = int32_t(uint32_t(F.bottom) | (j > 0 ? SEC : 0u));
+    cellinfo[CI * c0 + 0] = na(i, j);
+    cellinfo[CI * c0 + 1] = na(i + 1, j);
+    cellinfo[CI * c0 + 2] = na(i, j + 1);
+    cellinfo[CI * c0 + 3] = int32_t(F.diag);
+    cellinfo[CI * c0 + 4] = int32_t(uint32_t(F.left) | (i > 0 ? SEC : 0u));
+    cellinfo[CI * c0 + 5] = int32_t(uint32_t(F.bottom) | (j > 0 ? SEC : 0u));
     // upper-right triangle: nodes (na(i+1,j), na(i+1,j+1), na(i,j+1)), faces (top, diag, right)
-    cellinfo[6 * c1 + 0] = na(i + 1, j);
-    cellinfo[6 * c1 + 1] = na(i + 1, j + 1);
-    cellinfo[6 * c1 + 2] = na(i, j + 1);
-    cellinfo[6 * c1 + 3] = int32_t(F.top);
-    cellinfo[6 * c1 + 4] = int32_t(uint32_t(F.diag) | SEC);
-    cellinfo[6 * c1 + 5] = int32_t(F.right);
+    cellinfo[CI * c1 + 0] = na(i + 1, j);
+    cellinfo[CI * c1 + 1] = na(i + 1, j + 1);
+    cellinfo[CI * c1 + 2] = na(i, j + 1);
+    cellinfo[CI * c1 + 3] = int32_t(F.top);
+    cellinfo[CI * c1 + 4] = int32_t(uint32_t(F.diag) | SEC);
+    cellinfo[CI * c1 + 5] = int32_t(F.right);
     // faces created by this quad, (v1,v2) in the creating cell's local direction
     auto setf = [&](int64_t f, int32_t v1, int32_t v2, int64_t ca, int64_t cb) {
         facenode[2 * f] = v1; facenode[2 * f + 1] = v2;
@@ -276,15 +298,36 @@ void free_mesh(hdg_context* c) {
     F(c->d_cellinfo); F(c->d_nodes); F(c->d_facecell); F(c->d_facenode); F(c->d_bfaces); F(c->d_isbc);
     F(c->d_kcol); F(c->d_fq); F(c->d_Kd); F(c->d_Ko); F(c->d_rhs); F(c->d_Ke); F(c->d_bcval);
     F(c->d_x); F(c->d_r); F(c->d_p); F(c->d_Ap); F(c->d_dinv);
-    F(c->d_sigma); F(c->d_u); F(c->d_uhat_h);
+    F(c->d_sigma); F(c->d_u); F(c->d_uhat_h); F(c->d_stage_cells); F(c->d_stage_faces);
+    c->cap_ncell = c->cap_nnode = c->cap_nface = c->cap_nbface = 0;
     c->have_mesh = c->assembled = c->applied = c->solved = c->recovered = false;
+}
+
+// Device buffers are kept across hdg_set_mesh / hdg_set_rectangle_mesh calls with unchanged sizes
+// (cudaMalloc / cudaFree of ~1 GB costs far more than re-uploading the mesh).
+static bool same_capacity(const hdg_context* c, int64_t ncell, int64_t nnode, int64_t nface, int64_t nbface) {
+    return c->d_cellinfo && c->d_Ke && c->cap_ncell == ncell && c->cap_nnode == nnode && c->cap_nface == nface &&
+           c->cap_nbface >= nbface;
 }
 
 static hdg_status alloc_mesh(hdg_context* c) {
     if (c->ncell <= 0 || c->nface <= 0 || c->nnode <= 0) return set_err(c, HDG_ERR_INVALID, "empty mesh");
     if (c->nface >= (int64_t(1) << 31) || c->ncell >= (int64_t(1) << 31) || c->nnode >= (int64_t(1) << 31))
         return set_err(c, HDG_ERR_INVALID, "mesh too large for 32-bit device ids");
-    HDG_CUDA(c, cudaMalloc(&c->d_cellinfo, sizeof(int32_t) * 6 * c->ncell));
+    if (same_capacity(c, c->ncell, c->nnode, c->nface, c->nbface)) {
+        c->have_mesh = c->assembled = c->applied = c->solved = c->recovered = false;
+        HDG_CUDA(c, cudaMemsetAsync(c->d_isbc, 0, c->nface, c->stream));
+        HDG_CUDA(c, cudaMemsetAsync(c->d_kcol, 0xFF, sizeof(int32_t) * 4 * c->nface, c->stream));
+        return HDG_OK;
+    }
+    {
+        int64_t a = c->ncell, b = c->nnode, d = c->nface, e = c->nbface, x = c->nx, y = c->ny;
+        free_mesh(c);
+        c->ncell = a; c->nnode = b; c->nface = d; c->nbface = e; c->nx = x; c->ny = y;
+    }
+    HDG_CUDA(c, cudaMalloc(&c->d_bfaces, sizeof(int32_t) * std::max<int64_t>(c->nbface, 1)));
+    c->cap_ncell = c->ncell; c->cap_nnode = c->nnode; c->cap_nface = c->nface; c->cap_nbface = std::max<int64_t>(c->nbface, 1);
+    HDG_CUDA(c, cudaMalloc(&c->d_cellinfo, sizeof(int32_t) * CI * c->ncell));
     HDG_CUDA(c, cudaMalloc(&c->d_nodes, sizeof(double) * 2 * c->nnode));
     HDG_CUDA(c, cudaMalloc(&c->d_facecell, sizeof(int32_t) * 2 * c->nface));
     HDG_CUDA(c, cudaMalloc(&c->d_facenode, sizeof(int32_t) * 2 * c->nface));
@@ -297,6 +340,10 @@ static hdg_status alloc_mesh(hdg_context* c) {
 
 hdg_status alloc_system(hdg_context* c) {
     const int nt = c->tab.nt, ke = c->tab.m * (c->tab.t + 1);
+    if (c->d_Ke) {   // buffers kept from a previous mesh of the same size
+        HDG_CUDA(c, cudaMemsetAsync(c->d_Ko, 0, sizeof(double) * c->nface * 4 * nt * nt, c->stream));
+        return HDG_OK;
+    }
     int64_t ncell_pad = ceil_div(c->ncell, 32) * 32;
     HDG_CUDA(c, cudaMalloc(&c->d_Kd, sizeof(double) * c->nface * nt * nt));
     HDG_CUDA(c, cudaMalloc(&c->d_Ko, sizeof(double) * c->nface * 4 * nt * nt));
@@ -308,13 +355,12 @@ hdg_status alloc_system(hdg_context* c) {
 
 hdg_status mesh_from_host(hdg_context* c, const int64_t* cells, int64_t ncell, const double* nodes, int64_t nnode,
                           const int64_t* faces, int64_t nface, const int64_t* bfaces, int64_t nbface) {
-    free_mesh(c);
     c->ncell = ncell; c->nnode = nnode; c->nface = nface; c->nbface = nbface; c->nx = c->ny = 0;
     hdg_status st = alloc_mesh(c);
     if (st) return st;
-    int64_t *d_cells = nullptr, *d_faces = nullptr;
-    HDG_CUDA(c, cudaMalloc(&d_cells, sizeof(int64_t) * 6 * ncell));
-    HDG_CUDA(c, cudaMalloc(&d_faces, sizeof(int64_t) * 4 * nface));
+    if (!c->d_stage_cells) HDG_CUDA(c, cudaMalloc(&c->d_stage_cells, sizeof(int64_t) * 6 * ncell));
+    if (!c->d_stage_faces) HDG_CUDA(c, cudaMalloc(&c->d_stage_faces, sizeof(int64_t) * 4 * nface));
+    int64_t *d_cells = c->d_stage_cells, *d_faces = c->d_stage_faces;
     HDG_CUDA(c, cudaMemcpyAsync(d_cells, cells, sizeof(int64_t) * 6 * ncell, cudaMemcpyHostToDevice, c->stream));
     HDG_CUDA(c, cudaMemcpyAsync(d_faces, faces, sizeof(int64_t) * 4 * nface, cudaMemcpyHostToDevice, c->stream));
     HDG_CUDA(c, cudaMemcpyAsync(c->d_nodes, nodes, sizeof(double) * 2 * nnode, cudaMemcpyHostToDevice, c->stream));
@@ -322,21 +368,18 @@ hdg_status mesh_from_host(hdg_context* c, const int64_t* cells, int64_t ncell, c
     convert_faces<<<(unsigned)ceil_div(nface, B), B, 0, c->stream>>>(d_faces, nface, c->d_facecell, c->d_facenode);
     convert_cells<<<(unsigned)ceil_div(ncell, B), B, 0, c->stream>>>(d_cells, ncell, c->d_facecell, c->d_cellinfo);
     build_kcol<<<(unsigned)ceil_div(ncell, B), B, 0, c->stream>>>(c->d_cellinfo, ncell, c->d_kcol);
-    c->launches += 3;
+    build_partner<<<(unsigned)ceil_div(ncell, B), B, 0, c->stream>>>(c->d_cellinfo, ncell, c->d_facecell);
+    c->launches += 4;
     // Dirichlet face set: sort ascending on the host (the reference iterates faces 1..nface and
     // tests membership, src/boundary.jl:19-21, so the dof order is ascending face id)
     std::vector<int32_t> bf(nbface);
     for (int64_t i = 0; i < nbface; ++i) {
-        if (bfaces[i] < 1 || bfaces[i] > nface) {
-            cudaFree(d_cells); cudaFree(d_faces);
-            return set_err(c, HDG_ERR_INVALID, "boundary face id out of range");
-        }
+        if (bfaces[i] < 1 || bfaces[i] > nface) return set_err(c, HDG_ERR_INVALID, "boundary face id out of range");
         bf[i] = int32_t(bfaces[i] - 1);
     }
     std::sort(bf.begin(), bf.end());
     bf.erase(std::unique(bf.begin(), bf.end()), bf.end());
     c->nbface = int64_t(bf.size());
-    HDG_CUDA(c, cudaMalloc(&c->d_bfaces, sizeof(int32_t) * std::max<int64_t>(c->nbface, 1)));
     if (c->nbface) {
         HDG_CUDA(c, cudaMemcpyAsync(c->d_bfaces, bf.data(), sizeof(int32_t) * c->nbface, cudaMemcpyHostToDevice, c->stream));
         HDG_CUDA(c, cudaMemsetAsync(c->d_flags, 0, sizeof(int32_t) * NFLAGS, c->stream));
@@ -345,8 +388,6 @@ hdg_status mesh_from_host(hdg_context* c, const int64_t* cells, int64_t ncell, c
         HDG_CUDA(c, cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int32_t) * NFLAGS, cudaMemcpyDeviceToHost, c->stream));
     }
     HDG_CUDA(c, cudaStreamSynchronize(c->stream));
-    HDG_CUDA(c, cudaFree(d_cells));
-    HDG_CUDA(c, cudaFree(d_faces));
     if (c->nbface && c->h_flags[FLAG_NOT_BOUNDARY])
         return set_err(c, HDG_ERR_NOT_BOUNDARY, "Face " + std::to_string(c->h_flags[FLAG_NOT_BOUNDARY]) + " is not in boundary");
     st = alloc_system(c);
@@ -357,7 +398,6 @@ hdg_status mesh_from_host(hdg_context* c, const int64_t* cells, int64_t ncell, c
 
 hdg_status mesh_rectangle(hdg_context* c, int64_t nx, int64_t ny, double llx, double lly, double urx, double ury) {
     if (nx < 1 || ny < 1 || !(urx > llx) || !(ury > lly)) return set_err(c, HDG_ERR_INVALID, "rectangle_mesh: need nx,ny >= 1 and UR > LL");
-    free_mesh(c);
     c->nx = nx; c->ny = ny;
     c->ncell = 2 * nx * ny;
     c->nnode = (nx + 1) * (ny + 1);
@@ -369,14 +409,14 @@ hdg_status mesh_rectangle(hdg_context* c, int64_t nx, int64_t ny, double llx, do
     rect_nodes<<<(unsigned)ceil_div(c->nnode, B), B, 0, c->stream>>>(c->d_nodes, nx + 1, ny + 1, llx, lly, urx, ury);
     rect_cells<<<(unsigned)ceil_div(nx * ny, B), B, 0, c->stream>>>(nx, ny, c->d_cellinfo, c->d_facecell, c->d_facenode);
     build_kcol<<<(unsigned)ceil_div(c->ncell, B), B, 0, c->stream>>>(c->d_cellinfo, c->ncell, c->d_kcol);
-    c->launches += 3;
+    build_partner<<<(unsigned)ceil_div(c->ncell, B), B, 0, c->stream>>>(c->d_cellinfo, c->ncell, c->d_facecell);
+    c->launches += 4;
     // boundary = faces with one cell (src/generate_mesh.jl:60-89), ascending
     int32_t* flag = nullptr;
     int64_t *offs = nullptr, *d_tot = nullptr;
     HDG_CUDA(c, cudaMalloc(&flag, sizeof(int32_t) * c->nface));
     HDG_CUDA(c, cudaMalloc(&offs, sizeof(int64_t) * c->nface));
     HDG_CUDA(c, cudaMalloc(&d_tot, sizeof(int64_t)));
-    HDG_CUDA(c, cudaMalloc(&c->d_bfaces, sizeof(int32_t) * c->nbface));
     flag_boundary<<<(unsigned)ceil_div(c->nface, B), B, 0, c->stream>>>(c->d_facecell, c->nface, flag);
     c->launches += 1;
     st = exclusive_scan(c, flag, c->nface, offs, d_tot);
@@ -416,9 +456,9 @@ __global__ void export_cells(const int32_t* __restrict__ cellinfo, int64_t ncell
     int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (c >= ncell) return;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) cells[6 * c + k] = int64_t(cellinfo[6 * c + k]) + 1;
+    for (int k = 0; k < 3; ++k) cells[6 * c + k] = int64_t(cellinfo[CI * c + k]) + 1;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) cells[6 * c + 3 + k] = int64_t(uint32_t(cellinfo[6 * c + 3 + k]) & 0x7fffffffu) + 1;
+    for (int k = 0; k < 3; ++k) cells[6 * c + 3 + k] = int64_t(uint32_t(cellinfo[CI * c + 3 + k]) & 0x7fffffffu) + 1;
 }
 __global__ void export_faces(const int32_t* __restrict__ facecell, const int32_t* __restrict__ facenode, int64_t nface,
                              int64_t* __restrict__ faces) {

@@ -21,10 +21,10 @@ __global__ void __launch_bounds__(128) recover_kernel(const double* __restrict__
     constexpr int n = Ord<K>::n, nt = Ord<K>::nt, t = Ord<K>::t, m = Ord<K>::m, ke = Ord<K>::ke;
     const int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (c >= ncell) return;
-    const int2* ci = reinterpret_cast<const int2*>(cellinfo + 6 * c);
-    int2 p1 = __ldg(ci + 1), p2 = __ldg(ci + 2);
-    const int64_t f[3] = {int64_t(uint32_t(p1.y) & 0x7fffffffu), int64_t(uint32_t(p2.x) & 0x7fffffffu),
-                          int64_t(uint32_t(p2.y) & 0x7fffffffu)};
+    const int4* ci = reinterpret_cast<const int4*>(cellinfo + CI * c);
+    int4 p0 = __ldg(ci), p1 = __ldg(ci + 1);
+    const int64_t f[3] = {int64_t(uint32_t(p0.w) & 0x7fffffffu), int64_t(uint32_t(p1.x) & 0x7fffffffu),
+                          int64_t(uint32_t(p1.y) & 0x7fffffffu)};
     double ue[t];
 #pragma unroll
     for (int l = 0; l < 3; ++l)
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(RB) errornorm_kernel(const double* __restrict_
     const double pi = 3.141592653589793;
     double acc = 0.0;
     for (int64_t c = int64_t(blockIdx.x) * RB + threadIdx.x; c < ncell; c += int64_t(gridDim.x) * RB) {
-        const int32_t* ci = cellinfo + 6 * c;
+        const int32_t* ci = cellinfo + CI * c;
         double x[3][2];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {

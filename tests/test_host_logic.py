@@ -1,0 +1,96 @@
+"""Host-side logic of the Python mirror and the C port of the CPU path, checked against the numpy
+oracle.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+import hdg_b200 as hdg
+import hdg_oracle as orc
+import hdg_oracle_c as occ
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("root", ["figure2.1", "figure.1"])
+def test_parse_mesh_triangle_matches_oracle(root):
+    m = hdg.parse_mesh_triangle(os.path.join(GOLDEN, root))
+    mo = orc.parse_mesh_triangle(os.path.join(GOLDEN, root))
+    assert np.array_equal(m.cells[:, :3], mo.cells) and np.array_equal(m.cells[:, 3:], mo.cell_faces)
+    assert np.array_equal(m.faces, mo.faces) and np.array_equal(m.nodes, mo.nodes)
+    assert m.facesets["boundary"] == mo.facesets["boundary"]
+    assert m.faces.flags["F_CONTIGUOUS"] and m.cells.flags["C_CONTIGUOUS"]   # Julia layouts for the C ABI
+
+
+@pytest.mark.parametrize("nx,ny", [(1, 1), (4, 3), (9, 2), (16, 16)])
+def test_sort_based_face_numbering_equals_sequential(nx, ny):
+    mo = orc.rectangle_mesh(nx, ny)
+    cf, fa = hdg.number_faces(mo.cells)
+    assert np.array_equal(cf, mo.cell_faces) and np.array_equal(fa, mo.faces)
+
+
+def test_face_numbering_random_permutation():
+    rng = np.random.default_rng(3)
+    mo = orc.rectangle_mesh(7, 6)
+    perm = rng.permutation(mo.ncells)
+    tri = mo.cells[perm]
+    cells, cell_faces, faces = orc._build_cells_sequential([tuple(t) for t in tri], mo.nodes, mo.nfaces)
+    cf, fa = hdg.number_faces(tri)
+    assert np.array_equal(cf, cell_faces) and np.array_equal(fa, faces)
+
+
+def test_non_manifold_rejected():
+    with pytest.raises(ValueError):
+        hdg.number_faces(np.array([[1, 2, 3], [2, 1, 4], [1, 2, 5]]))
+
+
+def test_dirichlet_dofs_and_values():
+    mo = orc.parse_mesh_triangle(os.path.join(GOLDEN, "figure2.1"))
+    m = hdg.parse_mesh_triangle(os.path.join(GOLDEN, "figure2.1"))
+    for order in (1, 2, 3):
+        fe = hdg.GenericFiniteElement(hdg.Dubiner(2, hdg.RefTetrahedron, order))
+        Wh = hdg.ScalarFunctionSpace(m, fe, 2 * order)
+        Mh = hdg.ScalarTraceFunctionSpace(Wh, hdg.GenericFiniteElement(hdg.Legendre(1, hdg.RefTetrahedron, order)))
+        d = hdg.Dirichlet(hdg.TrialFunction(Mh), m, "boundary", lambda x: 0)
+        dofs, vals = orc.dirichlet(mo, orc.build_tables(order, 2 * order))
+        assert np.array_equal(d.prescribed_dofs, dofs) and np.array_equal(d.values, vals)
+    assert hdg.getnlocaldofs(Mh) == 3 * (order + 1)
+    with pytest.raises(NotImplementedError):
+        hdg.Dirichlet(hdg.TrialFunction(Mh), m, "boundary", lambda x: 1.0)
+
+
+def test_trial_function_storage():
+    m = hdg.parse_mesh_triangle(os.path.join(GOLDEN, "figure2.1"))
+    fe = hdg.GenericFiniteElement(hdg.Dubiner(2, hdg.RefTetrahedron, 1))
+    Wh, Vh = hdg.ScalarFunctionSpace(m, fe), hdg.VectorFunctionSpace(m, fe)
+    Mh = hdg.ScalarTraceFunctionSpace(Wh, hdg.GenericFiniteElement(hdg.Legendre(1, hdg.RefTetrahedron, 1)))
+    assert (hdg.getnlocaldofs(Vh), hdg.getnlocaldofs(Wh), hdg.getnlocaldofs(Mh)) == (6, 3, 6)   # test_FunctionSpace.jl:30-32
+    assert hdg.TrialFunction(Wh).m_values.shape == (4, 3) and hdg.TrialFunction(Vh).m_values.shape == (4, 6)
+    u = hdg.TrialFunction(Mh)
+    assert u.m_values.shape == (4, 2, 3) and np.all(np.isnan(u.m_values)) and u.m_values.flags["F_CONTIGUOUS"]
+
+
+@pytest.mark.parametrize("order,qd,nx", [(1, 2, 8), (2, 3, 5), (2, 4, 5), (3, 6, 4), (4, 9, 2)])
+def test_c_port_matches_numpy_oracle(order, qd, nx):
+    mesh = orc.rectangle_mesh(nx, nx + 1, (0, 0), (2.0, 1.0))
+    tab = orc.build_tables(order, qd)
+    asm = orc.doassemble(mesh, tab)
+    for nth in (1, 3):
+        K, rhs, Ke, be = occ.doassemble(mesh, tab, nthreads=nth)
+        assert np.array_equal(K.indptr, asm.K.indptr) and np.array_equal(K.indices, asm.K.indices)
+        assert np.allclose(K.data, asm.K.data, rtol=1e-12, atol=1e-13)
+        assert np.allclose(rhs, asm.rhs, rtol=1e-12, atol=1e-14)
+        assert np.allclose(Ke, asm.K_e, rtol=1e-11, atol=1e-13) and np.allclose(be, asm.b_e, rtol=1e-11, atol=1e-13)
+
+
+def test_c_pcg_matches_direct_solve():
+    mesh = orc.rectangle_mesh(12, 12)
+    tab = orc.build_tables(2, 4)
+    asm = orc.doassemble(mesh, tab)
+    dofs, vals = orc.dirichlet(mesh, tab)
+    Kb, rb, m = orc.apply_dirichlet(asm.K, asm.rhs, dofs, vals)
+    isbc = np.zeros(Kb.shape[0], np.uint8)
+    isbc[dofs - 1] = 1
+    x, it, rel = occ.pcg(Kb, rb, isbc, 1e-13, 5000, 2)
+    xd = orc.solve_direct(Kb, rb)
+    assert rel <= 1e-13 and np.abs(x - xd).max() < 1e-11 * np.abs(xd).max()
