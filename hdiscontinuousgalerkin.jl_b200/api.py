@@ -216,6 +216,28 @@ def parse_mesh_triangle(root_file):
     return PolygonalMesh(np.hstack([tri, cell_faces]), nodes, faces, {"boundary": boundary})
 
 
+def quad_face_base(i, j, nx):
+    """Number of faces created before quad (i,j) (0-based) by the first-encounter numbering of
+    rectangle_mesh (src/generate_mesh.jl:20-46,130-138)."""
+    if j == 0:
+        return 4 * i + (1 if i > 0 else 0)
+    return 4 * nx + 1 + (j - 1) * (3 * nx + 1) + 3 * i + (1 if i > 0 else 0)
+
+
+def strip_partition(nx, ny, rank, world):
+    """Mesh partition used on `world` GPUs: contiguous strips of quad rows = contiguous cell-id and
+    face-id ranges (0-based, half-open).  Mirrors mesh_rectangle in csrc/hdg_mesh.cu."""
+    if ny < world:
+        raise ValueError("need at least one quad row per rank")
+    j0, j1 = ny * rank // world, ny * (rank + 1) // world
+    nface = 3 * nx * ny + nx + ny
+    f0 = quad_face_base(0, j0, nx)
+    f1 = quad_face_base(0, j1, nx) if j1 < ny else nface
+    return dict(j0=j0, j1=j1, cell_begin=2 * nx * j0, cell_end=2 * nx * j1, face_begin=f0, face_end=f1,
+                ncell_global=2 * nx * ny, nface_global=nface, ghost_cells=nx if j1 < ny else 0,
+                ghost_faces=(nx if j0 > 0 else 0) + (2 * nx if j1 < ny else 0))
+
+
 def ref_table(order, quad_degree, name):
     """Reference table from the library's host-side builder (no device needed)."""
     lib = _lib.load()
@@ -249,6 +271,28 @@ class _Context:
             self.close()
         except Exception:
             pass
+
+    def comm_init(self, dist, device=None):
+        """Join the NCCL communicator of libhdg_b200: rank 0 creates the ncclUniqueId, torch.distributed
+        (any backend - it is only plumbing) broadcasts the 128 bytes, every rank calls hdg_comm_init.
+        Must be called before the mesh is set."""
+        import torch
+        rank, world = dist.get_rank(), dist.get_world_size()
+        buf = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            check(self.lib.hdg_comm_unique_id(buf.ctypes.data_as(C.POINTER(C.c_uint8))), None)
+        t = torch.from_numpy(buf)
+        if device is not None:
+            t = t.to(device)
+        dist.broadcast(t, src=0)
+        buf = t.cpu().numpy().copy()
+        check(self.lib.hdg_comm_init(self.h, rank, world, buf.ctypes.data_as(C.POINTER(C.c_uint8))), self.h)
+
+    def partition(self):
+        out = np.zeros(8, dtype=np.int64)
+        check(self.lib.hdg_get_partition(self.h, i64p(out)), self.h)
+        keys = ("cell_begin", "cell_end", "face_begin", "face_end", "ncell_global", "nface_global", "ghost_cells", "ghost_faces")
+        return dict(zip(keys, out.tolist()))
 
     def sizes(self):
         s = Sizes()

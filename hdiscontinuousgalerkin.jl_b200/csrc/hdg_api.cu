@@ -114,6 +114,7 @@ void hdg_destroy(hdg_context* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_mesh(c);
+    comm_destroy(c);
     if (c->d_rawtab) cudaFree(c->d_rawtab);
     if (c->d_flags) cudaFree(c->d_flags);
     if (c->d_scal) cudaFree(c->d_scal);
@@ -153,15 +154,17 @@ hdg_status hdg_get_sizes(const hdg_context* c, hdg_sizes* s) {
     std::memset(s, 0, sizeof(*s));
     s->n = c->tab.n; s->nt = c->tab.nt; s->m = c->tab.m; s->t = c->tab.t; s->nq = c->tab.nq; s->nfq = c->tab.nfq;
     if (c->have_mesh) {
-        s->ncell = c->ncell; s->nnode = c->nnode; s->nface = c->nface; s->nbface = c->nbface;
-        s->ndof = c->nface * c->tab.nt;
-        s->nnz = pattern_nnz(const_cast<hdg_context*>(c));
+        // multi-GPU: the counts of what this rank owns (hdg_get_partition gives the global ranges)
+        s->ncell = c->ncell_own; s->nnode = c->nnode; s->nface = c->nface_own; s->nbface = c->nbface;
+        s->ndof = c->nface_own * c->tab.nt;
+        s->nnz = comm_active(c) ? 0 : pattern_nnz(const_cast<hdg_context*>(c));
     }
     return HDG_OK;
 }
 
 hdg_status hdg_get_mesh(hdg_context* c, int64_t* cells, double* nodes, int64_t* faces, int64_t* bf) {
     if (!c) return HDG_ERR_INVALID;
+    if (comm_active(c)) return set_err(c, HDG_ERR_INVALID, "hdg_get_mesh is single-GPU (a rank holds a strip in local numbering)");
     cudaSetDevice(c->device);
     return mesh_download(c, cells, nodes, faces, bf);
 }
@@ -287,12 +290,14 @@ hdg_status hdg_errornorm(hdg_context* c, int32_t exact_id, double* err2) {
 
 hdg_status hdg_get_pattern(hdg_context* c, int64_t* colptr, int64_t* rowval) {
     if (!c) return HDG_ERR_INVALID;
+    if (comm_active(c)) return set_err(c, HDG_ERR_INVALID, "hdg_get_pattern is single-GPU");
     cudaSetDevice(c->device);
     return pattern_download(c, colptr, rowval);
 }
 
 hdg_status hdg_get_values(hdg_context* c, double* nzval) {
     if (!c || !nzval) return HDG_ERR_INVALID;
+    if (comm_active(c)) return set_err(c, HDG_ERR_INVALID, "hdg_get_values is single-GPU");
     cudaSetDevice(c->device);
     return values_download(c, nzval);
 }
@@ -300,7 +305,7 @@ hdg_status hdg_get_values(hdg_context* c, double* nzval) {
 hdg_status hdg_get_rhs(hdg_context* c, double* rhs) {
     if (!c || !rhs) return HDG_ERR_INVALID;
     if (!c->assembled) return set_err(c, HDG_ERR_INVALID, "hdg_get_rhs before hdg_assemble");
-    HDG_CUDA(c, cudaMemcpyAsync(rhs, c->d_rhs, sizeof(double) * c->nface * c->tab.nt, cudaMemcpyDeviceToHost, c->stream));
+    HDG_CUDA(c, cudaMemcpyAsync(rhs, c->d_rhs, sizeof(double) * c->nface_own * c->tab.nt, cudaMemcpyDeviceToHost, c->stream));
     HDG_CUDA(c, cudaStreamSynchronize(c->stream));
     return HDG_OK;
 }
@@ -308,7 +313,7 @@ hdg_status hdg_get_rhs(hdg_context* c, double* rhs) {
 hdg_status hdg_get_trace(hdg_context* c, double* uhat) {
     if (!c || !uhat) return HDG_ERR_INVALID;
     if (!c->d_x) return set_err(c, HDG_ERR_INVALID, "no trace solution yet");
-    HDG_CUDA(c, cudaMemcpyAsync(uhat, c->d_x, sizeof(double) * c->nface * c->tab.nt, cudaMemcpyDeviceToHost, c->stream));
+    HDG_CUDA(c, cudaMemcpyAsync(uhat, c->d_x, sizeof(double) * c->nface_own * c->tab.nt, cudaMemcpyDeviceToHost, c->stream));
     HDG_CUDA(c, cudaStreamSynchronize(c->stream));
     return HDG_OK;
 }
@@ -318,7 +323,9 @@ hdg_status hdg_set_trace(hdg_context* c, const double* uhat) {
     if (!c->have_mesh) return set_err(c, HDG_ERR_INVALID, "no mesh");
     cudaSetDevice(c->device);
     if (!c->d_x) HDG_CUDA(c, cudaMalloc(&c->d_x, sizeof(double) * c->nface * c->tab.nt));
-    HDG_CUDA(c, cudaMemcpyAsync(c->d_x, uhat, sizeof(double) * c->nface * c->tab.nt, cudaMemcpyHostToDevice, c->stream));
+    HDG_CUDA(c, cudaMemcpyAsync(c->d_x, uhat, sizeof(double) * c->nface_own * c->tab.nt, cudaMemcpyHostToDevice, c->stream));
+    hdg_status st = comm_halo_exchange(c, c->d_x, c->tab.nt);
+    if (st) return st;
     HDG_CUDA(c, cudaStreamSynchronize(c->stream));
     return HDG_OK;
 }
@@ -333,7 +340,7 @@ hdg_status hdg_get_meandiag(const hdg_context* c, double* m) {
 hdg_status hdg_get_local(hdg_context* c, int64_t cell, double* Ke, double* be) {
     if (!c) return HDG_ERR_INVALID;
     if (!c->assembled) return set_err(c, HDG_ERR_INVALID, "hdg_get_local before hdg_assemble");
-    if (cell < 1 || cell > c->ncell) return set_err(c, HDG_ERR_INVALID, "cell out of range");
+    if (cell < 1 || cell > c->ncell_own) return set_err(c, HDG_ERR_INVALID, "cell out of range");
     cudaSetDevice(c->device);
     return local_download(c, cell - 1, Ke, be);
 }
@@ -351,9 +358,9 @@ hdg_status hdg_get_mvalues(hdg_context* c, double* sigma, double* u, double* uha
     if (!c) return HDG_ERR_INVALID;
     if (!c->recovered) return set_err(c, HDG_ERR_INVALID, "hdg_get_mvalues before hdg_recover");
     const int n = c->tab.n, nt = c->tab.nt;
-    if (sigma) HDG_CUDA(c, cudaMemcpyAsync(sigma, c->d_sigma, sizeof(double) * c->ncell * 2 * n, cudaMemcpyDeviceToHost, c->stream));
-    if (u) HDG_CUDA(c, cudaMemcpyAsync(u, c->d_u, sizeof(double) * c->ncell * n, cudaMemcpyDeviceToHost, c->stream));
-    if (uhat_h) HDG_CUDA(c, cudaMemcpyAsync(uhat_h, c->d_uhat_h, sizeof(double) * c->ncell * nt * 3, cudaMemcpyDeviceToHost, c->stream));
+    if (sigma) HDG_CUDA(c, cudaMemcpyAsync(sigma, c->d_sigma, sizeof(double) * c->ncell_own * 2 * n, cudaMemcpyDeviceToHost, c->stream));
+    if (u) HDG_CUDA(c, cudaMemcpyAsync(u, c->d_u, sizeof(double) * c->ncell_own * n, cudaMemcpyDeviceToHost, c->stream));
+    if (uhat_h) HDG_CUDA(c, cudaMemcpyAsync(uhat_h, c->d_uhat_h, sizeof(double) * c->ncell_own * nt * 3, cudaMemcpyDeviceToHost, c->stream));
     HDG_CUDA(c, cudaStreamSynchronize(c->stream));
     return HDG_OK;
 }

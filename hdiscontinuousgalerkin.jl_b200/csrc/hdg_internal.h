@@ -64,7 +64,23 @@ struct Timer {
     bool pending = false;
 };
 
-struct Comm;  // multi-GPU state (hdg_comm.cu)
+// Multi-GPU state (hdg_comm.cu): one process per GPU, NCCL over NVLink.  The mesh is split into
+// strips of quad rows (contiguous cell-id and face-id ranges); every rank holds its owned cells and
+// faces plus a one-cell-deep ghost layer above and the ghost faces it references.
+struct Comm {
+    void* nccl = nullptr;          // ncclComm_t
+    int rank = 0, nranks = 1;
+    // strip [j0, j1) of quad rows of the global nx x ny mesh
+    int64_t j0 = 0, j1 = 0, ny_global = 0;
+    int64_t cell_begin = 0, face_begin = 0;          // global 0-based ids of the first owned cell / face
+    int64_t ncell_global = 0, nface_global = 0;
+    int64_t nbelow = 0, nabove = 0;                    // ghost faces owned by rank-1 / rank+1
+    // halo exchange of trace vectors: pack lists (local face ids) and buffers
+    int32_t* d_send_dn_idx = nullptr;  int64_t n_send_dn = 0;   // faces sent to rank-1 (its ghost-above layer)
+    int32_t* d_send_up_idx = nullptr;  int64_t n_send_up = 0;   // faces sent to rank+1 (its ghost-below layer)
+    double *d_send_dn = nullptr, *d_send_up = nullptr;
+    double* d_gscal = nullptr;       // all-reduced scalars
+};
 
 }  // namespace hdg
 
@@ -79,7 +95,8 @@ struct hdg_context {
     int ke_layout = hdg::KE_TILE32;
 
     // mesh (device)
-    int64_t ncell = 0, nnode = 0, nface = 0, nbface = 0;
+    int64_t ncell = 0, nnode = 0, nface = 0, nbface = 0;   // local totals (owned + ghost)
+    int64_t ncell_own = 0, nface_own = 0;                 // owned by this rank (== totals on one GPU)
     // ncell x CI int32 records: v0 v1 v2 (0-based node ids), f0 f1 f2 (0-based face ids, bit31 = this cell is
     // the face's second cell), partner word (per local face 8 bits: bit7 = neighbour cell lies in the same
     // 32-cell tile, bits0-4 its index in the tile, bits5-6 its local face index), boundary-face bits
@@ -174,5 +191,13 @@ hdg_status pcg_solve(hdg_context* c, double rtol, int maxit, hdg_solve_info* inf
 hdg_status recover(hdg_context* c);                             // hdg_recover.cu
 hdg_status errornorm(hdg_context* c, int exact_id, double* err2);
 hdg_status local_download(hdg_context* c, int64_t cell, double* Ke, double* be);
+
+// hdg_comm.cu
+bool comm_active(const hdg_context* c);
+hdg_status comm_allreduce_sum(hdg_context* c, double* d_buf, int count);                 // in place, on c->stream
+hdg_status comm_halo_exchange(hdg_context* c, double* d_vec, int nt);                    // fills the ghost segments of d_vec
+hdg_status comm_setup_halo(hdg_context* c, const std::vector<int32_t>& send_dn, const std::vector<int32_t>& send_up);
+void comm_free_halo(hdg_context* c);
+void comm_destroy(hdg_context* c);
 
 }  // namespace hdg

@@ -183,13 +183,13 @@ __global__ void mark_bfaces(const int32_t* __restrict__ bfaces, int64_t nb, cons
 // ------------------------------------------------------------------------------------------
 // structured mesh on the device: closed forms of the first-encounter numbering
 // ------------------------------------------------------------------------------------------
-__global__ void rect_nodes(double* __restrict__ nodes, int64_t nnx, int64_t nny, double llx, double lly,
-                           double urx, double ury) {
+__global__ void rect_nodes(double* __restrict__ nodes, int64_t nnx, int64_t nny_global, int64_t row0, int64_t nrows,
+                           double llx, double lly, double urx, double ury) {
     int64_t id = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (id >= nnx * nny) return;
-    int64_t i = id / nnx, j = id % nnx;   // row i, column j (src/generate_mesh.jl:1-18)
+    if (id >= nnx * nrows) return;
+    int64_t i = row0 + id / nnx, j = id % nnx;   // global row i, column j (src/generate_mesh.jl:1-18)
     // every product / sum rounded separately, as the Julia expression does (no FMA contraction)
-    double rb = double(i) / double(nny - 1);
+    double rb = double(i) / double(nny_global - 1);
     double omr = __dsub_rn(1.0, rb);
     // LL=(llx,lly) UL=(llx,ury) LR=(urx,lly) UR=(urx,ury)
     double x0 = __dadd_rn(__dmul_rn(llx, omr), __dmul_rn(rb, llx));
@@ -229,44 +229,80 @@ __host__ __device__ inline QuadFaces quad_faces(int64_t i, int64_t j, int64_t nx
     return q;
 }
 
-__global__ void rect_cells(int64_t nx, int64_t ny, int32_t* __restrict__ cellinfo, int32_t* __restrict__ facecell,
+// Strip [j0,j1) of quad rows of the global nx x ny mesh in LOCAL numbering:
+//   cells : owned cells (global id - 2*nx*j0), then one ghost cell per column (the lower-left triangle of row j1)
+//   faces : owned faces (global id - F0: everything the strip's quads create), then the ghost-below faces
+//           (tops of row j0-1, owned by rank-1), then the ghost-above faces (left and diagonal of the ghost cells)
+//   nodes : global id - j0*(nx+1)
+// facecell: -1 = no cell (domain boundary), -2 = a cell of another rank.
+struct Strip {
+    int64_t nx, ny, j0, j1, F0, nown, nbelow, ncell_own, node0;
+};
+
+__global__ void rect_cells(Strip S, int32_t* __restrict__ cellinfo, int32_t* __restrict__ facecell,
                            int32_t* __restrict__ facenode) {
-    int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (q >= nx * ny) return;
-    int64_t i = q % nx, j = q / nx, nnx = nx + 1;
-    auto na = [&](int64_t a, int64_t b) { return int32_t(a + b * nnx); };
-    QuadFaces F = quad_faces(i, j, nx);
+    const int64_t nx = S.nx, nnx = nx + 1;
+    int64_t ql = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t nrows = S.j1 - S.j0 + (S.j1 < S.ny ? 1 : 0);
+    if (ql >= nx * nrows) return;
+    const int64_t i = ql % nx, j = S.j0 + ql / nx;
+    auto na = [&](int64_t a, int64_t b) { return int32_t(a + b * nnx - S.node0); };
     const uint32_t SEC = 0x80000000u;
-    int64_t c0 = 2 * q, c1 = 2 * q + 1;
-    // lower-left triangle: nodes (na(i,j), na(i+1,j), na(i,j+1)), faces (diag, left, bottom)
-    cellinfo[CI * c0 + 0] = na(i, j);
-    cellinfo[CI * c0 + 1] = na(i + 1, j);
-    cellinfo[CI * c0 + 2] = na(i, j + 1);
-    cellinfo[CI * c0 + 3] = int32_t(F.diag);
-    cellinfo[CI * c0 + 4] = int32_t(uint32_t(F.left) | (i > 0 ? SEC : 0u));
-    cellinfo[CI * c0 + 5] = int32_t(uint32_t(F.bottom) | (j > 0 ? SEC : 0u));
-    // upper-right triangle: nodes (na(i+1,j), na(i+1,j+1), na(i,j+1)), faces (top, diag, right)
-    cellinfo[CI * c1 + 0] = na(i + 1, j);
-    cellinfo[CI * c1 + 1] = na(i + 1, j + 1);
-    cellinfo[CI * c1 + 2] = na(i, j + 1);
-    cellinfo[CI * c1 + 3] = int32_t(F.top);
-    cellinfo[CI * c1 + 4] = int32_t(uint32_t(F.diag) | SEC);
-    cellinfo[CI * c1 + 5] = int32_t(F.right);
-    // faces created by this quad, (v1,v2) in the creating cell's local direction
     auto setf = [&](int64_t f, int32_t v1, int32_t v2, int64_t ca, int64_t cb) {
         facenode[2 * f] = v1; facenode[2 * f + 1] = v2;
         facecell[2 * f] = int32_t(ca); facecell[2 * f + 1] = int32_t(cb);
     };
-    setf(F.diag, na(i + 1, j), na(i, j + 1), c0, c1);
-    if (i == 0) setf(F.left, na(i, j + 1), na(i, j), c0, -1);
-    if (j == 0) setf(F.bottom, na(i, j), na(i + 1, j), c0, -1);
-    setf(F.top, na(i + 1, j + 1), na(i, j + 1), c1, j + 1 < ny ? 2 * (q + nx) : -1);
-    setf(F.right, na(i + 1, j), na(i + 1, j + 1), c1, i + 1 < nx ? 2 * (q + 1) : -1);
+    const int64_t ghost_above0 = S.nown + S.nbelow;
+    if (j == S.j1) {
+        // ghost cell: lower-left triangle of quad (i, j1); its bottom face is the owned interface face
+        const int64_t cg = S.ncell_own + i;
+        const int64_t f_left = ghost_above0 + 2 * i, f_diag = f_left + 1;
+        const int64_t f_bottom = quad_faces(i, j - 1, nx).top - S.F0;
+        cellinfo[CI * cg + 0] = na(i, j);
+        cellinfo[CI * cg + 1] = na(i + 1, j);
+        cellinfo[CI * cg + 2] = na(i, j + 1);
+        cellinfo[CI * cg + 3] = int32_t(f_diag);
+        cellinfo[CI * cg + 4] = int32_t(uint32_t(f_left) | (i > 0 ? SEC : 0u));
+        cellinfo[CI * cg + 5] = int32_t(uint32_t(f_bottom) | SEC);
+        setf(f_diag, na(i + 1, j), na(i, j + 1), cg, -2);
+        if (i == 0) setf(f_left, na(i, j + 1), na(i, j), cg, -1);
+        else setf(f_left, na(i, j), na(i, j + 1), -2, cg);   // right face of quad (i-1, j1): created by a remote cell
+        return;
+    }
+    QuadFaces F = quad_faces(i, j, nx);
+    const int64_t q = (j - S.j0) * nx + i;
+    const int64_t c0 = 2 * q, c1 = 2 * q + 1;
+    const bool bottom_ghost = j == S.j0 && S.j0 > 0;
+    const int64_t f_diag = F.diag - S.F0, f_left = F.left - S.F0, f_top = F.top - S.F0, f_right = F.right - S.F0;
+    const int64_t f_bottom = bottom_ghost ? S.nown + i : F.bottom - S.F0;
+    // lower-left triangle: nodes (na(i,j), na(i+1,j), na(i,j+1)), faces (diag, left, bottom)
+    cellinfo[CI * c0 + 0] = na(i, j);
+    cellinfo[CI * c0 + 1] = na(i + 1, j);
+    cellinfo[CI * c0 + 2] = na(i, j + 1);
+    cellinfo[CI * c0 + 3] = int32_t(f_diag);
+    cellinfo[CI * c0 + 4] = int32_t(uint32_t(f_left) | (i > 0 ? SEC : 0u));
+    cellinfo[CI * c0 + 5] = int32_t(uint32_t(f_bottom) | (j > 0 ? SEC : 0u));
+    // upper-right triangle: nodes (na(i+1,j), na(i+1,j+1), na(i,j+1)), faces (top, diag, right)
+    cellinfo[CI * c1 + 0] = na(i + 1, j);
+    cellinfo[CI * c1 + 1] = na(i + 1, j + 1);
+    cellinfo[CI * c1 + 2] = na(i, j + 1);
+    cellinfo[CI * c1 + 3] = int32_t(f_top);
+    cellinfo[CI * c1 + 4] = int32_t(uint32_t(f_diag) | SEC);
+    cellinfo[CI * c1 + 5] = int32_t(f_right);
+    // faces created by this quad, (v1,v2) in the creating cell's local direction
+    setf(f_diag, na(i + 1, j), na(i, j + 1), c0, c1);
+    if (i == 0) setf(f_left, na(i, j + 1), na(i, j), c0, -1);
+    if (j == 0) setf(f_bottom, na(i, j), na(i + 1, j), c0, -1);
+    if (bottom_ghost) setf(f_bottom, na(i + 1, j), na(i, j), -2, c0);   // top face of quad (i, j0-1), created remotely
+    int64_t above = -1;
+    if (j + 1 < S.ny) above = j + 1 < S.j1 ? 2 * (q + nx) : S.ncell_own + i;
+    setf(f_top, na(i + 1, j + 1), na(i, j + 1), c1, above);
+    setf(f_right, na(i + 1, j), na(i + 1, j + 1), c1, i + 1 < nx ? 2 * (q + 1) : -1);
 }
 
 __global__ void flag_boundary(const int32_t* __restrict__ facecell, int64_t nface, int32_t* __restrict__ flag) {
     int64_t f = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (f < nface) flag[f] = facecell[2 * f + 1] < 0 ? 1 : 0;
+    if (f < nface) flag[f] = facecell[2 * f + 1] == -1 ? 1 : 0;
 }
 __global__ void compact_boundary(const int32_t* __restrict__ flag, const int64_t* __restrict__ offs, int64_t nface,
                                  int32_t* __restrict__ bfaces, uint8_t* __restrict__ isbc) {
@@ -321,9 +357,9 @@ static hdg_status alloc_mesh(hdg_context* c) {
         return HDG_OK;
     }
     {
-        int64_t a = c->ncell, b = c->nnode, d = c->nface, e = c->nbface, x = c->nx, y = c->ny;
+        int64_t a = c->ncell, b = c->nnode, d = c->nface, e = c->nbface, x = c->nx, y = c->ny, ao = c->ncell_own, fo = c->nface_own;
         free_mesh(c);
-        c->ncell = a; c->nnode = b; c->nface = d; c->nbface = e; c->nx = x; c->ny = y;
+        c->ncell = a; c->nnode = b; c->nface = d; c->nbface = e; c->nx = x; c->ny = y; c->ncell_own = ao; c->nface_own = fo;
     }
     HDG_CUDA(c, cudaMalloc(&c->d_bfaces, sizeof(int32_t) * std::max<int64_t>(c->nbface, 1)));
     c->cap_ncell = c->ncell; c->cap_nnode = c->nnode; c->cap_nface = c->nface; c->cap_nbface = std::max<int64_t>(c->nbface, 1);
@@ -355,7 +391,8 @@ hdg_status alloc_system(hdg_context* c) {
 
 hdg_status mesh_from_host(hdg_context* c, const int64_t* cells, int64_t ncell, const double* nodes, int64_t nnode,
                           const int64_t* faces, int64_t nface, const int64_t* bfaces, int64_t nbface) {
-    c->ncell = ncell; c->nnode = nnode; c->nface = nface; c->nbface = nbface; c->nx = c->ny = 0;
+    if (comm_active(c)) return set_err(c, HDG_ERR_INVALID, "multi-GPU runs partition hdg_set_rectangle_mesh; hdg_set_mesh is single-GPU");
+    c->ncell = c->ncell_own = ncell; c->nnode = nnode; c->nface = c->nface_own = nface; c->nbface = nbface; c->nx = c->ny = 0;
     hdg_status st = alloc_mesh(c);
     if (st) return st;
     if (!c->d_stage_cells) HDG_CUDA(c, cudaMalloc(&c->d_stage_cells, sizeof(int64_t) * 6 * ncell));
@@ -398,16 +435,39 @@ hdg_status mesh_from_host(hdg_context* c, const int64_t* cells, int64_t ncell, c
 
 hdg_status mesh_rectangle(hdg_context* c, int64_t nx, int64_t ny, double llx, double lly, double urx, double ury) {
     if (nx < 1 || ny < 1 || !(urx > llx) || !(ury > lly)) return set_err(c, HDG_ERR_INVALID, "rectangle_mesh: need nx,ny >= 1 and UR > LL");
+    // strip of quad rows owned by this rank (whole mesh on one GPU)
+    int64_t j0 = 0, j1 = ny;
+    const bool multi = comm_active(c);
+    if (multi) {
+        if (ny < c->comm->nranks) return set_err(c, HDG_ERR_INVALID, "need at least one quad row per rank");
+        j0 = ny * c->comm->rank / c->comm->nranks;
+        j1 = ny * (c->comm->rank + 1) / c->comm->nranks;
+    }
+    const int64_t nface_global = 3 * nx * ny + nx + ny;   // src/generate_mesh.jl:121
+    Strip S{};
+    S.nx = nx; S.ny = ny; S.j0 = j0; S.j1 = j1;
+    S.F0 = quad_base(0, j0, nx);
+    const int64_t F1 = j1 < ny ? quad_base(0, j1, nx) : nface_global;
+    S.nown = F1 - S.F0;
+    S.nbelow = j0 > 0 ? nx : 0;
+    const int64_t nabove = j1 < ny ? 2 * nx : 0;
+    S.ncell_own = 2 * nx * (j1 - j0);
+    S.node0 = j0 * (nx + 1);
+    const int64_t node_rows = (j1 - j0 + 1) + (j1 < ny ? 1 : 0);
     c->nx = nx; c->ny = ny;
-    c->ncell = 2 * nx * ny;
-    c->nnode = (nx + 1) * (ny + 1);
-    c->nface = 3 * nx * ny + nx + ny;   // src/generate_mesh.jl:121
-    c->nbface = 2 * (nx + ny);
+    c->ncell_own = S.ncell_own;
+    c->ncell = S.ncell_own + (j1 < ny ? nx : 0);
+    c->nnode = node_rows * (nx + 1);
+    c->nface_own = S.nown;
+    c->nface = S.nown + S.nbelow + nabove;
+    // Dirichlet faces among the local faces: left/right of every owned row, global bottom/top, left face of the ghost row
+    c->nbface = 2 * (j1 - j0) + (j0 == 0 ? nx : 0) + (j1 == ny ? nx : 0) + (j1 < ny ? 1 : 0);
     hdg_status st = alloc_mesh(c);
     if (st) return st;
     const int B = 256;
-    rect_nodes<<<(unsigned)ceil_div(c->nnode, B), B, 0, c->stream>>>(c->d_nodes, nx + 1, ny + 1, llx, lly, urx, ury);
-    rect_cells<<<(unsigned)ceil_div(nx * ny, B), B, 0, c->stream>>>(nx, ny, c->d_cellinfo, c->d_facecell, c->d_facenode);
+    rect_nodes<<<(unsigned)ceil_div(c->nnode, B), B, 0, c->stream>>>(c->d_nodes, nx + 1, ny + 1, j0, node_rows, llx, lly, urx, ury);
+    const int64_t nquad_threads = nx * (j1 - j0 + (j1 < ny ? 1 : 0));
+    rect_cells<<<(unsigned)ceil_div(nquad_threads, B), B, 0, c->stream>>>(S, c->d_cellinfo, c->d_facecell, c->d_facenode);
     build_kcol<<<(unsigned)ceil_div(c->ncell, B), B, 0, c->stream>>>(c->d_cellinfo, c->ncell, c->d_kcol);
     build_partner<<<(unsigned)ceil_div(c->ncell, B), B, 0, c->stream>>>(c->d_cellinfo, c->ncell, c->d_facecell);
     c->launches += 4;
@@ -428,6 +488,25 @@ hdg_status mesh_rectangle(hdg_context* c, int64_t nx, int64_t ny, double llx, do
     c->launches += 1;
     HDG_CUDA(c, cudaStreamSynchronize(c->stream));
     cudaFree(flag); cudaFree(offs); cudaFree(d_tot);
+    if (multi) {
+        Comm* m = c->comm;
+        m->j0 = j0; m->j1 = j1; m->ny_global = ny;
+        m->cell_begin = 2 * nx * j0; m->face_begin = S.F0;
+        m->ncell_global = 2 * nx * ny; m->nface_global = nface_global;
+        m->nbelow = S.nbelow; m->nabove = nabove;
+        // halo lists: what the neighbours hold as ghosts of my owned faces
+        std::vector<int32_t> send_dn, send_up;
+        if (j0 > 0)      // rank-1's ghost-above layer: [left(i,j0), diag(i,j0)] for every column
+            for (int64_t i = 0; i < nx; ++i) {
+                QuadFaces F = quad_faces(i, j0, nx);
+                send_dn.push_back(int32_t(F.left - S.F0));
+                send_dn.push_back(int32_t(F.diag - S.F0));
+            }
+        if (j1 < ny)     // rank+1's ghost-below layer: top(i, j1-1)
+            for (int64_t i = 0; i < nx; ++i) send_up.push_back(int32_t(quad_faces(i, j1 - 1, nx).top - S.F0));
+        st = comm_setup_halo(c, send_dn, send_up);
+        if (st) return st;
+    }
     st = alloc_system(c);
     if (st) return st;
     c->have_mesh = true;
@@ -435,7 +514,7 @@ hdg_status mesh_rectangle(hdg_context* c, int64_t nx, int64_t ny, double llx, do
 }
 
 hdg_status mesh_perturb(hdg_context* c, double fraction, uint64_t seed) {
-    if (!c->have_mesh || c->nx == 0) return set_err(c, HDG_ERR_INVALID, "hdg_perturb_nodes needs a rectangle mesh");
+    if (!c->have_mesh || c->nx == 0 || comm_active(c)) return set_err(c, HDG_ERR_INVALID, "hdg_perturb_nodes needs a single-GPU rectangle mesh");
     if (!(fraction >= 0.0 && fraction < 0.5)) return set_err(c, HDG_ERR_INVALID, "perturbation fraction must be in [0,0.5)");
     double h_nodes[4];
     // mesh extents from the first and last node

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(128) recover_kernel(const double* __restrict__
 
 template <int K> static hdg_status recover_t(hdg_context* c) {
     const int B = 128;
-    recover_kernel<K><<<(unsigned)ceil_div(c->ncell, B), B, 0, c->stream>>>(c->d_Ke, c->d_x, c->d_cellinfo, c->ncell,
+    recover_kernel<K><<<(unsigned)ceil_div(c->ncell_own, B), B, 0, c->stream>>>(c->d_Ke, c->d_x, c->d_cellinfo, c->ncell_own,
                                                                            c->d_sigma, c->d_u, c->d_uhat_h);
     c->launches += 1;
     HDG_CUDA(c, cudaGetLastError());
@@ -56,9 +56,9 @@ template <int K> static hdg_status recover_t(hdg_context* c) {
 hdg_status recover(hdg_context* c) {
     const int n = c->tab.n, nt = c->tab.nt;
     if (!c->d_sigma) {
-        HDG_CUDA(c, cudaMalloc(&c->d_sigma, sizeof(double) * c->ncell * 2 * n));
-        HDG_CUDA(c, cudaMalloc(&c->d_u, sizeof(double) * c->ncell * n));
-        HDG_CUDA(c, cudaMalloc(&c->d_uhat_h, sizeof(double) * c->ncell * nt * 3));
+        HDG_CUDA(c, cudaMalloc(&c->d_sigma, sizeof(double) * c->ncell_own * 2 * n));
+        HDG_CUDA(c, cudaMalloc(&c->d_u, sizeof(double) * c->ncell_own * n));
+        HDG_CUDA(c, cudaMalloc(&c->d_uhat_h, sizeof(double) * c->ncell_own * nt * 3));
     }
     timer_start(c, c->t_recover);
     hdg_status st = HDG_ERR_INVALID;
@@ -107,11 +107,13 @@ __global__ void __launch_bounds__(RB) errornorm_kernel(const double* __restrict_
 }
 
 hdg_status errornorm(hdg_context* c, int exact_id, double* err2) {
-    int np = int(std::min<int64_t>(ceil_div(c->ncell, RB), 1024));
+    int np = int(std::min<int64_t>(ceil_div(c->ncell_own, RB), 1024));
     timer_start(c, c->t_err);
-    errornorm_kernel<<<np, RB, 0, c->stream>>>(c->d_u, c->d_cellinfo, c->d_nodes, c->raw, c->ncell, exact_id, c->d_partials);
+    errornorm_kernel<<<np, RB, 0, c->stream>>>(c->d_u, c->d_cellinfo, c->d_nodes, c->raw, c->ncell_own, exact_id, c->d_partials);
     final_sum<<<1, RB, 0, c->stream>>>(c->d_partials, np, c->d_scal + 3);
     c->launches += 2;
+    hdg_status st = comm_allreduce_sum(c, c->d_scal + 3, 1);
+    if (st) return st;
     timer_stop(c, c->t_err);
     HDG_CUDA(c, cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(double) * 8, cudaMemcpyDeviceToHost, c->stream));
     HDG_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -21,6 +21,7 @@
 // converged, and the host polls that flag once per chunk.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "hdg_internal.h"
 #include "hdg_reduce.cuh"
@@ -94,13 +95,16 @@ __global__ void apply_bc_kernel(double* __restrict__ Kd, double* __restrict__ Ko
 }
 
 template <int NT> static hdg_status apply_t(hdg_context* c) {
-    int np = int(std::min<int64_t>(ceil_div(c->nface, RB), 1024));
-    diag_abs_partial<NT><<<np, RB, 0, c->stream>>>(c->d_Kd, c->nface, c->d_partials);
+    int np = int(std::min<int64_t>(ceil_div(c->nface_own, RB), 1024));
+    diag_abs_partial<NT><<<np, RB, 0, c->stream>>>(c->d_Kd, c->nface_own, c->d_partials);
     final_sum<<<1, RB, 0, c->stream>>>(c->d_partials, np, c->d_scal + S_MEANSUM);
     c->launches += 2;
+    hdg_status st = comm_allreduce_sum(c, c->d_scal + S_MEANSUM, 1);   // mean over ALL dofs of the global system
+    if (st) return st;
     HDG_CUDA(c, cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(double) * NSCAL, cudaMemcpyDeviceToHost, c->stream));
     HDG_CUDA(c, cudaStreamSynchronize(c->stream));
-    c->meandiag = c->h_scal[S_MEANSUM] / double(c->nface * NT);   // meandiag, src/boundary.jl:169-175
+    const int64_t nface_global = comm_active(c) ? c->comm->nface_global : c->nface;
+    c->meandiag = c->h_scal[S_MEANSUM] / double(nface_global * NT);   // meandiag, src/boundary.jl:169-175
     apply_bc_kernel<NT><<<(unsigned)ceil_div(c->nface, 128), 128, 0, c->stream>>>(
         c->d_Kd, c->d_Ko, c->d_rhs, c->d_kcol, c->d_isbc, c->d_bfaces, c->nbface, c->d_bcval, c->meandiag, c->nface);
     c->launches += 1;
@@ -125,6 +129,8 @@ hdg_status apply_dirichlet(hdg_context* c, const double* values) {
 }
 
 // ---- PCG ---------------------------------------------------------------------------------------
+struct PcgArgs;
+__device__ __forceinline__ double get_sum(const PcgArgs& a, int which);
 struct PcgArgs {
     const double* Kd;
     const double* Ko;
@@ -135,10 +141,22 @@ struct PcgArgs {
     double* part;      // NPART x MAX_PARTIALS
     double* scal;
     int32_t* flags;
-    int64_t nface;
+    int64_t nface;     // OWNED faces: rows of this rank (vectors also carry the ghost faces behind them)
+    const double* gscal;   // multi-GPU: all-reduced sums, one per partial array; nullptr on one GPU
     int np;            // number of partials == gridDim of the vector kernels
     double rtol;
 };
+
+__device__ __forceinline__ double get_sum(const PcgArgs& a, int which) {
+    if (a.gscal) return a.gscal[which];                                   // summed over ranks by NCCL
+    return reduce_partials(a.part + which * MAX_PARTIALS, a.np);          // fixed-order, every block identically
+}
+
+// multi-GPU: local sums of all partial arrays -> gscal slots (then all-reduced in place)
+__global__ void reduce_all(const double* __restrict__ part, int np, double* __restrict__ gscal) {
+    double s = reduce_partials(part + blockIdx.x * MAX_PARTIALS, np);
+    if (threadIdx.x == 0) gscal[blockIdx.x] = s;
+}
 
 template <int NT>
 __global__ void __launch_bounds__(RB) pcg_init(const PcgArgs a) {
@@ -169,7 +187,7 @@ __global__ void __launch_bounds__(RB) pcg_init(const PcgArgs a) {
 }
 
 __global__ void pcg_init_final(const PcgArgs a) {
-    double bb = reduce_partials(a.part + P_BB * MAX_PARTIALS, a.np);
+    double bb = get_sum(a, P_BB);
     if (threadIdx.x == 0) {
         a.scal[S_BNORM2] = bb;
         a.scal[S_RELRES] = bb > 0.0 ? 1.0 : 0.0;
@@ -212,8 +230,8 @@ __global__ void __launch_bounds__(RB) pcg_spmv(const PcgArgs a) {
 
 __global__ void __launch_bounds__(RB) pcg_update(const PcgArgs a, int64_t N, int parity) {
     if (*reinterpret_cast<volatile int32_t*>(a.flags + FLAG_DONE)) return;
-    const double pap = reduce_partials(a.part + P_PAP * MAX_PARTIALS, a.np);
-    const double rz = reduce_partials(a.part + (parity ? P_RZ1 : P_RZ0) * MAX_PARTIALS, a.np);
+    const double pap = get_sum(a, P_PAP);
+    const double rz = get_sum(a, parity ? P_RZ1 : P_RZ0);
     const double alpha = rz / pap;
     double rz_new = 0.0, rr = 0.0;
     for (int64_t row = int64_t(blockIdx.x) * RB + threadIdx.x; row < N; row += int64_t(gridDim.x) * RB) {
@@ -233,9 +251,9 @@ __global__ void __launch_bounds__(RB) pcg_update(const PcgArgs a, int64_t N, int
 
 __global__ void __launch_bounds__(RB) pcg_dir(const PcgArgs a, int64_t N, int parity, int iter) {
     if (*reinterpret_cast<volatile int32_t*>(a.flags + FLAG_DONE)) return;
-    const double rz_old = reduce_partials(a.part + (parity ? P_RZ1 : P_RZ0) * MAX_PARTIALS, a.np);
-    const double rz_new = reduce_partials(a.part + (parity ? P_RZ0 : P_RZ1) * MAX_PARTIALS, a.np);
-    const double rr = reduce_partials(a.part + P_RR * MAX_PARTIALS, a.np);
+    const double rz_old = get_sum(a, parity ? P_RZ1 : P_RZ0);
+    const double rz_new = get_sum(a, parity ? P_RZ0 : P_RZ1);
+    const double rr = get_sum(a, P_RR);
     const double bb = a.scal[S_BNORM2];
     const bool conv = rr <= a.rtol * a.rtol * bb;
     // the decision is recomputed identically by every block; a block that starts after block 0
@@ -254,13 +272,19 @@ __global__ void __launch_bounds__(RB) pcg_dir(const PcgArgs a, int64_t N, int pa
 }
 
 template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit, hdg_solve_info* info) {
-    const int64_t N = c->nface * NT;
-    if (!c->d_x) {
-        HDG_CUDA(c, cudaMalloc(&c->d_x, sizeof(double) * N));
-        HDG_CUDA(c, cudaMalloc(&c->d_r, sizeof(double) * N));
-        HDG_CUDA(c, cudaMalloc(&c->d_p, sizeof(double) * N));
-        HDG_CUDA(c, cudaMalloc(&c->d_Ap, sizeof(double) * N));
-        HDG_CUDA(c, cudaMalloc(&c->d_dinv, sizeof(double) * N));
+    const int64_t N = c->nface_own * NT;          // owned rows
+    const int64_t Nloc = c->nface * NT;           // owned + ghost entries of the vectors
+    const bool multi = comm_active(c);
+    if (!c->d_x) HDG_CUDA(c, cudaMalloc(&c->d_x, sizeof(double) * Nloc));
+    if (!c->d_r) {
+        HDG_CUDA(c, cudaMalloc(&c->d_r, sizeof(double) * Nloc));
+        HDG_CUDA(c, cudaMalloc(&c->d_p, sizeof(double) * Nloc));
+        HDG_CUDA(c, cudaMalloc(&c->d_Ap, sizeof(double) * Nloc));
+        HDG_CUDA(c, cudaMalloc(&c->d_dinv, sizeof(double) * Nloc));
+    }
+    if (multi) {
+        HDG_CUDA(c, cudaMemsetAsync(c->d_p, 0, sizeof(double) * Nloc, c->stream));
+        HDG_CUDA(c, cudaMemsetAsync(c->d_x, 0, sizeof(double) * Nloc, c->stream));
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -268,32 +292,49 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
     PcgArgs a{};
     a.Kd = c->d_Kd; a.Ko = c->d_Ko; a.kcol = c->d_kcol; a.isbc = c->d_isbc; a.rhs = c->d_rhs;
     a.x = c->d_x; a.r = c->d_r; a.p = c->d_p; a.Ap = c->d_Ap; a.dinv = c->d_dinv;
-    a.part = c->d_partials; a.scal = c->d_scal; a.flags = c->d_flags; a.nface = c->nface;
+    a.part = c->d_partials; a.scal = c->d_scal; a.flags = c->d_flags; a.nface = c->nface_own;
+    a.gscal = multi ? c->comm->d_gscal : nullptr;
     a.np = int(std::min<int64_t>(ceil_div(N, RB), std::min<int64_t>(int64_t(sms) * 8, MAX_PARTIALS)));
     a.rtol = rtol;
     const int G = a.np;
 
     timer_start(c, c->t_solve);
     HDG_CUDA(c, cudaMemsetAsync(c->d_flags, 0, sizeof(int32_t) * NFLAGS, c->stream));
+    hdg_status cst = HDG_OK;
+    auto global_sums = [&]() {   // multi-GPU: partial arrays -> all-reduced scalars
+        if (!multi) return;
+        reduce_all<<<NPART, RB, 0, c->stream>>>(c->d_partials, G, c->comm->d_gscal);
+        c->launches += 1;
+        hdg_status s2 = comm_allreduce_sum(c, c->comm->d_gscal, NPART);
+        if (s2) cst = s2;
+    };
     pcg_init<NT><<<G, RB, 0, c->stream>>>(a);
+    global_sums();
     pcg_init_final<<<1, RB, 0, c->stream>>>(a);
     c->launches += 2;
 
     // one CUDA graph = CHUNK iterations (even, so the rz double-buffer parity restarts at 0)
     const int CHUNK = 32;
+    const bool use_graph = getenv("HDG_NO_GRAPH") == nullptr;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
     auto enqueue_iter = [&](int it) {
         int parity = it & 1;
+        if (multi) {   // ghost entries of p from the neighbouring strips
+            hdg_status s2 = comm_halo_exchange(c, c->d_p, NT);
+            if (s2) cst = s2;
+        }
         pcg_spmv<NT><<<G, RB, 0, c->stream>>>(a);
+        global_sums();
         pcg_update<<<G, RB, 0, c->stream>>>(a, N, parity);
+        global_sums();
         pcg_dir<<<G, RB, 0, c->stream>>>(a, N, parity, it + 1);
     };
     int it = 0;
     bool done = false;
     while (it < maxit && !done) {
         int chunk = std::min(CHUNK, maxit - it);
-        if (chunk == CHUNK) {
+        if (chunk == CHUNK && use_graph) {
             // the iteration number baked into pcg_dir is relative; FLAG_ITERS is fixed up below
             if (!gexec) {
                 HDG_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
@@ -312,6 +353,10 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
         if (done) it += c->h_flags[FLAG_ITERS];
         else it += chunk;
     }
+    if (multi) {   // recovery reads the trace on the ghost faces below the strip
+        hdg_status s2 = comm_halo_exchange(c, c->d_x, NT);
+        if (s2) cst = s2;
+    }
     timer_stop(c, c->t_solve);
     if (gexec) cudaGraphExecDestroy(gexec);
     if (graph) cudaGraphDestroy(graph);
@@ -325,6 +370,7 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
         info->solve_ms = timer_ms(c->t_solve);
     }
     c->solved = true;
+    if (cst) return cst;
     if (!done) return set_err(c, HDG_ERR_NOT_CONVERGED, "PCG did not converge in " + std::to_string(maxit) + " iterations");
     return HDG_OK;
 }

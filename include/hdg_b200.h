@@ -176,6 +176,10 @@ hdg_status hdg_get_mvalues(hdg_context* ctx, double* sigma, double* u, double* u
  * trace values and all-reduces the dot products over NCCL, hdg_errornorm all-reduces. */
 hdg_status hdg_comm_unique_id(uint8_t id_out[128]);
 hdg_status hdg_comm_init(hdg_context* ctx, int32_t rank, int32_t nranks, const uint8_t id[128]);
+/* What this rank owns, global 0-based half-open ranges: out = {cell_begin, cell_end, face_begin, face_end,
+ * ncell_global, nface_global, ghost cells held, ghost faces held}.  Cell and face ids are the reference's
+ * global numbering minus one; trace dofs of face f are nt*f .. nt*f+nt-1. */
+hdg_status hdg_get_partition(const hdg_context* ctx, int64_t out[8]);
 
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* Device time (ms, CUDA events on the context stream) of the kernels of the last call of the

@@ -1,0 +1,82 @@
+"""Multi-GPU parity check, run under torchrun on N GPUs of one box:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py
+
+Every rank assembles / solves / recovers its strip of the global mesh; rank 0 repeats the same
+problem on one GPU and compares the concatenated trace solution (<= 1e-11 relative) and err2."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import hdg_b200 as hdg  # noqa: E402
+
+
+def solve(ctx, nx, ny, rtol):
+    lib = ctx.lib
+    hdg.check(lib.hdg_set_rectangle_mesh(ctx.h, nx, ny, 0.0, 0.0, 2.0, 1.0), ctx.h)
+    hdg.check(lib.hdg_assemble(ctx.h), ctx.h)
+    hdg.check(lib.hdg_apply_dirichlet(ctx.h, None), ctx.h)
+    info = hdg.api.SolveInfo()
+    hdg.check(lib.hdg_solve(ctx.h, rtol, 100000, C.byref(info)), ctx.h)
+    hdg.check(lib.hdg_recover(ctx.h), ctx.h)
+    e = C.c_double()
+    hdg.check(lib.hdg_errornorm(ctx.h, 1, C.byref(e)), ctx.h)
+    s = ctx.sizes()
+    x = np.empty(s.ndof)
+    hdg.check(lib.hdg_get_trace(ctx.h, hdg.api.f64p(x)), ctx.h)
+    u = np.empty((s.ncell, s.n), order="F")
+    hdg.check(lib.hdg_get_mvalues(ctx.h, None, hdg.api.f64p(u), None), ctx.h)
+    m = C.c_double()
+    hdg.check(lib.hdg_get_meandiag(ctx.h, C.byref(m)), ctx.h)
+    return x, u, e.value, info.iterations, m.value
+
+
+def main():
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    ok = True
+    for order, qd, nx, ny in ((1, 2, 48, 37), (2, 4, 24, 16), (3, 6, 16, 11)):
+        ctx = hdg._Context(order, qd, 1.0, 1, lr)
+        ctx.comm_init(dist, device=torch.device("cuda", lr))
+        x, u, err2, iters, md = solve(ctx, nx, ny, 1e-13)
+        part = ctx.partition()
+        exp = hdg.strip_partition(nx, ny, rank, world)
+        assert all(part[k] == exp[k] for k in exp if k in part), (part, exp)
+        nt = order + 1
+        # gather the owned pieces on rank 0
+        xs = [None] * world
+        us = [None] * world
+        dist.all_gather_object(xs, (part["face_begin"], x))
+        dist.all_gather_object(us, (part["cell_begin"], u))
+        ctx.close()
+        if rank == 0:
+            ref = hdg._Context(order, qd, 1.0, 1, lr)
+            xr, ur, e1, it1, md1 = solve(ref, nx, ny, 1e-13)
+            ref.close()
+            xg = np.concatenate([p[1] for p in sorted(xs, key=lambda p: p[0])])
+            ug = np.concatenate([p[1] for p in sorted(us, key=lambda p: p[0])], axis=0)
+            ex = np.abs(xg - xr).max() / np.abs(xr).max()
+            eu = np.abs(ug - ur).max() / np.abs(ur).max()
+            good = ex < 1e-10 and eu < 1e-10 and abs(err2 - e1) <= 1e-9 * e1 and abs(md - md1) <= 1e-13 * md1
+            ok &= good
+            print(f"k={order} {nx}x{ny} on {world} GPUs: iters {iters} (1 GPU: {it1})  relerr(uhat)={ex:.2e} relerr(u)={eu:.2e} "
+                  f"err2 {err2:.12e} vs {e1:.12e}  meandiag {md:.15g} vs {md1:.15g}  {'OK' if good else 'FAIL'}", flush=True)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    dist.barrier()
+    dist.destroy_process_group()
+    if not flag.item():
+        sys.exit(1)
+    if rank == 0:
+        print("multi-GPU parity OK")
+
+
+if __name__ == "__main__":
+    main()
