@@ -196,8 +196,84 @@ __global__ void pcg_init_final(const PcgArgs a) {
     }
 }
 
+// widest aligned vector load of N doubles whose address is a multiple of 8*N bytes (256-bit LDG on sm_100a)
+template <int N> __device__ __forceinline__ void load_vec(const double* __restrict__ src, double* v) {
+    if constexpr (N % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i += 4)
+            asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[i]), "=d"(v[i + 1]), "=d"(v[i + 2]), "=d"(v[i + 3]) : "l"(src + i));
+    } else if constexpr (N % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i += 2) {
+            double2 t = *reinterpret_cast<const double2*>(src + i);
+            v[i] = t.x; v[i + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = src[i];
+    }
+}
+template <int N> __device__ __forceinline__ void store_vec(double* __restrict__ dst, const double* v) {
+    if constexpr (N % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i += 4)
+            asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(dst + i), "d"(v[i]), "d"(v[i + 1]), "d"(v[i + 2]), "d"(v[i + 3]) : "memory");
+    } else if constexpr (N % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i += 2) *reinterpret_cast<double2*>(dst + i) = make_double2(v[i], v[i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) dst[i] = v[i];
+    }
+}
+
+// One thread per face = per block row: the diagonal block and the 4 off-diagonal blocks of a face are
+// 5*nt*nt contiguous-per-array doubles, fetched with the widest aligned vector loads (one 256-bit LDG per
+// 2x2 block at k=1); every sector that reaches the SM is fully used.
 template <int NT>
 __global__ void __launch_bounds__(RB) pcg_spmv(const PcgArgs a) {
+    if (*reinterpret_cast<volatile int32_t*>(a.flags + FLAG_DONE)) return;
+    constexpr int NT2 = NT * NT;
+    double pap = 0.0;
+    for (int64_t f = int64_t(blockIdx.x) * RB + threadIdx.x; f < a.nface; f += int64_t(gridDim.x) * RB) {
+        double y[NT], pf[NT], blk[NT2];
+        load_vec<NT>(a.p + f * NT, pf);
+        load_vec<NT2>(a.Kd + f * NT2, blk);
+#pragma unroll
+        for (int r = 0; r < NT; ++r) {
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < NT; ++b) s = fma(blk[b * NT + r], pf[b], s);
+            y[r] = s;
+        }
+        const int4 cols = *reinterpret_cast<const int4*>(a.kcol + 4 * f);
+        const int cc[4] = {cols.x, cols.y, cols.z, cols.w};
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+            if (cc[s4] < 0) continue;
+            double pg[NT];
+            load_vec<NT>(a.p + int64_t(cc[s4]) * NT, pg);
+            load_vec<NT2>(a.Ko + (f * 4 + s4) * NT2, blk);
+#pragma unroll
+            for (int r = 0; r < NT; ++r)
+#pragma unroll
+                for (int b = 0; b < NT; ++b) y[r] = fma(blk[b * NT + r], pg[b], y[r]);
+        }
+        const bool bc = a.isbc[f];
+#pragma unroll
+        for (int r = 0; r < NT; ++r) {
+            y[r] = bc ? y[r] : -y[r];
+            pap = fma(pf[r], y[r], pap);
+        }
+        store_vec<NT>(a.Ap + f * NT, y);
+    }
+    double tot = block_sum(pap);
+    if (threadIdx.x == 0) a.part[P_PAP * MAX_PARTIALS + blockIdx.x] = tot;
+}
+
+// One thread per scalar row (used for nt = 5, where the blocks are not 16-byte aligned).
+template <int NT>
+__global__ void __launch_bounds__(RB) pcg_spmv_rows(const PcgArgs a) {
     if (*reinterpret_cast<volatile int32_t*>(a.flags + FLAG_DONE)) return;
     constexpr int NT2 = NT * NT;
     const int64_t N = a.nface * NT;
@@ -324,7 +400,8 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
             hdg_status s2 = comm_halo_exchange(c, c->d_p, NT);
             if (s2) cst = s2;
         }
-        pcg_spmv<NT><<<G, RB, 0, c->stream>>>(a);
+        if constexpr (NT == 5) pcg_spmv_rows<NT><<<G, RB, 0, c->stream>>>(a);
+        else pcg_spmv<NT><<<G, RB, 0, c->stream>>>(a);
         global_sums();
         pcg_update<<<G, RB, 0, c->stream>>>(a, N, parity);
         global_sums();

@@ -1,0 +1,49 @@
+"""Summarise ncu reports (gpurun_out/*.ncu-rep) into small text files under profiles/.
+Usage: python profiles/summarize.py gpurun_out/prof_r1_elem_k1.ncu-rep [...]"""
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__m_l1tex2xbar_req_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "launch__registers_per_thread", "launch__block_size", "launch__grid_size", "launch__occupancy_limit_registers",
+    "launch__occupancy_limit_shared_mem", "smsp__inst_executed.sum", "sm__inst_executed_pipe_fp64.sum",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_red.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+    "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "sm__cycles_elapsed.max",
+    "smsp__average_warp_latency_issue_stalled_long_scoreboard.pct", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+]
+
+
+def main():
+    for rep in sys.argv[1:]:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(raw)))
+        hdr, units = rows[0], rows[1]
+        name_col = hdr.index("Kernel Name")
+        print(f"# {rep}")
+        for r in rows[2:]:
+            print(f"## kernel: {r[name_col][:110]}")
+            for h, u, v in zip(hdr, units, r):
+                if h in KEYS:
+                    print(f"{h:85s} {v:>18s} {u}")
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+            try:
+                tot = 0.0
+                for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    i = hdr.index(k)
+                    tot += float(r[i]) * scale[units[i]]
+                print(f"{'traffic = dram read + write':85s} {tot / 1e6:18.3f} Mbyte")
+            except Exception:
+                pass
+            print()
+
+
+if __name__ == "__main__":
+    main()
