@@ -8,6 +8,7 @@
 // (torch.distributed / MPI / Julia Distributed are all fine - plain bytes through the C ABI).
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "hdg_internal.h"
@@ -26,6 +27,7 @@ struct NcclApi {
     nccl_result_t (*CommInitRank)(nccl_comm_t*, int, nccl_uid_t, int) = nullptr;
     nccl_result_t (*CommDestroy)(nccl_comm_t) = nullptr;
     nccl_result_t (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    nccl_result_t (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
     nccl_result_t (*Send)(const void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
     nccl_result_t (*Recv)(void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
     nccl_result_t (*GroupStart)() = nullptr;
@@ -43,6 +45,7 @@ static bool load_nccl(std::string& why) {
     g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))sym("ncclCommInitRank");
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
     g_nccl.AllReduce = (decltype(g_nccl.AllReduce))sym("ncclAllReduce");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))sym("ncclAllGather");
     g_nccl.Send = (decltype(g_nccl.Send))sym("ncclSend");
     g_nccl.Recv = (decltype(g_nccl.Recv))sym("ncclRecv");
     g_nccl.GroupStart = (decltype(g_nccl.GroupStart))sym("ncclGroupStart");
@@ -132,9 +135,175 @@ hdg_status comm_setup_halo(hdg_context* c, const std::vector<int32_t>& send_dn, 
     return HDG_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Peer-memory path.  Every rank exposes (a) a small mailbox and (b) its PCG vector region through CUDA
+// IPC; the handles travel through one ncclAllGather.  After that the PCG needs no NCCL call: the SpMV
+// kernel loads the neighbours' interface values straight over NVLink, and the dot products are
+// combined by `xgpu_allreduce`, a one-block kernel that stores this rank's partial sums into every
+// rank's mailbox and spins (system-scope loads) until all ranks of the current epoch have arrived -
+// an all-reduce and a device-wide barrier across GPUs in ~one NVLink round trip.
+// ---------------------------------------------------------------------------------------------
+struct IpcRecord {
+    cudaIpcMemHandle_t handle;   // 64 bytes
+    int64_t ndof;
+    int64_t pad;
+};
+
+static hdg_status allgather_records(hdg_context* c, const IpcRecord& mine, std::vector<IpcRecord>& all) {
+    Comm* m = c->comm;
+    if (!g_nccl.AllGather) return set_err(c, HDG_ERR_NCCL, "ncclAllGather missing");
+    IpcRecord* d = nullptr;
+    HDG_CUDA(c, cudaMalloc(&d, sizeof(IpcRecord) * (m->nranks + 1)));
+    HDG_CUDA(c, cudaMemcpyAsync(d + m->nranks, &mine, sizeof(IpcRecord), cudaMemcpyHostToDevice, c->stream));
+    HDG_NCCL(c, g_nccl.AllGather(d + m->nranks, d, sizeof(IpcRecord), 0 /* ncclInt8 */, m->nccl, c->stream));
+    all.resize(m->nranks);
+    HDG_CUDA(c, cudaMemcpyAsync(all.data(), d, sizeof(IpcRecord) * m->nranks, cudaMemcpyDeviceToHost, c->stream));
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d);
+    return HDG_OK;
+}
+
+bool comm_p2p(const hdg_context* c) { return comm_active(c) && c->comm->p2p; }
+
+static hdg_status setup_mailboxes(hdg_context* c) {
+    Comm* m = c->comm;
+    const size_t bytes = sizeof(double) * 2 * m->nranks * MAILW;
+    HDG_CUDA(c, cudaMalloc(&m->d_mail, bytes));
+    HDG_CUDA(c, cudaMemset(m->d_mail, 0, bytes));
+    HDG_CUDA(c, cudaMalloc(&m->d_epoch, sizeof(unsigned long long)));
+    HDG_CUDA(c, cudaMemset(m->d_epoch, 0, sizeof(unsigned long long)));
+    IpcRecord mine{};
+    HDG_CUDA(c, cudaIpcGetMemHandle(&mine.handle, m->d_mail));
+    std::vector<IpcRecord> all;
+    hdg_status st = allgather_records(c, mine, all);
+    if (st) return st;
+    std::vector<double*> ptrs(m->nranks, nullptr);
+    for (int q = 0; q < m->nranks; ++q) {
+        if (q == m->rank) { ptrs[q] = m->d_mail; continue; }
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, all[q].handle, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return set_err(c, HDG_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+        }
+        m->ipc_opened.push_back(p);
+        ptrs[q] = static_cast<double*>(p);
+    }
+    HDG_CUDA(c, cudaMalloc(&m->d_peer_mail, sizeof(double*) * m->nranks));
+    HDG_CUDA(c, cudaMemcpy(m->d_peer_mail, ptrs.data(), sizeof(double*) * m->nranks, cudaMemcpyHostToDevice));
+    return HDG_OK;
+}
+
+void comm_unshare_vectors(hdg_context* c) {
+    if (!c->comm) return;
+    for (int w = 0; w < 2; ++w)
+        if (c->comm->peer_vec[w]) { cudaIpcCloseMemHandle(c->comm->peer_vec[w]); c->comm->peer_vec[w] = nullptr; }
+}
+
+hdg_status comm_share_vectors(hdg_context* c, void* region, int64_t ndof_own) {
+    Comm* m = c->comm;
+    comm_unshare_vectors(c);
+    IpcRecord mine{};
+    HDG_CUDA(c, cudaIpcGetMemHandle(&mine.handle, region));
+    mine.ndof = ndof_own;
+    std::vector<IpcRecord> all;
+    hdg_status st = allgather_records(c, mine, all);
+    if (st) return st;
+    const int nb[2] = {m->rank - 1, m->rank + 1};
+    for (int w = 0; w < 2; ++w) {
+        if (nb[w] < 0 || nb[w] >= m->nranks) continue;
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, all[nb[w]].handle, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return set_err(c, HDG_ERR_CUDA, std::string("cudaIpcOpenMemHandle(vectors): ") + cudaGetErrorString(e));
+        }
+        m->peer_vec[w] = p;
+        m->peer_ndof[w] = all[nb[w]].ndof;
+    }
+    return HDG_OK;
+}
+
+hdg_status comm_set_ghost_ridx(hdg_context* c, const std::vector<int32_t>& ridx) {
+    Comm* m = c->comm;
+    if (m->d_ghost_ridx) { cudaFree(m->d_ghost_ridx); m->d_ghost_ridx = nullptr; }
+    if (ridx.empty()) return HDG_OK;
+    HDG_CUDA(c, cudaMalloc(&m->d_ghost_ridx, sizeof(int32_t) * ridx.size()));
+    HDG_CUDA(c, cudaMemcpy(m->d_ghost_ridx, ridx.data(), sizeof(int32_t) * ridx.size(), cudaMemcpyHostToDevice));
+    return HDG_OK;
+}
+
+constexpr int XG_THREADS = 256;
+constexpr int XG_MAXPART = 2048;   // == MAX_PARTIALS of hdg_solve.cu
+
+__global__ void __launch_bounds__(XG_THREADS) xgpu_allreduce(const double* __restrict__ part, int np, int nvals,
+                                                             double* __restrict__ gscal, double* const* __restrict__ peer_mail,
+                                                             double* my_mail, unsigned long long* epoch_ctr, int rank, int nranks) {
+    __shared__ double loc[MAILW];
+    __shared__ double red[XG_THREADS / 32];
+    __shared__ unsigned long long e_sh;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // local sums of the partial arrays, fixed order
+    for (int w = 0; w < nvals; ++w) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < np; i += XG_THREADS) s += part[w * XG_MAXPART + i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) red[wid] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int k = 0; k < XG_THREADS / 32; ++k) t += red[k];
+            loc[w] = t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        e_sh = *epoch_ctr + 1;
+        *epoch_ctr = e_sh;
+    }
+    __syncthreads();
+    const unsigned long long e = e_sh;
+    const int buf = int(e & 1ull);
+    if (threadIdx.x < nranks) {
+        // my contribution -> slot [buf][rank] of rank `threadIdx.x` (values first, then the epoch word)
+        volatile double* dst = peer_mail[threadIdx.x] + size_t(buf * nranks + rank) * MAILW;
+        for (int w = 0; w < nvals; ++w) dst[1 + w] = loc[w];
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(dst) = e;
+        // wait for rank `threadIdx.x`'s contribution to arrive in my mailbox
+        volatile unsigned long long* flag =
+            reinterpret_cast<volatile unsigned long long*>(my_mail + size_t(buf * nranks + threadIdx.x) * MAILW);
+        while (*flag != e) { }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x < nvals) {
+        double s = 0.0;
+        for (int q = 0; q < nranks; ++q)   // rank order: identical result on every rank
+            s += reinterpret_cast<volatile double*>(my_mail)[size_t(buf * nranks + q) * MAILW + 1 + threadIdx.x];
+        gscal[threadIdx.x] = s;
+    }
+}
+
+hdg_status comm_p2p_allreduce(hdg_context* c, const double* d_partials, int np, int nvals) {
+    Comm* m = c->comm;
+    xgpu_allreduce<<<1, XG_THREADS, 0, c->stream>>>(d_partials, np, nvals, m->d_gscal, m->d_peer_mail, m->d_mail, m->d_epoch,
+                                                   m->rank, m->nranks);
+    c->launches += 1;
+    HDG_CUDA(c, cudaGetLastError());
+    return HDG_OK;
+}
+
 void comm_destroy(hdg_context* c) {
     if (!c->comm) return;
     comm_free_halo(c);
+    comm_unshare_vectors(c);
+    for (void* p : c->comm->ipc_opened) cudaIpcCloseMemHandle(p);
+    if (c->comm->d_mail) cudaFree(c->comm->d_mail);
+    if (c->comm->d_peer_mail) cudaFree(c->comm->d_peer_mail);
+    if (c->comm->d_epoch) cudaFree(c->comm->d_epoch);
+    if (c->comm->d_ghost_ridx) cudaFree(c->comm->d_ghost_ridx);
     if (c->comm->d_gscal) cudaFree(c->comm->d_gscal);
     if (c->comm->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm->nccl);
     delete c->comm;
@@ -181,6 +350,12 @@ hdg_status hdg_comm_init(hdg_context* c, int32_t rank, int32_t nranks, const uin
         return set_err(c, HDG_ERR_CUDA, "cudaMalloc failed");
     }
     c->comm = m;
+    // peer-memory mailboxes; on failure (no P2P / IPC) the NCCL path stays in use
+    if (nranks > 1 && getenv("HDG_NO_P2P") == nullptr && nranks <= XG_THREADS) {
+        hdg_status st = setup_mailboxes(c);
+        m->p2p = st == HDG_OK;
+        if (st != HDG_OK) c->err = "peer-memory path disabled: " + c->err;
+    }
     return HDG_OK;
 }
 

@@ -80,7 +80,17 @@ struct Comm {
     int32_t* d_send_up_idx = nullptr;  int64_t n_send_up = 0;   // faces sent to rank+1 (its ghost-below layer)
     double *d_send_dn = nullptr, *d_send_up = nullptr;
     double* d_gscal = nullptr;       // all-reduced scalars
+    // peer-memory path (CUDA IPC over NVLink): mailboxes for the flag-based all-reduce, neighbours' PCG vectors
+    bool p2p = false;
+    double* d_mail = nullptr;               // my mailbox [2][nranks][MAILW]
+    double** d_peer_mail = nullptr;         // device array: mailbox of every rank as mapped in this process
+    unsigned long long* d_epoch = nullptr;  // all-reduce epoch counter
+    void* peer_vec[2] = {nullptr, nullptr}; // mapped [r|dinv|p0|p1] region of rank-1 / rank+1
+    int64_t peer_ndof[2] = {0, 0};          // their owned dof counts
+    int32_t* d_ghost_ridx = nullptr;        // for every ghost face: its local face index on the owning rank
+    std::vector<void*> ipc_opened;
 };
+constexpr int MAILW = 8;   // doubles per mailbox slot: epoch word + up to 7 values
 
 }  // namespace hdg
 
@@ -131,7 +141,8 @@ struct hdg_context {
 
     // solver vectors
     double* d_x = nullptr;           // trace solution u_hat
-    double *d_r = nullptr, *d_p = nullptr, *d_Ap = nullptr, *d_dinv = nullptr;
+    double *d_r = nullptr, *d_p = nullptr, *d_Ap = nullptr, *d_dinv = nullptr;   // legacy 3-kernel path
+    double* d_vreg = nullptr;        // fused path: one region [r | dinv | p0 | p1] (shared with the neighbours over CUDA IPC)
     double* d_partials = nullptr;    // reduction partials
     double* d_scal = nullptr;        // device scalars
     int32_t* d_flags = nullptr;      // error / convergence flags
@@ -199,5 +210,10 @@ hdg_status comm_halo_exchange(hdg_context* c, double* d_vec, int nt);           
 hdg_status comm_setup_halo(hdg_context* c, const std::vector<int32_t>& send_dn, const std::vector<int32_t>& send_up);
 void comm_free_halo(hdg_context* c);
 void comm_destroy(hdg_context* c);
+bool comm_p2p(const hdg_context* c);
+hdg_status comm_share_vectors(hdg_context* c, void* region, int64_t ndof_own);              // maps the neighbours' regions
+void comm_unshare_vectors(hdg_context* c);
+hdg_status comm_p2p_allreduce(hdg_context* c, const double* d_partials, int np, int nvals);   // partial arrays -> d_gscal, all ranks
+hdg_status comm_set_ghost_ridx(hdg_context* c, const std::vector<int32_t>& ridx);
 
 }  // namespace hdg

@@ -334,6 +334,7 @@ void free_mesh(hdg_context* c) {
     F(c->d_cellinfo); F(c->d_nodes); F(c->d_facecell); F(c->d_facenode); F(c->d_bfaces); F(c->d_isbc);
     F(c->d_kcol); F(c->d_fq); F(c->d_Kd); F(c->d_Ko); F(c->d_rhs); F(c->d_Ke); F(c->d_bcval);
     F(c->d_x); F(c->d_r); F(c->d_p); F(c->d_Ap); F(c->d_dinv);
+    if (c->d_vreg) { comm_unshare_vectors(c); cudaFree(c->d_vreg); c->d_vreg = nullptr; }
     F(c->d_sigma); F(c->d_u); F(c->d_uhat_h); F(c->d_stage_cells); F(c->d_stage_faces);
     c->cap_ncell = c->cap_nnode = c->cap_nface = c->cap_nbface = 0;
     c->have_mesh = c->assembled = c->applied = c->solved = c->recovered = false;
@@ -505,6 +506,22 @@ hdg_status mesh_rectangle(hdg_context* c, int64_t nx, int64_t ny, double llx, do
         if (j1 < ny)     // rank+1's ghost-below layer: top(i, j1-1)
             for (int64_t i = 0; i < nx; ++i) send_up.push_back(int32_t(quad_faces(i, j1 - 1, nx).top - S.F0));
         st = comm_setup_halo(c, send_dn, send_up);
+        if (st) return st;
+        // ghost face -> local face index on the rank that owns it (peer-memory SpMV)
+        std::vector<int32_t> ridx;
+        if (j0 > 0) {
+            const int64_t jp = ny * (m->rank - 1) / m->nranks, F0p = quad_base(0, jp, nx);
+            for (int64_t i = 0; i < nx; ++i) ridx.push_back(int32_t(quad_faces(i, j0 - 1, nx).top - F0p));
+        }
+        if (j1 < ny) {
+            const int64_t F0n = quad_base(0, j1, nx);
+            for (int64_t i = 0; i < nx; ++i) {
+                QuadFaces F = quad_faces(i, j1, nx);
+                ridx.push_back(int32_t(F.left - F0n));
+                ridx.push_back(int32_t(F.diag - F0n));
+            }
+        }
+        st = comm_set_ghost_ridx(c, ridx);
         if (st) return st;
     }
     st = alloc_system(c);

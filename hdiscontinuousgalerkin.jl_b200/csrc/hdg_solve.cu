@@ -145,6 +145,11 @@ struct PcgArgs {
     const double* gscal;   // multi-GPU: all-reduced sums, one per partial array; nullptr on one GPU
     int np;            // number of partials == gridDim of the vector kernels
     double rtol;
+    // fused path
+    double* pbuf[2];   // search directions p_k (buffer k&1) and p_{k-1}
+    struct PeerVec { const double* r; const double* dinv; const double* p[2]; } peer[2];   // rank-1 / rank+1 over NVLink
+    const int32_t* ghost_ridx;   // ghost face -> local face index on its owner
+    int64_t nbelow;              // ghost faces owned by rank-1 (they come first)
 };
 
 __device__ __forceinline__ double get_sum(const PcgArgs& a, int which) {
@@ -452,7 +457,263 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
     return HDG_OK;
 }
 
+// =================================================================================================
+// Fused PCG: 2 kernels per iteration.
+//   pcg_fused_spmv  beta_k = rz_k/rz_{k-1}; convergence test; p_k = Dinv r_k + beta_k p_{k-1} formed ON THE FLY for the
+//                   row's own face (stored) and for its <= 4 neighbour faces (recomputed, not stored); Ap_k = D K p_k;
+//                   partials of p_k.Ap_k.  Neighbour faces that belong to another rank are read straight from that
+//                   rank's r / Dinv / p_{k-1} over NVLink (CUDA IPC mapping) - the halo exchange is part of the SpMV.
+//   pcg_update      alpha_k = rz_k/pAp_k; x += alpha p_k; r -= alpha Ap_k; partials of r.Dinv r and r.r
+// The two dot-product reductions are the only synchronisation points; on several GPUs each is one
+// `xgpu_allreduce` (mailbox all-reduce = barrier), which also orders the peer reads/writes of r and p:
+// r is rewritten only after every rank finished the SpMV that reads it, and p is double-buffered.
+// =================================================================================================
+template <int NT>
+__global__ void __launch_bounds__(RB) pcg_fused_init(const PcgArgs a) {
+    constexpr int NT2 = NT * NT;
+    const int64_t N = a.nface * NT;
+    double rz = 0.0, bb = 0.0;
+    for (int64_t row = int64_t(blockIdx.x) * RB + threadIdx.x; row < N; row += int64_t(gridDim.x) * RB) {
+        int64_t f = row / NT;
+        int aa = int(row - f * NT);
+        double sgn = a.isbc[f] ? 1.0 : -1.0;
+        double di = 1.0 / (sgn * a.Kd[f * NT2 + aa * NT + aa]);
+        double r = sgn * a.rhs[row];
+        a.dinv[row] = di;
+        a.r[row] = r;
+        a.pbuf[1][row] = 0.0;     // p_{-1}
+        a.x[row] = 0.0;
+        rz += r * (di * r);
+        bb += r * r;
+    }
+    double t1 = block_sum(rz), t2 = block_sum(bb);
+    if (threadIdx.x == 0) {
+        a.part[P_RZ0 * MAX_PARTIALS + blockIdx.x] = t1;
+        a.part[P_RZ1 * MAX_PARTIALS + blockIdx.x] = blockIdx.x == 0 ? INFINITY : 0.0;   // rz_{-1} = inf  ->  beta_0 = 0
+        a.part[P_BB * MAX_PARTIALS + blockIdx.x] = t2;
+        a.part[P_RR * MAX_PARTIALS + blockIdx.x] = t2;
+        a.part[P_PAP * MAX_PARTIALS + blockIdx.x] = 0.0;
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(RB) pcg_fused_spmv(const PcgArgs a, int parity, int kiter) {
+    if (*reinterpret_cast<volatile int32_t*>(a.flags + FLAG_DONE)) return;
+    constexpr int NT2 = NT * NT;
+    const double rr = get_sum(a, P_RR), bb = a.scal[S_BNORM2];
+    const bool conv = rr <= a.rtol * a.rtol * bb;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.scal[S_RELRES] = sqrt(rr / bb);
+        a.flags[FLAG_ITERS] = kiter;
+        if (conv) a.flags[FLAG_DONE] = 1;
+    }
+    if (conv) return;   // decided identically by every block (and every rank)
+    const double rz_k = get_sum(a, parity ? P_RZ1 : P_RZ0), rz_km1 = get_sum(a, parity ? P_RZ0 : P_RZ1);
+    const double beta = rz_k / rz_km1;
+    const double* __restrict__ pold = a.pbuf[parity ^ 1];
+    double* __restrict__ pnew = a.pbuf[parity];
+    double pap = 0.0;
+    for (int64_t f = int64_t(blockIdx.x) * RB + threadIdx.x; f < a.nface; f += int64_t(gridDim.x) * RB) {
+        double y[NT], pf[NT], t1[NT], t2[NT], blk[NT2];
+        load_vec<NT>(a.r + f * NT, t1);
+        load_vec<NT>(a.dinv + f * NT, t2);
+        load_vec<NT>(pold + f * NT, pf);
+#pragma unroll
+        for (int b = 0; b < NT; ++b) pf[b] = fma(beta, pf[b], t2[b] * t1[b]);
+        store_vec<NT>(pnew + f * NT, pf);
+        load_vec<NT2>(a.Kd + f * NT2, blk);
+#pragma unroll
+        for (int r = 0; r < NT; ++r) {
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < NT; ++b) s = fma(blk[b * NT + r], pf[b], s);
+            y[r] = s;
+        }
+        const int4 cols = *reinterpret_cast<const int4*>(a.kcol + 4 * f);
+        const int cc[4] = {cols.x, cols.y, cols.z, cols.w};
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+            const int64_t g = cc[s4];
+            if (g < 0) continue;
+            const double *rg, *dg, *pg;
+            if (g < a.nface) {
+                rg = a.r + g * NT; dg = a.dinv + g * NT; pg = pold + g * NT;
+            } else {   // face owned by a neighbouring rank: read its vectors over NVLink
+                const int64_t gi = g - a.nface;
+                const int w = gi < a.nbelow ? 0 : 1;
+                const int64_t ri = int64_t(a.ghost_ridx[gi]) * NT;
+                rg = a.peer[w].r + ri; dg = a.peer[w].dinv + ri; pg = a.peer[w].p[parity ^ 1] + ri;
+            }
+            double pv[NT];
+            load_vec<NT>(rg, t1);
+            load_vec<NT>(dg, t2);
+            load_vec<NT>(pg, pv);
+#pragma unroll
+            for (int b = 0; b < NT; ++b) pv[b] = fma(beta, pv[b], t2[b] * t1[b]);
+            load_vec<NT2>(a.Ko + (f * 4 + s4) * NT2, blk);
+#pragma unroll
+            for (int r = 0; r < NT; ++r)
+#pragma unroll
+                for (int b = 0; b < NT; ++b) y[r] = fma(blk[b * NT + r], pv[b], y[r]);
+        }
+        const bool bc = a.isbc[f];
+#pragma unroll
+        for (int r = 0; r < NT; ++r) {
+            y[r] = bc ? y[r] : -y[r];
+            pap = fma(pf[r], y[r], pap);
+        }
+        store_vec<NT>(a.Ap + f * NT, y);
+    }
+    double tot = block_sum(pap);
+    if (threadIdx.x == 0) a.part[P_PAP * MAX_PARTIALS + blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(RB) pcg_fused_update(const PcgArgs a, int64_t N, int parity) {
+    if (*reinterpret_cast<volatile int32_t*>(a.flags + FLAG_DONE)) return;
+    const double pap = get_sum(a, P_PAP);
+    const double rz = get_sum(a, parity ? P_RZ1 : P_RZ0);
+    const double alpha = rz / pap;
+    const double* __restrict__ p = a.pbuf[parity];
+    double rz_new = 0.0, rr = 0.0;
+    for (int64_t row = int64_t(blockIdx.x) * RB + threadIdx.x; row < N; row += int64_t(gridDim.x) * RB) {
+        double r = a.r[row];
+        a.x[row] = fma(alpha, p[row], a.x[row]);
+        r = fma(-alpha, a.Ap[row], r);
+        a.r[row] = r;
+        rz_new = fma(r * a.dinv[row], r, rz_new);
+        rr = fma(r, r, rr);
+    }
+    double t1 = block_sum(rz_new), t2 = block_sum(rr);
+    if (threadIdx.x == 0) {
+        a.part[(parity ? P_RZ0 : P_RZ1) * MAX_PARTIALS + blockIdx.x] = t1;
+        a.part[P_RR * MAX_PARTIALS + blockIdx.x] = t2;
+    }
+}
+
+// convergence test at the end of a chunk of iterations (the SpMV of the next iteration would do it otherwise)
+__global__ void __launch_bounds__(RB) pcg_fused_check(const PcgArgs a, int kiter) {
+    if (*reinterpret_cast<volatile int32_t*>(a.flags + FLAG_DONE)) return;
+    const double rr = get_sum(a, P_RR), bb = a.scal[S_BNORM2];
+    if (threadIdx.x == 0) {
+        a.scal[S_RELRES] = sqrt(rr / bb);
+        a.flags[FLAG_ITERS] = kiter;
+        if (rr <= a.rtol * a.rtol * bb) a.flags[FLAG_DONE] = 1;
+    }
+}
+
+template <int NT> static hdg_status pcg_fused_t(hdg_context* c, double rtol, int maxit, hdg_solve_info* info) {
+    const int64_t N = c->nface_own * NT, Nloc = c->nface * NT;
+    const bool multi = comm_active(c);
+    if (!c->d_x) HDG_CUDA(c, cudaMalloc(&c->d_x, sizeof(double) * Nloc));
+    if (!c->d_Ap) HDG_CUDA(c, cudaMalloc(&c->d_Ap, sizeof(double) * Nloc));
+    if (!c->d_vreg) {
+        HDG_CUDA(c, cudaMalloc(&c->d_vreg, sizeof(double) * 4 * N));
+        if (multi) {
+            hdg_status st = comm_share_vectors(c, c->d_vreg, N);
+            if (st) return st;
+        }
+    }
+    if (multi) HDG_CUDA(c, cudaMemsetAsync(c->d_x, 0, sizeof(double) * Nloc, c->stream));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    PcgArgs a{};
+    a.Kd = c->d_Kd; a.Ko = c->d_Ko; a.kcol = c->d_kcol; a.isbc = c->d_isbc; a.rhs = c->d_rhs;
+    a.x = c->d_x; a.r = c->d_vreg; a.dinv = c->d_vreg + N; a.pbuf[0] = c->d_vreg + 2 * N; a.pbuf[1] = c->d_vreg + 3 * N;
+    a.p = nullptr; a.Ap = c->d_Ap;
+    a.part = c->d_partials; a.scal = c->d_scal; a.flags = c->d_flags; a.nface = c->nface_own;
+    a.gscal = multi ? c->comm->d_gscal : nullptr;
+    if (multi) {
+        for (int w = 0; w < 2; ++w) {
+            const double* base = static_cast<const double*>(c->comm->peer_vec[w]);
+            const int64_t Np = c->comm->peer_ndof[w];
+            a.peer[w].r = base; a.peer[w].dinv = base ? base + Np : nullptr;
+            a.peer[w].p[0] = base ? base + 2 * Np : nullptr; a.peer[w].p[1] = base ? base + 3 * Np : nullptr;
+        }
+        a.ghost_ridx = c->comm->d_ghost_ridx;
+        a.nbelow = c->comm->nbelow;
+    }
+    a.np = int(std::min<int64_t>(ceil_div(c->nface_own, RB), std::min<int64_t>(int64_t(sms) * 8, MAX_PARTIALS)));
+    a.rtol = rtol;
+    const int G = a.np;
+    hdg_status cst = HDG_OK;
+    auto sums = [&]() {   // several GPUs: partial arrays -> sums over all ranks (also the inter-GPU barrier)
+        if (!multi) return;
+        hdg_status s2 = comm_p2p_allreduce(c, c->d_partials, G, NPART);
+        if (s2) cst = s2;
+    };
+    timer_start(c, c->t_solve);
+    HDG_CUDA(c, cudaMemsetAsync(c->d_flags, 0, sizeof(int32_t) * NFLAGS, c->stream));
+    pcg_fused_init<NT><<<G, RB, 0, c->stream>>>(a);
+    sums();
+    pcg_init_final<<<1, RB, 0, c->stream>>>(a);
+    c->launches += 2;
+    const int CHUNK = 32;   // even: the double-buffer parity restarts at 0 in every chunk
+    const bool use_graph = getenv("HDG_NO_GRAPH") == nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    auto enqueue_chunk = [&](int n) {
+        for (int k = 0; k < n; ++k) {
+            pcg_fused_spmv<NT><<<G, RB, 0, c->stream>>>(a, k & 1, k);
+            sums();
+            pcg_fused_update<<<G, RB, 0, c->stream>>>(a, N, k & 1);
+            sums();
+        }
+        pcg_fused_check<<<1, RB, 0, c->stream>>>(a, n);
+    };
+    int it = 0;
+    bool done = false;
+    while (it < maxit && !done) {
+        int chunk = std::min(CHUNK, maxit - it);
+        if (chunk == CHUNK && use_graph) {
+            if (!gexec) {
+                HDG_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                enqueue_chunk(CHUNK);
+                HDG_CUDA(c, cudaStreamEndCapture(c->stream, &graph));
+                HDG_CUDA(c, cudaGraphInstantiate(&gexec, graph, 0));
+            }
+            HDG_CUDA(c, cudaGraphLaunch(gexec, c->stream));
+        } else {
+            enqueue_chunk(chunk);
+        }
+        c->launches += 2 * chunk + 1;
+        HDG_CUDA(c, cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int32_t) * NFLAGS, cudaMemcpyDeviceToHost, c->stream));
+        HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+        done = c->h_flags[FLAG_DONE] != 0;
+        it += done ? c->h_flags[FLAG_ITERS] : chunk;
+    }
+    if (multi) {   // recovery reads the trace on the ghost faces below the strip
+        hdg_status s2 = comm_halo_exchange(c, c->d_x, NT);
+        if (s2) cst = s2;
+    }
+    timer_stop(c, c->t_solve);
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
+    HDG_CUDA(c, cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(double) * NSCAL, cudaMemcpyDeviceToHost, c->stream));
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (info) {
+        info->iterations = it;
+        info->converged = done ? 1 : 0;
+        info->relres = c->h_scal[S_RELRES];
+        info->bnorm = std::sqrt(c->h_scal[S_BNORM2]);
+        info->solve_ms = timer_ms(c->t_solve);
+    }
+    c->solved = true;
+    if (cst) return cst;
+    if (!done) return set_err(c, HDG_ERR_NOT_CONVERGED, "PCG did not converge in " + std::to_string(maxit) + " iterations");
+    return HDG_OK;
+}
+
 hdg_status pcg_solve(hdg_context* c, double rtol, int maxit, hdg_solve_info* info) {
+    // fused 2-kernel PCG on one GPU and, over peer memory, on several; the 3-kernel NCCL variant is the
+    // fallback when the GPUs cannot map each other's memory (or HDG_PCG_LEGACY is set)
+    const bool fused = getenv("HDG_PCG_LEGACY") == nullptr && (!comm_active(c) || comm_p2p(c));
+    if (fused) switch (c->tab.nt) {
+        case 2: return pcg_fused_t<2>(c, rtol, maxit, info);
+        case 3: return pcg_fused_t<3>(c, rtol, maxit, info);
+        case 4: return pcg_fused_t<4>(c, rtol, maxit, info);
+        case 5: return pcg_fused_t<5>(c, rtol, maxit, info);
+    }
     switch (c->tab.nt) {
         case 2: return pcg_t<2>(c, rtol, maxit, info);
         case 3: return pcg_t<3>(c, rtol, maxit, info);
