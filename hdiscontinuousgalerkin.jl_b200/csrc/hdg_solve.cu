@@ -31,7 +31,7 @@ namespace hdg {
 constexpr int MAX_PARTIALS = 2048;
 
 // d_scal layout
-enum Scal : int { S_BNORM2 = 0, S_RELRES = 1, S_MEANSUM = 2, NSCAL = 8 };
+enum Scal : int { S_BNORM2 = 0, S_RELRES = 1, S_MEANSUM = 2, S_ERR2 = 3, S_RZ = 4, NSCAL = 8 };
 // d_partials layout: 5 arrays of MAX_PARTIALS
 enum Part : int { P_PAP = 0, P_RZ0 = 1, P_RZ1 = 2, P_RR = 3, P_BB = 4, NPART = 5 };
 
@@ -145,10 +145,7 @@ struct PcgArgs {
     const double* gscal;   // multi-GPU: all-reduced sums, one per partial array; nullptr on one GPU
     int np;            // number of partials == gridDim of the vector kernels
     double rtol;
-    // fused path
-    double* pbuf[2];   // search directions p_k (buffer k&1) and p_{k-1}
-    struct PeerVec { const double* r; const double* dinv; const double* p[2]; } peer[2];   // rank-1 / rank+1 over NVLink
-    const int32_t* ghost_ridx;   // ghost face -> local face index on its owner
+    const int32_t* ghost_ridx;   // ghost face -> local face index on its owner (peer-memory SpMV)
     int64_t nbelow;              // ghost faces owned by rank-1 (they come first)
 };
 
@@ -458,69 +455,105 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
 }
 
 // =================================================================================================
-// Fused PCG: 2 kernels per iteration.
-//   pcg_fused_spmv  beta_k = rz_k/rz_{k-1}; convergence test; p_k = Dinv r_k + beta_k p_{k-1} formed ON THE FLY for the
-//                   row's own face (stored) and for its <= 4 neighbour faces (recomputed, not stored); Ap_k = D K p_k;
-//                   partials of p_k.Ap_k.  Neighbour faces that belong to another rank are read straight from that
-//                   rank's r / Dinv / p_{k-1} over NVLink (CUDA IPC mapping) - the halo exchange is part of the SpMV.
-//   pcg_update      alpha_k = rz_k/pAp_k; x += alpha p_k; r -= alpha Ap_k; partials of r.Dinv r and r.r
-// The two dot-product reductions are the only synchronisation points; on several GPUs each is one
-// `xgpu_allreduce` (mailbox all-reduce = barrier), which also orders the peer reads/writes of r and p:
-// r is rewritten only after every rank finished the SpMV that reads it, and p is double-buffered.
+// PCG, main path (one GPU, and several GPUs over peer memory): 3 kernels per iteration and NOTHING else -
+// no reduction kernels, no NCCL, no host synchronisation.
+//   pcg3_spmv    Ap = D K p + p.Ap          p of faces owned by a neighbouring rank is loaded straight from that
+//                                           rank's memory over NVLink (CUDA IPC mapping): the halo exchange is
+//                                           part of the SpMV
+//   pcg3_update  alpha = rz/pAp; x += alpha p; r -= alpha Ap; r.Dinv r, r.r
+//   pcg3_dir     beta = rz'/rz; convergence test; p = Dinv r + beta p
+// Reductions: every block writes its partial sums; the block that finishes LAST (ticket counter) adds the
+// partials in index order (bitwise reproducible) and stores the result, tagged with the iteration number, into
+// the mailbox of every rank (plain stores over NVLink + one system fence).  The consumer kernel polls its own
+// mailbox until all ranks of that iteration have arrived and adds the contributions in rank order, so all
+// ranks hold identical scalars.  A message is therefore both the all-reduce and the inter-GPU barrier that
+// orders the peer reads of p against its next overwrite; pcg3_dir additionally posts a value-less "p ready"
+// message that the next SpMV waits for.
 // =================================================================================================
-template <int NT>
-__global__ void __launch_bounds__(RB) pcg_fused_init(const PcgArgs a) {
-    constexpr int NT2 = NT * NT;
-    const int64_t N = a.nface * NT;
-    double rz = 0.0, bb = 0.0;
-    for (int64_t row = int64_t(blockIdx.x) * RB + threadIdx.x; row < N; row += int64_t(gridDim.x) * RB) {
-        int64_t f = row / NT;
-        int aa = int(row - f * NT);
-        double sgn = a.isbc[f] ? 1.0 : -1.0;
-        double di = 1.0 / (sgn * a.Kd[f * NT2 + aa * NT + aa]);
-        double r = sgn * a.rhs[row];
-        a.dinv[row] = di;
-        a.r[row] = r;
-        a.pbuf[1][row] = 0.0;     // p_{-1}
-        a.x[row] = 0.0;
-        rz += r * (di * r);
-        bb += r * r;
+enum Msg : int { MSG_PAP = 0, MSG_RZRR = 1, MSG_PREADY = 2, NMSG = 3 };
+
+struct Pcg3Sync {
+    unsigned long long base_iter;   // absolute index of iteration 0 of the current chunk (message tags = index + 1)
+    unsigned int ticket[NMSG];
+};
+
+struct Pcg3Args {
+    PcgArgs a;
+    Pcg3Sync* sync;
+    double* my_mail;            // [NMSG][2][nranks][MAILW]
+    double* const* peer_mail;   // the same region of every rank, as mapped here
+    const double* peer_p[2];    // p of rank-1 / rank+1
+    int rank, nranks;
+};
+
+__device__ __forceinline__ double* mail_slot(double* base, int msg, int buf, int nranks, int q) {
+    return base + (size_t(msg * 2 + buf) * nranks + q) * MAILW;
+}
+
+// called by every thread of every block after the block's partial sums were stored to part[slot_v][blockIdx]
+template <int NV>
+__device__ __forceinline__ void last_block_send(const Pcg3Args& A, int msg, unsigned long long tag, const int (&slots)[NV == 0 ? 1 : NV]) {
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(&A.sync->ticket[msg], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double vals[NV == 0 ? 1 : NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < A.a.np; i += RB) s += __ldcg(A.a.part + slots[v] * MAX_PARTIALS + i);
+        vals[v] = block_sum(s);
     }
-    double t1 = block_sum(rz), t2 = block_sum(bb);
-    if (threadIdx.x == 0) {
-        a.part[P_RZ0 * MAX_PARTIALS + blockIdx.x] = t1;
-        a.part[P_RZ1 * MAX_PARTIALS + blockIdx.x] = blockIdx.x == 0 ? INFINITY : 0.0;   // rz_{-1} = inf  ->  beta_0 = 0
-        a.part[P_BB * MAX_PARTIALS + blockIdx.x] = t2;
-        a.part[P_RR * MAX_PARTIALS + blockIdx.x] = t2;
-        a.part[P_PAP * MAX_PARTIALS + blockIdx.x] = 0.0;
+    if (threadIdx.x < A.nranks) {
+        volatile double* dst = mail_slot(A.peer_mail[threadIdx.x], msg, int(tag & 1ull), A.nranks, A.rank);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) dst[1 + v] = vals[v];
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(dst) = tag;
     }
+    if (threadIdx.x == 0) A.sync->ticket[msg] = 0;
+}
+
+// every block: wait until all ranks posted message `msg` with this tag, then add the values in rank order
+template <int NV>
+__device__ __forceinline__ void wait_message(const Pcg3Args& A, int msg, unsigned long long tag, double (&out)[NV == 0 ? 1 : NV]) {
+    __shared__ double sh[4];
+    const int buf = int(tag & 1ull);
+    if (threadIdx.x < A.nranks) {
+        volatile unsigned long long* flag =
+            reinterpret_cast<volatile unsigned long long*>(mail_slot(A.my_mail, msg, buf, A.nranks, threadIdx.x));
+        while (*flag != tag) { }
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0.0;
+        for (int q = 0; q < A.nranks; ++q)
+            s += reinterpret_cast<volatile double*>(mail_slot(A.my_mail, msg, buf, A.nranks, q))[1 + threadIdx.x];
+        sh[threadIdx.x] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < NV; ++v) out[v] = sh[v];
+    __syncthreads();
 }
 
 template <int NT>
-__global__ void __launch_bounds__(RB) pcg_fused_spmv(const PcgArgs a, int parity, int kiter) {
+__global__ void __launch_bounds__(RB) pcg3_spmv(const Pcg3Args A, int kiter) {
+    const PcgArgs& a = A.a;
     if (*reinterpret_cast<volatile int32_t*>(a.flags + FLAG_DONE)) return;
     constexpr int NT2 = NT * NT;
-    const double rr = get_sum(a, P_RR), bb = a.scal[S_BNORM2];
-    const bool conv = rr <= a.rtol * a.rtol * bb;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        a.scal[S_RELRES] = sqrt(rr / bb);
-        a.flags[FLAG_ITERS] = kiter;
-        if (conv) a.flags[FLAG_DONE] = 1;
+    const unsigned long long tag = A.sync->base_iter + kiter + 1;
+    if (A.nranks > 1) {   // the neighbours' p of this iteration must be complete before it is read
+        double none[1];
+        wait_message<0>(A, MSG_PREADY, tag, none);
     }
-    if (conv) return;   // decided identically by every block (and every rank)
-    const double rz_k = get_sum(a, parity ? P_RZ1 : P_RZ0), rz_km1 = get_sum(a, parity ? P_RZ0 : P_RZ1);
-    const double beta = rz_k / rz_km1;
-    const double* __restrict__ pold = a.pbuf[parity ^ 1];
-    double* __restrict__ pnew = a.pbuf[parity];
     double pap = 0.0;
     for (int64_t f = int64_t(blockIdx.x) * RB + threadIdx.x; f < a.nface; f += int64_t(gridDim.x) * RB) {
-        double y[NT], pf[NT], t1[NT], t2[NT], blk[NT2];
-        load_vec<NT>(a.r + f * NT, t1);
-        load_vec<NT>(a.dinv + f * NT, t2);
-        load_vec<NT>(pold + f * NT, pf);
-#pragma unroll
-        for (int b = 0; b < NT; ++b) pf[b] = fma(beta, pf[b], t2[b] * t1[b]);
-        store_vec<NT>(pnew + f * NT, pf);
+        double y[NT], pf[NT], blk[NT2];
+        load_vec<NT>(a.p + f * NT, pf);
         load_vec<NT2>(a.Kd + f * NT2, blk);
 #pragma unroll
         for (int r = 0; r < NT; ++r) {
@@ -535,21 +568,14 @@ __global__ void __launch_bounds__(RB) pcg_fused_spmv(const PcgArgs a, int parity
         for (int s4 = 0; s4 < 4; ++s4) {
             const int64_t g = cc[s4];
             if (g < 0) continue;
-            const double *rg, *dg, *pg;
-            if (g < a.nface) {
-                rg = a.r + g * NT; dg = a.dinv + g * NT; pg = pold + g * NT;
-            } else {   // face owned by a neighbouring rank: read its vectors over NVLink
+            const double* pg;
+            if (g < a.nface) pg = a.p + g * NT;
+            else {   // face owned by a neighbouring rank: its p comes over NVLink
                 const int64_t gi = g - a.nface;
-                const int w = gi < a.nbelow ? 0 : 1;
-                const int64_t ri = int64_t(a.ghost_ridx[gi]) * NT;
-                rg = a.peer[w].r + ri; dg = a.peer[w].dinv + ri; pg = a.peer[w].p[parity ^ 1] + ri;
+                pg = A.peer_p[gi < a.nbelow ? 0 : 1] + int64_t(a.ghost_ridx[gi]) * NT;
             }
             double pv[NT];
-            load_vec<NT>(rg, t1);
-            load_vec<NT>(dg, t2);
             load_vec<NT>(pg, pv);
-#pragma unroll
-            for (int b = 0; b < NT; ++b) pv[b] = fma(beta, pv[b], t2[b] * t1[b]);
             load_vec<NT2>(a.Ko + (f * 4 + s4) * NT2, blk);
 #pragma unroll
             for (int r = 0; r < NT; ++r)
@@ -566,18 +592,22 @@ __global__ void __launch_bounds__(RB) pcg_fused_spmv(const PcgArgs a, int parity
     }
     double tot = block_sum(pap);
     if (threadIdx.x == 0) a.part[P_PAP * MAX_PARTIALS + blockIdx.x] = tot;
+    const int slots[1] = {P_PAP};
+    last_block_send<1>(A, MSG_PAP, tag, slots);
 }
 
-__global__ void __launch_bounds__(RB) pcg_fused_update(const PcgArgs a, int64_t N, int parity) {
+__global__ void __launch_bounds__(RB) pcg3_update(const Pcg3Args A, int64_t N, int kiter) {
+    const PcgArgs& a = A.a;
     if (*reinterpret_cast<volatile int32_t*>(a.flags + FLAG_DONE)) return;
-    const double pap = get_sum(a, P_PAP);
-    const double rz = get_sum(a, parity ? P_RZ1 : P_RZ0);
-    const double alpha = rz / pap;
-    const double* __restrict__ p = a.pbuf[parity];
+    const unsigned long long tag = A.sync->base_iter + kiter + 1;
+    double pap[1];
+    wait_message<1>(A, MSG_PAP, tag, pap);
+    const double rz = a.scal[S_RZ];
+    const double alpha = rz / pap[0];
     double rz_new = 0.0, rr = 0.0;
     for (int64_t row = int64_t(blockIdx.x) * RB + threadIdx.x; row < N; row += int64_t(gridDim.x) * RB) {
         double r = a.r[row];
-        a.x[row] = fma(alpha, p[row], a.x[row]);
+        a.x[row] = fma(alpha, a.p[row], a.x[row]);
         r = fma(-alpha, a.Ap[row], r);
         a.r[row] = r;
         rz_new = fma(r * a.dinv[row], r, rz_new);
@@ -585,81 +615,178 @@ __global__ void __launch_bounds__(RB) pcg_fused_update(const PcgArgs a, int64_t 
     }
     double t1 = block_sum(rz_new), t2 = block_sum(rr);
     if (threadIdx.x == 0) {
-        a.part[(parity ? P_RZ0 : P_RZ1) * MAX_PARTIALS + blockIdx.x] = t1;
+        a.part[P_RZ0 * MAX_PARTIALS + blockIdx.x] = t1;
         a.part[P_RR * MAX_PARTIALS + blockIdx.x] = t2;
     }
+    const int slots[2] = {P_RZ0, P_RR};
+    last_block_send<2>(A, MSG_RZRR, tag, slots);
 }
 
-// convergence test at the end of a chunk of iterations (the SpMV of the next iteration would do it otherwise)
-__global__ void __launch_bounds__(RB) pcg_fused_check(const PcgArgs a, int kiter) {
+__global__ void __launch_bounds__(RB) pcg3_dir(const Pcg3Args A, int64_t N, int kiter) {
+    const PcgArgs& a = A.a;
     if (*reinterpret_cast<volatile int32_t*>(a.flags + FLAG_DONE)) return;
-    const double rr = get_sum(a, P_RR), bb = a.scal[S_BNORM2];
+    const unsigned long long tag = A.sync->base_iter + kiter + 1;
+    double v[2];
+    wait_message<2>(A, MSG_RZRR, tag, v);
+    const double rz_new = v[0], rr = v[1], rz_old = a.scal[S_RZ], bb = a.scal[S_BNORM2];
+    const bool conv = rr <= a.rtol * a.rtol * bb;
+    // S_RZ is read by every block of this kernel before the LAST block overwrites it (see below)
+    const double beta = rz_new / rz_old;
+    if (!conv)
+        for (int64_t row = int64_t(blockIdx.x) * RB + threadIdx.x; row < N; row += int64_t(gridDim.x) * RB)
+            a.p[row] = fma(beta, a.p[row], a.dinv[row] * a.r[row]);
+    // last block: publish rz for the next iteration, the convergence state, and "p ready" to the neighbours
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(&A.sync->ticket[MSG_PREADY], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
     if (threadIdx.x == 0) {
+        a.scal[S_RZ] = rz_new;
         a.scal[S_RELRES] = sqrt(rr / bb);
-        a.flags[FLAG_ITERS] = kiter;
-        if (rr <= a.rtol * a.rtol * bb) a.flags[FLAG_DONE] = 1;
+        a.flags[FLAG_ITERS] = kiter + 1;
+        if (conv) a.flags[FLAG_DONE] = 1;
+        A.sync->ticket[MSG_PREADY] = 0;
+    }
+    if (!conv && A.nranks > 1 && threadIdx.x < A.nranks) {
+        volatile double* dst = mail_slot(A.peer_mail[threadIdx.x], MSG_PREADY, int((tag + 1) & 1ull), A.nranks, A.rank);
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(dst) = tag + 1;
     }
 }
 
-template <int NT> static hdg_status pcg_fused_t(hdg_context* c, double rtol, int maxit, hdg_solve_info* info) {
+template <int NT>
+__global__ void __launch_bounds__(RB) pcg3_init(const PcgArgs a) {
+    // r = D b ; dinv = 1/diag(D K) ; p = z = dinv r ; x = 0 ; partials of r.z and b.b
+    constexpr int NT2 = NT * NT;
+    const int64_t N = a.nface * NT;
+    double rz = 0.0, bb = 0.0;
+    for (int64_t row = int64_t(blockIdx.x) * RB + threadIdx.x; row < N; row += int64_t(gridDim.x) * RB) {
+        int64_t f = row / NT;
+        int aa = int(row - f * NT);
+        double sgn = a.isbc[f] ? 1.0 : -1.0;
+        double di = 1.0 / (sgn * a.Kd[f * NT2 + aa * NT + aa]);
+        double r = sgn * a.rhs[row];
+        double z = di * r;
+        a.dinv[row] = di;
+        a.r[row] = r;
+        a.p[row] = z;
+        a.x[row] = 0.0;
+        rz += r * z;
+        bb += r * r;
+    }
+    double t1 = block_sum(rz), t2 = block_sum(bb);
+    if (threadIdx.x == 0) {
+        a.part[P_RZ0 * MAX_PARTIALS + blockIdx.x] = t1;
+        a.part[P_BB * MAX_PARTIALS + blockIdx.x] = t2;
+        a.part[P_PAP * MAX_PARTIALS + blockIdx.x] = 0.0;
+        a.part[P_RZ1 * MAX_PARTIALS + blockIdx.x] = 0.0;
+        a.part[P_RR * MAX_PARTIALS + blockIdx.x] = 0.0;
+    }
+}
+
+// after the (all-reduced) sums of pcg3_init are available: scalars, flags, and the "p ready" tags of iteration 0
+// (the all-reduce that precedes this kernel already is a barrier over all ranks)
+__global__ void pcg3_init_final(const Pcg3Args A) {
+    const PcgArgs& a = A.a;
+    const double bb = get_sum(a, P_BB), rz = get_sum(a, P_RZ0);
+    if (threadIdx.x == 0) {
+        a.scal[S_BNORM2] = bb;
+        a.scal[S_RZ] = rz;
+        a.scal[S_RELRES] = bb > 0.0 ? 1.0 : 0.0;
+        a.flags[FLAG_DONE] = bb > 0.0 ? 0 : 1;   // b == 0 -> x = 0 is the solution
+        a.flags[FLAG_ITERS] = 0;
+        for (int m = 0; m < NMSG; ++m) A.sync->ticket[m] = 0;
+    }
+    if (threadIdx.x < A.nranks) {
+        const unsigned long long tag = A.sync->base_iter + 1;
+        *reinterpret_cast<volatile unsigned long long*>(mail_slot(A.my_mail, MSG_PREADY, int(tag & 1ull), A.nranks, threadIdx.x)) = tag;
+    }
+}
+
+// end of a chunk of `n` iterations: advance the absolute iteration index (skip ahead after convergence so that no
+// message tag is ever reused by a later solve)
+__global__ void pcg3_advance(const Pcg3Args A, int n) {
+    if (threadIdx.x == 0) A.sync->base_iter += A.a.flags[FLAG_DONE] ? n + 8 : n;
+}
+
+template <int NT> static hdg_status pcg3_t(hdg_context* c, double rtol, int maxit, hdg_solve_info* info) {
     const int64_t N = c->nface_own * NT, Nloc = c->nface * NT;
     const bool multi = comm_active(c);
+    const int nranks = multi ? c->comm->nranks : 1, rank = multi ? c->comm->rank : 0;
     if (!c->d_x) HDG_CUDA(c, cudaMalloc(&c->d_x, sizeof(double) * Nloc));
     if (!c->d_Ap) HDG_CUDA(c, cudaMalloc(&c->d_Ap, sizeof(double) * Nloc));
     if (!c->d_vreg) {
-        HDG_CUDA(c, cudaMalloc(&c->d_vreg, sizeof(double) * 4 * N));
+        HDG_CUDA(c, cudaMalloc(&c->d_vreg, sizeof(double) * 3 * N));
         if (multi) {
             hdg_status st = comm_share_vectors(c, c->d_vreg, N);
             if (st) return st;
         }
     }
+    if (!c->d_pcg_sync) {
+        HDG_CUDA(c, cudaMalloc(&c->d_pcg_sync, sizeof(Pcg3Sync)));
+        HDG_CUDA(c, cudaMemset(c->d_pcg_sync, 0, sizeof(Pcg3Sync)));
+    }
+    double* my_mail = nullptr;
+    double* const* peer_mail = nullptr;
+    if (multi) {
+        my_mail = c->comm->d_mail + 2 * nranks * MAILW;             // behind the xgpu_allreduce mailbox
+        peer_mail = c->comm->d_peer_mail + nranks;                  // second row: pointers to the PCG mailboxes
+    } else {
+        if (!c->d_pcg_mail) {
+            HDG_CUDA(c, cudaMalloc(&c->d_pcg_mail, sizeof(double) * NMSG * 2 * MAILW + sizeof(double*)));
+            HDG_CUDA(c, cudaMemset(c->d_pcg_mail, 0, sizeof(double) * NMSG * 2 * MAILW));
+            double* self = c->d_pcg_mail;
+            HDG_CUDA(c, cudaMemcpy(c->d_pcg_mail + NMSG * 2 * MAILW, &self, sizeof(double*), cudaMemcpyHostToDevice));
+        }
+        my_mail = c->d_pcg_mail;
+        peer_mail = reinterpret_cast<double* const*>(c->d_pcg_mail + NMSG * 2 * MAILW);
+    }
     if (multi) HDG_CUDA(c, cudaMemsetAsync(c->d_x, 0, sizeof(double) * Nloc, c->stream));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    PcgArgs a{};
+    Pcg3Args A{};
+    PcgArgs& a = A.a;
     a.Kd = c->d_Kd; a.Ko = c->d_Ko; a.kcol = c->d_kcol; a.isbc = c->d_isbc; a.rhs = c->d_rhs;
-    a.x = c->d_x; a.r = c->d_vreg; a.dinv = c->d_vreg + N; a.pbuf[0] = c->d_vreg + 2 * N; a.pbuf[1] = c->d_vreg + 3 * N;
-    a.p = nullptr; a.Ap = c->d_Ap;
+    a.x = c->d_x; a.r = c->d_vreg; a.dinv = c->d_vreg + N; a.p = c->d_vreg + 2 * N; a.Ap = c->d_Ap;
     a.part = c->d_partials; a.scal = c->d_scal; a.flags = c->d_flags; a.nface = c->nface_own;
     a.gscal = multi ? c->comm->d_gscal : nullptr;
+    a.np = int(std::min<int64_t>(ceil_div(c->nface_own, RB), std::min<int64_t>(int64_t(sms) * 8, MAX_PARTIALS)));
+    a.rtol = rtol;
+    A.sync = static_cast<Pcg3Sync*>(c->d_pcg_sync);
+    A.my_mail = my_mail; A.peer_mail = peer_mail; A.rank = rank; A.nranks = nranks;
     if (multi) {
         for (int w = 0; w < 2; ++w) {
             const double* base = static_cast<const double*>(c->comm->peer_vec[w]);
-            const int64_t Np = c->comm->peer_ndof[w];
-            a.peer[w].r = base; a.peer[w].dinv = base ? base + Np : nullptr;
-            a.peer[w].p[0] = base ? base + 2 * Np : nullptr; a.peer[w].p[1] = base ? base + 3 * Np : nullptr;
+            A.peer_p[w] = base ? base + 2 * c->comm->peer_ndof[w] : nullptr;
         }
         a.ghost_ridx = c->comm->d_ghost_ridx;
         a.nbelow = c->comm->nbelow;
     }
-    a.np = int(std::min<int64_t>(ceil_div(c->nface_own, RB), std::min<int64_t>(int64_t(sms) * 8, MAX_PARTIALS)));
-    a.rtol = rtol;
     const int G = a.np;
     hdg_status cst = HDG_OK;
-    auto sums = [&]() {   // several GPUs: partial arrays -> sums over all ranks (also the inter-GPU barrier)
-        if (!multi) return;
-        hdg_status s2 = comm_p2p_allreduce(c, c->d_partials, G, NPART);
-        if (s2) cst = s2;
-    };
     timer_start(c, c->t_solve);
     HDG_CUDA(c, cudaMemsetAsync(c->d_flags, 0, sizeof(int32_t) * NFLAGS, c->stream));
-    pcg_fused_init<NT><<<G, RB, 0, c->stream>>>(a);
-    sums();
-    pcg_init_final<<<1, RB, 0, c->stream>>>(a);
+    pcg3_init<NT><<<G, RB, 0, c->stream>>>(a);
+    if (multi) {   // sums of b.b and r.z over all ranks; also the barrier before the first peer read of p
+        hdg_status s2 = comm_p2p_allreduce(c, c->d_partials, G, NPART);
+        if (s2) cst = s2;
+    }
+    pcg3_init_final<<<1, RB, 0, c->stream>>>(A);
     c->launches += 2;
-    const int CHUNK = 32;   // even: the double-buffer parity restarts at 0 in every chunk
+    const int CHUNK = 32;
     const bool use_graph = getenv("HDG_NO_GRAPH") == nullptr;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
     auto enqueue_chunk = [&](int n) {
         for (int k = 0; k < n; ++k) {
-            pcg_fused_spmv<NT><<<G, RB, 0, c->stream>>>(a, k & 1, k);
-            sums();
-            pcg_fused_update<<<G, RB, 0, c->stream>>>(a, N, k & 1);
-            sums();
+            pcg3_spmv<NT><<<G, RB, 0, c->stream>>>(A, k);
+            pcg3_update<<<G, RB, 0, c->stream>>>(A, N, k);
+            pcg3_dir<<<G, RB, 0, c->stream>>>(A, N, k);
         }
-        pcg_fused_check<<<1, RB, 0, c->stream>>>(a, n);
+        pcg3_advance<<<1, 32, 0, c->stream>>>(A, n);
     };
     int it = 0;
     bool done = false;
@@ -676,7 +803,7 @@ template <int NT> static hdg_status pcg_fused_t(hdg_context* c, double rtol, int
         } else {
             enqueue_chunk(chunk);
         }
-        c->launches += 2 * chunk + 1;
+        c->launches += 3 * chunk + 1;
         HDG_CUDA(c, cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int32_t) * NFLAGS, cudaMemcpyDeviceToHost, c->stream));
         HDG_CUDA(c, cudaStreamSynchronize(c->stream));
         done = c->h_flags[FLAG_DONE] != 0;
@@ -705,14 +832,14 @@ template <int NT> static hdg_status pcg_fused_t(hdg_context* c, double rtol, int
 }
 
 hdg_status pcg_solve(hdg_context* c, double rtol, int maxit, hdg_solve_info* info) {
-    // fused 2-kernel PCG on one GPU and, over peer memory, on several; the 3-kernel NCCL variant is the
+    // mailbox PCG on one GPU and, over peer memory, on several; the NCCL variant is the
     // fallback when the GPUs cannot map each other's memory (or HDG_PCG_LEGACY is set)
     const bool fused = getenv("HDG_PCG_LEGACY") == nullptr && (!comm_active(c) || comm_p2p(c));
     if (fused) switch (c->tab.nt) {
-        case 2: return pcg_fused_t<2>(c, rtol, maxit, info);
-        case 3: return pcg_fused_t<3>(c, rtol, maxit, info);
-        case 4: return pcg_fused_t<4>(c, rtol, maxit, info);
-        case 5: return pcg_fused_t<5>(c, rtol, maxit, info);
+        case 2: return pcg3_t<2>(c, rtol, maxit, info);
+        case 3: return pcg3_t<3>(c, rtol, maxit, info);
+        case 4: return pcg3_t<4>(c, rtol, maxit, info);
+        case 5: return pcg3_t<5>(c, rtol, maxit, info);
     }
     switch (c->tab.nt) {
         case 2: return pcg_t<2>(c, rtol, maxit, info);
