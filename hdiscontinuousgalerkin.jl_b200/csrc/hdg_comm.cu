@@ -361,6 +361,45 @@ hdg_status hdg_comm_init(hdg_context* c, int32_t rank, int32_t nranks, const uin
     return HDG_OK;
 }
 
+// Debug / measurement: round-trip latency of the mailbox exchange between all ranks (iters exchanges in ONE kernel).
+__global__ void pingpong_kernel(double* const* peer_mail, double* my_mail, int rank, int nranks, int iters, unsigned long long tag0) {
+    for (int it = 0; it < iters; ++it) {
+        unsigned long long tag = tag0 + it + 1;
+        int buf = int(tag & 1ull);
+        if (threadIdx.x < nranks) {
+            volatile double* dst = peer_mail[threadIdx.x] + size_t(buf * nranks + rank) * MAILW;
+            dst[1] = double(it);
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long*>(dst) = tag;
+            volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(my_mail + size_t(buf * nranks + threadIdx.x) * MAILW);
+            while (*flag != tag) { }
+        }
+        __syncthreads();
+    }
+}
+
+hdg_status hdg_comm_pingpong(hdg_context* c, int32_t iters, double* usec_per_exchange) {
+    if (!c || !usec_per_exchange) return HDG_ERR_INVALID;
+    if (!comm_p2p(c)) return set_err(c, HDG_ERR_INVALID, "peer-memory path not active");
+    Comm* m = c->comm;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    // tags far above anything xgpu_allreduce uses in this mailbox
+    static unsigned long long tag0 = 1ull << 40;
+    pingpong_kernel<<<1, 32, 0, c->stream>>>(m->d_peer_mail, m->d_mail, m->rank, m->nranks, 8, tag0);
+    tag0 += 1024;
+    cudaEventRecord(a, c->stream);
+    pingpong_kernel<<<1, 32, 0, c->stream>>>(m->d_peer_mail, m->d_mail, m->rank, m->nranks, iters, tag0);
+    cudaEventRecord(b, c->stream);
+    tag0 += (unsigned long long)iters + 1024;
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *usec_per_exchange = 1e3 * ms / iters;
+    return HDG_OK;
+}
+
 hdg_status hdg_get_partition(const hdg_context* c, int64_t out[8]) {
     if (!c || !out) return HDG_ERR_INVALID;
     if (!c->have_mesh) return set_err(const_cast<hdg_context*>(c), HDG_ERR_INVALID, "no mesh");

@@ -474,6 +474,7 @@ enum Msg : int { MSG_PAP = 0, MSG_RZRR = 1, MSG_PREADY = 2, NMSG = 3 };
 
 struct Pcg3Sync {
     unsigned long long base_iter;   // absolute index of iteration 0 of the current chunk (message tags = index + 1)
+    double val[NMSG][2];            // the reduced (all ranks) values of the latest message of each kind
     unsigned int ticket[NMSG];
 };
 
@@ -507,7 +508,11 @@ __device__ __forceinline__ void last_block_send(const Pcg3Args& A, int msg, unsi
         for (int i = threadIdx.x; i < A.a.np; i += RB) s += __ldcg(A.a.part + slots[v] * MAX_PARTIALS + i);
         vals[v] = block_sum(s);
     }
-    if (threadIdx.x < A.nranks) {
+    if (A.nranks == 1) {
+        if (threadIdx.x == 0)
+#pragma unroll
+            for (int v = 0; v < NV; ++v) A.sync->val[msg][v] = vals[v];
+    } else if (threadIdx.x < A.nranks) {
         volatile double* dst = mail_slot(A.peer_mail[threadIdx.x], msg, int(tag & 1ull), A.nranks, A.rank);
 #pragma unroll
         for (int v = 0; v < NV; ++v) dst[1 + v] = vals[v];
@@ -517,27 +522,25 @@ __device__ __forceinline__ void last_block_send(const Pcg3Args& A, int msg, unsi
     if (threadIdx.x == 0) A.sync->ticket[msg] = 0;
 }
 
-// every block: wait until all ranks posted message `msg` with this tag, then add the values in rank order
-template <int NV>
-__device__ __forceinline__ void wait_message(const Pcg3Args& A, int msg, unsigned long long tag, double (&out)[NV == 0 ? 1 : NV]) {
-    __shared__ double sh[4];
+// Several GPUs: a one-warp kernel between producer and consumer waits (stream-ordered) until every rank has
+// posted message `msg` of this iteration and adds the contributions in rank order -> sync->val.  Keeping the
+// polling out of the big kernels avoids thousands of pollers hammering the L2 line the remote store targets.
+__global__ void pcg3_wait(const Pcg3Args A, int msg, int nv, int kiter, int tag_offset) {
+    if (*reinterpret_cast<volatile int32_t*>(A.a.flags + FLAG_DONE)) return;
+    const unsigned long long tag = A.sync->base_iter + kiter + 1 + tag_offset;
     const int buf = int(tag & 1ull);
     if (threadIdx.x < A.nranks) {
         volatile unsigned long long* flag =
             reinterpret_cast<volatile unsigned long long*>(mail_slot(A.my_mail, msg, buf, A.nranks, threadIdx.x));
         while (*flag != tag) { }
     }
-    __syncthreads();
-    if (threadIdx.x < NV) {
+    __syncwarp();
+    if (threadIdx.x < nv) {
         double s = 0.0;
         for (int q = 0; q < A.nranks; ++q)
             s += reinterpret_cast<volatile double*>(mail_slot(A.my_mail, msg, buf, A.nranks, q))[1 + threadIdx.x];
-        sh[threadIdx.x] = s;
+        A.sync->val[msg][threadIdx.x] = s;
     }
-    __syncthreads();
-#pragma unroll
-    for (int v = 0; v < NV; ++v) out[v] = sh[v];
-    __syncthreads();
 }
 
 template <int NT>
@@ -546,10 +549,6 @@ __global__ void __launch_bounds__(RB) pcg3_spmv(const Pcg3Args A, int kiter) {
     if (*reinterpret_cast<volatile int32_t*>(a.flags + FLAG_DONE)) return;
     constexpr int NT2 = NT * NT;
     const unsigned long long tag = A.sync->base_iter + kiter + 1;
-    if (A.nranks > 1) {   // the neighbours' p of this iteration must be complete before it is read
-        double none[1];
-        wait_message<0>(A, MSG_PREADY, tag, none);
-    }
     double pap = 0.0;
     for (int64_t f = int64_t(blockIdx.x) * RB + threadIdx.x; f < a.nface; f += int64_t(gridDim.x) * RB) {
         double y[NT], pf[NT], blk[NT2];
@@ -600,10 +599,8 @@ __global__ void __launch_bounds__(RB) pcg3_update(const Pcg3Args A, int64_t N, i
     const PcgArgs& a = A.a;
     if (*reinterpret_cast<volatile int32_t*>(a.flags + FLAG_DONE)) return;
     const unsigned long long tag = A.sync->base_iter + kiter + 1;
-    double pap[1];
-    wait_message<1>(A, MSG_PAP, tag, pap);
     const double rz = a.scal[S_RZ];
-    const double alpha = rz / pap[0];
+    const double alpha = rz / A.sync->val[MSG_PAP][0];
     double rz_new = 0.0, rr = 0.0;
     for (int64_t row = int64_t(blockIdx.x) * RB + threadIdx.x; row < N; row += int64_t(gridDim.x) * RB) {
         double r = a.r[row];
@@ -626,9 +623,7 @@ __global__ void __launch_bounds__(RB) pcg3_dir(const Pcg3Args A, int64_t N, int 
     const PcgArgs& a = A.a;
     if (*reinterpret_cast<volatile int32_t*>(a.flags + FLAG_DONE)) return;
     const unsigned long long tag = A.sync->base_iter + kiter + 1;
-    double v[2];
-    wait_message<2>(A, MSG_RZRR, tag, v);
-    const double rz_new = v[0], rr = v[1], rz_old = a.scal[S_RZ], bb = a.scal[S_BNORM2];
+    const double rz_new = A.sync->val[MSG_RZRR][0], rr = A.sync->val[MSG_RZRR][1], rz_old = a.scal[S_RZ], bb = a.scal[S_BNORM2];
     const bool conv = rr <= a.rtol * a.rtol * bb;
     // S_RZ is read by every block of this kernel before the LAST block overwrites it (see below)
     const double beta = rz_new / rz_old;
@@ -711,6 +706,16 @@ __global__ void pcg3_advance(const Pcg3Args A, int n) {
     if (threadIdx.x == 0) A.sync->base_iter += A.a.flags[FLAG_DONE] ? n + 8 : n;
 }
 
+// after convergence: ghost entries of x (the faces below the strip, read by the recovery) from the owners' memory
+__global__ void pcg3_fetch_ghost_x(const Pcg3Args A, int64_t nghost, int nt, double* __restrict__ x) {
+    int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (k >= nghost * nt) return;
+    int64_t gi = k / nt;
+    int a = int(k - gi * nt);
+    const double* src = A.peer_p[gi < A.a.nbelow ? 0 : 1];
+    x[(A.a.nface + gi) * nt + a] = src[int64_t(A.a.ghost_ridx[gi]) * nt + a];
+}
+
 template <int NT> static hdg_status pcg3_t(hdg_context* c, double rtol, int maxit, hdg_solve_info* info) {
     const int64_t N = c->nface_own * NT, Nloc = c->nface * NT;
     const bool multi = comm_active(c);
@@ -780,10 +785,14 @@ template <int NT> static hdg_status pcg3_t(hdg_context* c, double rtol, int maxi
     const bool use_graph = getenv("HDG_NO_GRAPH") == nullptr;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
+    const bool waits = multi && getenv("HDG_DBG_NOWAIT") == nullptr;   // debug: free-running ranks (wrong numerics, timing only)
     auto enqueue_chunk = [&](int n) {
         for (int k = 0; k < n; ++k) {
+            if (waits) pcg3_wait<<<1, 32, 0, c->stream>>>(A, MSG_PREADY, 0, k, 0);   // neighbours' p complete
             pcg3_spmv<NT><<<G, RB, 0, c->stream>>>(A, k);
+            if (waits) pcg3_wait<<<1, 32, 0, c->stream>>>(A, MSG_PAP, 1, k, 0);
             pcg3_update<<<G, RB, 0, c->stream>>>(A, N, k);
+            if (waits) pcg3_wait<<<1, 32, 0, c->stream>>>(A, MSG_RZRR, 2, k, 0);
             pcg3_dir<<<G, RB, 0, c->stream>>>(A, N, k);
         }
         pcg3_advance<<<1, 32, 0, c->stream>>>(A, n);
@@ -809,8 +818,18 @@ template <int NT> static hdg_status pcg3_t(hdg_context* c, double rtol, int maxi
         done = c->h_flags[FLAG_DONE] != 0;
         it += done ? c->h_flags[FLAG_ITERS] : chunk;
     }
-    if (multi) {   // recovery reads the trace on the ghost faces below the strip
-        hdg_status s2 = comm_halo_exchange(c, c->d_x, NT);
+    if (multi) {
+        // recovery reads the trace on the ghost faces below the strip: publish x through the shared p slot,
+        // barrier, pull the ghost values over NVLink, barrier (p is rewritten by the next solve)
+        const int64_t nghost = c->nface - c->nface_own;
+        HDG_CUDA(c, cudaMemcpyAsync(a.p, c->d_x, sizeof(double) * N, cudaMemcpyDeviceToDevice, c->stream));
+        hdg_status s2 = comm_p2p_allreduce(c, c->d_partials, G, 0);
+        if (s2) cst = s2;
+        if (nghost > 0) {
+            pcg3_fetch_ghost_x<<<(unsigned)ceil_div(nghost * NT, 256), 256, 0, c->stream>>>(A, nghost, NT, c->d_x);
+            c->launches += 1;
+        }
+        s2 = comm_p2p_allreduce(c, c->d_partials, G, 0);
         if (s2) cst = s2;
     }
     timer_stop(c, c->t_solve);

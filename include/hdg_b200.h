@@ -180,6 +180,8 @@ hdg_status hdg_comm_init(hdg_context* ctx, int32_t rank, int32_t nranks, const u
  * ncell_global, nface_global, ghost cells held, ghost faces held}.  Cell and face ids are the reference's
  * global numbering minus one; trace dofs of face f are nt*f .. nt*f+nt-1. */
 hdg_status hdg_get_partition(const hdg_context* ctx, int64_t out[8]);
+/* Measurement helper: mean latency (microseconds) of one all-to-all mailbox exchange over peer memory. */
+hdg_status hdg_comm_pingpong(hdg_context* ctx, int32_t iters, double* usec_per_exchange);
 
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* Device time (ms, CUDA events on the context stream) of the kernels of the last call of the
