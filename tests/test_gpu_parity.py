@@ -145,6 +145,66 @@ def test_perturbed_mesh():
     _check_assembly(mo, 3, 6)
 
 
+def test_tau_not_one_both_paths():
+    # tau enters Ce, Fe (not He - the reference's He has no tau, examples/poisson2D_HDG.jl:149); oracle restates that
+    mo = orc.rectangle_mesh(3, 3)
+    for local_solver in (0, 1):
+        tab = orc.build_tables(2, 4)
+        asm = orc.doassemble(mo, tab, orc.source_poisson, 2.5)
+        mesh = host_mesh_from_oracle(mo)
+        Vh, Wh, Mh = _spaces(mesh, 2, 4)
+        K, b, K_e, b_e = hdg.doassemble(Vh, Wh, Mh, 2.5, hdg.poisson_source, local_solver=local_solver)
+        assert relerr(K.nzval(), asm.K.data) < RTOL and relerr(b.to_numpy(), asm.rhs) < RTOL
+        assert max(relerr(K_e[c], asm.K_e[c]) for c in range(mo.ncells)) < RTOL
+
+
+def test_nonzero_dirichlet_values_through_abi():
+    """apply! with prescribed values v != 0 (rhs lift f -= v K[:,d], f[d] = v m; src/boundary.jl:129-157)."""
+    mo = orc.rectangle_mesh(4, 3)
+    tab = orc.build_tables(2, 4)
+    asm = orc.doassemble(mo, tab)
+    dofs, _ = orc.dirichlet(mo, tab)
+    vals = np.cos(np.arange(dofs.size) * 0.37) + 0.1
+    Kb, rb, m = orc.apply_dirichlet(asm.K, asm.rhs, dofs, vals)
+    r = _assemble(mo, 2, 4)
+    ctx = r["K"]._ctx
+    hdg.check(ctx.lib.hdg_apply_dirichlet(ctx.h, hdg.api.f64p(np.ascontiguousarray(vals))), ctx.h)
+    assert relerr(r["K"].nzval(), Kb.data) < RTOL
+    assert relerr(r["b"].to_numpy(), rb) < RTOL
+    assert abs(hdg.meandiag(r["K"]) - m) < 1e-13 * m
+    uhat, info = hdg.solve(r["K"], r["b"], rtol=1e-14)
+    assert relerr(uhat.to_numpy(), orc.solve_direct(Kb, rb)) < RTOL
+
+
+def test_repeated_solve_and_reassembly_same_context():
+    mesh = hdg.rectangle_mesh(hdg.TriangleCell, (12, 9), (0.0, 0.0), (2.0, 1.0))
+    Vh, Wh, Mh = _spaces(mesh, 1, 2)
+    K, b, K_e, b_e = hdg.doassemble(Vh, Wh, Mh)
+    ctx = K._ctx
+    dbc = hdg.Dirichlet(hdg.TrialFunction(Mh), mesh, "boundary", lambda x: 0)
+    hdg.apply_(K, b, dbc)
+    x1, i1 = hdg.solve(K, b, rtol=1e-12)
+    x1 = x1.to_numpy()
+    x2, i2 = hdg.solve(K, b, rtol=1e-12)          # second solve on the same system: identical, bit for bit
+    assert i1["iterations"] == i2["iterations"] and np.array_equal(x1, x2.to_numpy())
+    hdg.check(ctx.lib.hdg_assemble(ctx.h), ctx.h)   # re-assembly resets the state machine
+    with pytest.raises(hdg.HDGError):
+        hdg.solve(K, b)                             # apply! must come first again
+    hdg.apply_(K, b, dbc)
+    x3, _ = hdg.solve(K, b, rtol=1e-12)
+    assert np.array_equal(x1, x3.to_numpy())
+
+
+def test_maxit_reports_not_converged():
+    mesh = hdg.rectangle_mesh(hdg.TriangleCell, (16, 16), (0.0, 0.0), (1.0, 1.0))
+    Vh, Wh, Mh = _spaces(mesh, 1, 2)
+    K, b, _, _ = hdg.doassemble(Vh, Wh, Mh)
+    hdg.apply_(K, b, hdg.Dirichlet(hdg.TrialFunction(Mh), mesh, "boundary", lambda x: 0))
+    for maxit in (5, 37):
+        with pytest.raises(hdg.NotConvergedError):
+            hdg.solve(K, b, rtol=1e-14, maxit=maxit)
+
+
 # ---------------------------------------------------------------------------------- full driver
 @pytest.mark.parametrize("order,qd,nx", [(1, 2, 10), (2, 4, 8), (2, 3, 6), (3, 6, 6), (4, 9, 4)])
 def test_full_driver_vs_oracle(order, qd, nx):
