@@ -325,6 +325,15 @@ def main():
                "recover_roofline": {"bound": "hbm", "achieved": RECOVER_BYTES[order] * ncell / (rec_ms * 1e-3) / 1e9, "peak": peak,
                                     "unit": "GB/s", "frac": RECOVER_BYTES[order] * ncell / (rec_ms * 1e-3) / 1e9 / peak},
                "err2": err2.value}
+        if order >= 2:   # block-Jacobi (nt x nt face blocks) on the same system
+            hdg.check(lib.hdg_set_preconditioner(ctx.h, 1), ctx.h)
+            info2 = hdg.api.SolveInfo()
+            st = lib.hdg_solve(ctx.h, args.rtol, args.maxit, C.byref(info2))
+            if st not in (0, 7):
+                hdg.check(st, ctx.h)
+            pcg["block_jacobi"] = {"iterations": info2.iterations, "converged": bool(info2.converged), "solve_s": info2.solve_ms * 1e-3,
+                                   "ms_per_iter": info2.solve_ms / max(info2.iterations, 1), "relres": info2.relres}
+            hdg.check(lib.hdg_set_preconditioner(ctx.h, 0), ctx.h)
 
     # ---------------- CPU baseline on the box's host cores (rank 0, N=1 only) ----------------
     cpu = None

@@ -90,6 +90,7 @@ SIGNATURES = {
     "hdg_assemble": (C.c_int, [_P]),
     "hdg_apply_dirichlet": (C.c_int, [_P, _F64P]),
     "hdg_solve": (C.c_int, [_P, C.c_double, C.c_int32, C.POINTER(SolveInfo)]),
+    "hdg_set_preconditioner": (C.c_int, [_P, C.c_int32]),
     "hdg_recover": (C.c_int, [_P]),
     "hdg_errornorm": (C.c_int, [_P, C.c_int32, _F64P]),
     "hdg_assemble_async": (C.c_int, [_P]),

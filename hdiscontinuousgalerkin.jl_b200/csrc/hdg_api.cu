@@ -275,6 +275,13 @@ hdg_status hdg_solve(hdg_context* c, double rtol, int32_t maxit, hdg_solve_info*
     return pcg_solve(c, rtol, maxit, info);
 }
 
+hdg_status hdg_set_preconditioner(hdg_context* c, int32_t id) {
+    if (!c) return HDG_ERR_INVALID;
+    if (id < 0 || id > 1) return set_err(c, HDG_ERR_INVALID, "unknown preconditioner id");
+    c->precond = id;
+    return HDG_OK;
+}
+
 hdg_status hdg_recover(hdg_context* c) {
     if (!c) return HDG_ERR_INVALID;
     if (!c->assembled || !c->d_x) return set_err(c, HDG_ERR_INVALID, "hdg_recover needs hdg_assemble and a trace solution (hdg_solve / hdg_set_trace)");

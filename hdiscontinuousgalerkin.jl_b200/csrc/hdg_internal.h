@@ -144,6 +144,8 @@ struct hdg_context {
     double *d_r = nullptr, *d_p = nullptr, *d_Ap = nullptr, *d_dinv = nullptr;   // legacy 3-kernel path
     double* d_vreg = nullptr;        // main PCG path: one region [r | dinv | p] (shared with the neighbours over CUDA IPC)
     void* d_pcg_sync = nullptr;      // iteration counter + last-block tickets
+    double* d_binv = nullptr;        // block-Jacobi: inverted face-diagonal blocks
+    int precond = 0;                 // 0 Jacobi, 1 block-Jacobi
     double* d_pcg_mail = nullptr;    // single-GPU mailbox of the PCG messages
     double* d_partials = nullptr;    // reduction partials
     double* d_scal = nullptr;        // device scalars

@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(RB) pcg3_update(const Pcg3Args A, int64_t N, i
     last_block_send<2>(A, MSG_RZRR, tag, slots);
 }
 
-__global__ void __launch_bounds__(RB) pcg3_dir(const Pcg3Args A, int64_t N, int kiter) {
+__global__ void __launch_bounds__(RB) pcg3_dir(const Pcg3Args A, int64_t N, int kiter, int z_in_ap) {
     const PcgArgs& a = A.a;
     if (*reinterpret_cast<volatile int32_t*>(a.flags + FLAG_DONE)) return;
     const unsigned long long tag = A.sync->base_iter + kiter + 1;
@@ -627,9 +627,14 @@ __global__ void __launch_bounds__(RB) pcg3_dir(const Pcg3Args A, int64_t N, int 
     const bool conv = rr <= a.rtol * a.rtol * bb;
     // S_RZ is read by every block of this kernel before the LAST block overwrites it (see below)
     const double beta = rz_new / rz_old;
-    if (!conv)
-        for (int64_t row = int64_t(blockIdx.x) * RB + threadIdx.x; row < N; row += int64_t(gridDim.x) * RB)
-            a.p[row] = fma(beta, a.p[row], a.dinv[row] * a.r[row]);
+    if (!conv) {
+        if (z_in_ap)   // block-Jacobi: z = M^-1 r was left in the Ap buffer by pcg3_update_blk
+            for (int64_t row = int64_t(blockIdx.x) * RB + threadIdx.x; row < N; row += int64_t(gridDim.x) * RB)
+                a.p[row] = fma(beta, a.p[row], a.Ap[row]);
+        else
+            for (int64_t row = int64_t(blockIdx.x) * RB + threadIdx.x; row < N; row += int64_t(gridDim.x) * RB)
+                a.p[row] = fma(beta, a.p[row], a.dinv[row] * a.r[row]);
+    }
     // last block: publish rz for the next iteration, the convergence state, and "p ready" to the neighbours
     __shared__ bool is_last;
     __threadfence();
@@ -679,6 +684,108 @@ __global__ void __launch_bounds__(RB) pcg3_init(const PcgArgs a) {
         a.part[P_RZ1 * MAX_PARTIALS + blockIdx.x] = 0.0;
         a.part[P_RR * MAX_PARTIALS + blockIdx.x] = 0.0;
     }
+}
+
+// ---- block-Jacobi variant: M = blockdiag(D K_ff), the nt x nt face-diagonal blocks --------------
+// The trace matrix is naturally blocked by face, so the preconditioner costs one nt x nt mat-vec per face; z is
+// kept in the Ap buffer (dead after the update) for the direction update.  Thread per face, vector loads.
+template <int NT> __device__ __forceinline__ void invert_block(double (&a)[NT * NT]) {
+    // in-place Gauss-Jordan without pivoting on a symmetric positive definite block (column-major)
+#pragma unroll
+    for (int k = 0; k < NT; ++k) {
+        const double ip = 1.0 / a[k * NT + k];
+        a[k * NT + k] = 1.0;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) a[j * NT + k] *= ip;            // row k
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            if (i == k) continue;
+            const double f = a[k * NT + i];
+            a[k * NT + i] = 0.0;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) a[j * NT + i] = fma(-f, a[j * NT + k], a[j * NT + i]);
+        }
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(RB) pcg3_init_blk(const PcgArgs a, double* __restrict__ binv) {
+    constexpr int NT2 = NT * NT;
+    double rz = 0.0, bb = 0.0;
+    for (int64_t f = int64_t(blockIdx.x) * RB + threadIdx.x; f < a.nface; f += int64_t(gridDim.x) * RB) {
+        double B[NT2], r[NT], z[NT], zero[NT];
+        load_vec<NT2>(a.Kd + f * NT2, B);
+        load_vec<NT>(a.rhs + f * NT, r);
+        const double sgn = a.isbc[f] ? 1.0 : -1.0;
+#pragma unroll
+        for (int e = 0; e < NT2; ++e) B[e] *= sgn;
+#pragma unroll
+        for (int e = 0; e < NT; ++e) { r[e] *= sgn; zero[e] = 0.0; }
+        invert_block<NT>(B);
+        store_vec<NT2>(binv + f * NT2, B);
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) s = fma(B[j * NT + i], r[j], s);
+            z[i] = s;
+            rz = fma(r[i], s, rz);
+            bb = fma(r[i], r[i], bb);
+        }
+        store_vec<NT>(a.r + f * NT, r);
+        store_vec<NT>(a.p + f * NT, z);
+        store_vec<NT>(a.x + f * NT, zero);
+    }
+    double t1 = block_sum(rz), t2 = block_sum(bb);
+    if (threadIdx.x == 0) {
+        a.part[P_RZ0 * MAX_PARTIALS + blockIdx.x] = t1;
+        a.part[P_BB * MAX_PARTIALS + blockIdx.x] = t2;
+        a.part[P_PAP * MAX_PARTIALS + blockIdx.x] = 0.0;
+        a.part[P_RZ1 * MAX_PARTIALS + blockIdx.x] = 0.0;
+        a.part[P_RR * MAX_PARTIALS + blockIdx.x] = 0.0;
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(RB) pcg3_update_blk(const Pcg3Args A, const double* __restrict__ binv, int kiter) {
+    const PcgArgs& a = A.a;
+    if (*reinterpret_cast<volatile int32_t*>(a.flags + FLAG_DONE)) return;
+    constexpr int NT2 = NT * NT;
+    const unsigned long long tag = A.sync->base_iter + kiter + 1;
+    const double alpha = a.scal[S_RZ] / A.sync->val[MSG_PAP][0];
+    double rz_new = 0.0, rr = 0.0;
+    for (int64_t f = int64_t(blockIdx.x) * RB + threadIdx.x; f < a.nface; f += int64_t(gridDim.x) * RB) {
+        double r[NT], p[NT], q[NT], x[NT], B[NT2];
+        load_vec<NT>(a.r + f * NT, r);
+        load_vec<NT>(a.p + f * NT, p);
+        load_vec<NT>(a.Ap + f * NT, q);
+        load_vec<NT>(a.x + f * NT, x);
+        load_vec<NT2>(binv + f * NT2, B);
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            x[i] = fma(alpha, p[i], x[i]);
+            r[i] = fma(-alpha, q[i], r[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) s = fma(B[j * NT + i], r[j], s);
+            q[i] = s;                                   // z = M^-1 r
+            rz_new = fma(r[i], s, rz_new);
+            rr = fma(r[i], r[i], rr);
+        }
+        store_vec<NT>(a.x + f * NT, x);
+        store_vec<NT>(a.r + f * NT, r);
+        store_vec<NT>(a.Ap + f * NT, q);                // Ap is dead now: keep z there for pcg3_dir_blk
+    }
+    double t1 = block_sum(rz_new), t2 = block_sum(rr);
+    if (threadIdx.x == 0) {
+        a.part[P_RZ0 * MAX_PARTIALS + blockIdx.x] = t1;
+        a.part[P_RR * MAX_PARTIALS + blockIdx.x] = t2;
+    }
+    const int slots[2] = {P_RZ0, P_RR};
+    last_block_send<2>(A, MSG_RZRR, tag, slots);
 }
 
 // after the (all-reduced) sums of pcg3_init are available: scalars, flags, and the "p ready" tags of iteration 0
@@ -774,7 +881,10 @@ template <int NT> static hdg_status pcg3_t(hdg_context* c, double rtol, int maxi
     hdg_status cst = HDG_OK;
     timer_start(c, c->t_solve);
     HDG_CUDA(c, cudaMemsetAsync(c->d_flags, 0, sizeof(int32_t) * NFLAGS, c->stream));
-    pcg3_init<NT><<<G, RB, 0, c->stream>>>(a);
+    const bool blockjac = c->precond == 1;
+    if (blockjac && !c->d_binv) HDG_CUDA(c, cudaMalloc(&c->d_binv, sizeof(double) * c->nface_own * NT * NT));
+    if (blockjac) pcg3_init_blk<NT><<<G, RB, 0, c->stream>>>(a, c->d_binv);
+    else pcg3_init<NT><<<G, RB, 0, c->stream>>>(a);
     if (multi) {   // sums of b.b and r.z over all ranks; also the barrier before the first peer read of p
         hdg_status s2 = comm_p2p_allreduce(c, c->d_partials, G, NPART);
         if (s2) cst = s2;
@@ -791,9 +901,10 @@ template <int NT> static hdg_status pcg3_t(hdg_context* c, double rtol, int maxi
             if (waits) pcg3_wait<<<1, 32, 0, c->stream>>>(A, MSG_PREADY, 0, k, 0);   // neighbours' p complete
             pcg3_spmv<NT><<<G, RB, 0, c->stream>>>(A, k);
             if (waits) pcg3_wait<<<1, 32, 0, c->stream>>>(A, MSG_PAP, 1, k, 0);
-            pcg3_update<<<G, RB, 0, c->stream>>>(A, N, k);
+            if (blockjac) pcg3_update_blk<NT><<<G, RB, 0, c->stream>>>(A, c->d_binv, k);
+            else pcg3_update<<<G, RB, 0, c->stream>>>(A, N, k);
             if (waits) pcg3_wait<<<1, 32, 0, c->stream>>>(A, MSG_RZRR, 2, k, 0);
-            pcg3_dir<<<G, RB, 0, c->stream>>>(A, N, k);
+            pcg3_dir<<<G, RB, 0, c->stream>>>(A, N, k, blockjac ? 1 : 0);
         }
         pcg3_advance<<<1, 32, 0, c->stream>>>(A, n);
     };

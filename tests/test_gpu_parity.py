@@ -195,6 +195,23 @@ def test_repeated_solve_and_reassembly_same_context():
     assert np.array_equal(x1, x3.to_numpy())
 
 
+@pytest.mark.parametrize("order,qd", [(1, 2), (2, 4), (3, 6), (4, 9)])
+def test_block_jacobi_preconditioner(order, qd):
+    nx = 10
+    ro = orc.run_poisson(orc.rectangle_mesh(nx, nx), order, qd)
+    mesh = hdg.rectangle_mesh(hdg.TriangleCell, (nx, nx), (0.0, 0.0), (1.0, 1.0))
+    Vh, Wh, Mh = _spaces(mesh, order, qd)
+    K, b, _, _ = hdg.doassemble(Vh, Wh, Mh)
+    hdg.apply_(K, b, hdg.Dirichlet(hdg.TrialFunction(Mh), mesh, "boundary", lambda x: 0))
+    xj, ij = hdg.solve(K, b, rtol=1e-14, precond="jacobi")
+    xb, ib = hdg.solve(K, b, rtol=1e-14, precond="block")
+    assert relerr(xj.to_numpy(), ro["uhat"]) < RTOL and relerr(xb.to_numpy(), ro["uhat"]) < RTOL
+    if order == 1:
+        assert ib["iterations"] == ij["iterations"]          # the 2x2 face blocks are diagonal
+    else:
+        assert ib["iterations"] < ij["iterations"]
+
+
 def test_maxit_reports_not_converged():
     mesh = hdg.rectangle_mesh(hdg.TriangleCell, (16, 16), (0.0, 0.0), (1.0, 1.0))
     Vh, Wh, Mh = _spaces(mesh, 1, 2)
