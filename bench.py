@@ -155,6 +155,7 @@ def main():
     ap.add_argument("--maxit", type=int, default=40000)
     ap.add_argument("--no-pcg", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-faces", action="store_true", help="also upload mesh.faces in the e2e step (it is rebuilt on the device otherwise)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
@@ -274,7 +275,7 @@ def main():
 
         def e2e_step():
             hdg.check(lib.hdg_set_mesh(ctx2.h, hdg.api.i64p(cells), ncell, hdg.api.f64p(nodes), nnode_s,
-                                       hdg.api.i64p(faces), nface_s, hdg.api.i64p(bfaces), nbf_s), ctx2.h)
+                                       hdg.api.i64p(faces) if args.e2e_faces else None, nface_s, hdg.api.i64p(bfaces), nbf_s), ctx2.h)
             hdg.check(lib.hdg_assemble(ctx2.h), ctx2.h)
             hdg.check(lib.hdg_get_rhs(ctx2.h, hdg.api.f64p(rhs_out)), ctx2.h)
 
@@ -291,10 +292,11 @@ def main():
             tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
-        h2d = cells.nbytes + nodes.nbytes + faces.nbytes + bfaces.nbytes
+        h2d = cells.nbytes + nodes.nbytes + (faces.nbytes if args.e2e_faces else 0) + bfaces.nbytes
         e2e = {"value": ncell * world / dt, "unit": "elements/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(rhs_out.nbytes), "ms_per_step": dt * 1e3, "steps": ke2e,
-               "what": "hdg_set_mesh(host Julia-layout arrays) + hdg_assemble + hdg_get_rhs(host)"}
+               "what": "hdg_set_mesh(pinned host arrays in the Julia layouts: cells, nodes, boundary set"
+                       + (", faces" if args.e2e_faces else "; mesh.faces is rebuilt on the device") + ") + hdg_assemble + hdg_get_rhs(host)"}
         ctx2.close()
 
     # ---------------- trace solve (Jacobi-PCG), recovery, error ----------------

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libhdg_b200.so")
+LIB_PATH = os.environ.get("HDG_B200_LIB", os.path.join(_HERE, "lib", "libhdg_b200.so"))   # override: kernel-variant experiments
 
 HDG_OK = 0
 STATUS_NAMES = {

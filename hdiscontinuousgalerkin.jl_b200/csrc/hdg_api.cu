@@ -134,7 +134,7 @@ void hdg_destroy(hdg_context* c) {
 hdg_status hdg_set_mesh(hdg_context* c, const int64_t* cells, int64_t ncell, const double* nodes, int64_t nnode,
                         const int64_t* faces, int64_t nface, const int64_t* bfaces, int64_t nbface) {
     if (!c) return HDG_ERR_INVALID;
-    if (!cells || !nodes || !faces || (nbface > 0 && !bfaces)) return set_err(c, HDG_ERR_INVALID, "null mesh array");
+    if (!cells || !nodes || (nbface > 0 && !bfaces)) return set_err(c, HDG_ERR_INVALID, "null mesh array");
     cudaSetDevice(c->device);
     return mesh_from_host(c, cells, ncell, nodes, nnode, faces, nface, bfaces, nbface);
 }

@@ -95,7 +95,11 @@ __device__ __forceinline__ void load_geometry(const ElemArgs& a, int64_t c, Cell
 __device__ __forceinline__ double source_value(int source_id, double x, double y) {
     // f of examples/poisson2D_HDG.jl:55
     const double pi = 3.141592653589793;
+#ifdef HDG_USE_SINPI
+    return 2.0 * (pi * pi) * sinpi(x) * sinpi(y);
+#else
     return 2.0 * (pi * pi) * sin(pi * x) * sin(pi * y);
+#endif
 }
 
 // strict lower triangle index
@@ -137,7 +141,10 @@ template <int K> struct SchurCfg {
     static constexpr int min_blocks = K == 1 ? MINB1 : (K == 2 ? MINB2 : 1);
     static constexpr bool stage_diag = K <= 3;      // face-diagonal blocks + rhs staged in shared memory (in-warp pairing)
     static constexpr bool l_smem = K >= 3;          // LDL' factor in shared memory (register pressure)
-    static constexpr bool stage_off = K == 1;       // off-diagonal blocks staged too -> one 256-bit store per block
+#ifndef K1_STAGE_OFF
+#define K1_STAGE_OFF 1
+#endif
+    static constexpr bool stage_off = K == 1 && K1_STAGE_OFF;       // off-diagonal blocks staged too -> one 256-bit store per block
     static constexpr int nL = Ord<K>::n * (Ord<K>::n - 1) / 2;
     static constexpr int smem_doubles = (l_smem ? nL : 0) + (stage_diag ? Stage<K>::n_base : 0) + (stage_off ? Stage<K>::n_off : 0);
 };

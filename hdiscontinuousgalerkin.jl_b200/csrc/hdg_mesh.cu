@@ -120,6 +120,43 @@ __global__ void convert_faces(const int64_t* __restrict__ faces, int64_t nface, 
     facecell[2 * f + 1] = int32_t(faces[f + 3 * nface] - 1);   // 0 -> -1 (no second cell)
 }
 
+// faces == NULL at the boundary: rebuild the face table from the cells alone.  A face's first cell is the one that
+// encountered it first in the reference's sequential numbering (src/generate_mesh.jl:20-46) = the adjacent cell
+// with the smaller id; (v1,v2) is that cell's local direction.
+__global__ void derive_facecell(const int64_t* __restrict__ cells, int64_t ncell, int32_t* __restrict__ facecell) {
+    int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int64_t f = cells[6 * c + 3 + k] - 1;
+        atomicMin(&facecell[2 * f + 0], int32_t(c));
+        atomicMax(&facecell[2 * f + 1], int32_t(c));
+    }
+}
+__global__ void init_facecell(int32_t* __restrict__ facecell, int64_t nface) {
+    int64_t f = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (f < nface) *reinterpret_cast<int2*>(facecell + 2 * f) = make_int2(0x7fffffff, -1);
+}
+__global__ void derive_facenode(const int64_t* __restrict__ cells, int64_t ncell, int32_t* __restrict__ facecell,
+                                int32_t* __restrict__ facenode) {
+    int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    const int k1[3] = {1, 2, 0}, k2[3] = {2, 0, 1};   // reference_edge_nodes ((2,3),(3,1),(1,2)), src/mesh.jl:26
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int64_t f = cells[6 * c + 3 + k] - 1;
+        if (facecell[2 * f] == int32_t(c)) {
+            facenode[2 * f + 0] = int32_t(cells[6 * c + k1[k]] - 1);
+            facenode[2 * f + 1] = int32_t(cells[6 * c + k2[k]] - 1);
+        }
+    }
+}
+__global__ void finish_facecell(int32_t* __restrict__ facecell, int64_t nface) {
+    int64_t f = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (f >= nface) return;
+    if (facecell[2 * f + 1] == facecell[2 * f]) facecell[2 * f + 1] = -1;   // one adjacent cell: boundary face
+}
+
 __global__ void convert_cells(const int64_t* __restrict__ cells, int64_t ncell, const int32_t* __restrict__ facecell,
                               int32_t* __restrict__ cellinfo) {
     int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -398,13 +435,21 @@ hdg_status mesh_from_host(hdg_context* c, const int64_t* cells, int64_t ncell, c
     hdg_status st = alloc_mesh(c);
     if (st) return st;
     if (!c->d_stage_cells) HDG_CUDA(c, cudaMalloc(&c->d_stage_cells, sizeof(int64_t) * 6 * ncell));
-    if (!c->d_stage_faces) HDG_CUDA(c, cudaMalloc(&c->d_stage_faces, sizeof(int64_t) * 4 * nface));
+    if (faces && !c->d_stage_faces) HDG_CUDA(c, cudaMalloc(&c->d_stage_faces, sizeof(int64_t) * 4 * nface));
     int64_t *d_cells = c->d_stage_cells, *d_faces = c->d_stage_faces;
     HDG_CUDA(c, cudaMemcpyAsync(d_cells, cells, sizeof(int64_t) * 6 * ncell, cudaMemcpyHostToDevice, c->stream));
-    HDG_CUDA(c, cudaMemcpyAsync(d_faces, faces, sizeof(int64_t) * 4 * nface, cudaMemcpyHostToDevice, c->stream));
+    if (faces) HDG_CUDA(c, cudaMemcpyAsync(d_faces, faces, sizeof(int64_t) * 4 * nface, cudaMemcpyHostToDevice, c->stream));
     HDG_CUDA(c, cudaMemcpyAsync(c->d_nodes, nodes, sizeof(double) * 2 * nnode, cudaMemcpyHostToDevice, c->stream));
     const int B = 256;
-    convert_faces<<<(unsigned)ceil_div(nface, B), B, 0, c->stream>>>(d_faces, nface, c->d_facecell, c->d_facenode);
+    if (faces) {
+        convert_faces<<<(unsigned)ceil_div(nface, B), B, 0, c->stream>>>(d_faces, nface, c->d_facecell, c->d_facenode);
+    } else {
+        init_facecell<<<(unsigned)ceil_div(nface, B), B, 0, c->stream>>>(c->d_facecell, nface);
+        derive_facecell<<<(unsigned)ceil_div(ncell, B), B, 0, c->stream>>>(d_cells, ncell, c->d_facecell);
+        derive_facenode<<<(unsigned)ceil_div(ncell, B), B, 0, c->stream>>>(d_cells, ncell, c->d_facecell, c->d_facenode);
+        finish_facecell<<<(unsigned)ceil_div(nface, B), B, 0, c->stream>>>(c->d_facecell, nface);
+        c->launches += 4;
+    }
     convert_cells<<<(unsigned)ceil_div(ncell, B), B, 0, c->stream>>>(d_cells, ncell, c->d_facecell, c->d_cellinfo);
     build_kcol<<<(unsigned)ceil_div(ncell, B), B, 0, c->stream>>>(c->d_cellinfo, ncell, c->d_kcol);
     build_partner<<<(unsigned)ceil_div(ncell, B), B, 0, c->stream>>>(c->d_cellinfo, ncell, c->d_facecell);

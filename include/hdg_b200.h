@@ -91,7 +91,10 @@ const char* hdg_version(void);
  * it out.  cells: ncell x 6 Int64 row-major (3 node ids, 3 face ids) == Vector{Cell{2,3,3}};
  * nodes: nnode x 2 doubles == Vector{Node{2,Float64}}; faces: COLUMN-major nface x 4 Int64
  * (v1 v2 cell1 cell2|0) == Matrix{Int}; bfaces: the Dirichlet face set (getfaceset(mesh,
- * "boundary"), any order, 1-based).  Replaces CellIterator/reinit! gathers (src/iterator.jl:48-57). */
+ * "boundary"), any order, 1-based).  Replaces CellIterator/reinit! gathers (src/iterator.jl:48-57).
+ * faces may be NULL: the face table is then rebuilt on the device from the cells (the first cell of a face is
+ * the adjacent cell with the smaller id, exactly what the first-encounter numbering produces), which saves
+ * the host-to-device copy of the largest array; nface must still be given. */
 hdg_status hdg_set_mesh(hdg_context* ctx,
                         const int64_t* cells, int64_t ncell,
                         const double* nodes, int64_t nnode,

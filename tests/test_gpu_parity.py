@@ -53,6 +53,23 @@ def test_reference_mesh_goldens_through_abi():
     assert m.getfaceset("boundary") == {3, 7, 9, 16, 2, 11, 12, 15}
 
 
+@pytest.mark.parametrize("root", ["figure2.1", "figure.1", None])
+def test_face_table_rebuilt_on_device_when_not_passed(root):
+    """hdg_set_mesh(faces = NULL): mesh.faces is reconstructed from the cells, bit for bit."""
+    mo = orc.parse_mesh_triangle(os.path.join(GOLDEN, root)) if root else orc.rectangle_mesh(9, 7)
+    cells = np.ascontiguousarray(np.hstack([mo.cells, mo.cell_faces]))
+    bf = mo.boundary_faces_sorted()
+    ctx = hdg._Context(1, 2)
+    hdg.check(ctx.lib.hdg_set_mesh(ctx.h, hdg.api.i64p(cells), mo.ncells, hdg.api.f64p(np.ascontiguousarray(mo.nodes)), mo.nnodes,
+                                   None, mo.nfaces, hdg.api.i64p(bf), bf.size), ctx.h)
+    m = ctx.download_mesh()
+    assert np.array_equal(m.faces, mo.faces) and np.array_equal(m.cells, cells)
+    hdg.check(ctx.lib.hdg_assemble(ctx.h), ctx.h)
+    asm = orc.doassemble(mo, orc.build_tables(1, 2))
+    assert relerr(hdg.TraceMatrix(ctx).nzval(), asm.K.data) < RTOL
+    ctx.close()
+
+
 @pytest.mark.parametrize("order", [1, 2, 3])
 def test_pattern_bit_exact(order):
     mo = orc.rectangle_mesh(5, 4)
