@@ -154,7 +154,9 @@ def main():
     ap.add_argument("--rtol", type=float, default=1e-12)
     ap.add_argument("--maxit", type=int, default=40000)
     ap.add_argument("--no-pcg", action="store_true")
+    ap.add_argument("--ly", type=float, default=0.0, help="height of the global domain [0,2]x[0,ly] (default: number of GPUs)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--local-solver", type=int, default=0, help="1: literal quadrature + dense LU element kernel")
     ap.add_argument("--e2e-faces", action="store_true", help="also upload mesh.faces in the e2e step (it is rebuilt on the device otherwise)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -182,13 +184,14 @@ def main():
     W = max(args.warmup, 3)
     K = args.steps
 
-    ctx = hdg._Context(order, qd, 1.0, 1, local_rank)
+    ctx = hdg._Context(order, qd, 1.0, 1, local_rank, args.local_solver)
     lib = ctx.lib
     # weak scaling: ONE global mesh nx x (ny*world) on [0,2]x[0,world]; every rank owns a strip of ny quad
     # rows (+ a recomputed one-cell ghost layer); u_ex = sin(pi x) sin(pi y) still vanishes on the boundary
     if world > 1:
         ctx.comm_init(dist, device=torch.device("cuda", local_rank))
-    hdg.check(lib.hdg_set_rectangle_mesh(ctx.h, nx, ny * world, 0.0, 0.0, 2.0, float(world)), ctx.h)
+    ly = args.ly if args.ly > 0 else float(world)
+    hdg.check(lib.hdg_set_rectangle_mesh(ctx.h, nx, ny * world, 0.0, 0.0, 2.0, ly), ctx.h)
     if args.perturb > 0:
         hdg.check(lib.hdg_perturb_nodes(ctx.h, args.perturb, 12345), ctx.h)
     s = ctx.sizes()
@@ -271,7 +274,7 @@ def main():
         assert (sh.ncell, sh.nnode, sh.nface, sh.nbface) == (ncell, nodes.shape[0], faces.shape[1], bfaces.shape[0])
         hdg.check(lib.hdg_get_mesh(ctxh.h, hdg.api.i64p(cells), hdg.api.f64p(nodes), hdg.api.i64p(faces), hdg.api.i64p(bfaces)), ctxh.h)
         ctxh.close()
-        ctx2 = hdg._Context(order, qd, 1.0, 1, local_rank)
+        ctx2 = hdg._Context(order, qd, 1.0, 1, local_rank, args.local_solver)
 
         def e2e_step():
             hdg.check(lib.hdg_set_mesh(ctx2.h, hdg.api.i64p(cells), ncell, hdg.api.f64p(nodes), nnode_s,
@@ -357,7 +360,7 @@ def main():
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"C2: Poisson HDG k={order} quad_degree={qd} tau=1, rectangle_mesh {nx}x{ny} per GPU "
-                                   f"({ncell} elements, {int(s.ndof)} trace dofs per GPU) - global mesh {nx}x{ny*world} on [0,2]x[0,{world}]",
+                                   f"({ncell} elements, {int(s.ndof)} trace dofs per GPU) - global mesh {nx}x{ny*world} on [0,2]x[0,{ly:g}]",
                        "parallelism": f"strips of quad rows, {world} rank(s), NCCL halo + all-reduce in the PCG only",
                        "l2": f"inputs+outputs per step {ALG_BYTES[order]*ncell/1e6:.0f} MB > 126 MB L2 (no explicit flush needed)",
                        "perturb": args.perturb, "elements_per_gpu": ncell},

@@ -183,6 +183,13 @@ def test_end_to_end_error_bounds(fig21):
     r = orc.run_poisson(orc.rectangle_mesh(10, 10), 1)
     assert r["err2"] <= 0.00006                                               # examples/poisson2D_HDG.jl:218
     assert r["asm"].K.shape == (640, 640) and r["asm"].K.nnz == 6080
+    # regression values of the restatement recorded in SURVEY.md section 6 / BASELINE.md section 1
+    assert abs(r["meandiag"] - 9.485018480631883) < 1e-12
+    assert abs(np.abs(r["asm"].K).sum() - 15917.863160055884) < 1e-8
+    assert abs(r["asm"].rhs.sum() - (-7.999958742811353)) < 1e-11
+    assert abs(np.linalg.norm(r["uhat"]) - 8.658950189552586) < 1e-11
+    assert abs(r["uhat"][0] - 1.615527554721488e-02) < 1e-13
+    assert abs(r["err2"] - 5.364546646411725e-05) < 1e-15
     # the condensed matrix is symmetric negative semi-definite; apply! makes it indefinite
     K = r["asm"].K.toarray()
     assert np.abs(K - K.T).max() < 1e-13
