@@ -134,11 +134,23 @@ template <int K> struct Stage {
 #define MINB1 5
 #endif
 #ifndef MINB2
-#define MINB2 3
+#define MINB2 2
 #endif
 template <int K> struct SchurCfg {
     static constexpr int threads = K >= 4 ? 64 : 128;
     static constexpr int min_blocks = K == 1 ? MINB1 : (K == 2 ? MINB2 : 1);
+#ifndef CU1
+#define CU1 7
+#endif
+#ifndef CU2
+#define CU2 10
+#endif
+#ifndef CU3
+#define CU3 1
+#endif
+    // unroll factor of the column loop: fully unrolled for k=1 (column-dependent selects and indexed constant
+    // loads disappear: measured 0.170 -> 0.153 ms per 1M elements)
+    static constexpr int col_unroll = K == 1 ? CU1 : (K == 2 ? CU2 : (K == 3 ? CU3 : 1));
     static constexpr bool stage_diag = K <= 3;      // face-diagonal blocks + rhs staged in shared memory (in-warp pairing)
     static constexpr bool l_smem = K >= 3;          // LDL' factor in shared memory (register pressure)
 #ifndef K1_STAGE_OFF
@@ -257,7 +269,8 @@ __global__ void __launch_bounds__(SchurCfg<K>::threads, SchurCfg<K>::min_blocks)
         constexpr int64_t nt2 = nt * nt;
 
         // ---- one column of [K_e | b_e] at a time ------------------------------------------------
-#pragma unroll 1
+        constexpr int col_unroll = SchurCfg<K>::col_unroll;
+#pragma unroll col_unroll
         for (int col = 0; col <= t; ++col) {
             const bool isb = col == t;
             const int l = isb ? 0 : col / nt;
