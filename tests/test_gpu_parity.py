@@ -153,6 +153,43 @@ def test_user_source_values():
     _check_assembly(mo, 2, 4, f=f, fo=f)
 
 
+@pytest.mark.parametrize("seed,order,qd", [(0, 1, 2), (1, 1, 2), (2, 2, 4), (3, 3, 6), (4, 4, 9), (5, 2, 3)])
+def test_randomly_permuted_unstructured_mesh(seed, order, qd):
+    """Cells in random order (first-encounter face numbering redone by the host mirror), jittered nodes, random
+    rotation of each cell's vertex list: exercises every first/second, orientation and in-warp pairing combination."""
+    rng = np.random.default_rng(seed)
+    base = orc.rectangle_mesh(9, 8)
+    nodes = base.nodes.copy()
+    interior = np.ones(base.nnodes, bool)
+    interior[np.unique(base.faces[base.faces[:, 3] == 0, :2]) - 1] = False
+    nodes[interior] += rng.uniform(-0.025, 0.025, size=(interior.sum(), 2))
+    tri = base.cells[rng.permutation(base.ncells)]
+    rot = rng.integers(0, 3, size=tri.shape[0])
+    tri = np.stack([np.roll(t, -r) for t, r in zip(tri, rot)])            # still counter-clockwise
+    cells_o, cf_o, faces_o = orc._build_cells_sequential([tuple(t) for t in tri], nodes, base.nfaces)
+    cf, faces = hdg.number_faces(tri)
+    assert np.array_equal(cf, cf_o) and np.array_equal(faces, faces_o)
+    bnd = set((np.flatnonzero(faces[:, 3] == 0) + 1).tolist())
+    mo = orc.Mesh(cells_o, cf_o, nodes, faces_o, {"boundary": bnd})
+    r, asm, tab = _check_assembly(mo, order, qd)
+    # and the whole driver on the same mesh
+    ro = orc.run_poisson(mo, order, qd)
+    res = hdg.poisson2D_HDG(r["mesh"], order, qd, rtol=1e-14)
+    assert relerr(res["uhat"].to_numpy(), ro["uhat"]) < RTOL
+    assert relerr(res["u_h"].m_values, ro["u"]) < RTOL and relerr(res["sigma_h"].m_values, ro["sigma"]) < RTOL
+    # err2 ~ 1e-13 for k=4 is a sum of squares of differences at the 1e-7 level: 1e-16 perturbations of u move it by ~1e-8 relative
+    assert abs(res["err2"] - ro["err2"]) <= 1e-9 * ro["err2"] + 1e-20
+
+
+@pytest.mark.parametrize("nx,ny", [(1, 1), (1, 2), (33, 1)])
+def test_tiny_and_thin_meshes(nx, ny):
+    mo = orc.rectangle_mesh(nx, ny)
+    ro = orc.run_poisson(mo, 2, 4)
+    r = hdg.poisson2D_HDG(hdg.rectangle_mesh(hdg.TriangleCell, (nx, ny), (0.0, 0.0), (1.0, 1.0)), 2, 4, rtol=1e-14)
+    # every face of a 1x1 mesh but the diagonal is a Dirichlet face
+    assert relerr(r["uhat"].to_numpy(), ro["uhat"]) < RTOL and abs(r["err2"] - ro["err2"]) <= 1e-9 * ro["err2"] + 1e-20
+
+
 def test_perturbed_mesh():
     rng = np.random.default_rng(7)
     mo = orc.rectangle_mesh(6, 5)
