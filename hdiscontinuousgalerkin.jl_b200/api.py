@@ -197,6 +197,24 @@ def number_faces(tri_nodes):
     return cell_faces, faces
 
 
+def number_faces_gpu(tri_nodes, nodes):
+    """First-encounter face numbering on the device (hdg_number_faces): same result as `number_faces`, plus the
+    counter-clockwise fix of _check_node_data.  Returns (cells (ncell,6), faces (nface,4) F-order)."""
+    tri = np.ascontiguousarray(tri_nodes, dtype=np.int64)
+    xy = np.ascontiguousarray(nodes, dtype=np.float64)
+    ctx = _Context(order=1)
+    try:
+        nface = C.c_int64()
+        check(ctx.lib.hdg_number_faces(ctx.h, i64p(tri), tri.shape[0], f64p(xy), xy.shape[0], None, None, 0, C.byref(nface)), ctx.h)
+        cells = np.empty((tri.shape[0], 6), np.int64)
+        faces = np.empty((nface.value, 4), np.int64, order="F")
+        check(ctx.lib.hdg_number_faces(ctx.h, i64p(tri), tri.shape[0], f64p(xy), xy.shape[0], i64p(cells), i64p(faces),
+                                       nface.value, C.byref(nface)), ctx.h)
+    finally:
+        ctx.close()
+    return cells, faces
+
+
 def parse_mesh_triangle(root_file):
     """parse_mesh_triangle(root_file), src/triangle_mesh.jl:115-126 (.node/.edge/.ele reader)."""
     nodes = np.array([[float(r[1]), float(r[2])] for r in _triangle_rows(root_file + ".node")])

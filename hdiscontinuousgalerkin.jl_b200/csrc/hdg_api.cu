@@ -145,6 +145,14 @@ hdg_status hdg_set_rectangle_mesh(hdg_context* c, int64_t nx, int64_t ny, double
     return mesh_rectangle(c, nx, ny, llx, lly, urx, ury);
 }
 
+hdg_status hdg_number_faces(hdg_context* c, const int64_t* tri, int64_t ncell, const double* nodes, int64_t nnode,
+                            int64_t* cells_out, int64_t* faces_out, int64_t faces_capacity, int64_t* nface_out) {
+    if (!c || !tri || !nodes || !nface_out) return HDG_ERR_INVALID;
+    if (ncell < 1 || nnode < 3) return set_err(c, HDG_ERR_INVALID, "empty mesh");
+    cudaSetDevice(c->device);
+    return number_faces_host(c, tri, ncell, nodes, nnode, cells_out, faces_out, faces_capacity, nface_out);
+}
+
 hdg_status hdg_perturb_nodes(hdg_context* c, double fraction, uint64_t seed) {
     if (!c) return HDG_ERR_INVALID;
     cudaSetDevice(c->device);

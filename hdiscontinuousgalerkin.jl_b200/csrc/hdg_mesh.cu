@@ -366,6 +366,163 @@ __global__ void perturb_nodes_k(double* __restrict__ nodes, int64_t nnx, int64_t
 }
 
 // ------------------------------------------------------------------------------------------
+// First-encounter face numbering of an arbitrary triangle list on the device
+// (src/generate_mesh.jl:20-46 / src/triangle_mesh.jl:66-101 are a sequential hash-table insert).
+// Parallel equivalent: every (cell, local face) is an "encounter" at position p = 3*cell + local face.
+//   1. an open-addressing hash table maps the edge key (min node, max node) to the SMALLEST position that
+//      encounters it (atomicCAS on the key, atomicMin on the position);
+//   2. a position is a first encounter iff the table holds it; an exclusive scan of those flags ranks the first
+//      encounters in position order = the reference's face ids;
+//   3. every position looks its face up; the first encounter writes (v1, v2, cell, 0), the other one writes cell2.
+// ------------------------------------------------------------------------------------------
+struct EdgeTable {
+    unsigned long long* keys;   // 0 = empty (node ids are >= 1)
+    int* minpos;
+    unsigned long long mask;    // capacity - 1 (power of two)
+};
+__device__ __forceinline__ unsigned long long edge_hash(unsigned long long k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return k;
+}
+__device__ __forceinline__ void tri_nodes_ccw(const int64_t* __restrict__ tri, const double* __restrict__ nodes, int64_t c, int64_t v[3]) {
+    v[0] = tri[3 * c]; v[1] = tri[3 * c + 1]; v[2] = tri[3 * c + 2];
+    // _check_node_data, src/generate_mesh.jl:49-57: swap vertices 2 and 3 of a clockwise triangle
+    double ax = nodes[2 * (v[1] - 1)] - nodes[2 * (v[0] - 1)], ay = nodes[2 * (v[1] - 1) + 1] - nodes[2 * (v[0] - 1) + 1];
+    double bx = nodes[2 * (v[2] - 1)] - nodes[2 * (v[0] - 1)], by = nodes[2 * (v[2] - 1) + 1] - nodes[2 * (v[0] - 1) + 1];
+    if (__dsub_rn(__dmul_rn(ax, by), __dmul_rn(ay, bx)) < 0) { int64_t t = v[1]; v[1] = v[2]; v[2] = t; }
+}
+__device__ __forceinline__ unsigned long long edge_key(const int64_t v[3], int l, int64_t* v1, int64_t* v2) {
+    const int k1[3] = {1, 2, 0}, k2[3] = {2, 0, 1};
+    int64_t a = v[k1[l]], b = v[k2[l]];
+    if (v1) { *v1 = a; *v2 = b; }
+    int64_t lo = a < b ? a : b, hi = a < b ? b : a;
+    return (static_cast<unsigned long long>(lo) << 32) | static_cast<unsigned long long>(hi);
+}
+__global__ void edge_insert(const int64_t* __restrict__ tri, const double* __restrict__ nodes, int64_t ncell, EdgeTable T) {
+    int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (p >= 3 * ncell) return;
+    int64_t c = p / 3, v[3];
+    int l = int(p - 3 * c);
+    tri_nodes_ccw(tri, nodes, c, v);
+    unsigned long long key = edge_key(v, l, nullptr, nullptr);
+    unsigned long long h = edge_hash(key) & T.mask;
+    while (true) {
+        unsigned long long prev = atomicCAS(&T.keys[h], 0ull, key);
+        if (prev == 0ull || prev == key) { atomicMin(&T.minpos[h], int(p)); return; }
+        h = (h + 1) & T.mask;
+    }
+}
+__device__ __forceinline__ unsigned long long edge_find(const EdgeTable& T, unsigned long long key) {
+    unsigned long long h = edge_hash(key) & T.mask;
+    while (T.keys[h] != key) h = (h + 1) & T.mask;
+    return h;
+}
+__global__ void edge_flag_first(const int64_t* __restrict__ tri, const double* __restrict__ nodes, int64_t ncell, EdgeTable T,
+                                int32_t* __restrict__ flag) {
+    int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (p >= 3 * ncell) return;
+    int64_t c = p / 3, v[3];
+    tri_nodes_ccw(tri, nodes, c, v);
+    unsigned long long h = edge_find(T, edge_key(v, int(p - 3 * c), nullptr, nullptr));
+    flag[p] = T.minpos[h] == int(p) ? 1 : 0;
+}
+__global__ void edge_number(const int64_t* __restrict__ tri, const double* __restrict__ nodes, int64_t ncell, EdgeTable T,
+                            const int64_t* __restrict__ rank, int64_t nface, int64_t* __restrict__ cells_out,
+                            int64_t* __restrict__ faces_out, int32_t* __restrict__ err) {
+    int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (p >= 3 * ncell) return;
+    int64_t c = p / 3, v[3], v1, v2;
+    int l = int(p - 3 * c);
+    tri_nodes_ccw(tri, nodes, c, v);
+    unsigned long long h = edge_find(T, edge_key(v, l, &v1, &v2));
+    int first = T.minpos[h];
+    int64_t f = rank[first];
+    if (l == 0) { cells_out[6 * c] = v[0]; cells_out[6 * c + 1] = v[1]; cells_out[6 * c + 2] = v[2]; }
+    cells_out[6 * c + 3 + l] = f + 1;
+    if (first == int(p)) {            // column-major nface x 4: v1 v2 cell1 (cell2 stays 0 unless a second encounter writes it)
+        faces_out[f] = v1; faces_out[f + nface] = v2; faces_out[f + 2 * nface] = c + 1;
+    } else {
+        unsigned long long old = atomicExch(reinterpret_cast<unsigned long long*>(&faces_out[f + 3 * nface]), static_cast<unsigned long long>(c + 1));
+        if (old != 0ull) atomicExch(err, int32_t(f + 1));   // a third cell on one edge: non-manifold
+    }
+}
+
+// tri: ncell x 3 Int64 (1-based node ids, any orientation); outputs in the Julia layouts (cells ncell x 6, faces nface x 4
+// column-major).  *nface_out is the number of distinct edges.  Buffers are device pointers owned by the caller.
+static hdg_status number_faces_device(hdg_context* c, const int64_t* d_tri, const double* d_nodes, int64_t ncell,
+                                      int64_t* d_cells_out, int64_t* d_faces_out, int64_t* nface_out) {
+    if (3 * ncell >= (int64_t(1) << 31)) return set_err(c, HDG_ERR_INVALID, "mesh too large");
+    unsigned long long cap = 1;
+    while (cap < static_cast<unsigned long long>(6 * ncell)) cap <<= 1;   // load factor <= 1/2 even if every edge were distinct
+    EdgeTable T{};
+    T.mask = cap - 1;
+    int32_t* flag = nullptr;
+    int64_t *rank = nullptr, *d_tot = nullptr;
+    HDG_CUDA(c, cudaMalloc(&T.keys, sizeof(unsigned long long) * cap));
+    HDG_CUDA(c, cudaMalloc(&T.minpos, sizeof(int) * cap));
+    HDG_CUDA(c, cudaMalloc(&flag, sizeof(int32_t) * 3 * ncell));
+    HDG_CUDA(c, cudaMalloc(&rank, sizeof(int64_t) * 3 * ncell));
+    HDG_CUDA(c, cudaMalloc(&d_tot, sizeof(int64_t)));
+    HDG_CUDA(c, cudaMemsetAsync(T.keys, 0, sizeof(unsigned long long) * cap, c->stream));
+    HDG_CUDA(c, cudaMemsetAsync(T.minpos, 0x7f, sizeof(int) * cap, c->stream));
+    const int B = 256;
+    const unsigned G = (unsigned)ceil_div(3 * ncell, B);
+    edge_insert<<<G, B, 0, c->stream>>>(d_tri, d_nodes, ncell, T);
+    edge_flag_first<<<G, B, 0, c->stream>>>(d_tri, d_nodes, ncell, T, flag);
+    c->launches += 2;
+    hdg_status st = exclusive_scan(c, flag, 3 * ncell, rank, d_tot);
+    if (st) return st;
+    int64_t nface = 0;
+    HDG_CUDA(c, cudaMemcpy(&nface, d_tot, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    *nface_out = nface;
+    if (d_faces_out) {
+        HDG_CUDA(c, cudaMemsetAsync(d_faces_out, 0, sizeof(int64_t) * 4 * nface, c->stream));
+        HDG_CUDA(c, cudaMemsetAsync(c->d_flags, 0, sizeof(int32_t) * NFLAGS, c->stream));
+        edge_number<<<G, B, 0, c->stream>>>(d_tri, d_nodes, ncell, T, rank, nface, d_cells_out, d_faces_out, c->d_flags + FLAG_NOT_BOUNDARY);
+        c->launches += 1;
+        HDG_CUDA(c, cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int32_t) * NFLAGS, cudaMemcpyDeviceToHost, c->stream));
+        HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    cudaFree(T.keys); cudaFree(T.minpos); cudaFree(flag); cudaFree(rank); cudaFree(d_tot);
+    if (d_faces_out && c->h_flags[FLAG_NOT_BOUNDARY])
+        return set_err(c, HDG_ERR_INVALID, "non-manifold mesh: an edge is shared by more than two cells (face " +
+                                               std::to_string(c->h_flags[FLAG_NOT_BOUNDARY]) + ")");
+    return HDG_OK;
+}
+
+// C-ABI helper behind hdg_number_faces: host in / host out
+hdg_status number_faces_host(hdg_context* c, const int64_t* tri, int64_t ncell, const double* nodes, int64_t nnode,
+                             int64_t* cells_out, int64_t* faces_out, int64_t faces_capacity, int64_t* nface_out) {
+    int64_t *d_tri = nullptr, *d_cells = nullptr, *d_faces = nullptr;
+    double* d_nodes = nullptr;
+    HDG_CUDA(c, cudaMalloc(&d_tri, sizeof(int64_t) * 3 * ncell));
+    HDG_CUDA(c, cudaMalloc(&d_nodes, sizeof(double) * 2 * nnode));
+    HDG_CUDA(c, cudaMalloc(&d_cells, sizeof(int64_t) * 6 * ncell));
+    HDG_CUDA(c, cudaMalloc(&d_faces, sizeof(int64_t) * 4 * 3 * ncell));
+    HDG_CUDA(c, cudaMemcpyAsync(d_tri, tri, sizeof(int64_t) * 3 * ncell, cudaMemcpyHostToDevice, c->stream));
+    HDG_CUDA(c, cudaMemcpyAsync(d_nodes, nodes, sizeof(double) * 2 * nnode, cudaMemcpyHostToDevice, c->stream));
+    int64_t nface = 0;
+    hdg_status st = number_faces_device(c, d_tri, d_nodes, ncell, nullptr, nullptr, &nface);   // count first
+    if (st == HDG_OK) {
+        *nface_out = nface;
+        if (faces_out && cells_out) {
+            if (faces_capacity < nface) st = set_err(c, HDG_ERR_INVALID, "faces buffer too small");
+            else {
+                st = number_faces_device(c, d_tri, d_nodes, ncell, d_cells, d_faces, &nface);
+                if (st == HDG_OK) {
+                    HDG_CUDA(c, cudaMemcpyAsync(cells_out, d_cells, sizeof(int64_t) * 6 * ncell, cudaMemcpyDeviceToHost, c->stream));
+                    // device faces are column-major with leading dimension nface; so is the caller's (nface x 4)
+                    HDG_CUDA(c, cudaMemcpyAsync(faces_out, d_faces, sizeof(int64_t) * 4 * nface, cudaMemcpyDeviceToHost, c->stream));
+                    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+                }
+            }
+        }
+    }
+    cudaFree(d_tri); cudaFree(d_nodes); cudaFree(d_cells); cudaFree(d_faces);
+    return st;
+}
+
+// ------------------------------------------------------------------------------------------
 void free_mesh(hdg_context* c) {
     auto F = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     F(c->d_cellinfo); F(c->d_nodes); F(c->d_facecell); F(c->d_facenode); F(c->d_bfaces); F(c->d_isbc);

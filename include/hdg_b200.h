@@ -108,6 +108,15 @@ hdg_status hdg_set_mesh(hdg_context* ctx,
 hdg_status hdg_set_rectangle_mesh(hdg_context* ctx, int64_t nx, int64_t ny,
                                   double llx, double lly, double urx, double ury);
 
+/* First-encounter face numbering of an arbitrary triangle list on the device - the job of _build_cells
+ * (src/generate_mesh.jl:20-46) / parse_cells! (src/triangle_mesh.jl:48-108), which are sequential hash-table
+ * inserts in the reference.  tri: ncell x 3 Int64 node ids (1-based, either orientation: clockwise cells get
+ * vertices 2,3 swapped like _check_node_data, src/generate_mesh.jl:49-57).  Outputs in the Julia layouts:
+ * cells_out ncell x 6 (nodes, faces), faces_out nface x 4 column-major (v1 v2 cell1 cell2|0), bit-identical to the
+ * reference's numbering.  Call with cells_out = faces_out = NULL to obtain *nface_out first. */
+hdg_status hdg_number_faces(hdg_context* ctx, const int64_t* tri, int64_t ncell, const double* nodes, int64_t nnode,
+                            int64_t* cells_out, int64_t* faces_out, int64_t faces_capacity, int64_t* nface_out);
+
 /* Deterministic interior-node jitter (fraction of h) to defeat translation invariance in
  * benchmarks (SURVEY Appendix A integrity note).  Applies to the device mesh in place. */
 hdg_status hdg_perturb_nodes(hdg_context* ctx, double fraction, uint64_t seed);

@@ -53,6 +53,34 @@ def test_reference_mesh_goldens_through_abi():
     assert m.getfaceset("boundary") == {3, 7, 9, 16, 2, 11, 12, 15}
 
 
+@pytest.mark.parametrize("case", ["figure2.1", "figure.1", "rect", "permuted", "clockwise"])
+def test_device_face_numbering_bit_exact(case):
+    """hdg_number_faces (hash table + scan on the GPU) == the reference's sequential first-encounter numbering."""
+    rng = np.random.default_rng(11)
+    if case in ("figure2.1", "figure.1"):
+        mo = orc.parse_mesh_triangle(os.path.join(GOLDEN, case))
+        tri, nodes = mo.cells.copy(), mo.nodes
+    else:
+        base = orc.rectangle_mesh(23, 17, (0.0, 0.0), (2.0, 1.0))
+        tri, nodes = base.cells.copy(), base.nodes
+        if case != "rect":
+            tri = tri[rng.permutation(tri.shape[0])]
+        if case == "clockwise":
+            flip = rng.random(tri.shape[0]) < 0.5
+            tri[flip] = tri[flip][:, [0, 2, 1]]
+    ccw = [orc._check_node_data(nodes, *t) for t in tri]
+    cells_o, cf_o, faces_o = orc._build_cells_sequential(ccw, nodes, 3 * tri.shape[0])
+    cells, faces = hdg.number_faces_gpu(tri, nodes)
+    assert np.array_equal(cells[:, :3], cells_o) and np.array_equal(cells[:, 3:], cf_o)
+    assert np.array_equal(faces, faces_o)
+
+
+def test_device_face_numbering_rejects_non_manifold():
+    nodes = np.array([[0., 0.], [1., 0.], [0., 1.], [1., 1.], [0.5, -1.]])
+    with pytest.raises(hdg.HDGError):
+        hdg.number_faces_gpu(np.array([[1, 2, 3], [2, 4, 3], [1, 5, 2], [1, 2, 4]]), nodes)
+
+
 @pytest.mark.parametrize("root", ["figure2.1", "figure.1", None])
 def test_face_table_rebuilt_on_device_when_not_passed(root):
     """hdg_set_mesh(faces = NULL): mesh.faces is reconstructed from the cells, bit for bit."""
