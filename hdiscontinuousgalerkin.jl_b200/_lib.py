@@ -106,6 +106,7 @@ SIGNATURES = {
     "hdg_get_local": (C.c_int, [_P, C.c_int64, _F64P, _F64P]),
     "hdg_get_condensed": (C.c_int, [_P, C.c_int64, _F64P, _F64P]),
     "hdg_get_mvalues": (C.c_int, [_P, _F64P, _F64P, _F64P]),
+    "hdg_nodal_avg": (C.c_int, [_P, _F64P]),
     "hdg_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "hdg_comm_init": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]),
     "hdg_get_partition": (C.c_int, [_P, _I64P]),

@@ -597,6 +597,16 @@ def errornorm(u_h, u_ex=poisson_exact, norm_type="L2"):
     return e.value
 
 
+def nodal_avg(u_h):
+    """nodal_avg(u_h), src/DiscreteFunctions.jl:81-95 (u_h must have been filled by get_usigma_)."""
+    ctx = u_h._ctx
+    if ctx is None:
+        raise HDGError(1, "nodal_avg before get_usigma_")
+    out = np.empty(u_h.fs.mesh.getnnodes())
+    check(ctx.lib.hdg_nodal_avg(ctx.h, f64p(out)), ctx.h)
+    return out
+
+
 def poisson2D_HDG(mesh=None, order=1, quad_degree=None, tau=1.0, rtol=1e-13, maxit=200000):
     """The driver examples/poisson2D_HDG.jl:37-218 end to end.  Returns a dict of results."""
     if mesh is None:

@@ -116,8 +116,6 @@ void hdg_destroy(hdg_context* c) {
     free_mesh(c);
     comm_destroy(c);
     if (c->d_rawtab) cudaFree(c->d_rawtab);
-    if (c->d_pcg_sync) cudaFree(c->d_pcg_sync);
-    if (c->d_pcg_mail) cudaFree(c->d_pcg_mail);
     if (c->d_flags) cudaFree(c->d_flags);
     if (c->d_scal) cudaFree(c->d_scal);
     if (c->d_partials) cudaFree(c->d_partials);
@@ -380,6 +378,14 @@ hdg_status hdg_get_mvalues(hdg_context* c, double* sigma, double* u, double* uha
     if (uhat_h) HDG_CUDA(c, cudaMemcpyAsync(uhat_h, c->d_uhat_h, sizeof(double) * c->ncell_own * nt * 3, cudaMemcpyDeviceToHost, c->stream));
     HDG_CUDA(c, cudaStreamSynchronize(c->stream));
     return HDG_OK;
+}
+
+hdg_status hdg_nodal_avg(hdg_context* c, double* out) {
+    if (!c || !out) return HDG_ERR_INVALID;
+    if (!c->recovered) return set_err(c, HDG_ERR_INVALID, "hdg_nodal_avg before hdg_recover");
+    if (comm_active(c)) return set_err(c, HDG_ERR_INVALID, "hdg_nodal_avg is single-GPU");
+    cudaSetDevice(c->device);
+    return nodal_average(c, out);
 }
 
 hdg_status hdg_last_phase_ms(const hdg_context* cc, const char* phase, double* ms) {

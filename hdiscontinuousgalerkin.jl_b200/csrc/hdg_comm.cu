@@ -167,7 +167,7 @@ bool comm_p2p(const hdg_context* c) { return comm_active(c) && c->comm->p2p; }
 
 static hdg_status setup_mailboxes(hdg_context* c) {
     Comm* m = c->comm;
-    const size_t bytes = sizeof(double) * (2 + 3 * 2) * m->nranks * MAILW;   // xgpu_allreduce mailbox + 3 PCG message mailboxes
+    const size_t bytes = sizeof(double) * 2 * m->nranks * MAILW;
     HDG_CUDA(c, cudaMalloc(&m->d_mail, bytes));
     HDG_CUDA(c, cudaMemset(m->d_mail, 0, bytes));
     HDG_CUDA(c, cudaMalloc(&m->d_epoch, sizeof(unsigned long long)));
@@ -189,10 +189,8 @@ static hdg_status setup_mailboxes(hdg_context* c) {
         m->ipc_opened.push_back(p);
         ptrs[q] = static_cast<double*>(p);
     }
-    std::vector<double*> both(ptrs);
-    for (int q = 0; q < m->nranks; ++q) both.push_back(ptrs[q] + 2 * m->nranks * MAILW);   // PCG mailboxes
-    HDG_CUDA(c, cudaMalloc(&m->d_peer_mail, sizeof(double*) * both.size()));
-    HDG_CUDA(c, cudaMemcpy(m->d_peer_mail, both.data(), sizeof(double*) * both.size(), cudaMemcpyHostToDevice));
+    HDG_CUDA(c, cudaMalloc(&m->d_peer_mail, sizeof(double*) * m->nranks));
+    HDG_CUDA(c, cudaMemcpy(m->d_peer_mail, ptrs.data(), sizeof(double*) * m->nranks, cudaMemcpyHostToDevice));
     return HDG_OK;
 }
 

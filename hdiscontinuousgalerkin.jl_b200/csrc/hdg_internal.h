@@ -82,10 +82,10 @@ struct Comm {
     double* d_gscal = nullptr;       // all-reduced scalars
     // peer-memory path (CUDA IPC over NVLink): mailboxes for the flag-based all-reduce, neighbours' PCG vectors
     bool p2p = false;
-    double* d_mail = nullptr;               // my mailboxes: [2][nranks][MAILW] (xgpu_allreduce) + [3][2][nranks][MAILW] (PCG messages)
-    double** d_peer_mail = nullptr;         // device array [2][nranks]: both mailboxes of every rank as mapped in this process
+    double* d_mail = nullptr;               // my mailbox [2][nranks][MAILW] (double-buffered by epoch parity)
+    double** d_peer_mail = nullptr;         // device array [nranks]: the mailbox of every rank as mapped in this process
     unsigned long long* d_epoch = nullptr;  // all-reduce epoch counter
-    void* peer_vec[2] = {nullptr, nullptr}; // mapped [r|dinv|p] region of rank-1 / rank+1
+    void* peer_vec[2] = {nullptr, nullptr}; // mapped p vector of rank-1 / rank+1
     int64_t peer_ndof[2] = {0, 0};          // their owned dof counts
     int32_t* d_ghost_ridx = nullptr;        // for every ghost face: its local face index on the owning rank
     std::vector<void*> ipc_opened;
@@ -141,12 +141,9 @@ struct hdg_context {
 
     // solver vectors
     double* d_x = nullptr;           // trace solution u_hat
-    double *d_r = nullptr, *d_p = nullptr, *d_Ap = nullptr, *d_dinv = nullptr;   // legacy 3-kernel path
-    double* d_vreg = nullptr;        // main PCG path: one region [r | dinv | p] (shared with the neighbours over CUDA IPC)
-    void* d_pcg_sync = nullptr;      // iteration counter + last-block tickets
+    double *d_r = nullptr, *d_p = nullptr, *d_Ap = nullptr, *d_dinv = nullptr;   // d_p is mapped by the neighbouring ranks (CUDA IPC)
     double* d_binv = nullptr;        // block-Jacobi: inverted face-diagonal blocks
     int precond = 0;                 // 0 Jacobi, 1 block-Jacobi
-    double* d_pcg_mail = nullptr;    // single-GPU mailbox of the PCG messages
     double* d_partials = nullptr;    // reduction partials
     double* d_scal = nullptr;        // device scalars
     int32_t* d_flags = nullptr;      // error / convergence flags
@@ -208,6 +205,7 @@ hdg_status pcg_solve(hdg_context* c, double rtol, int maxit, hdg_solve_info* inf
 hdg_status recover(hdg_context* c);                             // hdg_recover.cu
 hdg_status errornorm(hdg_context* c, int exact_id, double* err2);
 hdg_status local_download(hdg_context* c, int64_t cell, double* Ke, double* be);
+hdg_status nodal_average(hdg_context* c, double* out);
 
 // hdg_comm.cu
 bool comm_active(const hdg_context* c);

@@ -121,6 +121,53 @@ hdg_status errornorm(hdg_context* c, int exact_id, double* err2) {
     return HDG_OK;
 }
 
+// ---- nodal_avg(u_h) (src/DiscreteFunctions.jl:81-95): vertex values of the discontinuous u_h averaged per node --------
+// value(u_h,node,cell) (:70-79) evaluates the cell's expansion at xi = Jinv (x_node - x_1), i.e. at the reference vertices.
+__global__ void nodal_accumulate(const double* __restrict__ u, const int32_t* __restrict__ cellinfo, int64_t ncell, int n,
+                                 const double* __restrict__ vtab /* n x 3 */, double* __restrict__ sum, int32_t* __restrict__ cnt) {
+    int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int i = 0; i < n; ++i) {
+        double ui = u[c + ncell * i];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[k] = fma(ui, vtab[3 * i + k], v[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int32_t node = cellinfo[CI * c + k];
+        atomicAdd(&sum[node], v[k]);
+        atomicAdd(&cnt[node], 1);
+    }
+}
+__global__ void nodal_divide(double* __restrict__ sum, const int32_t* __restrict__ cnt, int64_t nnode) {
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < nnode) sum[i] = sum[i] / double(cnt[i]);
+}
+
+hdg_status nodal_average(hdg_context* c, double* out) {
+    const int n = c->tab.n;
+    std::vector<double> vt(size_t(n) * 3);
+    const double vx[3] = {0.0, 1.0, 0.0}, vy[3] = {0.0, 0.0, 1.0};   // reference vertices, src/shapes.jl:14-18
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < 3; ++k) dubiner_eval(i + 1, vx[k], vy[k], &vt[3 * i + k], nullptr, nullptr);
+    double *d_vt = nullptr, *d_sum = nullptr;
+    int32_t* d_cnt = nullptr;
+    HDG_CUDA(c, cudaMalloc(&d_vt, sizeof(double) * vt.size()));
+    HDG_CUDA(c, cudaMalloc(&d_sum, sizeof(double) * c->nnode));
+    HDG_CUDA(c, cudaMalloc(&d_cnt, sizeof(int32_t) * c->nnode));
+    HDG_CUDA(c, cudaMemcpyAsync(d_vt, vt.data(), sizeof(double) * vt.size(), cudaMemcpyHostToDevice, c->stream));
+    HDG_CUDA(c, cudaMemsetAsync(d_sum, 0, sizeof(double) * c->nnode, c->stream));
+    HDG_CUDA(c, cudaMemsetAsync(d_cnt, 0, sizeof(int32_t) * c->nnode, c->stream));
+    nodal_accumulate<<<(unsigned)ceil_div(c->ncell_own, 128), 128, 0, c->stream>>>(c->d_u, c->d_cellinfo, c->ncell_own, n, d_vt, d_sum, d_cnt);
+    nodal_divide<<<(unsigned)ceil_div(c->nnode, 256), 256, 0, c->stream>>>(d_sum, d_cnt, c->nnode);
+    c->launches += 2;
+    HDG_CUDA(c, cudaMemcpyAsync(out, d_sum, sizeof(double) * c->nnode, cudaMemcpyDeviceToHost, c->stream));
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d_vt); cudaFree(d_sum); cudaFree(d_cnt);
+    return HDG_OK;
+}
+
 // ---- K_element[cell], b_element[cell] ----------------------------------------------------------------
 __global__ void gather_local(const double* __restrict__ Ke, int64_t c, int m, int t, double* __restrict__ out) {
     // out: K_e column-major m x t, then b_e (m)

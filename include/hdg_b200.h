@@ -184,6 +184,10 @@ hdg_status hdg_get_condensed(hdg_context* ctx, int64_t cell, double* Ate, double
  * sigma ncell x 2n, u ncell x n, uhat ncell x nt x 3.  Any pointer may be NULL. */
 hdg_status hdg_get_mvalues(hdg_context* ctx, double* sigma, double* u, double* uhat_h);
 
+/* nodal_avg(u_h) (src/DiscreteFunctions.jl:81-95): the discontinuous u_h evaluated at the vertices of every cell
+ * (value(u_h,node,cell), :70-79) and averaged over the cells sharing a node; nnode doubles.  Plotting helper. */
+hdg_status hdg_nodal_avg(hdg_context* ctx, double* out);
+
 /* ---- multi-GPU (one process per GPU) ------------------------------------------------------
  * The caller (torch.distributed / MPI / Julia Distributed) creates a 128-byte ncclUniqueId on
  * rank 0 with hdg_comm_unique_id, broadcasts it, and every rank calls hdg_comm_init.  After

@@ -649,6 +649,22 @@ def errornorm(mesh, tab, u_vals, u_ex=exact_poisson):
     return tot
 
 
+def nodal_avg(mesh, tab, u_vals):
+    """nodal_avg(u_h) with value(u_h,node,cell), src/DiscreteFunctions.jl:70-95."""
+    acc = np.zeros(mesh.nnodes)
+    cnt = np.zeros(mesh.nnodes, dtype=np.int64)
+    for c in range(mesh.ncells):
+        x = mesh.nodes[mesh.cells[c] - 1]
+        g = reinit(tab, x)
+        for node in mesh.cells[c]:
+            xi = g.Jinv @ (mesh.nodes[node - 1] - x[0])          # reference_coordinate, src/DiscreteFunctions.jl:63-64
+            xi = np.clip(xi, 0.0, 1.0)                            # rounding may leave the reference triangle by 1 ulp
+            u = sum(u_vals[c, i] * dubiner_value(i + 1, xi[0], xi[1]) for i in range(tab.n))
+            acc[node - 1] += u
+            cnt[node - 1] += 1
+    return acc / cnt
+
+
 def run_poisson(mesh, order=1, quad_degree=None, tau=1.0):
     """The whole driver examples/poisson2D_HDG.jl:37-218 on `mesh`."""
     tab = build_tables(order, quad_degree)

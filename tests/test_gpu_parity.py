@@ -324,6 +324,15 @@ def test_full_driver_vs_oracle(order, qd, nx):
     assert abs(r["err2"] - ro["err2"]) <= 1e-9 * ro["err2"] + 1e-18
 
 
+@pytest.mark.parametrize("order,qd", [(1, 2), (3, 6)])
+def test_nodal_avg(order, qd):
+    mo = orc.rectangle_mesh(7, 5)
+    ro = orc.run_poisson(mo, order, qd)
+    r = hdg.poisson2D_HDG(hdg.rectangle_mesh(hdg.TriangleCell, (7, 5), (0.0, 0.0), (1.0, 1.0)), order, qd, rtol=1e-14)
+    avg = hdg.nodal_avg(r["u_h"])
+    assert relerr(avg, orc.nodal_avg(mo, ro["tab"], ro["u"])) < 1e-9
+
+
 def test_reference_error_bounds():
     # examples/poisson2D_HDG.jl:218 and test/test_FunctionSpace.jl:243
     r = hdg.poisson2D_HDG()                      # as shipped: 10x10, k=1
