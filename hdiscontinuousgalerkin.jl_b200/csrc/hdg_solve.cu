@@ -207,7 +207,7 @@ template <int N> __device__ __forceinline__ void load_vec(const double* __restri
     if constexpr (N % 4 == 0) {
 #pragma unroll
         for (int i = 0; i < N; i += 4)
-            asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[i]), "=d"(v[i + 1]), "=d"(v[i + 2]), "=d"(v[i + 3]) : "l"(src + i));
+            asm("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[i]), "=d"(v[i + 1]), "=d"(v[i + 2]), "=d"(v[i + 3]) : "l"(src + i));
     } else if constexpr (N % 2 == 0) {
 #pragma unroll
         for (int i = 0; i < N; i += 2) {
@@ -237,47 +237,61 @@ template <int N> __device__ __forceinline__ void store_vec(double* __restrict__ 
 // 5*nt*nt contiguous-per-array doubles, fetched with the widest aligned vector loads (one 256-bit LDG per
 // 2x2 block at k=1); every sector that reaches the SM is fully used.
 template <int NT>
+__device__ __forceinline__ void spmv_face(const PcgArgs& a, int64_t f, double (&y)[NT], double (&pf)[NT]) {
+    constexpr int NT2 = NT * NT;
+    double blk[NT2];
+    load_vec<NT>(a.p + f * NT, pf);
+    load_vec<NT2>(a.Kd + f * NT2, blk);
+#pragma unroll
+    for (int r = 0; r < NT; ++r) {
+        double s = 0.0;
+#pragma unroll
+        for (int b = 0; b < NT; ++b) s = fma(blk[b * NT + r], pf[b], s);
+        y[r] = s;
+    }
+    const int4 cols = *reinterpret_cast<const int4*>(a.kcol + 4 * f);
+    const int cc[4] = {cols.x, cols.y, cols.z, cols.w};
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4) {
+        const int64_t g = cc[s4];
+        if (g < 0) continue;
+        const double* src = a.p + g * NT;
+        if (g >= a.nface && a.ghost_ridx) {   // face owned by a neighbouring rank: its p comes straight over NVLink
+            const int64_t gi = g - a.nface;
+            src = a.peer_p[gi < a.nbelow ? 0 : 1] + int64_t(a.ghost_ridx[gi]) * NT;
+        }
+        double pg[NT];
+        load_vec<NT>(src, pg);
+        load_vec<NT2>(a.Ko + (f * 4 + s4) * NT2, blk);
+#pragma unroll
+        for (int r = 0; r < NT; ++r)
+#pragma unroll
+            for (int b = 0; b < NT; ++b) y[r] = fma(blk[b * NT + r], pg[b], y[r]);
+    }
+    const bool bc = a.isbc[f];
+#pragma unroll
+    for (int r = 0; r < NT; ++r) y[r] = bc ? y[r] : -y[r];
+}
+
+template <int NT>
 __global__ void __launch_bounds__(RB) pcg_spmv(const PcgArgs a) {
     if (*reinterpret_cast<volatile int32_t*>(a.flags + FLAG_DONE)) return;
-    constexpr int NT2 = NT * NT;
     double pap = 0.0;
-    for (int64_t f = int64_t(blockIdx.x) * RB + threadIdx.x; f < a.nface; f += int64_t(gridDim.x) * RB) {
-        double y[NT], pf[NT], blk[NT2];
-        load_vec<NT>(a.p + f * NT, pf);
-        load_vec<NT2>(a.Kd + f * NT2, blk);
+    const int64_t stride = int64_t(gridDim.x) * RB;
+    // two faces per trip: the loads of both are in flight before either result is stored
+    for (int64_t f0 = int64_t(blockIdx.x) * RB + threadIdx.x; f0 < a.nface; f0 += 2 * stride) {
+        const int64_t f1 = f0 + stride;
+        double y0[NT], p0[NT], y1[NT], p1[NT];
+        spmv_face<NT>(a, f0, y0, p0);
+        if (f1 < a.nface) spmv_face<NT>(a, f1, y1, p1);
 #pragma unroll
-        for (int r = 0; r < NT; ++r) {
-            double s = 0.0;
+        for (int r = 0; r < NT; ++r) pap = fma(p0[r], y0[r], pap);
+        store_vec<NT>(a.Ap + f0 * NT, y0);
+        if (f1 < a.nface) {
 #pragma unroll
-            for (int b = 0; b < NT; ++b) s = fma(blk[b * NT + r], pf[b], s);
-            y[r] = s;
+            for (int r = 0; r < NT; ++r) pap = fma(p1[r], y1[r], pap);
+            store_vec<NT>(a.Ap + f1 * NT, y1);
         }
-        const int4 cols = *reinterpret_cast<const int4*>(a.kcol + 4 * f);
-        const int cc[4] = {cols.x, cols.y, cols.z, cols.w};
-#pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) {
-            const int64_t g = cc[s4];
-            if (g < 0) continue;
-            const double* src = a.p + g * NT;
-            if (g >= a.nface && a.ghost_ridx) {   // face owned by a neighbouring rank: its p comes straight over NVLink
-                const int64_t gi = g - a.nface;
-                src = a.peer_p[gi < a.nbelow ? 0 : 1] + int64_t(a.ghost_ridx[gi]) * NT;
-            }
-            double pg[NT];
-            load_vec<NT>(src, pg);
-            load_vec<NT2>(a.Ko + (f * 4 + s4) * NT2, blk);
-#pragma unroll
-            for (int r = 0; r < NT; ++r)
-#pragma unroll
-                for (int b = 0; b < NT; ++b) y[r] = fma(blk[b * NT + r], pg[b], y[r]);
-        }
-        const bool bc = a.isbc[f];
-#pragma unroll
-        for (int r = 0; r < NT; ++r) {
-            y[r] = bc ? y[r] : -y[r];
-            pap = fma(pf[r], y[r], pap);
-        }
-        store_vec<NT>(a.Ap + f * NT, y);
     }
     double tot = block_sum(pap);
     if (threadIdx.x == 0) a.part[P_PAP * MAX_PARTIALS + blockIdx.x] = tot;
@@ -326,13 +340,35 @@ __global__ void __launch_bounds__(RB) pcg_update(const PcgArgs a, int64_t N, int
     const double rz = get_sum(a, parity ? P_RZ1 : P_RZ0);
     const double alpha = rz / pap;
     double rz_new = 0.0, rr = 0.0;
-    for (int64_t row = int64_t(blockIdx.x) * RB + threadIdx.x; row < N; row += int64_t(gridDim.x) * RB) {
-        double p = a.p[row], r = a.r[row];
-        a.x[row] = fma(alpha, p, a.x[row]);
-        r = fma(-alpha, a.Ap[row], r);
-        a.r[row] = r;
-        rz_new = fma(r * a.dinv[row], r, rz_new);
-        rr = fma(r, r, rr);
+    // 4 rows per thread and trip, all loads issued before the first store (memory-level parallelism: these
+    // streaming kernels are latency-, not instruction-bound); the summation order per thread stays fixed
+    const double* __restrict__ pp = a.p;
+    const double* __restrict__ qq = a.Ap;
+    const double* __restrict__ dd = a.dinv;
+    double* __restrict__ xx = a.x;
+    double* __restrict__ rrp = a.r;
+    constexpr int U = 4;
+    const int64_t stride = int64_t(gridDim.x) * RB;
+    for (int64_t row0 = int64_t(blockIdx.x) * RB + threadIdx.x; row0 < N; row0 += stride * U) {
+        double p[U], r[U], q[U], x[U], d[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t row = row0 + u * stride;
+            const bool ok = row < N;
+            p[u] = ok ? pp[row] : 0.0; r[u] = ok ? rrp[row] : 0.0; q[u] = ok ? qq[row] : 0.0;
+            x[u] = ok ? xx[row] : 0.0; d[u] = ok ? dd[row] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t row = row0 + u * stride;
+            if (row < N) {
+                xx[row] = fma(alpha, p[u], x[u]);
+                const double rn = fma(-alpha, q[u], r[u]);
+                rrp[row] = rn;
+                rz_new = fma(rn * d[u], rn, rz_new);
+                rr = fma(rn, rn, rr);
+            }
+        }
     }
     double t1 = block_sum(rz_new), t2 = block_sum(rr);
     if (threadIdx.x == 0) {
@@ -362,9 +398,27 @@ __global__ void __launch_bounds__(RB) pcg_dir(const PcgArgs a, int64_t N, int pa
     if (z_in_ap)   // block-Jacobi: z = M^-1 r was left in the Ap buffer by pcg_update_blk
         for (int64_t row = int64_t(blockIdx.x) * RB + threadIdx.x; row < N; row += int64_t(gridDim.x) * RB)
             a.p[row] = fma(beta, a.p[row], a.Ap[row]);
-    else
-        for (int64_t row = int64_t(blockIdx.x) * RB + threadIdx.x; row < N; row += int64_t(gridDim.x) * RB)
-            a.p[row] = fma(beta, a.p[row], a.dinv[row] * a.r[row]);
+    else {
+        double* __restrict__ pp = a.p;
+        const double* __restrict__ dd = a.dinv;
+        const double* __restrict__ rp = a.r;
+        constexpr int U = 4;
+        const int64_t stride = int64_t(gridDim.x) * RB;
+        for (int64_t row0 = int64_t(blockIdx.x) * RB + threadIdx.x; row0 < N; row0 += stride * U) {
+            double p[U], r[U], d[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t row = row0 + u * stride;
+                const bool ok = row < N;
+                p[u] = ok ? pp[row] : 0.0; r[u] = ok ? rp[row] : 0.0; d[u] = ok ? dd[row] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t row = row0 + u * stride;
+                if (row < N) pp[row] = fma(beta, p[u], d[u] * r[u]);
+            }
+        }
+    }
 }
 
 template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit, hdg_solve_info* info);
