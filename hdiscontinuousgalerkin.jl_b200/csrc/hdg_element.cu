@@ -156,7 +156,8 @@ template <int K> struct SchurCfg {
 #ifndef K1_STAGE_OFF
 #define K1_STAGE_OFF 1
 #endif
-    static constexpr bool stage_off = K == 1 && K1_STAGE_OFF;       // off-diagonal blocks staged too -> one 256-bit store per block
+    static constexpr bool stage_off = K == 1 && K1_STAGE_OFF == 1;  // off-diagonal blocks staged in shared memory -> one 256-bit store per block
+    static constexpr bool hold_off = K == 1 && K1_STAGE_OFF == 2;   // ... or held in registers until the block is complete (needs the fully unrolled column loop)
     static constexpr int nL = Ord<K>::n * (Ord<K>::n - 1) / 2;
     static constexpr int smem_doubles = (l_smem ? nL : 0) + (stage_diag ? Stage<K>::n_base : 0) + (stage_off ? Stage<K>::n_off : 0);
 };
@@ -166,6 +167,8 @@ __global__ void __launch_bounds__(SchurCfg<K>::threads, SchurCfg<K>::min_blocks)
     constexpr int n = Ord<K>::n, nt = Ord<K>::nt, t = Ord<K>::t, ke = Ord<K>::ke;
     constexpr int nL = SchurCfg<K>::nL;
     constexpr bool L_SMEM = SchurCfg<K>::l_smem, STAGE_OFF = SchurCfg<K>::stage_off, STAGE_DIAG = SchurCfg<K>::stage_diag;
+    constexpr bool HOLD_OFF = SchurCfg<K>::hold_off;
+    static_assert(!HOLD_OFF || SchurCfg<K>::col_unroll == Ord<K>::t + 1, "hold_off needs the fully unrolled column loop");
     constexpr int B = SchurCfg<K>::threads;
     using St = Stage<K>;
     const DevTables<K>& T = ctab<K>();
@@ -268,6 +271,7 @@ __global__ void __launch_bounds__(SchurCfg<K>::threads, SchurCfg<K>::min_blocks)
         double* __restrict__ Ke_tile = a.Ke + ((c >> 5) * ke) * 32 + (c & 31);
         constexpr int64_t nt2 = nt * nt;
 
+        double hold[HOLD_OFF ? 3 : 1][2][nt][nt];   // HOLD_OFF: columns of the off-diagonal blocks until a block is complete
         // ---- one column of [K_e | b_e] at a time ------------------------------------------------
         constexpr int col_unroll = SchurCfg<K>::col_unroll;
 #pragma unroll col_unroll
@@ -375,7 +379,19 @@ __global__ void __launch_bounds__(SchurCfg<K>::threads, SchurCfg<K>::min_blocks)
                         }
                     } else {
                         const int s = (l - lp + 3) % 3 - 1;
-                        if constexpr (STAGE_OFF) {
+                        if constexpr (HOLD_OFF) {
+#pragma unroll
+                            for (int ip = 0; ip < nt; ++ip) hold[lp][s][j][ip] = val[ip];
+                            if (j == nt - 1) {   // block (row face lp, column face l) complete: one 256-bit store
+                                double blk[nt * nt];
+#pragma unroll
+                                for (int jj = 0; jj < nt; ++jj)
+#pragma unroll
+                                    for (int ip = 0; ip < nt; ++ip) blk[jj * nt + ip] = hold[lp][s][jj][ip];
+                                const int64_t f_lp = g.f[lp] & 0x7fffffffu;
+                                store_vec<nt * nt>(a.Ko + (f_lp * 4 + int(g.f[lp] >> 31) * 2 + s) * nt2, blk);
+                            }
+                        } else if constexpr (STAGE_OFF) {
 #pragma unroll
                             for (int ip = 0; ip < nt; ++ip) stg[(St::off(lp, 0, 0, ip) + (s * nt + j) * nt) * B] = val[ip];
                         } else {
