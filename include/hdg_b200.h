@@ -103,8 +103,8 @@ hdg_status hdg_set_mesh(hdg_context* ctx,
 
 /* rectangle_mesh(TriangleCell,(nx,ny),LL,UR) (src/generate_mesh.jl:101-143) generated on the
  * device with the reference's node coordinates and first-encounter face numbering; the
- * "boundary" face set becomes the Dirichlet set.  Restricted to rows [row_begin,row_end) of
- * quads when used by a rank of a multi-GPU run (pass 0, ny for the whole mesh). */
+ * "boundary" face set becomes the Dirichlet set.  After hdg_comm_init every rank passes the SAME global
+ * (nx, ny, LL, UR) and keeps the strip of quad rows it owns (hdg_get_partition) plus a one-cell ghost layer. */
 hdg_status hdg_set_rectangle_mesh(hdg_context* ctx, int64_t nx, int64_t ny,
                                   double llx, double lly, double urx, double ury);
 
