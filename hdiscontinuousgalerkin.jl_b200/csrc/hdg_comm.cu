@@ -236,27 +236,19 @@ hdg_status comm_set_ghost_ridx(hdg_context* c, const std::vector<int32_t>& ridx)
 constexpr int XG_THREADS = 256;
 constexpr int XG_MAXPART = 2048;   // == MAX_PARTIALS of hdg_solve.cu
 
-__global__ void __launch_bounds__(XG_THREADS) xgpu_allreduce(const double* __restrict__ part, int np, int nvals,
+__global__ void __launch_bounds__(XG_THREADS) xgpu_allreduce(const double* __restrict__ part, int np, unsigned slot_mask,
                                                              double* __restrict__ gscal, double* const* __restrict__ peer_mail,
                                                              double* my_mail, unsigned long long* epoch_ctr, int rank, int nranks) {
     __shared__ double loc[MAILW];
-    __shared__ double red[XG_THREADS / 32];
     __shared__ unsigned long long e_sh;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    // local sums of the partial arrays, fixed order
-    for (int w = 0; w < nvals; ++w) {
+    // warp w adds the partials of slot w in a fixed order (lane-strided, then a shuffle tree)
+    if (wid < MAILW - 1 && ((slot_mask >> wid) & 1u)) {
         double s = 0.0;
-        for (int i = threadIdx.x; i < np; i += XG_THREADS) s += part[w * XG_MAXPART + i];
+        for (int i = lane; i < np; i += 32) s += part[wid * XG_MAXPART + i];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) red[wid] = s;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double t = 0.0;
-            for (int k = 0; k < XG_THREADS / 32; ++k) t += red[k];
-            loc[w] = t;
-        }
-        __syncthreads();
+        if (lane == 0) loc[wid] = s;
     }
     if (threadIdx.x == 0) {
         e_sh = *epoch_ctr + 1;
@@ -268,7 +260,8 @@ __global__ void __launch_bounds__(XG_THREADS) xgpu_allreduce(const double* __res
     if (threadIdx.x < nranks) {
         // my contribution -> slot [buf][rank] of rank `threadIdx.x` (values first, then the epoch word)
         volatile double* dst = peer_mail[threadIdx.x] + size_t(buf * nranks + rank) * MAILW;
-        for (int w = 0; w < nvals; ++w) dst[1 + w] = loc[w];
+        for (int w = 0; w < MAILW - 1; ++w)
+            if ((slot_mask >> w) & 1u) dst[1 + w] = loc[w];
         __threadfence_system();
         *reinterpret_cast<volatile unsigned long long*>(dst) = e;
         // wait for rank `threadIdx.x`'s contribution to arrive in my mailbox
@@ -278,7 +271,7 @@ __global__ void __launch_bounds__(XG_THREADS) xgpu_allreduce(const double* __res
         __threadfence_system();
     }
     __syncthreads();
-    if (threadIdx.x < nvals) {
+    if (threadIdx.x < MAILW - 1 && ((slot_mask >> threadIdx.x) & 1u)) {
         double s = 0.0;
         for (int q = 0; q < nranks; ++q)   // rank order: identical result on every rank
             s += reinterpret_cast<volatile double*>(my_mail)[size_t(buf * nranks + q) * MAILW + 1 + threadIdx.x];
@@ -286,9 +279,9 @@ __global__ void __launch_bounds__(XG_THREADS) xgpu_allreduce(const double* __res
     }
 }
 
-hdg_status comm_p2p_allreduce(hdg_context* c, const double* d_partials, int np, int nvals) {
+hdg_status comm_p2p_allreduce(hdg_context* c, const double* d_partials, int np, unsigned slot_mask) {
     Comm* m = c->comm;
-    xgpu_allreduce<<<1, XG_THREADS, 0, c->stream>>>(d_partials, np, nvals, m->d_gscal, m->d_peer_mail, m->d_mail, m->d_epoch,
+    xgpu_allreduce<<<1, XG_THREADS, 0, c->stream>>>(d_partials, np, slot_mask, m->d_gscal, m->d_peer_mail, m->d_mail, m->d_epoch,
                                                    m->rank, m->nranks);
     c->launches += 1;
     HDG_CUDA(c, cudaGetLastError());

@@ -217,7 +217,7 @@ void comm_destroy(hdg_context* c);
 bool comm_p2p(const hdg_context* c);
 hdg_status comm_share_vectors(hdg_context* c, void* region, int64_t ndof_own);              // maps the neighbours' regions
 void comm_unshare_vectors(hdg_context* c);
-hdg_status comm_p2p_allreduce(hdg_context* c, const double* d_partials, int np, int nvals);   // partial arrays -> d_gscal, all ranks
+hdg_status comm_p2p_allreduce(hdg_context* c, const double* d_partials, int np, unsigned slot_mask);   // selected partial arrays -> d_gscal, all ranks (mask 0: barrier only)
 hdg_status comm_set_ghost_ridx(hdg_context* c, const std::vector<int32_t>& ridx);
 
 }  // namespace hdg

@@ -580,17 +580,17 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
     HDG_CUDA(c, cudaMemsetAsync(c->d_flags, 0, sizeof(int32_t) * NFLAGS, c->stream));
     hdg_status cst = HDG_OK;
     auto note = [&](hdg_status s2) { if (s2) cst = s2; };
-    auto global_sums = [&](int nvals) {   // several GPUs: partial arrays -> sums over all ranks (+ inter-GPU barrier)
+    auto global_sums = [&](unsigned mask) {   // several GPUs: selected partial arrays -> sums over all ranks (+ inter-GPU barrier)
         if (!multi) return;
-        if (p2p) { note(comm_p2p_allreduce(c, c->d_partials, G, nvals)); return; }
-        if (nvals == 0) return;
+        if (p2p) { note(comm_p2p_allreduce(c, c->d_partials, G, mask)); return; }
+        if (mask == 0) return;
         reduce_all<<<NPART, RB, 0, c->stream>>>(c->d_partials, G, c->comm->d_gscal);
         c->launches += 1;
         note(comm_allreduce_sum(c, c->comm->d_gscal, NPART));
     };
     if (blockjac) pcg_init_blk<NT><<<G, RB, 0, c->stream>>>(a, c->d_binv);
     else pcg_init<NT><<<G, RB, 0, c->stream>>>(a);
-    global_sums(NPART);
+    global_sums((1u << NPART) - 1);
     pcg_init_final<<<1, RB, 0, c->stream>>>(a);
     c->launches += 2;
 
@@ -604,10 +604,10 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
         if (multi && !p2p) note(comm_halo_exchange(c, c->d_p, NT));   // NCCL fallback: ghost entries of p
         if constexpr (NT == 5) pcg_spmv_rows<NT><<<G, RB, 0, c->stream>>>(a);
         else pcg_spmv<NT><<<G, RB, 0, c->stream>>>(a);
-        global_sums(NPART);      // p.Ap; every rank has finished reading p
+        global_sums(1u << P_PAP);      // p.Ap; every rank has finished reading p
         if (blockjac) pcg_update_blk<NT><<<G, RB, 0, c->stream>>>(a, c->d_binv, parity);
         else pcg_update<<<G, RB, 0, c->stream>>>(a, N, parity);
-        global_sums(NPART);      // r.z, r.r
+        global_sums((1u << (parity ? P_RZ0 : P_RZ1)) | (1u << P_RR));      // r.z, r.r
         pcg_dir<<<G, RB, 0, c->stream>>>(a, N, parity, it + 1, blockjac ? 1 : 0);
         if (p2p) global_sums(0);  // barrier: p complete on every rank before the next SpMV reads it
     };
