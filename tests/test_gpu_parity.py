@@ -10,6 +10,7 @@ import pytest
 
 import hdg_b200 as hdg
 import hdg_oracle as orc
+from fixtures_util import triangle_root
 
 pytestmark = pytest.mark.gpu
 
@@ -58,7 +59,7 @@ def test_device_face_numbering_bit_exact(case):
     """hdg_number_faces (hash table + scan on the GPU) == the reference's sequential first-encounter numbering."""
     rng = np.random.default_rng(11)
     if case in ("figure2.1", "figure.1"):
-        mo = orc.parse_mesh_triangle(os.path.join(GOLDEN, case))
+        mo = orc.parse_mesh_triangle(triangle_root(case))
         tri, nodes = mo.cells.copy(), mo.nodes
     else:
         base = orc.rectangle_mesh(23, 17, (0.0, 0.0), (2.0, 1.0))
@@ -84,7 +85,7 @@ def test_device_face_numbering_rejects_non_manifold():
 @pytest.mark.parametrize("root", ["figure2.1", "figure.1", None])
 def test_face_table_rebuilt_on_device_when_not_passed(root):
     """hdg_set_mesh(faces = NULL): mesh.faces is reconstructed from the cells, bit for bit."""
-    mo = orc.parse_mesh_triangle(os.path.join(GOLDEN, root)) if root else orc.rectangle_mesh(9, 7)
+    mo = orc.parse_mesh_triangle(triangle_root(root)) if root else orc.rectangle_mesh(9, 7)
     cells = np.ascontiguousarray(np.hstack([mo.cells, mo.cell_faces]))
     bf = mo.boundary_faces_sorted()
     ctx = hdg._Context(1, 2)
@@ -159,13 +160,13 @@ def test_assembly_rectangle(order, qd):
 
 @pytest.mark.parametrize("order,qd", CONFIGS)
 def test_assembly_triangle_fixture(order, qd):
-    mo = orc.parse_mesh_triangle(os.path.join(GOLDEN, "figure2.1"))
+    mo = orc.parse_mesh_triangle(triangle_root("figure2.1"))
     _check_assembly(mo, order, qd)
 
 
 @pytest.mark.parametrize("order,qd", [(1, 2), (3, 6)])
 def test_assembly_unstructured_62(order, qd):
-    mo = orc.parse_mesh_triangle(os.path.join(GOLDEN, "figure.1"))
+    mo = orc.parse_mesh_triangle(triangle_root("figure.1"))
     _check_assembly(mo, order, qd)
 
 
@@ -338,7 +339,7 @@ def test_reference_error_bounds():
     r = hdg.poisson2D_HDG()                      # as shipped: 10x10, k=1
     assert r["err2"] <= 0.00006
     assert abs(r["err2"] - 5.364546646411725e-05) < 1e-14
-    m = hdg.parse_mesh_triangle(os.path.join(GOLDEN, "figure2.1"))
+    m = hdg.parse_mesh_triangle(triangle_root("figure2.1"))
     r = hdg.poisson2D_HDG(m, 1)
     assert r["err2"] <= 0.12
     assert abs(r["err2"] - 0.11019700386004985) < 1e-12

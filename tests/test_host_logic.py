@@ -7,6 +7,7 @@ import pytest
 
 import hdg_b200 as hdg
 import hdg_oracle as orc
+from fixtures_util import triangle_root
 import hdg_oracle_c as occ
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -14,8 +15,8 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 @pytest.mark.parametrize("root", ["figure2.1", "figure.1"])
 def test_parse_mesh_triangle_matches_oracle(root):
-    m = hdg.parse_mesh_triangle(os.path.join(GOLDEN, root))
-    mo = orc.parse_mesh_triangle(os.path.join(GOLDEN, root))
+    m = hdg.parse_mesh_triangle(triangle_root(root))
+    mo = orc.parse_mesh_triangle(triangle_root(root))
     assert np.array_equal(m.cells[:, :3], mo.cells) and np.array_equal(m.cells[:, 3:], mo.cell_faces)
     assert np.array_equal(m.faces, mo.faces) and np.array_equal(m.nodes, mo.nodes)
     assert m.facesets["boundary"] == mo.facesets["boundary"]
@@ -45,8 +46,8 @@ def test_non_manifold_rejected():
 
 
 def test_dirichlet_dofs_and_values():
-    mo = orc.parse_mesh_triangle(os.path.join(GOLDEN, "figure2.1"))
-    m = hdg.parse_mesh_triangle(os.path.join(GOLDEN, "figure2.1"))
+    mo = orc.parse_mesh_triangle(triangle_root("figure2.1"))
+    m = hdg.parse_mesh_triangle(triangle_root("figure2.1"))
     for order in (1, 2, 3):
         fe = hdg.GenericFiniteElement(hdg.Dubiner(2, hdg.RefTetrahedron, order))
         Wh = hdg.ScalarFunctionSpace(m, fe, 2 * order)
@@ -60,7 +61,7 @@ def test_dirichlet_dofs_and_values():
 
 
 def test_trial_function_storage():
-    m = hdg.parse_mesh_triangle(os.path.join(GOLDEN, "figure2.1"))
+    m = hdg.parse_mesh_triangle(triangle_root("figure2.1"))
     fe = hdg.GenericFiniteElement(hdg.Dubiner(2, hdg.RefTetrahedron, 1))
     Wh, Vh = hdg.ScalarFunctionSpace(m, fe), hdg.VectorFunctionSpace(m, fe)
     Mh = hdg.ScalarTraceFunctionSpace(Wh, hdg.GenericFiniteElement(hdg.Legendre(1, hdg.RefTetrahedron, 1)))

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import hdg_oracle as orc
+from fixtures_util import triangle_root
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 sq2, sq3, sq6 = math.sqrt(2), math.sqrt(3), math.sqrt(6)
@@ -14,7 +15,7 @@ sq2, sq3, sq6 = math.sqrt(2), math.sqrt(3), math.sqrt(6)
 
 @pytest.fixture(scope="module")
 def fig21():
-    return orc.parse_mesh_triangle(os.path.join(GOLDEN, "figure2.1"))
+    return orc.parse_mesh_triangle(triangle_root("figure2.1"))
 
 
 # ---- test/test_mesh.jl -----------------------------------------------------------------------
