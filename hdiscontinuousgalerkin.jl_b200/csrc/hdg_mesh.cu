@@ -527,8 +527,9 @@ void free_mesh(hdg_context* c) {
     auto F = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     F(c->d_cellinfo); F(c->d_nodes); F(c->d_facecell); F(c->d_facenode); F(c->d_bfaces); F(c->d_isbc);
     F(c->d_kcol); F(c->d_fq); F(c->d_Kd); F(c->d_Ko); F(c->d_rhs); F(c->d_Ke); F(c->d_bcval);
-    if (c->d_p) comm_unshare_vectors(c);   // close the neighbours' p mappings before the vectors go away
-    F(c->d_x); F(c->d_r); F(c->d_p); F(c->d_Ap); F(c->d_dinv);
+    if (c->d_p) comm_unshare_vectors(c);   // close the neighbours' mappings before the vectors go away
+    F(c->d_x); F(c->d_p); F(c->d_Ap);
+    c->d_r = c->d_dinv = nullptr;          // r and Dinv live inside the d_p region
     F(c->d_binv);
     F(c->d_sigma); F(c->d_u); F(c->d_uhat_h); F(c->d_stage_cells); F(c->d_stage_faces);
     c->cap_ncell = c->cap_nnode = c->cap_nface = c->cap_nbface = 0;

@@ -150,6 +150,11 @@ struct PcgArgs {
     double rtol;
     const int32_t* ghost_ridx;   // ghost face -> local face index on its owner (peer-memory SpMV)
     const double* peer_p[2];     // p of rank-1 / rank+1, mapped over NVLink (nullptr: ghost values live behind the owned part of p)
+    const double* peer_r[2];     // ghost_mode 2: the neighbours' r, Dinv (peer_p then points at their PREVIOUS direction)
+    const double* peer_dinv[2];
+    double* pnext;               // where pcg_dir writes the next direction (p is double-buffered)
+    int ghost_mode;              // 0 local ghost segment (NCCL halo), 1 peer p read in place, 2 peer p recomputed on the fly
+    int parity;                  // iteration parity (which r.z partial array is current)
     int64_t nbelow;              // ghost faces owned by rank-1 (they come first)
 };
 
@@ -188,6 +193,7 @@ __global__ void __launch_bounds__(RB) pcg_init(const PcgArgs a) {
     double t1 = block_sum(rz), t2 = block_sum(bb);
     if (threadIdx.x == 0) {
         a.part[P_RZ0 * MAX_PARTIALS + blockIdx.x] = t1;
+        a.part[P_RZ1 * MAX_PARTIALS + blockIdx.x] = blockIdx.x == 0 ? 1.0 : 0.0;   // "r.z of iteration -1": any finite value (p_{-1} = 0)
         a.part[P_BB * MAX_PARTIALS + blockIdx.x] = t2;
     }
 }
@@ -256,12 +262,27 @@ __device__ __forceinline__ void spmv_face(const PcgArgs& a, int64_t f, double (&
         const int64_t g = cc[s4];
         if (g < 0) continue;
         const double* src = a.p + g * NT;
-        if (g >= a.nface && a.ghost_ridx) {   // face owned by a neighbouring rank: its p comes straight over NVLink
-            const int64_t gi = g - a.nface;
-            src = a.peer_p[gi < a.nbelow ? 0 : 1] + int64_t(a.ghost_ridx[gi]) * NT;
-        }
         double pg[NT];
-        load_vec<NT>(src, pg);
+        if (g >= a.nface && a.ghost_mode) {   // face owned by a neighbouring rank: its p comes straight over NVLink
+            const int64_t gi = g - a.nface;
+            const int w = gi < a.nbelow ? 0 : 1;
+            const int64_t ro = int64_t(a.ghost_ridx[gi]) * NT;
+            if (a.ghost_mode == 2) {
+                // the neighbour is still writing p_k (pcg_dir runs concurrently, no barrier in between): rebuild it from
+                // what is complete - its r_k, Dinv and p_{k-1} (other buffer) - exactly as its pcg_dir does
+                const double beta = get_sum(a, a.parity ? P_RZ1 : P_RZ0) / get_sum(a, a.parity ? P_RZ0 : P_RZ1);
+                double rg[NT], dg[NT];
+                load_vec<NT>(a.peer_p[w] + ro, pg);
+                load_vec<NT>(a.peer_r[w] + ro, rg);
+                load_vec<NT>(a.peer_dinv[w] + ro, dg);
+#pragma unroll
+                for (int b = 0; b < NT; ++b) pg[b] = fma(beta, pg[b], dg[b] * rg[b]);
+            } else {
+                load_vec<NT>(a.peer_p[w] + ro, pg);
+            }
+        } else {
+            load_vec<NT>(src, pg);
+        }
         load_vec<NT2>(a.Ko + (f * 4 + s4) * NT2, blk);
 #pragma unroll
         for (int r = 0; r < NT; ++r)
@@ -319,7 +340,7 @@ __global__ void __launch_bounds__(RB) pcg_spmv_rows(const PcgArgs a) {
         for (int s = 0; s < 4; ++s) {
             if (cc[s] < 0) continue;
             const double* pg = a.p + int64_t(cc[s]) * NT;
-            if (cc[s] >= a.nface && a.ghost_ridx) {
+            if (cc[s] >= a.nface && a.ghost_mode) {
                 const int64_t gi = cc[s] - a.nface;
                 pg = a.peer_p[gi < a.nbelow ? 0 : 1] + int64_t(a.ghost_ridx[gi]) * NT;
             }
@@ -397,9 +418,10 @@ __global__ void __launch_bounds__(RB) pcg_dir(const PcgArgs a, int64_t N, int pa
     const double beta = rz_new / rz_old;
     if (z_in_ap)   // block-Jacobi: z = M^-1 r was left in the Ap buffer by pcg_update_blk
         for (int64_t row = int64_t(blockIdx.x) * RB + threadIdx.x; row < N; row += int64_t(gridDim.x) * RB)
-            a.p[row] = fma(beta, a.p[row], a.Ap[row]);
+            a.pnext[row] = fma(beta, a.p[row], a.Ap[row]);
     else {
-        double* __restrict__ pp = a.p;
+        const double* __restrict__ pp = a.p;
+        double* __restrict__ pn = a.pnext;
         const double* __restrict__ dd = a.dinv;
         const double* __restrict__ rp = a.r;
         constexpr int U = 4;
@@ -415,7 +437,7 @@ __global__ void __launch_bounds__(RB) pcg_dir(const PcgArgs a, int64_t N, int pa
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int64_t row = row0 + u * stride;
-                if (row < N) pp[row] = fma(beta, p[u], d[u] * r[u]);
+                if (row < N) pn[row] = fma(beta, p[u], d[u] * r[u]);
             }
         }
     }
@@ -478,7 +500,7 @@ __global__ void __launch_bounds__(RB) pcg_init_blk(const PcgArgs a, double* __re
         a.part[P_RZ0 * MAX_PARTIALS + blockIdx.x] = t1;
         a.part[P_BB * MAX_PARTIALS + blockIdx.x] = t2;
         a.part[P_PAP * MAX_PARTIALS + blockIdx.x] = 0.0;
-        a.part[P_RZ1 * MAX_PARTIALS + blockIdx.x] = 0.0;
+        a.part[P_RZ1 * MAX_PARTIALS + blockIdx.x] = blockIdx.x == 0 ? 1.0 : 0.0;
         a.part[P_RR * MAX_PARTIALS + blockIdx.x] = 0.0;
     }
 }
@@ -543,37 +565,56 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
     const bool p2p = multi && comm_p2p(c);
     const bool blockjac = c->precond == 1;
     if (!c->d_x) HDG_CUDA(c, cudaMalloc(&c->d_x, sizeof(double) * Nloc));
-    if (!c->d_r) {
-        HDG_CUDA(c, cudaMalloc(&c->d_r, sizeof(double) * Nloc));
-        HDG_CUDA(c, cudaMalloc(&c->d_p, sizeof(double) * Nloc));
+    if (!c->d_p) {
+        // one region [p0 | p1 | r | Dinv], each Nloc long: the neighbouring ranks map it (CUDA IPC) and read all four
+        HDG_CUDA(c, cudaMalloc(&c->d_p, sizeof(double) * 4 * Nloc));
         HDG_CUDA(c, cudaMalloc(&c->d_Ap, sizeof(double) * Nloc));
-        HDG_CUDA(c, cudaMalloc(&c->d_dinv, sizeof(double) * Nloc));
-        if (p2p) {   // neighbours map my p (collective: every rank gets here in its first solve)
-            hdg_status st = comm_share_vectors(c, c->d_p, N);
+        c->d_r = c->d_p + 2 * Nloc;
+        c->d_dinv = c->d_p + 3 * Nloc;
+        if (p2p) {   // collective: every rank gets here in its first solve
+            hdg_status st = comm_share_vectors(c, c->d_p, Nloc);
             if (st) return st;
         }
     }
     if (blockjac && !c->d_binv) HDG_CUDA(c, cudaMalloc(&c->d_binv, sizeof(double) * c->nface_own * NT * NT));
-    if (multi) {
-        HDG_CUDA(c, cudaMemsetAsync(c->d_p, 0, sizeof(double) * Nloc, c->stream));
-        HDG_CUDA(c, cudaMemsetAsync(c->d_x, 0, sizeof(double) * Nloc, c->stream));
-    }
+    HDG_CUDA(c, cudaMemsetAsync(c->d_p, 0, sizeof(double) * 2 * Nloc, c->stream));   // p_{-1} = 0, ghost segments = 0
+    if (multi) HDG_CUDA(c, cudaMemsetAsync(c->d_x, 0, sizeof(double) * Nloc, c->stream));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     PcgArgs a{};
     a.Kd = c->d_Kd; a.Ko = c->d_Ko; a.kcol = c->d_kcol; a.isbc = c->d_isbc; a.rhs = c->d_rhs;
-    a.x = c->d_x; a.r = c->d_r; a.p = c->d_p; a.Ap = c->d_Ap; a.dinv = c->d_dinv;
+    a.x = c->d_x; a.r = c->d_r; a.p = c->d_p; a.pnext = c->d_p + Nloc; a.Ap = c->d_Ap; a.dinv = c->d_dinv;
     a.part = c->d_partials; a.scal = c->d_scal; a.flags = c->d_flags; a.nface = c->nface_own;
     a.gscal = multi ? c->comm->d_gscal : nullptr;
+    // ghost_mode 2 (no barrier between pcg_dir and the next SpMV) needs the point-Jacobi z = Dinv r; with block-Jacobi
+    // or the row-wise nt = 5 SpMV the neighbours' finished p is read after a barrier (mode 1)
+    const int ghost_mode = !p2p ? 0 : ((blockjac || NT == 5 || getenv("HDG_PCG_BARRIER")) ? 1 : 2);
     if (p2p) {
-        a.peer_p[0] = static_cast<const double*>(c->comm->peer_vec[0]);
-        a.peer_p[1] = static_cast<const double*>(c->comm->peer_vec[1]);
         a.ghost_ridx = c->comm->d_ghost_ridx;
         a.nbelow = c->comm->nbelow;
+        a.ghost_mode = ghost_mode;
     }
     a.np = int(std::min<int64_t>(ceil_div(c->nface_own, RB), std::min<int64_t>(int64_t(sms) * 8, MAX_PARTIALS)));
     a.rtol = rtol;
+    // argument sets of even / odd iterations: p_k lives in buffer k & 1
+    PcgArgs arg[2] = {a, a};
+    for (int par = 0; par < 2; ++par) {
+        arg[par].parity = par;
+        arg[par].p = c->d_p + par * Nloc;
+        arg[par].pnext = c->d_p + (par ^ 1) * Nloc;
+        if (p2p)
+            for (int w = 0; w < 2; ++w) {
+                const double* base = static_cast<const double*>(c->comm->peer_vec[w]);
+                if (!base) continue;
+                const int64_t Np = c->comm->peer_ndof[w];
+                // mode 1: the neighbour's p_k; mode 2: its p_{k-1} (other buffer) + r + Dinv
+                arg[par].peer_p[w] = base + (ghost_mode == 2 ? (par ^ 1) : par) * Np;
+                arg[par].peer_r[w] = base + 2 * Np;
+                arg[par].peer_dinv[w] = base + 3 * Np;
+            }
+    }
+    a = arg[0];
     const int G = a.np;
 
     timer_start(c, c->t_solve);
@@ -600,16 +641,17 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
     auto enqueue_iter = [&](int it) {
-        int parity = it & 1;
-        if (multi && !p2p) note(comm_halo_exchange(c, c->d_p, NT));   // NCCL fallback: ghost entries of p
-        if constexpr (NT == 5) pcg_spmv_rows<NT><<<G, RB, 0, c->stream>>>(a);
-        else pcg_spmv<NT><<<G, RB, 0, c->stream>>>(a);
-        global_sums(1u << P_PAP);      // p.Ap; every rank has finished reading p
-        if (blockjac) pcg_update_blk<NT><<<G, RB, 0, c->stream>>>(a, c->d_binv, parity);
-        else pcg_update<<<G, RB, 0, c->stream>>>(a, N, parity);
-        global_sums((1u << (parity ? P_RZ0 : P_RZ1)) | (1u << P_RR));      // r.z, r.r
-        pcg_dir<<<G, RB, 0, c->stream>>>(a, N, parity, it + 1, blockjac ? 1 : 0);
-        if (p2p) global_sums(0);  // barrier: p complete on every rank before the next SpMV reads it
+        const int parity = it & 1;
+        const PcgArgs& ak = arg[parity];
+        if (multi && !p2p) note(comm_halo_exchange(c, ak.p, NT));   // NCCL fallback: ghost entries of p
+        if constexpr (NT == 5) pcg_spmv_rows<NT><<<G, RB, 0, c->stream>>>(ak);
+        else pcg_spmv<NT><<<G, RB, 0, c->stream>>>(ak);
+        global_sums(1u << P_PAP);      // p.Ap; every rank has finished reading the neighbours' vectors
+        if (blockjac) pcg_update_blk<NT><<<G, RB, 0, c->stream>>>(ak, c->d_binv, parity);
+        else pcg_update<<<G, RB, 0, c->stream>>>(ak, N, parity);
+        global_sums((1u << (parity ? P_RZ0 : P_RZ1)) | (1u << P_RR));      // r.z, r.r; r complete on every rank
+        pcg_dir<<<G, RB, 0, c->stream>>>(ak, N, parity, it + 1, blockjac ? 1 : 0);
+        if (ghost_mode == 1) global_sums(0);  // barrier: p complete on every rank before the next SpMV reads it
     };
     int it = 0;
     bool done = false;
@@ -637,10 +679,13 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
     if (multi) {   // recovery reads the trace on the ghost faces below the strip
         if (p2p) {   // publish x through the shared p array, barrier, pull the ghost values over NVLink, barrier
             const int64_t nghost = c->nface - c->nface_own;
+            global_sums(0);   // nobody reads p any more
             HDG_CUDA(c, cudaMemcpyAsync(c->d_p, c->d_x, sizeof(double) * N, cudaMemcpyDeviceToDevice, c->stream));
             global_sums(0);
+            PcgArgs af = arg[0];
+            for (int w = 0; w < 2; ++w) af.peer_p[w] = static_cast<const double*>(c->comm->peer_vec[w]);   // buffer 0 of the neighbours
             if (nghost > 0) {
-                pcg_fetch_ghost_x<<<(unsigned)ceil_div(nghost * NT, 256), 256, 0, c->stream>>>(a, nghost, NT, c->d_x);
+                pcg_fetch_ghost_x<<<(unsigned)ceil_div(nghost * NT, 256), 256, 0, c->stream>>>(af, nghost, NT, c->d_x);
                 c->launches += 1;
             }
             global_sums(0);
