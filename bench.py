@@ -32,6 +32,7 @@ QD_FOR_ORDER = {1: 2, 2: 4, 3: 6, 4: 9}
 ALG_BYTES = {1: 840, 2: 2088, 3: 4200, 4: 7392}
 ALG_FLOPS = {1: 3090, 2: 18648, 3: 73896, 4: 268350}
 RECOVER_BYTES = {1: 600, 2: 1656, 3: 3456, 4: 6240}
+CONFIG_NAME = {1: "C2", 2: "C3", 3: "C4", 4: "C5 (k=4)"}
 
 
 def measured_peaks():
@@ -359,7 +360,7 @@ def main():
             "metric": "HDG elements/sec (assemble+condense+scatter)", "value": value, "unit": "elements/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C2: Poisson HDG k={order} quad_degree={qd} tau=1, rectangle_mesh {nx}x{ny} per GPU "
+            "config": {"workload": f"{CONFIG_NAME.get(order, 'custom')}: Poisson HDG k={order} quad_degree={qd} tau=1, rectangle_mesh {nx}x{ny} per GPU "
                                    f"({ncell} elements, {int(s.ndof)} trace dofs per GPU) - global mesh {nx}x{ny*world} on [0,2]x[0,{ly:g}]",
                        "parallelism": f"strips of quad rows, {world} rank(s), NCCL halo + all-reduce in the PCG only",
                        "l2": f"inputs+outputs per step {ALG_BYTES[order]*ncell/1e6:.0f} MB > 126 MB L2 (no explicit flush needed)",

@@ -23,6 +23,8 @@
 // contributing cell -> plain stores.  Face-diagonal blocks and rhs entries have at most two
 // contributions -> RED.ADD.F64 onto zeroed storage, which is bitwise deterministic because a
 // two-term IEEE sum is commutative.
+#include <cstdlib>
+
 #include "hdg_internal.h"
 
 namespace hdg {
@@ -648,6 +650,207 @@ __global__ void __launch_bounds__(128) element_lu_kernel(const LuArgs A) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// General path, order 1: one THREAD per element (a warp per element leaves most lanes idle at m = 9; measured 4.8x
+// faster than the warp kernel.  At k = 2 the per-thread [Me | rhs] no longer fits registers and the warp kernel wins).
+// Literal quadrature (examples/poisson2D_HDG.jl:88-153) into a per-thread [Me | rhs] (registers at k=1, L1-backed
+// local memory at k=2), LU WITHOUT pivoting: Me = [A -B; B' C] has a positive definite symmetric part
+// (x'Me x = s'As + u'Cu), so elimination in the natural order is stable, every lane walks the same index sequence
+// (coalesced local-memory traffic, no divergence), and the result agrees with LAPACK's pivoted LU to rounding.
+// A zero / non-finite pivot raises the singular flag (the reference's SingularException).
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(128) element_lu_thread_kernel(const LuArgs A) {
+    constexpr int n = Ord<K>::n, nt = Ord<K>::nt, nv = 2 * n, m = Ord<K>::m, t = Ord<K>::t, nc = t + 1, ke = Ord<K>::ke;
+    const ElemArgs& a = A.e;
+    const RawTablesDev& R = A.raw;
+    const int64_t c = a.cell_begin + int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= a.cell_end) return;
+    CellGeom g;
+    load_geometry(a, c, g);
+    if (!g.ok) {
+        atomicCAS(&a.flags[FLAG_BAD_GEOM], 0, int32_t(c + 1));
+        return;
+    }
+    const double tau = a.tau;
+    const bool ori[3] = {g.v[2] > g.v[1], g.v[0] > g.v[2], g.v[1] > g.v[0]};
+    double Me[m][m], Rh[m][nc], Fl[n][t];
+#pragma unroll
+    for (int i = 0; i < m; ++i) {
+#pragma unroll
+        for (int j = 0; j < m; ++j) Me[i][j] = 0.0;
+#pragma unroll
+        for (int j = 0; j < nc; ++j) Rh[i][j] = 0.0;
+    }
+    // cell integrals A, B (:88-104) and rhs be (:106-114)
+    for (int q = 0; q < R.nq; ++q) {
+        const double dO = g.detJ * R.qw[q];
+        double fv;
+        if (a.source_id == 0) fv = a.fq[c * R.nq + q];
+        else {
+            double xq = R.Mgeo[3 * q] * g.x[0][0] + R.Mgeo[3 * q + 1] * g.x[1][0] + R.Mgeo[3 * q + 2] * g.x[2][0];
+            double yq = R.Mgeo[3 * q] * g.x[0][1] + R.Mgeo[3 * q + 1] * g.x[1][1] + R.Mgeo[3 * q + 2] * g.x[2][1];
+            fv = source_value(a.source_id, xq, yq);
+        }
+        double Nq[n], gx[n], gy[n];
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            Nq[i] = R.N[i + n * q];
+            const double dr = R.dN[(i + n * q) * 2], ds = R.dN[(i + n * q) * 2 + 1];
+            gx[i] = dr * g.G00 + ds * g.G10;   // dNdxi . Jinv
+            gy[i] = dr * g.G01 + ds * g.G11;
+        }
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                const double mass = (Nq[j] * Nq[i]) * dO;
+                Me[i][j] += mass;
+                Me[n + i][n + j] += mass;
+                const double bx = (Nq[j] * gx[i]) * dO, by = (Nq[j] * gy[i]) * dO;
+                Me[i][nv + j] -= bx;
+                Me[n + i][nv + j] -= by;
+                Me[nv + j][i] += bx;
+                Me[nv + j][n + i] += by;
+            }
+            Rh[nv + i][t] += fv * Nq[i] * dO;
+        }
+    }
+    // face integrals C, F (:116-143); E = F (x) normal
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+#pragma unroll
+        for (int j = 0; j < t; ++j) Fl[i][j] = 0.0;
+#pragma unroll
+    for (int l = 0; l < 3; ++l)
+        for (int p = 0; p < R.nfq; ++p) {
+            const double dS = g.dJf[l] * R.fw[p];
+            const int po = ori[l] ? p : R.nfq - 1 - p;
+            double Ep[n], Eo[n], Tp[nt];
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+                Ep[i] = R.E[i + n * (p + R.nfq * l)];
+                Eo[i] = R.E[i + n * (po + R.nfq * l)];
+            }
+#pragma unroll
+            for (int j = 0; j < nt; ++j) Tp[j] = R.T[j + nt * p];
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+#pragma unroll
+                for (int j = 0; j < n; ++j) Me[nv + i][nv + j] += tau * (Ep[j] * Ep[i]) * dS;
+#pragma unroll
+                for (int j = 0; j < nt; ++j) Fl[i][l * nt + j] += (Tp[j] * Eo[i]) * dS;
+            }
+        }
+    double nrm[3][2];
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        nrm[l][0] = g.wn[l][0] / g.dJf[l];
+        nrm[l][1] = g.wn[l][1] / g.dJf[l];
+    }
+    // right-hand sides [-E; F | 0; be]
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+#pragma unroll
+        for (int col = 0; col < t; ++col) {
+            const int l = col / nt;
+            Rh[i][col] = -Fl[i][col] * nrm[l][0];
+            Rh[n + i][col] = -Fl[i][col] * nrm[l][1];
+            Rh[nv + i][col] = tau * Fl[i][col];
+        }
+    // LU without pivoting + forward elimination of the right-hand sides
+    // k = 1: everything unrolled (arrays live in registers); k = 2: outer loops rolled, [Me | rhs] in local memory
+    constexpr int UO = K == 1 ? 64 : 1;
+    bool singular = false;
+#pragma unroll UO
+    for (int k = 0; k < m; ++k) {
+        const double piv = Me[k][k];
+        singular = singular || !(fabs(piv) > 0.0) || !isfinite(piv);
+        const double ip = 1.0 / piv;
+#pragma unroll UO
+        for (int i = k + 1; i < m; ++i) {
+            const double lik = Me[i][k] * ip;
+#pragma unroll UO
+            for (int j = k + 1; j < m; ++j) Me[i][j] = fma(-lik, Me[k][j], Me[i][j]);
+#pragma unroll
+            for (int j = 0; j < nc; ++j) Rh[i][j] = fma(-lik, Rh[k][j], Rh[i][j]);
+        }
+    }
+    if (singular) {
+        atomicCAS(&a.flags[FLAG_SINGULAR], 0, int32_t(c + 1));
+        return;
+    }
+#pragma unroll UO
+    for (int i = m - 1; i >= 0; --i) {
+        const double id = 1.0 / Me[i][i];
+#pragma unroll
+        for (int j = 0; j < nc; ++j) {
+            double s = Rh[i][j];
+#pragma unroll UO
+            for (int k = i + 1; k < m; ++k) s = fma(-Me[i][k], Rh[k][j], s);
+            Rh[i][j] = s * id;
+        }
+    }
+    const bool dbg = a.dbg_At != nullptr;
+    if (!dbg) {
+        double* __restrict__ Ke_tile = a.Ke + ((c >> 5) * ke) * 32 + (c & 31);
+#pragma unroll
+        for (int i = 0; i < m; ++i)
+#pragma unroll
+            for (int j = 0; j < nc; ++j) Ke_tile[int64_t(i * nc + j) * 32] = Rh[i][j];
+    }
+    // Ate = [E;F]' K_e - He ; bte = -[E;F]' b_e ; scatter (plain stores for single-contribution blocks, RED otherwise)
+    constexpr int64_t nt2 = nt * nt;
+#pragma unroll
+    for (int lp = 0; lp < 3; ++lp) {
+        const int64_t f_lp = g.f[lp] & 0x7fffffffu;
+        const int sec = int(g.f[lp] >> 31);
+#pragma unroll UO
+        for (int col = 0; col < nc; ++col) {
+            double val[nt];
+#pragma unroll
+            for (int ip = 0; ip < nt; ++ip) {
+                double s = 0.0;
+#pragma unroll
+                for (int i = 0; i < n; ++i) {
+                    const double f = Fl[i][lp * nt + ip];
+                    s = fma(f * nrm[lp][0], Rh[i][col], s);
+                    s = fma(f * nrm[lp][1], Rh[n + i][col], s);
+                    s = fma(tau * f, Rh[nv + i][col], s);
+                }
+                val[ip] = s;
+            }
+            if (col == t) {
+#pragma unroll
+                for (int ip = 0; ip < nt; ++ip) {
+                    if (dbg) a.dbg_bt[lp * nt + ip] = -val[ip];
+                    else atomicAdd(&a.rhs[f_lp * nt + ip], -val[ip]);
+                }
+                continue;
+            }
+            const int l = col / nt, j = col - l * nt;
+            if (l == lp) {   // He (:144-151)
+#pragma unroll
+                for (int ip = 0; ip < nt; ++ip) {
+                    double h = 0.0;
+                    for (int p = 0; p < R.nfq; ++p) h += (R.T[j + nt * p] * R.T[ip + nt * p]) * (g.dJf[l] * R.fw[p]);
+                    val[ip] -= h;
+                }
+            }
+            if (dbg) {
+#pragma unroll
+                for (int ip = 0; ip < nt; ++ip) a.dbg_At[col * t + lp * nt + ip] = val[ip];
+            } else if (l == lp) {
+#pragma unroll
+                for (int ip = 0; ip < nt; ++ip) atomicAdd(&a.Kd[f_lp * nt2 + j * nt + ip], val[ip]);
+            } else {
+                const int slot = sec * 2 + ((l - lp + 3) % 3 - 1);
+                store_vec<nt>(a.Ko + (f_lp * 4 + slot) * nt2 + j * nt, val);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 template <int K> static void fill_dev_tables(const RefTables& R, DevTables<K>& D) {
     auto cp = [](const std::vector<double>& src, double* dst, size_t cap) {
         for (size_t i = 0; i < cap; ++i) dst[i] = i < src.size() ? src[i] : 0.0;
@@ -706,6 +909,14 @@ template <int K> static hdg_status launch_schur(hdg_context* c, const ElemArgs& 
 }
 
 static hdg_status launch_elements(hdg_context* c, ElemArgs a) {
+    if (c->use_lu && c->tab.order == 1 && getenv("HDG_LU_WARP") == nullptr) {   // k = 2 measured 2.4x slower than the warp kernel (local-memory bound)
+        LuArgs A{a, c->raw, c->tab.n, c->tab.nt};
+        int64_t ncell = a.cell_end - a.cell_begin;
+        element_lu_thread_kernel<1><<<(unsigned)ceil_div(ncell, 128), 128, 0, c->stream>>>(A);
+        c->launches += 1;
+        HDG_CUDA(c, cudaGetLastError());
+        return HDG_OK;
+    }
     if (c->use_lu) {
         LuArgs A{a, c->raw, c->tab.n, c->tab.nt};
         const int m = c->tab.m, t = c->tab.t, ld = (m + t + 1) | 1;
