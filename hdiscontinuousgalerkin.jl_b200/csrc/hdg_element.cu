@@ -946,8 +946,7 @@ static hdg_status launch_elements(hdg_context* c, ElemArgs a) {
 
 hdg_status launch_element_kernels(hdg_context* c) {
     const int nt = c->tab.nt;
-    HDG_CUDA(c, cudaMemsetAsync(c->d_Kd, 0, sizeof(double) * c->nface * nt * nt, c->stream));
-    HDG_CUDA(c, cudaMemsetAsync(c->d_rhs, 0, sizeof(double) * c->nface * nt, c->stream));
+    HDG_CUDA(c, cudaMemsetAsync(c->d_Kd, 0, sizeof(double) * c->nface * (nt * nt + nt), c->stream));   // Kd and rhs (contiguous)
     ElemArgs a{};
     a.cellinfo = c->d_cellinfo; a.nodes = c->d_nodes; a.fq = c->d_fq;
     a.Ke = c->d_Ke; a.Kd = c->d_Kd; a.Ko = c->d_Ko; a.rhs = c->d_rhs; a.flags = c->d_flags;

@@ -526,7 +526,8 @@ hdg_status number_faces_host(hdg_context* c, const int64_t* tri, int64_t ncell, 
 void free_mesh(hdg_context* c) {
     auto F = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     F(c->d_cellinfo); F(c->d_nodes); F(c->d_facecell); F(c->d_facenode); F(c->d_bfaces); F(c->d_isbc);
-    F(c->d_kcol); F(c->d_fq); F(c->d_Kd); F(c->d_Ko); F(c->d_rhs); F(c->d_Ke); F(c->d_bcval);
+    F(c->d_kcol); F(c->d_fq); F(c->d_Kd); F(c->d_Ko); F(c->d_Ke); F(c->d_bcval);
+    c->d_rhs = nullptr;   // lives behind d_Kd (one allocation, one memset per assembly)
     if (c->d_p) comm_unshare_vectors(c);   // close the neighbours' mappings before the vectors go away
     F(c->d_x); F(c->d_p); F(c->d_Ap);
     c->d_r = c->d_dinv = nullptr;          // r and Dinv live inside the d_p region
@@ -573,14 +574,12 @@ static hdg_status alloc_mesh(hdg_context* c) {
 
 hdg_status alloc_system(hdg_context* c) {
     const int nt = c->tab.nt, ke = c->tab.m * (c->tab.t + 1);
-    if (c->d_Ke) {   // buffers kept from a previous mesh of the same size
-        HDG_CUDA(c, cudaMemsetAsync(c->d_Ko, 0, sizeof(double) * c->nface * 4 * nt * nt, c->stream));
-        return HDG_OK;
-    }
+    if (c->d_Ke) return HDG_OK;   // buffers kept from a previous mesh of the same size (unused Ko slots are never read)
     int64_t ncell_pad = ceil_div(c->ncell, 32) * 32;
-    HDG_CUDA(c, cudaMalloc(&c->d_Kd, sizeof(double) * c->nface * nt * nt));
+    // face-diagonal blocks and rhs share one allocation: both are zeroed before every assembly (RED targets)
+    HDG_CUDA(c, cudaMalloc(&c->d_Kd, sizeof(double) * c->nface * (nt * nt + nt)));
+    c->d_rhs = c->d_Kd + c->nface * nt * nt;
     HDG_CUDA(c, cudaMalloc(&c->d_Ko, sizeof(double) * c->nface * 4 * nt * nt));
-    HDG_CUDA(c, cudaMalloc(&c->d_rhs, sizeof(double) * c->nface * nt));
     HDG_CUDA(c, cudaMalloc(&c->d_Ke, sizeof(double) * ncell_pad * ke));
     HDG_CUDA(c, cudaMemsetAsync(c->d_Ko, 0, sizeof(double) * c->nface * 4 * nt * nt, c->stream));
     return HDG_OK;
