@@ -196,7 +196,7 @@ static hdg_status setup_mailboxes(hdg_context* c) {
 
 void comm_unshare_vectors(hdg_context* c) {
     if (!c->comm) return;
-    for (int w = 0; w < 2; ++w)
+    for (int w = 0; w < MAXR; ++w)
         if (c->comm->peer_vec[w]) { cudaIpcCloseMemHandle(c->comm->peer_vec[w]); c->comm->peer_vec[w] = nullptr; }
 }
 
@@ -209,27 +209,34 @@ hdg_status comm_share_vectors(hdg_context* c, void* region, int64_t ndof_own) {
     std::vector<IpcRecord> all;
     hdg_status st = allgather_records(c, mine, all);
     if (st) return st;
-    const int nb[2] = {m->rank - 1, m->rank + 1};
-    for (int w = 0; w < 2; ++w) {
-        if (nb[w] < 0 || nb[w] >= m->nranks) continue;
+    for (int q = 0; q < m->nranks && q < MAXR; ++q) {
+        if (q == m->rank || !((m->need_rank >> q) & 1u)) continue;
         void* p = nullptr;
-        cudaError_t e = cudaIpcOpenMemHandle(&p, all[nb[w]].handle, cudaIpcMemLazyEnablePeerAccess);
+        cudaError_t e = cudaIpcOpenMemHandle(&p, all[q].handle, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) {
             cudaGetLastError();
             return set_err(c, HDG_ERR_CUDA, std::string("cudaIpcOpenMemHandle(vectors): ") + cudaGetErrorString(e));
         }
-        m->peer_vec[w] = p;
-        m->peer_ndof[w] = all[nb[w]].ndof;
+        m->peer_vec[q] = p;
+        m->peer_ndof[q] = all[q].ndof;
     }
     return HDG_OK;
 }
 
-hdg_status comm_set_ghost_ridx(hdg_context* c, const std::vector<int32_t>& ridx) {
+hdg_status comm_set_ghosts(hdg_context* c, const std::vector<int32_t>& ridx, const std::vector<int32_t>& owner) {
     Comm* m = c->comm;
     if (m->d_ghost_ridx) { cudaFree(m->d_ghost_ridx); m->d_ghost_ridx = nullptr; }
+    if (m->d_ghost_owner) { cudaFree(m->d_ghost_owner); m->d_ghost_owner = nullptr; }
+    m->need_rank = 0;
+    for (int32_t q : owner) {
+        if (q < 0 || q >= MAXR) return set_err(c, HDG_ERR_INVALID, "ghost face owned by a rank outside the box");
+        m->need_rank |= 1u << q;
+    }
     if (ridx.empty()) return HDG_OK;
     HDG_CUDA(c, cudaMalloc(&m->d_ghost_ridx, sizeof(int32_t) * ridx.size()));
+    HDG_CUDA(c, cudaMalloc(&m->d_ghost_owner, sizeof(int32_t) * owner.size()));
     HDG_CUDA(c, cudaMemcpy(m->d_ghost_ridx, ridx.data(), sizeof(int32_t) * ridx.size(), cudaMemcpyHostToDevice));
+    HDG_CUDA(c, cudaMemcpy(m->d_ghost_owner, owner.data(), sizeof(int32_t) * owner.size(), cudaMemcpyHostToDevice));
     return HDG_OK;
 }
 
@@ -297,6 +304,7 @@ void comm_destroy(hdg_context* c) {
     if (c->comm->d_peer_mail) cudaFree(c->comm->d_peer_mail);
     if (c->comm->d_epoch) cudaFree(c->comm->d_epoch);
     if (c->comm->d_ghost_ridx) cudaFree(c->comm->d_ghost_ridx);
+    if (c->comm->d_ghost_owner) cudaFree(c->comm->d_ghost_owner);
     if (c->comm->d_gscal) cudaFree(c->comm->d_gscal);
     if (c->comm->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm->nccl);
     delete c->comm;
@@ -344,7 +352,7 @@ hdg_status hdg_comm_init(hdg_context* c, int32_t rank, int32_t nranks, const uin
     }
     c->comm = m;
     // peer-memory mailboxes; on failure (no P2P / IPC) the NCCL path stays in use
-    if (nranks > 1 && getenv("HDG_NO_P2P") == nullptr && nranks <= XG_THREADS) {
+    if (nranks > 1 && getenv("HDG_NO_P2P") == nullptr && nranks <= MAXR) {
         hdg_status st = setup_mailboxes(c);
         m->p2p = st == HDG_OK;
         if (st != HDG_OK) c->err = "peer-memory path disabled: " + c->err;

@@ -67,6 +67,8 @@ struct Timer {
 // Multi-GPU state (hdg_comm.cu): one process per GPU, NCCL over NVLink.  The mesh is split into
 // strips of quad rows (contiguous cell-id and face-id ranges); every rank holds its owned cells and
 // faces plus a one-cell-deep ghost layer above and the ghost faces it references.
+constexpr int MAXR = 8;   // GPUs of one box
+
 struct Comm {
     void* nccl = nullptr;          // ncclComm_t
     int rank = 0, nranks = 1;
@@ -85,9 +87,12 @@ struct Comm {
     double* d_mail = nullptr;               // my mailbox [2][nranks][MAILW] (double-buffered by epoch parity)
     double** d_peer_mail = nullptr;         // device array [nranks]: the mailbox of every rank as mapped in this process
     unsigned long long* d_epoch = nullptr;  // all-reduce epoch counter
-    void* peer_vec[2] = {nullptr, nullptr}; // mapped p vector of rank-1 / rank+1
-    int64_t peer_ndof[2] = {0, 0};          // their owned dof counts
+    void* peer_vec[MAXR] = {};              // mapped PCG vector region of the ranks that own ghost faces of mine
+    int64_t peer_ndof[MAXR] = {};           // their local dof counts (stride of the four vectors inside the region)
+    unsigned need_rank = 0;                 // bit q: some ghost face of mine is owned by rank q
     int32_t* d_ghost_ridx = nullptr;        // for every ghost face: its local face index on the owning rank
+    int32_t* d_ghost_owner = nullptr;       // ... and the owning rank
+    bool general_mesh = false;              // partition of an hdg_set_mesh mesh (no NCCL halo lists)
     std::vector<void*> ipc_opened;
 };
 constexpr int MAILW = 8;   // doubles per mailbox slot: epoch word + up to 7 values
@@ -218,6 +223,6 @@ bool comm_p2p(const hdg_context* c);
 hdg_status comm_share_vectors(hdg_context* c, void* region, int64_t ndof_own);              // maps the neighbours' regions
 void comm_unshare_vectors(hdg_context* c);
 hdg_status comm_p2p_allreduce(hdg_context* c, const double* d_partials, int np, unsigned slot_mask);   // selected partial arrays -> d_gscal, all ranks (mask 0: barrier only)
-hdg_status comm_set_ghost_ridx(hdg_context* c, const std::vector<int32_t>& ridx);
+hdg_status comm_set_ghosts(hdg_context* c, const std::vector<int32_t>& ridx, const std::vector<int32_t>& owner);
 
 }  // namespace hdg

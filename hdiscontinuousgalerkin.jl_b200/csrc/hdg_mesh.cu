@@ -585,9 +585,137 @@ hdg_status alloc_system(hdg_context* c) {
     return HDG_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// hdg_set_mesh on several GPUs: every rank receives the whole mesh and keeps a contiguous range of cell ids.
+// With the reference's first-encounter numbering the faces a rank's cells create also form a contiguous id range
+// (= the trace rows it owns).  Like for the strips of hdg_set_rectangle_mesh, the cells of other ranks that touch an
+// owned face are recomputed as ghost cells, and the faces they (or the owned cells) reference beyond the owned range
+// become ghost columns whose p values are read from the owner's memory during the SpMV.
+// ------------------------------------------------------------------------------------------
+__global__ void mark_isbc_list(const int32_t* __restrict__ bfaces, int64_t nb, uint8_t* __restrict__ isbc) {
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < nb) isbc[bfaces[i]] = 1;
+}
+
+static hdg_status mesh_from_host_partitioned(hdg_context* c, const int64_t* cells, int64_t ncell, const double* nodes,
+                                             int64_t nnode, const int64_t* faces, int64_t nface, const int64_t* bfaces,
+                                             int64_t nbface) {
+    Comm* m = c->comm;
+    const int R = m->nranks, r = m->rank;
+    if (!faces) return set_err(c, HDG_ERR_INVALID, "hdg_set_mesh on several GPUs needs the faces array");
+    if (ncell < R) return set_err(c, HDG_ERR_INVALID, "need at least one cell per rank");
+    auto FC = [&](int64_t f, int col) { return faces[f + col * nface]; };   // column-major nface x 4, 1-based
+    for (int64_t f = 1; f < nface; ++f)
+        if (FC(f, 2) < FC(f - 1, 2))
+            return set_err(c, HDG_ERR_INVALID, "hdg_set_mesh on several GPUs needs first-encounter face numbering (faces ordered by their first cell)");
+    std::vector<int64_t> c0(R + 1), F0(R + 1);
+    for (int q = 0; q <= R; ++q) c0[q] = ncell * q / R;
+    for (int q = 0; q <= R; ++q) {   // first face whose first cell is >= c0[q]
+        int64_t lo = 0, hi = nface;
+        while (lo < hi) { int64_t mid = (lo + hi) / 2; if (FC(mid, 2) - 1 < c0[q]) lo = mid + 1; else hi = mid; }
+        F0[q] = lo;
+    }
+    const int64_t cb = c0[r], ce = c0[r + 1], fb = F0[r], fe = F0[r + 1];
+    const int64_t ncown = ce - cb, nown = fe - fb;
+    // ghost cells: second cells of owned faces that live on another rank
+    std::vector<int64_t> gcells;
+    for (int64_t f = fb; f < fe; ++f) {
+        int64_t c2 = FC(f, 3) - 1;
+        if (c2 >= 0 && (c2 < cb || c2 >= ce)) gcells.push_back(c2);
+    }
+    std::sort(gcells.begin(), gcells.end());
+    gcells.erase(std::unique(gcells.begin(), gcells.end()), gcells.end());
+    const int64_t ncloc = ncown + int64_t(gcells.size());
+    auto local_cell = [&](int64_t cg) -> int32_t {   // global 0-based cell -> local id, -2 if not held here
+        if (cg >= cb && cg < ce) return int32_t(cg - cb);
+        auto it = std::lower_bound(gcells.begin(), gcells.end(), cg);
+        if (it != gcells.end() && *it == cg) return int32_t(ncown + (it - gcells.begin()));
+        return -2;
+    };
+    auto global_cell = [&](int64_t cl) { return cl < ncown ? cb + cl : gcells[cl - ncown]; };
+    // ghost faces: faces of local cells outside the owned range
+    std::vector<int64_t> gfaces;
+    for (int64_t cl = 0; cl < ncloc; ++cl) {
+        const int64_t cg = global_cell(cl);
+        for (int k = 0; k < 3; ++k) {
+            int64_t f = cells[6 * cg + 3 + k] - 1;
+            if (f < fb || f >= fe) gfaces.push_back(f);
+        }
+    }
+    std::sort(gfaces.begin(), gfaces.end());
+    gfaces.erase(std::unique(gfaces.begin(), gfaces.end()), gfaces.end());
+    const int64_t nfloc = nown + int64_t(gfaces.size());
+    auto local_face = [&](int64_t f) -> int64_t {
+        if (f >= fb && f < fe) return f - fb;
+        return nown + (std::lower_bound(gfaces.begin(), gfaces.end(), f) - gfaces.begin());
+    };
+    auto global_face = [&](int64_t fl) { return fl < nown ? fb + fl : gfaces[fl - nown]; };
+    // device-format arrays
+    std::vector<int32_t> cellinfo(size_t(ncloc) * CI, 0), facecell(size_t(nfloc) * 2), facenode(size_t(nfloc) * 2), bf;
+    for (int64_t cl = 0; cl < ncloc; ++cl) {
+        const int64_t cg = global_cell(cl);
+        for (int k = 0; k < 3; ++k) cellinfo[CI * cl + k] = int32_t(cells[6 * cg + k] - 1);   // node ids stay global
+        for (int k = 0; k < 3; ++k) {
+            const int64_t f = cells[6 * cg + 3 + k] - 1;
+            const uint32_t sec = (FC(f, 3) - 1 == cg) ? 0x80000000u : 0u;
+            cellinfo[CI * cl + 3 + k] = int32_t(uint32_t(local_face(f)) | sec);
+        }
+    }
+    std::vector<uint8_t> isdir(size_t(nface), 0);
+    for (int64_t i = 0; i < nbface; ++i) {
+        if (bfaces[i] < 1 || bfaces[i] > nface) return set_err(c, HDG_ERR_INVALID, "boundary face id out of range");
+        if (FC(bfaces[i] - 1, 3) != 0) return set_err(c, HDG_ERR_NOT_BOUNDARY, "Face " + std::to_string(bfaces[i]) + " is not in boundary");
+        isdir[bfaces[i] - 1] = 1;
+    }
+    for (int64_t fl = 0; fl < nfloc; ++fl) {
+        const int64_t f = global_face(fl);
+        facenode[2 * fl] = int32_t(FC(f, 0) - 1);
+        facenode[2 * fl + 1] = int32_t(FC(f, 1) - 1);
+        facecell[2 * fl] = local_cell(FC(f, 2) - 1);
+        facecell[2 * fl + 1] = FC(f, 3) == 0 ? -1 : local_cell(FC(f, 3) - 1);
+        if (isdir[f]) bf.push_back(int32_t(fl));
+    }
+    // ghost face -> (owner rank, local index there)
+    std::vector<int32_t> ridx, owner;
+    for (int64_t f : gfaces) {
+        int q = int(std::upper_bound(F0.begin(), F0.end(), f) - F0.begin()) - 1;
+        owner.push_back(q);
+        ridx.push_back(int32_t(f - F0[q]));
+    }
+    c->ncell = ncloc; c->ncell_own = ncown; c->nnode = nnode; c->nface = nfloc; c->nface_own = nown;
+    c->nbface = int64_t(bf.size()); c->nx = c->ny = 0;
+    hdg_status st = alloc_mesh(c);
+    if (st) return st;
+    HDG_CUDA(c, cudaMemcpyAsync(c->d_cellinfo, cellinfo.data(), sizeof(int32_t) * cellinfo.size(), cudaMemcpyHostToDevice, c->stream));
+    HDG_CUDA(c, cudaMemcpyAsync(c->d_facecell, facecell.data(), sizeof(int32_t) * facecell.size(), cudaMemcpyHostToDevice, c->stream));
+    HDG_CUDA(c, cudaMemcpyAsync(c->d_facenode, facenode.data(), sizeof(int32_t) * facenode.size(), cudaMemcpyHostToDevice, c->stream));
+    HDG_CUDA(c, cudaMemcpyAsync(c->d_nodes, nodes, sizeof(double) * 2 * nnode, cudaMemcpyHostToDevice, c->stream));
+    const int B = 256;
+    build_kcol<<<(unsigned)ceil_div(ncloc, B), B, 0, c->stream>>>(c->d_cellinfo, ncloc, c->d_kcol);
+    build_partner<<<(unsigned)ceil_div(ncloc, B), B, 0, c->stream>>>(c->d_cellinfo, ncloc, c->d_facecell);
+    c->launches += 2;
+    if (!bf.empty()) {
+        HDG_CUDA(c, cudaMemcpyAsync(c->d_bfaces, bf.data(), sizeof(int32_t) * bf.size(), cudaMemcpyHostToDevice, c->stream));
+        mark_isbc_list<<<(unsigned)ceil_div(int64_t(bf.size()), B), B, 0, c->stream>>>(c->d_bfaces, int64_t(bf.size()), c->d_isbc);
+        c->launches += 1;
+    }
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    m->j0 = m->j1 = m->ny_global = 0;
+    m->cell_begin = cb; m->face_begin = fb; m->ncell_global = ncell; m->nface_global = nface;
+    m->nbelow = m->nabove = 0;
+    m->general_mesh = true;
+    comm_free_halo(c);
+    st = comm_set_ghosts(c, ridx, owner);
+    if (st) return st;
+    st = alloc_system(c);
+    if (st) return st;
+    c->have_mesh = true;
+    return HDG_OK;
+}
+
 hdg_status mesh_from_host(hdg_context* c, const int64_t* cells, int64_t ncell, const double* nodes, int64_t nnode,
                           const int64_t* faces, int64_t nface, const int64_t* bfaces, int64_t nbface) {
-    if (comm_active(c)) return set_err(c, HDG_ERR_INVALID, "multi-GPU runs partition hdg_set_rectangle_mesh; hdg_set_mesh is single-GPU");
+    if (comm_active(c)) return mesh_from_host_partitioned(c, cells, ncell, nodes, nnode, faces, nface, bfaces, nbface);
     c->ncell = c->ncell_own = ncell; c->nnode = nnode; c->nface = c->nface_own = nface; c->nbface = nbface; c->nx = c->ny = 0;
     hdg_status st = alloc_mesh(c);
     if (st) return st;
@@ -711,10 +839,13 @@ hdg_status mesh_rectangle(hdg_context* c, int64_t nx, int64_t ny, double llx, do
         st = comm_setup_halo(c, send_dn, send_up);
         if (st) return st;
         // ghost face -> local face index on the rank that owns it (peer-memory SpMV)
-        std::vector<int32_t> ridx;
+        std::vector<int32_t> ridx, owner;
         if (j0 > 0) {
             const int64_t jp = ny * (m->rank - 1) / m->nranks, F0p = quad_base(0, jp, nx);
-            for (int64_t i = 0; i < nx; ++i) ridx.push_back(int32_t(quad_faces(i, j0 - 1, nx).top - F0p));
+            for (int64_t i = 0; i < nx; ++i) {
+                ridx.push_back(int32_t(quad_faces(i, j0 - 1, nx).top - F0p));
+                owner.push_back(m->rank - 1);
+            }
         }
         if (j1 < ny) {
             const int64_t F0n = quad_base(0, j1, nx);
@@ -722,9 +853,12 @@ hdg_status mesh_rectangle(hdg_context* c, int64_t nx, int64_t ny, double llx, do
                 QuadFaces F = quad_faces(i, j1, nx);
                 ridx.push_back(int32_t(F.left - F0n));
                 ridx.push_back(int32_t(F.diag - F0n));
+                owner.push_back(m->rank + 1);
+                owner.push_back(m->rank + 1);
             }
         }
-        st = comm_set_ghost_ridx(c, ridx);
+        m->general_mesh = false;
+        st = comm_set_ghosts(c, ridx, owner);
         if (st) return st;
     }
     st = alloc_system(c);

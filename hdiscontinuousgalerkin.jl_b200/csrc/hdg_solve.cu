@@ -149,13 +149,13 @@ struct PcgArgs {
     int np;            // number of partials == gridDim of the vector kernels
     double rtol;
     const int32_t* ghost_ridx;   // ghost face -> local face index on its owner (peer-memory SpMV)
-    const double* peer_p[2];     // p of rank-1 / rank+1, mapped over NVLink (nullptr: ghost values live behind the owned part of p)
-    const double* peer_r[2];     // ghost_mode 2: the neighbours' r, Dinv (peer_p then points at their PREVIOUS direction)
-    const double* peer_dinv[2];
+    const int32_t* ghost_owner;  // ... and the rank that owns it
+    const double* peer_p[MAXR];  // p of the other ranks, mapped over NVLink (ghost_mode 0: ghost values live behind the owned part of p)
+    const double* peer_r[MAXR];  // ghost_mode 2: the neighbours' r, Dinv (peer_p then points at their PREVIOUS direction)
+    const double* peer_dinv[MAXR];
     double* pnext;               // where pcg_dir writes the next direction (p is double-buffered)
     int ghost_mode;              // 0 local ghost segment (NCCL halo), 1 peer p read in place, 2 peer p recomputed on the fly
     int parity;                  // iteration parity (which r.z partial array is current)
-    int64_t nbelow;              // ghost faces owned by rank-1 (they come first)
 };
 
 __device__ __forceinline__ double get_sum(const PcgArgs& a, int which) {
@@ -265,7 +265,7 @@ __device__ __forceinline__ void spmv_face(const PcgArgs& a, int64_t f, double (&
         double pg[NT];
         if (g >= a.nface && a.ghost_mode) {   // face owned by a neighbouring rank: its p comes straight over NVLink
             const int64_t gi = g - a.nface;
-            const int w = gi < a.nbelow ? 0 : 1;
+            const int w = a.ghost_owner[gi];
             const int64_t ro = int64_t(a.ghost_ridx[gi]) * NT;
             if (a.ghost_mode == 2) {
                 // the neighbour is still writing p_k (pcg_dir runs concurrently, no barrier in between): rebuild it from
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(RB) pcg_spmv_rows(const PcgArgs a) {
             const double* pg = a.p + int64_t(cc[s]) * NT;
             if (cc[s] >= a.nface && a.ghost_mode) {
                 const int64_t gi = cc[s] - a.nface;
-                pg = a.peer_p[gi < a.nbelow ? 0 : 1] + int64_t(a.ghost_ridx[gi]) * NT;
+                pg = a.peer_p[a.ghost_owner[gi]] + int64_t(a.ghost_ridx[gi]) * NT;
             }
 #pragma unroll
             for (int b = 0; b < NT; ++b) y = fma(ko[s * NT2 + b * NT], pg[b], y);
@@ -550,7 +550,7 @@ __global__ void pcg_fetch_ghost_x(const PcgArgs a, int64_t nghost, int nt, doubl
     if (k >= nghost * nt) return;
     int64_t gi = k / nt;
     int e = int(k - gi * nt);
-    const double* src = a.peer_p[gi < a.nbelow ? 0 : 1];
+    const double* src = a.peer_p[a.ghost_owner[gi]];
     x[(a.nface + gi) * nt + e] = src[int64_t(a.ghost_ridx[gi]) * nt + e];
 }
 
@@ -563,6 +563,8 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
     const int64_t Nloc = c->nface * NT;           // owned + ghost entries of the vectors
     const bool multi = comm_active(c);
     const bool p2p = multi && comm_p2p(c);
+    if (multi && !p2p && c->comm->general_mesh)
+        return set_err(c, HDG_ERR_NCCL, "partitioned hdg_set_mesh meshes need the peer-memory path (CUDA IPC between the GPUs)");
     const bool blockjac = c->precond == 1;
     if (!c->d_x) HDG_CUDA(c, cudaMalloc(&c->d_x, sizeof(double) * Nloc));
     if (!c->d_p) {
@@ -592,7 +594,7 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
     const int ghost_mode = !p2p ? 0 : ((blockjac || NT == 5 || getenv("HDG_PCG_BARRIER")) ? 1 : 2);
     if (p2p) {
         a.ghost_ridx = c->comm->d_ghost_ridx;
-        a.nbelow = c->comm->nbelow;
+        a.ghost_owner = c->comm->d_ghost_owner;
         a.ghost_mode = ghost_mode;
     }
     a.np = int(std::min<int64_t>(ceil_div(c->nface_own, RB), std::min<int64_t>(int64_t(sms) * 8, MAX_PARTIALS)));
@@ -604,7 +606,7 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
         arg[par].p = c->d_p + par * Nloc;
         arg[par].pnext = c->d_p + (par ^ 1) * Nloc;
         if (p2p)
-            for (int w = 0; w < 2; ++w) {
+            for (int w = 0; w < MAXR; ++w) {
                 const double* base = static_cast<const double*>(c->comm->peer_vec[w]);
                 if (!base) continue;
                 const int64_t Np = c->comm->peer_ndof[w];
@@ -683,7 +685,7 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
             HDG_CUDA(c, cudaMemcpyAsync(c->d_p, c->d_x, sizeof(double) * N, cudaMemcpyDeviceToDevice, c->stream));
             global_sums(0);
             PcgArgs af = arg[0];
-            for (int w = 0; w < 2; ++w) af.peer_p[w] = static_cast<const double*>(c->comm->peer_vec[w]);   // buffer 0 of the neighbours
+            for (int w = 0; w < MAXR; ++w) af.peer_p[w] = static_cast<const double*>(c->comm->peer_vec[w]);   // buffer 0 of the neighbours
             if (nghost > 0) {
                 pcg_fetch_ghost_x<<<(unsigned)ceil_div(nghost * NT, 256), 256, 0, c->stream>>>(af, nghost, NT, c->d_x);
                 c->launches += 1;

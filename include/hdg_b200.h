@@ -94,7 +94,9 @@ const char* hdg_version(void);
  * "boundary"), any order, 1-based).  Replaces CellIterator/reinit! gathers (src/iterator.jl:48-57).
  * faces may be NULL: the face table is then rebuilt on the device from the cells (the first cell of a face is
  * the adjacent cell with the smaller id, exactly what the first-encounter numbering produces), which saves
- * the host-to-device copy of the largest array; nface must still be given. */
+ * the host-to-device copy of the largest array; nface must still be given.
+ * After hdg_comm_init every rank passes the SAME whole mesh (faces required, first-encounter numbering) and keeps
+ * a contiguous range of cells and of the faces they create, plus ghost cells / ghost columns (hdg_get_partition). */
 hdg_status hdg_set_mesh(hdg_context* ctx,
                         const int64_t* cells, int64_t ncell,
                         const double* nodes, int64_t nnode,

@@ -17,9 +17,14 @@ sys.path.insert(0, ROOT)
 import hdg_b200 as hdg  # noqa: E402
 
 
-def solve(ctx, nx, ny, rtol):
+def solve(ctx, nx, ny, rtol, host_mesh=None):
     lib = ctx.lib
-    hdg.check(lib.hdg_set_rectangle_mesh(ctx.h, nx, ny, 0.0, 0.0, 2.0, 1.0), ctx.h)
+    if host_mesh is None:
+        hdg.check(lib.hdg_set_rectangle_mesh(ctx.h, nx, ny, 0.0, 0.0, 2.0, 1.0), ctx.h)
+    else:   # hdg_set_mesh: every rank passes the whole mesh, the library keeps a contiguous cell range + ghosts
+        cells, nodes, faces, bf = host_mesh
+        hdg.check(lib.hdg_set_mesh(ctx.h, hdg.api.i64p(cells), cells.shape[0], hdg.api.f64p(nodes), nodes.shape[0],
+                                   hdg.api.i64p(faces), faces.shape[0], hdg.api.i64p(bf), bf.size), ctx.h)
     hdg.check(lib.hdg_assemble(ctx.h), ctx.h)
     hdg.check(lib.hdg_apply_dirichlet(ctx.h, None), ctx.h)
     info = hdg.api.SolveInfo()
@@ -68,6 +73,46 @@ def main():
             ok &= good
             print(f"k={order} {nx}x{ny} on {world} GPUs: iters {iters} (1 GPU: {it1})  relerr(uhat)={ex:.2e} relerr(u)={eu:.2e} "
                   f"err2 {err2:.12e} vs {e1:.12e}  meandiag {md:.15g} vs {md1:.15g}  {'OK' if good else 'FAIL'}", flush=True)
+    # ---- unstructured meshes through hdg_set_mesh: a jittered mesh with randomly permuted cells (scattered
+    # subdomains: every rank neighbours every other) and the same mesh in its natural order
+    rng = np.random.default_rng(5)
+    gen = hdg._Context(1, 2, 1.0, 1, lr)
+    hdg.check(gen.lib.hdg_set_rectangle_mesh(gen.h, 19, 14, 0.0, 0.0, 2.0, 1.0), gen.h)
+    base = gen.download_mesh()
+    gen.close()
+    nodes = base.nodes.copy()
+    bnodes = np.unique(base.faces[base.faces[:, 3] == 0, :2]) - 1
+    interior = np.ones(nodes.shape[0], bool)
+    interior[bnodes] = False
+    nodes[interior] += rng.uniform(-0.012, 0.012, size=(interior.sum(), 2))
+    for label, perm in (("natural", np.arange(base.cells.shape[0])), ("permuted", rng.permutation(base.cells.shape[0]))):
+        cf, faces = hdg.number_faces(base.cells[perm, :3])
+        cells = np.ascontiguousarray(np.hstack([base.cells[perm, :3], cf]))
+        faces = np.asfortranarray(faces)
+        bf = np.flatnonzero(faces[:, 3] == 0).astype(np.int64) + 1
+        for order, qd in ((1, 2), (3, 6)):
+            ctx = hdg._Context(order, qd, 1.0, 1, lr)
+            ctx.comm_init(dist, device=torch.device("cuda", lr))
+            x, u, err2, iters, md = solve(ctx, 0, 0, 1e-13, (cells, nodes, faces, bf))
+            part = ctx.partition()
+            xs, us = [None] * world, [None] * world
+            dist.all_gather_object(xs, (part["face_begin"], x))
+            dist.all_gather_object(us, (part["cell_begin"], u))
+            ghosts = [None] * world
+            dist.all_gather_object(ghosts, (part["ghost_cells"], part["ghost_faces"]))
+            ctx.close()
+            if rank == 0:
+                ref = hdg._Context(order, qd, 1.0, 1, lr)
+                xr, ur, e1, it1, md1 = solve(ref, 0, 0, 1e-13, (cells, nodes, faces, bf))
+                ref.close()
+                xg = np.concatenate([p[1] for p in sorted(xs, key=lambda p: p[0])])
+                ug = np.concatenate([p[1] for p in sorted(us, key=lambda p: p[0])], axis=0)
+                ex = np.abs(xg - xr).max() / np.abs(xr).max()
+                eu = np.abs(ug - ur).max() / np.abs(ur).max()
+                good = xg.shape == xr.shape and ex < 1e-10 and eu < 1e-10 and abs(err2 - e1) <= 1e-9 * e1 + 1e-20 and abs(md - md1) <= 1e-13 * md1
+                ok &= good
+                print(f"hdg_set_mesh {label} k={order} on {world} GPUs: iters {iters} (1 GPU: {it1}) ghosts/rank {ghosts}  "
+                      f"relerr(uhat)={ex:.2e} relerr(u)={eu:.2e} err2 {err2:.6e} vs {e1:.6e}  {'OK' if good else 'FAIL'}", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.barrier()
