@@ -9,6 +9,7 @@
 module HDGB200
 
 using HDiscontinuousGalerkin
+using SparseArrays, LinearAlgebra
 import HDiscontinuousGalerkin: getnbasefunctions, getncells, getnfaces, getfaceset
 
 const lib = get(ENV, "LIBHDG_B200", "libhdg_b200.so")

@@ -210,6 +210,31 @@ def test_randomly_permuted_unstructured_mesh(seed, order, qd):
     assert abs(res["err2"] - ro["err2"]) <= 1e-9 * ro["err2"] + 1e-20
 
 
+@pytest.mark.parametrize("seed,order,qd", [(0, 1, 2), (1, 2, 4), (2, 3, 6)])
+def test_random_delaunay_mesh(seed, order, qd):
+    """Unstructured Delaunay triangulation of random points in the unit square (varying shapes and vertex valence),
+    numbered on the device (hdg_number_faces), assembled / solved / recovered, against the oracle."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(seed)
+    g = np.linspace(0.0, 1.0, 7)
+    border = np.array([[x, y] for x in g for y in g if x in (0.0, 1.0) or y in (0.0, 1.0)])
+    pts = np.vstack([border, 0.08 + 0.84 * rng.random((70, 2))])
+    tri = Delaunay(pts).simplices.astype(np.int64) + 1
+    cells, faces = hdg.number_faces_gpu(tri, pts)
+    e1, e2 = pts[cells[:, 1] - 1] - pts[cells[:, 0] - 1], pts[cells[:, 2] - 1] - pts[cells[:, 0] - 1]
+    area = 0.5 * (e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0])   # positive: hdg_number_faces made every cell counter-clockwise
+    keep = area > 1e-6                      # Delaunay may return (near-)degenerate slivers on the collinear border points
+    assert keep.all()
+    bnd = set((np.flatnonzero(faces[:, 3] == 0) + 1).tolist())
+    mo = orc.Mesh(cells[:, :3].copy(), cells[:, 3:].copy(), pts, np.ascontiguousarray(faces), {"boundary": bnd})
+    r, asm, tab = _check_assembly(mo, order, qd)
+    ro = orc.run_poisson(mo, order, qd)
+    res = hdg.poisson2D_HDG(r["mesh"], order, qd, rtol=1e-14)
+    assert relerr(res["uhat"].to_numpy(), ro["uhat"]) < RTOL
+    assert relerr(res["u_h"].m_values, ro["u"]) < RTOL and relerr(res["sigma_h"].m_values, ro["sigma"]) < RTOL
+    assert abs(res["err2"] - ro["err2"]) <= 1e-9 * ro["err2"] + 1e-20
+
+
 @pytest.mark.parametrize("nx,ny", [(1, 1), (1, 2), (33, 1)])
 def test_tiny_and_thin_meshes(nx, ny):
     mo = orc.rectangle_mesh(nx, ny)

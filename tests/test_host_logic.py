@@ -40,6 +40,20 @@ def test_face_numbering_random_permutation():
     assert np.array_equal(cf, cell_faces) and np.array_equal(fa, faces)
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_face_numbering_random_delaunay(seed):
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(seed)
+    pts = rng.random((60, 2))
+    tri = Delaunay(pts).simplices.astype(np.int64) + 1
+    ccw = np.array([orc._check_node_data(pts, *t) for t in tri], dtype=np.int64)
+    cells, cell_faces, faces = orc._build_cells_sequential([tuple(t) for t in ccw], pts, 3 * len(ccw))
+    cf, fa = hdg.number_faces(ccw)
+    assert np.array_equal(cf, cell_faces) and np.array_equal(fa, faces)
+    # Euler: V - E + F = 1 for a triangulated disc
+    assert pts.shape[0] - fa.shape[0] + ccw.shape[0] == 1
+
+
 def test_non_manifold_rejected():
     with pytest.raises(ValueError):
         hdg.number_faces(np.array([[1, 2, 3], [2, 1, 4], [1, 2, 5]]))
