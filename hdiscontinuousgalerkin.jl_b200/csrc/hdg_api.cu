@@ -116,6 +116,7 @@ void hdg_destroy(hdg_context* c) {
     free_mesh(c);
     comm_destroy(c);
     if (c->d_rawtab) cudaFree(c->d_rawtab);
+    if (c->d_devtab) cudaFree(c->d_devtab);
     if (c->d_flags) cudaFree(c->d_flags);
     if (c->d_scal) cudaFree(c->d_scal);
     if (c->d_partials) cudaFree(c->d_partials);
@@ -187,6 +188,18 @@ static const std::vector<double>* table_by_name(const RefTables& T, const std::s
     if (s == "E") return &T.E;
     if (s == "T") return &T.T;
     if (s == "Mhat") return &T.Mhat;
+    // reference matrices consumed by the device kernels (hdg_tables.h)
+    if (s == "Tr") return &T.Tr;
+    if (s == "Ts") return &T.Ts;
+    if (s == "Prr") return &T.Prr;
+    if (s == "Prs") return &T.Prs;
+    if (s == "Pss") return &T.Pss;
+    if (s == "Chat") return &T.Chat;
+    if (s == "Fhat") return &T.Fhat;
+    if (s == "MF") return &T.MF;
+    if (s == "Qr") return &T.Qr;
+    if (s == "Qs") return &T.Qs;
+    if (s == "Hhat") return &T.Hhat;
     return nullptr;
 }
 

@@ -23,9 +23,12 @@
 // contributing cell -> plain stores.  Face-diagonal blocks and rhs entries have at most two
 // contributions -> RED.ADD.F64 onto zeroed storage, which is bitwise deterministic because a
 // two-term IEEE sum is commutative.
+#include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 #include "hdg_internal.h"
+#include "hdg_sparsity.h"
 
 namespace hdg {
 
@@ -462,6 +465,10 @@ __global__ void __launch_bounds__(SchurCfg<K>::threads, SchurCfg<K>::min_blocks)
     }
 }
 
+}  // namespace hdg
+#include "hdg_element_quad.cuh"
+namespace hdg {
+
 // ---------------------------------------------------------------------------------------------
 // General path: literal quadrature + dense LU with partial pivoting, one warp per element.
 // Follows examples/poisson2D_HDG.jl:88-174 term by term.
@@ -868,16 +875,49 @@ template <int K> static void fill_dev_tables(const RefTables& R, DevTables<K>& D
     D.pad = 0;
 }
 
+// element_quad_kernel skips the products hdg_sparsity.h calls structurally zero: check the header against the tables
+// this context actually built (any rule that integrates the mass matrix exactly gives the same reference matrices).
+template <int K> static bool sparsity_matches(const DevTables<K>& D) {
+    constexpr int n = Ord<K>::n, t = Ord<K>::t;
+    auto amax = [](const double* p, int cnt) { double m = 0.0; for (int i = 0; i < cnt; ++i) m = std::max(m, std::fabs(p[i])); return m; };
+    const double mr = amax(D.Tr, n * n), ms = amax(D.Ts, n * n), mf = amax(D.Fhat, n * t);
+    const double tol = 1e-10;
+    for (int i = 0; i < n; ++i) {
+        for (int k = 0; k < n; ++k) {
+            if (!((Sparsity<K>::tr(i) >> k) & 1u) && std::fabs(D.Tr[i * n + k]) > tol * mr) return false;
+            if (!((Sparsity<K>::ts(i) >> k) & 1u) && std::fabs(D.Ts[i * n + k]) > tol * ms) return false;
+        }
+        for (int j = 0; j < t; ++j)
+            if (!((Sparsity<K>::fh(i) >> j) & 1u) && std::fabs(D.Fhat[i * t + j]) > tol * mf) return false;
+    }
+    return true;
+}
+
+template <int K, typename Sym> static hdg_status upload_dev_tables(hdg_context* c, const Sym& symbol) {
+    static DevTables<K> D;
+    fill_dev_tables<K>(c->tab, D);
+    HDG_CUDA(c, cudaMemcpyToSymbol(symbol, &D, sizeof(D)));
+    // global-memory copy for lane-varying indices (element_quad_kernel)
+    if (c->d_devtab) cudaFree(c->d_devtab);
+    c->d_devtab = nullptr;
+    HDG_CUDA(c, cudaMalloc(&c->d_devtab, sizeof(D)));
+    HDG_CUDA(c, cudaMemcpy(c->d_devtab, &D, sizeof(D), cudaMemcpyHostToDevice));
+    c->quad_ok = sparsity_matches<K>(D);
+    return HDG_OK;
+}
+
 hdg_status upload_tables(hdg_context* c) {
     const RefTables& R = c->tab;
     if (R.nq > MAX_NQ || R.nfq > MAX_NFQ) return set_err(c, HDG_ERR_UNSUPPORTED_RULE, "quadrature rule too large for the device tables");
     if (!c->use_lu) {
+        hdg_status st = HDG_OK;
         switch (R.order) {
-            case 1: { static DevTables<1> D; fill_dev_tables<1>(R, D); HDG_CUDA(c, cudaMemcpyToSymbol(c_tab1, &D, sizeof(D))); break; }
-            case 2: { static DevTables<2> D; fill_dev_tables<2>(R, D); HDG_CUDA(c, cudaMemcpyToSymbol(c_tab2, &D, sizeof(D))); break; }
-            case 3: { static DevTables<3> D; fill_dev_tables<3>(R, D); HDG_CUDA(c, cudaMemcpyToSymbol(c_tab3, &D, sizeof(D))); break; }
-            case 4: { static DevTables<4> D; fill_dev_tables<4>(R, D); HDG_CUDA(c, cudaMemcpyToSymbol(c_tab4, &D, sizeof(D))); break; }
+            case 1: st = upload_dev_tables<1>(c, c_tab1); break;
+            case 2: st = upload_dev_tables<2>(c, c_tab2); break;
+            case 3: st = upload_dev_tables<3>(c, c_tab3); break;
+            case 4: st = upload_dev_tables<4>(c, c_tab4); break;
         }
+        if (st) return st;
     }
     // raw tables in global memory (LU path, error norm)
     std::vector<double> buf;
@@ -908,6 +948,24 @@ template <int K> static hdg_status launch_schur(hdg_context* c, const ElemArgs& 
     return HDG_OK;
 }
 
+// Orders >= 2: four lanes per element (hdg_element_quad.cuh).  HDG_ELEM_V1=1 selects the thread-per-element kernel
+// (A/B measurements); it is also the fallback if hdg_sparsity.h does not match the tables of this context.
+template <int K> static hdg_status launch_quad(hdg_context* c, const ElemArgs& a) {
+    using Q = QuadCfg<K>;
+    auto kern = element_quad_kernel<K>;
+    if (Q::smem > 48 * 1024) HDG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Q::smem)));
+    int64_t ncell = a.cell_end - a.cell_begin;
+    kern<<<(unsigned)ceil_div(ncell, Q::cells), Q::threads, Q::smem, c->stream>>>(a, static_cast<const DevTables<K>*>(c->d_devtab));
+    c->launches += 1;
+    HDG_CUDA(c, cudaGetLastError());
+    return HDG_OK;
+}
+
+static bool use_quad_kernel(const hdg_context* c) {
+    static const bool v1 = getenv("HDG_ELEM_V1") != nullptr;
+    return c->tab.order >= 2 && c->quad_ok && c->d_devtab != nullptr && !v1;
+}
+
 static hdg_status launch_elements(hdg_context* c, ElemArgs a) {
     if (c->use_lu && c->tab.order == 1 && getenv("HDG_LU_WARP") == nullptr) {   // k = 2 measured 2.4x slower than the warp kernel (local-memory bound)
         LuArgs A{a, c->raw, c->tab.n, c->tab.nt};
@@ -934,6 +992,13 @@ static hdg_status launch_elements(hdg_context* c, ElemArgs a) {
         hdg_status st = upload_tables(c);
         if (st) return st;
         g_table_owner[c->tab.order] = c;
+    }
+    if (use_quad_kernel(c)) {
+        switch (c->tab.order) {
+            case 2: return launch_quad<2>(c, a);
+            case 3: return launch_quad<3>(c, a);
+            case 4: return launch_quad<4>(c, a);
+        }
     }
     switch (c->tab.order) {
         case 1: return launch_schur<1>(c, a);

@@ -130,7 +130,9 @@ hdg_status hdg_get_mesh(hdg_context* ctx, int64_t* cells, double* nodes, int64_t
 
 /* Reference tables, for checking against the Julia-side tables.  name is one of
  * "qpoints"(nq*2) "qweights"(nq) "fpoints"(nfq) "fweights"(nfq) "N"(n*nq, N[i,q] at i+n*q)
- * "dNdxi"(n*nq*2) "E"(n*nfq*3, [i + n*(p + nfq*l)]) "T"(nt*nfq).  Returns the number of
+ * "dNdxi"(n*nq*2) "E"(n*nfq*3, [i + n*(p + nfq*l)]) "T"(nt*nfq), or one of the derived reference
+ * matrices the kernels consume (row-major, hdg_tables.h): "Tr" "Ts" "Prr" "Prs" "Pss" (n*n),
+ * "Chat"(3*n*n) "Fhat" "MF" "Qr" "Qs" (n*t) "Hhat"(nt*nt).  Returns the number of
  * doubles written through *count (buf may be NULL to query). */
 hdg_status hdg_get_table(const hdg_context* ctx, const char* name, double* buf, int64_t* count);
 /* Same tables without a context (host-only table builder; needs no device). */
