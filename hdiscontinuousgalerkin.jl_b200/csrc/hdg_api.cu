@@ -116,7 +116,6 @@ void hdg_destroy(hdg_context* c) {
     free_mesh(c);
     comm_destroy(c);
     if (c->d_rawtab) cudaFree(c->d_rawtab);
-    if (c->d_devtab) cudaFree(c->d_devtab);
     if (c->d_flags) cudaFree(c->d_flags);
     if (c->d_scal) cudaFree(c->d_scal);
     if (c->d_partials) cudaFree(c->d_partials);

@@ -897,11 +897,6 @@ template <int K, typename Sym> static hdg_status upload_dev_tables(hdg_context* 
     static DevTables<K> D;
     fill_dev_tables<K>(c->tab, D);
     HDG_CUDA(c, cudaMemcpyToSymbol(symbol, &D, sizeof(D)));
-    // global-memory copy for lane-varying indices (element_quad_kernel)
-    if (c->d_devtab) cudaFree(c->d_devtab);
-    c->d_devtab = nullptr;
-    HDG_CUDA(c, cudaMalloc(&c->d_devtab, sizeof(D)));
-    HDG_CUDA(c, cudaMemcpy(c->d_devtab, &D, sizeof(D), cudaMemcpyHostToDevice));
     c->quad_ok = sparsity_matches<K>(D);
     return HDG_OK;
 }
@@ -955,7 +950,7 @@ template <int K> static hdg_status launch_quad(hdg_context* c, const ElemArgs& a
     auto kern = element_quad_kernel<K>;
     if (Q::smem > 48 * 1024) HDG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Q::smem)));
     int64_t ncell = a.cell_end - a.cell_begin;
-    kern<<<(unsigned)ceil_div(ncell, Q::cells), Q::threads, Q::smem, c->stream>>>(a, static_cast<const DevTables<K>*>(c->d_devtab));
+    kern<<<(unsigned)ceil_div(ncell, Q::cells), Q::threads, Q::smem, c->stream>>>(a);
     c->launches += 1;
     HDG_CUDA(c, cudaGetLastError());
     return HDG_OK;
@@ -963,7 +958,7 @@ template <int K> static hdg_status launch_quad(hdg_context* c, const ElemArgs& a
 
 static bool use_quad_kernel(const hdg_context* c) {
     static const bool v1 = getenv("HDG_ELEM_V1") != nullptr;
-    return c->tab.order >= 2 && c->quad_ok && c->d_devtab != nullptr && !v1;
+    return c->tab.order >= 2 && c->quad_ok && !v1;
 }
 
 static hdg_status launch_elements(hdg_context* c, ElemArgs a) {

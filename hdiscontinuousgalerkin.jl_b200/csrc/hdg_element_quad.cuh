@@ -1,42 +1,37 @@
-// element_quad_kernel<K>: the fused blocks + condensation + scatter pass for orders k >= 2, FOUR lanes per element.
+// element_quad_kernel<K>: the fused blocks + condensation + scatter pass for orders k >= 2, FOUR threads per element.
 //
 // Same mathematics and the same outputs as element_schur_kernel<K> (hdg_element.cu; reference:
 // examples/poisson2D_HDG.jl:77-184), different mapping.  At k >= 2 a thread per element needs 220-255 registers
 // and 0.8-1.9 kB of shared memory, which leaves 8 warps per SM and long FP64 dependency chains (ncu: issue active
-// 27-30 %).  Here the t+1 right-hand-side columns of an element - they are independent once S = C + B'A^-1 B is
-// factored - are dealt round-robin to 4 adjacent lanes, so a lane carries one column at a time:
-//   phase 1  S (n x n) is formed and factored L D L' cooperatively (lane q owns rows q, q+4, ...), L in shared
-//            memory; the load vector be is integrated with the quadrature points split over the 4 lanes and
-//            summed with two shuffles;
-//   phase 2  every lane solves its columns: u = S^-1 r, sigma = A^-1 (r1 + B u) row by row; each row is stored
-//            to [K_e | b_e] as soon as it exists and folded into the 3 nt accumulators of its Ate column.
-//            Products with structural zeros of the reference matrices Tr, Ts, Fhat are skipped at compile time
-//            (hdg_sparsity.h, validated on the host against the tables actually built);
+// 27-30 %, FP64 pipe 28-33 %).  The t+1 right-hand-side columns of an element are independent once
+// S = C + B'A^-1 B is factored, so a block of 128 threads takes one 32-cell tile and splits every element 4 ways:
+//   phase 0  (thread = cell tid%32, warp w = tid/32)  geometry; warp w forms rows w, w+4, ... of S and integrates the
+//            load vector be over the quadrature points w, w+4, ...; all reference-matrix operands are warp-uniform
+//            (constant bank); S and the partial load vectors go to shared memory;
+//   phase 1  (thread = cell tid/4, lane q = tid%4)  S is factored L D L' by 4 adjacent lanes: lane q owns rows
+//            q, q+4, ... and keeps them in registers, the pivot row is read from shared memory, pivots travel by
+//            shuffle; L and D^-1 overwrite S in shared memory;
+//   phase 2  (thread = cell tid%32, warp w = tid/32)  warp w solves the columns w, w+4, ... of [K_e | b_e] for the 32
+//            cells of the tile, CB columns at a time so that one shared-memory load of an L entry feeds CB FMAs.  The
+//            column index is warp-uniform, so reference-matrix operands come from the constant bank, and a store
+//            instruction writes one 256-byte row segment of the tile.  sigma = A^-1(r1 + B u) is formed row by row,
+//            stored, and folded into the 3 nt accumulators of the Ate column; products with structural zeros of
+//            Tr, Ts, Fhat are skipped at compile time (hdg_sparsity.h, validated on the host against the tables);
 //   phase 3  the face-diagonal blocks and rhs entries staged in shared memory are paired with the neighbour cell
-//            of the same 32-cell tile and stored (RED.ADD.F64 only when the neighbour is in another tile).
-// A block is 128 threads = one 32-cell tile of the [K_e | b_e] layout; a warp stores 4 columns x 8 cells per
-// instruction = 4 full 64-byte segments.
+//            of the same tile and stored (RED.ADD.F64 only when the neighbour is in another tile), warp w = face w.
 #pragma once
 
 namespace hdg {
 
-template <int K> struct QuadCfg {
-    static constexpr int n = Ord<K>::n, nt = Ord<K>::nt, t = Ord<K>::t;
-    static constexpr int G = 4;                       // lanes per element
-    static constexpr int cells = 32;                  // cells per block = one Ke tile
-    static constexpr int threads = G * cells;
-    static constexpr int R = (n + G - 1) / G;         // rows of S per lane
-    static constexpr int CC = (t + 1 + G - 1) / G;    // columns per lane
-    static constexpr int nL = n * (n - 1) / 2;
-    // shared-memory record per cell, stored [entry][cell]
-    static constexpr int o_L = 0;
-    static constexpr int o_dinv = o_L + nL;
-    static constexpr int o_be = o_dinv + n;
-    static constexpr int o_ca = o_be + n;             // ca[3], cb[3], dJf[3]
-    static constexpr int o_diag = o_ca + 9;
-    static constexpr int o_rhs = o_diag + 3 * nt * nt;
-    static constexpr int entries = o_rhs + 3 * nt;
-    static constexpr size_t smem = sizeof(double) * entries * cells;
+#ifndef QCB2
+#define QCB2 3
+#endif
+#ifndef QCB3
+#define QCB3 1
+#endif
+#ifndef QCB4
+#define QCB4 1
+#endif
 #ifndef QMINB2
 #define QMINB2 4
 #endif
@@ -46,87 +41,118 @@ template <int K> struct QuadCfg {
 #ifndef QMINB4
 #define QMINB4 3
 #endif
+
+template <int K> struct QuadCfg {
+    static constexpr int n = Ord<K>::n, nt = Ord<K>::nt, t = Ord<K>::t;
+    static constexpr int G = 4;                       // threads per element
+    static constexpr int cells = 32;                  // cells per block = one Ke tile
+    static constexpr int threads = G * cells;
+    static constexpr int CS = 33;                     // stride of one entry row in shared memory (odd: the 4-lanes-per-cell phase spreads over the banks)
+    static constexpr int R = (n + G - 1) / G;         // rows of S per lane (phase 1)
+    static constexpr int CC = (t + 1 + G - 1) / G;    // columns per warp (phase 2)
+    static constexpr int CB = K == 2 ? QCB2 : (K == 3 ? QCB3 : QCB4);   // columns per batch
+    static constexpr int NB = (CC + CB - 1) / CB;
+    static constexpr int nL = n * (n - 1) / 2;
+    // shared-memory record per cell, stored [entry][cell]
+    static constexpr int o_L = 0;                     // strict lower triangle of S, overwritten by L
+    static constexpr int o_dinv = o_L + nL;           // diagonal of S, overwritten by D^-1
+    static constexpr int o_be = o_dinv + n;
+    static constexpr int o_status = o_be + n;
+    static constexpr int o_diag = o_status + 1;       // staging of the face-diagonal blocks (phases 2-3); partial be sums (phases 0-1)
+    static constexpr int o_rhs = o_diag + 3 * nt * nt;
+    static constexpr int entries = o_rhs + 3 * nt;
+    static_assert(3 * nt * nt + 3 * nt >= 4 * n, "partial load vectors alias the staging area");
+    static constexpr size_t smem = sizeof(double) * entries * CS;
     static constexpr int min_blocks = K == 2 ? QMINB2 : (K == 3 ? QMINB3 : QMINB4);
 };
 
+// phase 0, rows i = W, W+4, ... of S = C + B'A^-1 B = tau sum_l |wn_l| Chat_l + detJ (al Prr + be Prs + ga Pss); W is a
+// template parameter so that every reference-matrix operand has a compile-time constant-bank address
+template <int K, int W>
+__device__ __forceinline__ void form_S_rows(double* __restrict__ sm, const double cf0, const double cf1, const double cf2,
+                                            const double al, const double be, const double ga) {
+    using Q = QuadCfg<K>;
+    constexpr int n = Q::n, CS = Q::CS;
+    const DevTables<K>& T = ctab<K>();
+#pragma unroll
+    for (int i = W; i < n; i += 4)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            double s = cf0 * T.Chat[(0 * n + i) * n + j];
+            s = fma(cf1, T.Chat[(1 * n + i) * n + j], s);
+            s = fma(cf2, T.Chat[(2 * n + i) * n + j], s);
+            s = fma(al, T.Prr[i * n + j], s);
+            s = fma(be, T.Prs[i * n + j], s);
+            s = fma(ga, T.Pss[i * n + j], s);
+            sm[(i == j ? Q::o_dinv + j : Q::o_L + tri(i, j)) * CS] = s;
+        }
+}
+
 template <int K>
-__global__ void __launch_bounds__(QuadCfg<K>::threads, QuadCfg<K>::min_blocks)
-element_quad_kernel(const ElemArgs a, const DevTables<K>* __restrict__ gt) {
+__global__ void __launch_bounds__(QuadCfg<K>::threads, QuadCfg<K>::min_blocks) element_quad_kernel(const ElemArgs a) {
     using Q = QuadCfg<K>;
     using Sp = Sparsity<K>;
-    constexpr int n = Q::n, nt = Q::nt, t = Q::t, ke = Ord<K>::ke, CS = Q::cells, R = Q::R;
+    constexpr int n = Q::n, nt = Q::nt, t = Q::t, ke = Ord<K>::ke, CS = Q::CS, R = Q::R, CB = Q::CB;
     constexpr int64_t nt2 = nt * nt;
-    const DevTables<K>& T = ctab<K>();          // uniform-index operands (constant bank)
+    const DevTables<K>& T = ctab<K>();          // warp-uniform operands (constant bank)
     extern __shared__ double smem[];
-    const int q = threadIdx.x & 3, ci = threadIdx.x >> 2;
-    double* const sm = smem + ci;               // this cell's record: sm[entry * CS]
-    const unsigned lane = threadIdx.x & 31u;
-
-    int64_t c = a.cell_begin + int64_t(blockIdx.x) * CS + ci;
-    bool active = c < a.cell_end;
-    if (!active) c = a.cell_end - 1;            // all lanes run (shuffles); only the stores are masked
     const bool dbg = a.dbg_At != nullptr;
-    CellGeom g;
-    load_geometry(a, c, g);
-    if (active && !g.ok) {
-        if (q == 0) atomicCAS(&a.flags[FLAG_BAD_GEOM], 0, int32_t(c + 1));
-        active = false;
-    }
+    const int64_t tile0 = a.cell_begin + int64_t(blockIdx.x) * Q::cells;
+    const int w = threadIdx.x >> 5, ci = threadIdx.x & 31;
+    double* const sm = smem + ci;               // record of cell ci: sm[entry * CS]
+    const int64_t c = tile0 + ci;
+    bool active = c < a.cell_end;
+    const int64_t cl = active ? c : a.cell_end - 1;      // padding cells compute on the last cell; nothing of theirs is stored
     const double tau = a.tau;
-    const bool o0 = g.v[2] > g.v[1], o1 = g.v[0] > g.v[2], o2 = g.v[1] > g.v[0];   // face_orientation, src/mesh.jl:51-54
-    const double cf0 = tau * g.dJf[0], cf1 = tau * g.dJf[1], cf2 = tau * g.dJf[2];
 
-    // ---- phase 1a: load vector be, quadrature points dealt to the 4 lanes ---------------------------------
+    // =========================== phase 0: lane = cell, warp w = rows / quadrature points w, w+4, ... ========
+    CellGeom g;
+    load_geometry(a, cl, g);
+    const double cf0 = tau * g.dJf[0], cf1 = tau * g.dJf[1], cf2 = tau * g.dJf[2];
     {
+        const double al = g.detJ * (g.G00 * g.G00 + g.G01 * g.G01);
+        const double be = g.detJ * (g.G00 * g.G10 + g.G01 * g.G11);
+        const double ga = g.detJ * (g.G10 * g.G10 + g.G11 * g.G11);
+        switch (w) {
+            case 0: form_S_rows<K, 0>(sm, cf0, cf1, cf2, al, be, ga); break;
+            case 1: form_S_rows<K, 1>(sm, cf0, cf1, cf2, al, be, ga); break;
+            case 2: form_S_rows<K, 2>(sm, cf0, cf1, cf2, al, be, ga); break;
+            default: form_S_rows<K, 3>(sm, cf0, cf1, cf2, al, be, ga); break;
+        }
+        // partial load vector: detJ sum_{q = w, w+4, ...} w_q f(x_q) N[i,q]   (poisson2D_HDG.jl:106-114)
         double bev[n];
 #pragma unroll
         for (int i = 0; i < n; ++i) bev[i] = 0.0;
-        for (int qq = q; qq < a.nq; qq += 4) {
+        for (int qq = w; qq < a.nq; qq += 4) {
             double fv;
-            if (a.source_id == 0) fv = a.fq[c * a.nq + qq];
+            if (a.source_id == 0) fv = a.fq[cl * a.nq + qq];
             else {
-                const double m0 = __ldg(&gt->Mgeo[3 * qq]), m1 = __ldg(&gt->Mgeo[3 * qq + 1]), m2 = __ldg(&gt->Mgeo[3 * qq + 2]);
+                const double m0 = T.Mgeo[3 * qq], m1 = T.Mgeo[3 * qq + 1], m2 = T.Mgeo[3 * qq + 2];
                 const double xq = m0 * g.x[0][0] + m1 * g.x[1][0] + m2 * g.x[2][0];
                 const double yq = m0 * g.x[0][1] + m1 * g.x[1][1] + m2 * g.x[2][1];
                 fv = source_value(a.source_id, xq, yq);
             }
 #pragma unroll
-            for (int i = 0; i < n; ++i) bev[i] = fma(__ldg(&gt->WN[qq * n + i]), fv, bev[i]);
+            for (int i = 0; i < n; ++i) bev[i] = fma(T.WN[qq * n + i], fv, bev[i]);
         }
 #pragma unroll
-        for (int i = 0; i < n; ++i) {
-            double s = bev[i];
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (q == (i & 3)) sm[(Q::o_be + i) * CS] = s * g.detJ;
-        }
-        if (q == 0) {
-#pragma unroll
-            for (int l = 0; l < 3; ++l) {
-                sm[(Q::o_ca + l) * CS] = g.G00 * g.wn[l][0] + g.G01 * g.wn[l][1];        // B'A^-1 E_l = ca_l Qr_l + cb_l Qs_l
-                sm[(Q::o_ca + 3 + l) * CS] = g.G10 * g.wn[l][0] + g.G11 * g.wn[l][1];
-                sm[(Q::o_ca + 6 + l) * CS] = g.dJf[l];
-            }
-        }
+        for (int i = 0; i < n; ++i) sm[(Q::o_diag + w * n + i) * CS] = bev[i] * g.detJ;
     }
+    __syncthreads();
 
-    // ---- phase 1b: S = C + B'A^-1 B, L D L' with the rows dealt to the 4 lanes ------------------------------
+    // =========================== phase 1: 4 lanes per cell, L D L' of S ======================================
     {
-        const double al = g.detJ * (g.G00 * g.G00 + g.G01 * g.G01);
-        const double be = g.detJ * (g.G00 * g.G10 + g.G01 * g.G11);
-        const double ga = g.detJ * (g.G10 * g.G10 + g.G11 * g.G11);
-        const double* __restrict__ gC = gt->Chat + q * n;      // row i = q + 4r  ->  offset (4r) n + j
-        const double* __restrict__ gPrr = gt->Prr + q * n;
-        const double* __restrict__ gPrs = gt->Prs + q * n;
-        const double* __restrict__ gPss = gt->Pss + q * n;
-        double dd[n];
+        const int q = threadIdx.x & 3, pc = threadIdx.x >> 2;
+        const unsigned lane = threadIdx.x & 31u;
+        double* const sp = smem + pc;           // record of cell pc
+        // lane q owns rows q, q+4, ...; its rows of L stay in registers, the pivot row is read from shared memory
+        double Lr[R][n], dd[n];
         bool spd = true;
-        __syncwarp();
 #pragma unroll
         for (int j = 0; j < n; ++j) {
             double ljd[n];
 #pragma unroll
-            for (int k = 0; k < j; ++k) ljd[k] = sm[(Q::o_L + tri(j, k)) * CS] * dd[k];     // L[j][k] d_k
+            for (int k = 0; k < j; ++k) ljd[k] = sp[(Q::o_L + tri(j, k)) * CS] * dd[k];     // L[j][k] d_k
             double colr[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -134,16 +160,9 @@ element_quad_kernel(const ElemArgs a, const DevTables<K>* __restrict__ gt) {
                 if (4 * r + 3 < j || 4 * r >= n) continue;         // compile-time: no row of this slot is in [j, n)
                 const int i = q + 4 * r;
                 if (i >= j && i < n) {
-                    const int o = 4 * r * n + j;
-                    double s = cf0 * __ldg(gC + o);
-                    s = fma(cf1, __ldg(gC + n * n + o), s);
-                    s = fma(cf2, __ldg(gC + 2 * n * n + o), s);
-                    s = fma(al, __ldg(gPrr + o), s);
-                    s = fma(be, __ldg(gPrs + o), s);
-                    s = fma(ga, __ldg(gPss + o), s);
-                    const double* Li = sm + (Q::o_L + i * (i - 1) / 2) * CS;
+                    double s = sp[(i == j ? Q::o_dinv + j : Q::o_L + i * (i - 1) / 2 + j) * CS];
 #pragma unroll
-                    for (int k = 0; k < j; ++k) s = fma(-Li[k * CS], ljd[k], s);
+                    for (int k = 0; k < j; ++k) s = fma(-Lr[r][k], ljd[k], s);
                     colr[r] = s;
                 }
             }
@@ -151,144 +170,187 @@ element_quad_kernel(const ElemArgs a, const DevTables<K>* __restrict__ gt) {
             spd = spd && (dj > 0.0);
             dd[j] = dj;
             const double dinv = 1.0 / dj;
-            if (q == (j & 3)) sm[(Q::o_dinv + j) * CS] = dinv;
+            if (q == (j & 3)) sp[(Q::o_dinv + j) * CS] = dinv;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
+                Lr[r][j] = 0.0;
                 if (4 * r + 3 <= j || 4 * r >= n) continue;
                 const int i = q + 4 * r;
-                if (i > j && i < n) sm[(Q::o_L + i * (i - 1) / 2 + j) * CS] = colr[r] * dinv;
+                if (i > j && i < n) {
+                    Lr[r][j] = colr[r] * dinv;
+                    sp[(Q::o_L + i * (i - 1) / 2 + j) * CS] = Lr[r][j];
+                }
             }
             __syncwarp();
         }
-        if (active && !spd) {
-            if (q == 0) atomicCAS(&a.flags[FLAG_SINGULAR], 0, int32_t(c + 1));
-            active = false;
+        // be = sum of the 4 partial vectors (fixed order)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = q + 4 * r;
+            if (i < n) {
+                const double* pp = sp + (Q::o_diag + i) * CS;
+                sp[(Q::o_be + i) * CS] = ((pp[0] + pp[n * CS]) + pp[2 * n * CS]) + pp[3 * n * CS];
+            }
         }
+        if (q == 0) sp[Q::o_status * CS] = spd ? 1.0 : -1.0;
     }
+    __syncthreads();
 
-    // ---- phase 2: one column of [K_e | b_e] at a time, columns q, q+4, ... ----------------------------------
+    // =========================== phase 2: lane = cell, warp = column group =================================
+    if (active && !g.ok) {
+        if (w == 0) atomicCAS(&a.flags[FLAG_BAD_GEOM], 0, int32_t(c + 1));
+        active = false;
+    }
+    if (active && sm[Q::o_status * CS] < 0.0) {
+        if (w == 0) atomicCAS(&a.flags[FLAG_SINGULAR], 0, int32_t(c + 1));
+        active = false;
+    }
+    const bool o0 = g.v[2] > g.v[1], o1 = g.v[0] > g.v[2], o2 = g.v[1] > g.v[0];   // face_orientation, src/mesh.jl:51-54
     const double idet = 1.0 / g.detJ;
     double* __restrict__ const Ke_tile = a.Ke + ((c >> 5) * ke) * 32 + (c & 31);
-#pragma unroll 1
-    for (int cc = 0; cc < Q::CC; ++cc) {
-        const int col = q + 4 * cc;
-        if (col > t) break;
-        const bool isb = col == t;
-        const int l = isb ? 0 : col / nt;
-        const int j = isb ? 0 : col - l * nt;
-        const bool o_l = l == 0 ? o0 : (l == 1 ? o1 : o2);
-        const double scol = (isb || o_l || !(j & 1)) ? 1.0 : -1.0;      // Legendre parity of a reversed face
-        const double dJf_l = sm[(Q::o_ca + 6 + l) * CS];
+    const volatile double* const smv = sm;      // volatile: keeps the L loads next to their uses (hoisted they spill)
 
-        double u[n];
-        if (isb) {
+#pragma unroll 1
+    for (int b = 0; b < Q::NB; ++b) {
+        const int col0 = w + 4 * CB * b;        // columns col0, col0 + 4, ... (warp-uniform)
+        if (col0 > t) break;
+        double u[CB][n];
+        // right-hand sides: [-E;F] columns reduced to the u-block  (B'A^-1 E_l = ca_l Qr_l + cb_l Qs_l), or be
 #pragma unroll
-            for (int i = 0; i < n; ++i) u[i] = sm[(Q::o_be + i) * CS];
-        } else {
-            const double cf = tau * dJf_l, ca_l = sm[(Q::o_ca + l) * CS], cb_l = sm[(Q::o_ca + 3 + l) * CS];
+        for (int cb = 0; cb < CB; ++cb) {
+            const int col = col0 + 4 * cb;
+            if (col < t) {
+                const int l = col / nt;
+                const double wnx = l == 0 ? g.wn[0][0] : (l == 1 ? g.wn[1][0] : g.wn[2][0]);
+                const double wny = l == 0 ? g.wn[0][1] : (l == 1 ? g.wn[1][1] : g.wn[2][1]);
+                const double cf = l == 0 ? cf0 : (l == 1 ? cf1 : cf2);
+                const double ca_l = g.G00 * wnx + g.G01 * wny, cb_l = g.G10 * wnx + g.G11 * wny;
 #pragma unroll
-            for (int i = 0; i < n; ++i) {
-                double r = cf * __ldg(&gt->Fhat[i * t + col]);
-                r = fma(ca_l, __ldg(&gt->Qr[i * t + col]), r);
-                u[i] = fma(cb_l, __ldg(&gt->Qs[i * t + col]), r);
+                for (int i = 0; i < n; ++i) {
+                    double r = cf * T.Fhat[i * t + col];
+                    r = fma(ca_l, T.Qr[i * t + col], r);
+                    u[cb][i] = fma(cb_l, T.Qs[i * t + col], r);
+                }
+            } else if (col == t) {
+#pragma unroll
+                for (int i = 0; i < n; ++i) u[cb][i] = sm[(Q::o_be + i) * CS];
+            } else {
+#pragma unroll
+                for (int i = 0; i < n; ++i) u[cb][i] = 0.0;
             }
         }
-        // S u = r  by L D L'
-        const volatile double* const smv = sm;
-        // (the compiler barriers keep the n(n-1) shared-memory loads next to their uses: hoisted to the top they
-        //  cost 2 registers each and spill)
+        // S u = r  by L D L', one load of every L entry for the CB columns
 #pragma unroll
-        for (int i = 1; i < n; ++i) {
+        for (int i = 1; i < n; ++i)
 #pragma unroll
-            for (int k = 0; k < i; ++k) u[i] = fma(-smv[(Q::o_L + tri(i, k)) * CS], u[k], u[i]);
-            asm volatile("" ::: "memory");
-        }
+            for (int k = 0; k < i; ++k) {
+                const double lik = smv[(Q::o_L + tri(i, k)) * CS];
 #pragma unroll
-        for (int i = 0; i < n; ++i) u[i] *= sm[(Q::o_dinv + i) * CS];
-        asm volatile("" ::: "memory");
-#pragma unroll
-        for (int i = n - 2; i >= 0; --i) {
-#pragma unroll
-            for (int k = i + 1; k < n; ++k) u[i] = fma(-smv[(Q::o_L + tri(k, i)) * CS], u[k], u[i]);
-            asm volatile("" ::: "memory");
-        }
-
-        // sigma = A^-1 (r1 + B u) row by row; column of Ate = [E;F]'K_e - He accumulated on the fly
-        const double wnx_l = l == 0 ? g.wn[0][0] : (l == 1 ? g.wn[1][0] : g.wn[2][0]);
-        const double wny_l = l == 0 ? g.wn[0][1] : (l == 1 ? g.wn[1][1] : g.wn[2][1]);
-        const double ex = isb ? 0.0 : wnx_l * idet, ey = isb ? 0.0 : wny_l * idet;
-        double val[3][nt];
-#pragma unroll
-        for (int lp = 0; lp < 3; ++lp)
-#pragma unroll
-            for (int ip = 0; ip < nt; ++ip) val[lp][ip] = 0.0;
-        double* __restrict__ const Kp = Ke_tile + int64_t(col) * 32;
+                for (int cb = 0; cb < CB; ++cb) u[cb][i] = fma(-lik, u[cb][k], u[cb][i]);
+            }
 #pragma unroll
         for (int i = 0; i < n; ++i) {
-            double p = 0.0, s = 0.0;
+            const double di = smv[(Q::o_dinv + i) * CS];
 #pragma unroll
-            for (int k = 0; k < n; ++k) {
-                if ((Sp::tr(i) >> k) & 1u) p = fma(T.Tr[i * n + k], u[k], p);
-                if ((Sp::ts(i) >> k) & 1u) s = fma(T.Ts[i * n + k], u[k], s);
-            }
-            const double mf = isb ? 0.0 : __ldg(&gt->MF[i * t + col]);
-            const double sx = fma(g.G00, p, fma(g.G10, s, -ex * mf));
-            const double sy = fma(g.G01, p, fma(g.G11, s, -ey * mf));
-            if (active && !dbg) {
-                Kp[int64_t(i * (t + 1)) * 32] = scol * sx;
-                Kp[int64_t((n + i) * (t + 1)) * 32] = scol * sy;
-                Kp[int64_t((2 * n + i) * (t + 1)) * 32] = scol * u[i];
-            }
-            const double w0 = fma(g.wn[0][0], sx, fma(g.wn[0][1], sy, cf0 * u[i]));
-            const double w1 = fma(g.wn[1][0], sx, fma(g.wn[1][1], sy, cf1 * u[i]));
-            const double w2 = fma(g.wn[2][0], sx, fma(g.wn[2][1], sy, cf2 * u[i]));
-#pragma unroll
-            for (int ip = 0; ip < nt; ++ip) {
-                if ((Sp::fh(i) >> (0 * nt + ip)) & 1u) val[0][ip] = fma(T.Fhat[i * t + 0 * nt + ip], w0, val[0][ip]);
-                if ((Sp::fh(i) >> (1 * nt + ip)) & 1u) val[1][ip] = fma(T.Fhat[i * t + 1 * nt + ip], w1, val[1][ip]);
-                if ((Sp::fh(i) >> (2 * nt + ip)) & 1u) val[2][ip] = fma(T.Fhat[i * t + 2 * nt + ip], w2, val[2][ip]);
-            }
+            for (int cb = 0; cb < CB; ++cb) u[cb][i] *= di;
         }
 #pragma unroll
-        for (int lp = 0; lp < 3; ++lp) {
-            const bool o_lp = lp == 0 ? o0 : (lp == 1 ? o1 : o2);
-            double v[nt];
+        for (int i = n - 2; i >= 0; --i)
 #pragma unroll
-            for (int ip = 0; ip < nt; ++ip) {
-                const double srow = (o_lp || !(ip & 1)) ? 1.0 : -1.0;
-                v[ip] = val[lp][ip] * (srow * scol);
+            for (int k = i + 1; k < n; ++k) {
+                const double lki = smv[(Q::o_L + tri(k, i)) * CS];
+#pragma unroll
+                for (int cb = 0; cb < CB; ++cb) u[cb][i] = fma(-lki, u[cb][k], u[cb][i]);
             }
-            if (isb) {                                   // bte = -[E;F]' b_e
+
+        // per column: sigma = A^-1 (r1 + B u) row by row; column of Ate = [E;F]'K_e - He accumulated on the fly
+#pragma unroll
+        for (int cb = 0; cb < CB; ++cb) {
+            const int col = col0 + 4 * cb;
+            if (col > t) break;
+            const bool isb = col == t;
+            const int l = isb ? 0 : col / nt;
+            const int j = isb ? 0 : col - l * nt;
+            const bool o_l = l == 0 ? o0 : (l == 1 ? o1 : o2);
+            const double scol = (isb || o_l || !(j & 1)) ? 1.0 : -1.0;      // Legendre parity of a reversed face
+            const double dJf_l = l == 0 ? g.dJf[0] : (l == 1 ? g.dJf[1] : g.dJf[2]);
+            const double wnx_l = l == 0 ? g.wn[0][0] : (l == 1 ? g.wn[1][0] : g.wn[2][0]);
+            const double wny_l = l == 0 ? g.wn[0][1] : (l == 1 ? g.wn[1][1] : g.wn[2][1]);
+            const double ex = isb ? 0.0 : wnx_l * idet, ey = isb ? 0.0 : wny_l * idet;
+            const int mcol = isb ? 0 : col;
+            double val[3][nt];
+#pragma unroll
+            for (int lp = 0; lp < 3; ++lp)
+#pragma unroll
+                for (int ip = 0; ip < nt; ++ip) val[lp][ip] = 0.0;
+            double* __restrict__ const Kp = Ke_tile + int64_t(col) * 32;
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+                double p = 0.0, s = 0.0;
+#pragma unroll
+                for (int k = 0; k < n; ++k) {
+                    if ((Sp::tr(i) >> k) & 1u) p = fma(T.Tr[i * n + k], u[cb][k], p);
+                    if ((Sp::ts(i) >> k) & 1u) s = fma(T.Ts[i * n + k], u[cb][k], s);
+                }
+                const double mf = T.MF[i * t + mcol];
+                const double sx = fma(g.G00, p, fma(g.G10, s, -ex * mf));
+                const double sy = fma(g.G01, p, fma(g.G11, s, -ey * mf));
+                if (active && !dbg) {               // 256-byte row segments of the tile
+                    Kp[int64_t(i * (t + 1)) * 32] = scol * sx;
+                    Kp[int64_t((n + i) * (t + 1)) * 32] = scol * sy;
+                    Kp[int64_t((2 * n + i) * (t + 1)) * 32] = scol * u[cb][i];
+                }
+                const double w0 = fma(g.wn[0][0], sx, fma(g.wn[0][1], sy, cf0 * u[cb][i]));
+                const double w1 = fma(g.wn[1][0], sx, fma(g.wn[1][1], sy, cf1 * u[cb][i]));
+                const double w2 = fma(g.wn[2][0], sx, fma(g.wn[2][1], sy, cf2 * u[cb][i]));
 #pragma unroll
                 for (int ip = 0; ip < nt; ++ip) {
-                    if (dbg) { if (active) a.dbg_bt[lp * nt + ip] = -v[ip]; }
-                    else sm[(Q::o_rhs + lp * nt + ip) * CS] = -v[ip];
+                    if ((Sp::fh(i) >> (0 * nt + ip)) & 1u) val[0][ip] = fma(T.Fhat[i * t + 0 * nt + ip], w0, val[0][ip]);
+                    if ((Sp::fh(i) >> (1 * nt + ip)) & 1u) val[1][ip] = fma(T.Fhat[i * t + 1 * nt + ip], w1, val[1][ip]);
+                    if ((Sp::fh(i) >> (2 * nt + ip)) & 1u) val[2][ip] = fma(T.Fhat[i * t + 2 * nt + ip], w2, val[2][ip]);
                 }
-            } else if (lp == l) {                        // face-diagonal block, minus He (poisson2D_HDG.jl:144-151)
+            }
+#pragma unroll
+            for (int lp = 0; lp < 3; ++lp) {
+                const bool o_lp = lp == 0 ? o0 : (lp == 1 ? o1 : o2);
+                double v[nt];
 #pragma unroll
                 for (int ip = 0; ip < nt; ++ip) {
-                    const double h = fma(-dJf_l, __ldg(&gt->Hhat[ip * nt + j]), v[ip]);
-                    if (dbg) { if (active) a.dbg_At[col * t + lp * nt + ip] = h; }
-                    else sm[(Q::o_diag + (lp * nt + j) * nt + ip) * CS] = h;
+                    const double srow = (o_lp || !(ip & 1)) ? 1.0 : -1.0;
+                    v[ip] = val[lp][ip] * (srow * scol);
                 }
-            } else if (dbg) {
+                if (isb) {                                   // bte = -[E;F]' b_e
 #pragma unroll
-                for (int ip = 0; ip < nt; ++ip) if (active) a.dbg_At[col * t + lp * nt + ip] = v[ip];
-            } else if (active) {                         // off-diagonal block: exactly one contributing cell
-                const int s = (l - lp + 3) % 3 - 1;
-                const int64_t f_lp = g.f[lp] & 0x7fffffffu;
-                const int slot = int(g.f[lp] >> 31) * 2 + s;
-                store_vec<nt>(a.Ko + (f_lp * 4 + slot) * nt2 + j * nt, v);
+                    for (int ip = 0; ip < nt; ++ip) {
+                        if (dbg) { if (active) a.dbg_bt[lp * nt + ip] = -v[ip]; }
+                        else sm[(Q::o_rhs + lp * nt + ip) * CS] = -v[ip];
+                    }
+                } else if (lp == l) {                        // face-diagonal block, minus He (poisson2D_HDG.jl:144-151)
+#pragma unroll
+                    for (int ip = 0; ip < nt; ++ip) {
+                        const double h = fma(-dJf_l, T.Hhat[ip * nt + j], v[ip]);
+                        if (dbg) { if (active) a.dbg_At[col * t + lp * nt + ip] = h; }
+                        else sm[(Q::o_diag + (lp * nt + j) * nt + ip) * CS] = h;
+                    }
+                } else if (dbg) {
+#pragma unroll
+                    for (int ip = 0; ip < nt; ++ip) if (active) a.dbg_At[col * t + lp * nt + ip] = v[ip];
+                } else if (active) {                         // off-diagonal block: exactly one contributing cell
+                    const int s = (l - lp + 3) % 3 - 1;
+                    const int64_t f_lp = g.f[lp] & 0x7fffffffu;
+                    const int slot = int(g.f[lp] >> 31) * 2 + s;
+                    store_vec<nt>(a.Ko + (f_lp * 4 + slot) * nt2 + j * nt, v);
+                }
             }
         }
     }
     if (dbg) return;
 
-    // ---- phase 3: scatter of the staged face-diagonal blocks and rhs entries (see element_schur_kernel) ------
+    // =========================== phase 3: scatter of the staged blocks, warp w = local face w =================
     __syncthreads();
-    if (!active || q == 3) return;
+    if (!active || w == 3) return;
     {
-        const int l = q;
+        const int l = w;
         const uint32_t fl = l == 0 ? g.f[0] : (l == 1 ? g.f[1] : g.f[2]);
         const int64_t f = fl & 0x7fffffffu;
         const uint32_t sec = fl >> 31;

@@ -134,7 +134,6 @@ struct hdg_context {
     // raw tables on device (LU path + error norm)
     double* d_rawtab = nullptr;
     hdg::RawTablesDev raw{};
-    void* d_devtab = nullptr;        // DevTables<order> in global memory (lane-varying indices, element_quad_kernel)
     bool quad_ok = false;            // hdg_sparsity.h matches the tables of this context
 
     // trace system, block-ELL: diagonal blocks + 4 off-diagonal blocks per face, blocks column-major nt x nt

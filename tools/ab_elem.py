@@ -62,6 +62,7 @@ def main():
     ap.add_argument("--child", type=int, default=0)
     ap.add_argument("--dump", default="")
     ap.add_argument("--peak", type=float, default=6454.0)
+    ap.add_argument("--libs", default="", help="comma-separated variant names: hdiscontinuousgalerkin.jl_b200/variants/lib_NAME.so")
     a = ap.parse_args()
     if a.child:
         child(a.child, a.nx, a.ny, a.reps, a.dump)
@@ -70,9 +71,13 @@ def main():
     for k in [int(x) for x in a.orders.split(",")]:
         nx, ny = (a.nx, a.ny) if k < 4 else (a.nx // 2, a.ny // 2)
         res = {}
-        for tag, env in (("v1", {"HDG_ELEM_V1": "1"}), ("quad", {})):
+        arms = [("v1", {"HDG_ELEM_V1": "1"}), ("quad", {})]
+        for nm in [x for x in a.libs.split(",") if x]:
+            arms.append((nm, {"HDG_B200_LIB": os.path.join(ROOT, "hdiscontinuousgalerkin.jl_b200", "variants", f"lib_{nm}.so")}))
+        for tag, env in arms:
             e = dict(os.environ)
             e.pop("HDG_ELEM_V1", None)
+            e.pop("HDG_B200_LIB", None)
             e.update(env)
             dump = f"/tmp/ab_{k}_{tag}.npz"
             p = subprocess.run([sys.executable, __file__, "--child", str(k), "--nx", str(nx), "--ny", str(ny), "--reps", str(a.reps),
@@ -86,7 +91,7 @@ def main():
             r["hbm_frac"] = ALG_BYTES[k] * r["el_per_s"] / (a.peak * 1e9)
             res[tag] = r
             print(f"k={k} {tag:5s} {r['ncell']} cells  {r['ms_med']:.3f} ms (min {r['ms_min']:.3f})  {r['el_per_s']:.3e} el/s  HBM frac {r['hbm_frac']:.3f}", flush=True)
-        if len(res) == 2:
+        if "v1" in res and "quad" in res:
             A, B = np.load(f"/tmp/ab_{k}_v1.npz"), np.load(f"/tmp/ab_{k}_quad.npz")
             for name in ("rhs", "nz", "loc"):
                 d = np.abs(A[name] - B[name]).max() / max(np.abs(A[name]).max(), 1e-300)
