@@ -24,7 +24,7 @@
 namespace hdg {
 
 #ifndef QCB2
-#define QCB2 3
+#define QCB2 1
 #endif
 #ifndef QCB3
 #define QCB3 1
@@ -60,7 +60,8 @@ template <int K> struct QuadCfg {
     static constexpr int o_status = o_be + n;
     static constexpr int o_diag = o_status + 1;       // staging of the face-diagonal blocks (phases 2-3); partial be sums (phases 0-1)
     static constexpr int o_rhs = o_diag + 3 * nt * nt;
-    static constexpr int entries = o_rhs + 3 * nt;
+    static constexpr int o_scr = o_rhs + 3 * nt;      // phase 2: solutions of the 2nd ... CB-th column of a batch, per warp
+    static constexpr int entries = o_scr + 4 * (CB - 1) * n;
     static_assert(3 * nt * nt + 3 * nt >= 4 * n, "partial load vectors alias the staging area");
     static constexpr size_t smem = sizeof(double) * entries * CS;
     static constexpr int min_blocks = K == 2 ? QMINB2 : (K == 3 ? QMINB3 : QMINB4);
@@ -263,11 +264,25 @@ __global__ void __launch_bounds__(QuadCfg<K>::threads, QuadCfg<K>::min_blocks) e
                 for (int cb = 0; cb < CB; ++cb) u[cb][i] = fma(-lki, u[cb][k], u[cb][i]);
             }
 
-        // per column: sigma = A^-1 (r1 + B u) row by row; column of Ate = [E;F]'K_e - He accumulated on the fly
+        // per column: sigma = A^-1 (r1 + B u) row by row; column of Ate = [E;F]'K_e - He accumulated on the fly.
+        // The columns of a batch are processed one after the other by ONE copy of the code (the solutions of the 2nd,
+        // 3rd ... column wait in a per-thread shared-memory scratch), so the register need is that of a single column.
+        double uc[n];
 #pragma unroll
+        for (int i = 0; i < n; ++i) uc[i] = u[0][i];
+        double* const scr = sm + (Q::o_scr + w * (CB - 1) * n) * CS;
+#pragma unroll
+        for (int cb = 1; cb < CB; ++cb)
+#pragma unroll
+            for (int i = 0; i < n; ++i) scr[((cb - 1) * n + i) * CS] = u[cb][i];
+#pragma unroll 1
         for (int cb = 0; cb < CB; ++cb) {
             const int col = col0 + 4 * cb;
             if (col > t) break;
+            if (cb > 0) {
+#pragma unroll
+                for (int i = 0; i < n; ++i) uc[i] = scr[((cb - 1) * n + i) * CS];
+            }
             const bool isb = col == t;
             const int l = isb ? 0 : col / nt;
             const int j = isb ? 0 : col - l * nt;
@@ -289,8 +304,8 @@ __global__ void __launch_bounds__(QuadCfg<K>::threads, QuadCfg<K>::min_blocks) e
                 double p = 0.0, s = 0.0;
 #pragma unroll
                 for (int k = 0; k < n; ++k) {
-                    if ((Sp::tr(i) >> k) & 1u) p = fma(T.Tr[i * n + k], u[cb][k], p);
-                    if ((Sp::ts(i) >> k) & 1u) s = fma(T.Ts[i * n + k], u[cb][k], s);
+                    if ((Sp::tr(i) >> k) & 1u) p = fma(T.Tr[i * n + k], uc[k], p);
+                    if ((Sp::ts(i) >> k) & 1u) s = fma(T.Ts[i * n + k], uc[k], s);
                 }
                 const double mf = T.MF[i * t + mcol];
                 const double sx = fma(g.G00, p, fma(g.G10, s, -ex * mf));
@@ -298,11 +313,11 @@ __global__ void __launch_bounds__(QuadCfg<K>::threads, QuadCfg<K>::min_blocks) e
                 if (active && !dbg) {               // 256-byte row segments of the tile
                     Kp[int64_t(i * (t + 1)) * 32] = scol * sx;
                     Kp[int64_t((n + i) * (t + 1)) * 32] = scol * sy;
-                    Kp[int64_t((2 * n + i) * (t + 1)) * 32] = scol * u[cb][i];
+                    Kp[int64_t((2 * n + i) * (t + 1)) * 32] = scol * uc[i];
                 }
-                const double w0 = fma(g.wn[0][0], sx, fma(g.wn[0][1], sy, cf0 * u[cb][i]));
-                const double w1 = fma(g.wn[1][0], sx, fma(g.wn[1][1], sy, cf1 * u[cb][i]));
-                const double w2 = fma(g.wn[2][0], sx, fma(g.wn[2][1], sy, cf2 * u[cb][i]));
+                const double w0 = fma(g.wn[0][0], sx, fma(g.wn[0][1], sy, cf0 * uc[i]));
+                const double w1 = fma(g.wn[1][0], sx, fma(g.wn[1][1], sy, cf1 * uc[i]));
+                const double w2 = fma(g.wn[2][0], sx, fma(g.wn[2][1], sy, cf2 * uc[i]));
 #pragma unroll
                 for (int ip = 0; ip < nt; ++ip) {
                     if ((Sp::fh(i) >> (0 * nt + ip)) & 1u) val[0][ip] = fma(T.Fhat[i * t + 0 * nt + ip], w0, val[0][ip]);
