@@ -563,9 +563,9 @@ def meandiag(K):
 
 def solve(K, b, rtol=1e-13, maxit=200000, precond="jacobi"):
     """u_hat = K \\ b (examples/poisson2D_HDG.jl:195) by Jacobi-PCG on the sign-fixed system
-    (precond="block" uses the nt x nt face-diagonal blocks).  Returns (DeviceVector, info dict)."""
+    (precond="block" uses the nt x nt face-diagonal blocks, precond="mg" adds the P1-vertex multigrid V-cycle).  Returns (DeviceVector, info dict)."""
     ctx = K._ctx
-    check(ctx.lib.hdg_set_preconditioner(ctx.h, {"jacobi": 0, "block": 1}[precond]), ctx.h)
+    check(ctx.lib.hdg_set_preconditioner(ctx.h, {"jacobi": 0, "block": 1, "mg": 2}[precond]), ctx.h)
     info = SolveInfo()
     check(ctx.lib.hdg_solve(ctx.h, float(rtol), int(maxit), C.byref(info)), ctx.h)
     d = dict(iterations=info.iterations, converged=bool(info.converged), relres=info.relres,

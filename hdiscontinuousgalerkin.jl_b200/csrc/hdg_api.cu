@@ -87,7 +87,7 @@ hdg_status hdg_create(const hdg_params* prm, hdg_context** out) {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate");
     if (cudaMalloc(&c->d_flags, sizeof(int32_t) * NFLAGS) != cudaSuccess) return fail("cudaMalloc");
     if (cudaMalloc(&c->d_scal, sizeof(double) * 8) != cudaSuccess) return fail("cudaMalloc");
-    if (cudaMalloc(&c->d_partials, sizeof(double) * 5 * 2048) != cudaSuccess) return fail("cudaMalloc");
+    if (cudaMalloc(&c->d_partials, sizeof(double) * 8 * 2048) != cudaSuccess) return fail("cudaMalloc");
     if (cudaMallocHost(&c->h_flags, sizeof(int32_t) * NFLAGS) != cudaSuccess) return fail("cudaMallocHost");
     if (cudaMallocHost(&c->h_scal, sizeof(double) * 8) != cudaSuccess) return fail("cudaMallocHost");
     cudaMemset(c->d_flags, 0, sizeof(int32_t) * NFLAGS);
@@ -118,6 +118,7 @@ void hdg_destroy(hdg_context* c) {
     if (c->d_rawtab) cudaFree(c->d_rawtab);
     if (c->d_flags) cudaFree(c->d_flags);
     if (c->d_scal) cudaFree(c->d_scal);
+    mg_free(c);
     if (c->d_partials) cudaFree(c->d_partials);
     if (c->h_flags) cudaFreeHost(c->h_flags);
     if (c->h_scal) cudaFreeHost(c->h_scal);
@@ -295,7 +296,7 @@ hdg_status hdg_solve(hdg_context* c, double rtol, int32_t maxit, hdg_solve_info*
 
 hdg_status hdg_set_preconditioner(hdg_context* c, int32_t id) {
     if (!c) return HDG_ERR_INVALID;
-    if (id < 0 || id > 1) return set_err(c, HDG_ERR_INVALID, "unknown preconditioner id");
+    if (id < 0 || id > 2) return set_err(c, HDG_ERR_INVALID, "unknown preconditioner id");
     c->precond = id;
     return HDG_OK;
 }

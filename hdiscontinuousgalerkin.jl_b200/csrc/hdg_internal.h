@@ -149,7 +149,8 @@ struct hdg_context {
     double* d_x = nullptr;           // trace solution u_hat
     double *d_r = nullptr, *d_p = nullptr, *d_Ap = nullptr, *d_dinv = nullptr;   // d_p is mapped by the neighbouring ranks (CUDA IPC)
     double* d_binv = nullptr;        // block-Jacobi: inverted face-diagonal blocks
-    int precond = 0;                 // 0 Jacobi, 1 block-Jacobi
+    int precond = 0;                 // 0 Jacobi, 1 block-Jacobi, 2 block-Jacobi + P1-vertex multigrid (hdg_mg.cu)
+    void* mg = nullptr;              // hdg::MgData
     double* d_partials = nullptr;    // reduction partials
     double* d_scal = nullptr;        // device scalars
     int32_t* d_flags = nullptr;      // error / convergence flags
@@ -183,7 +184,7 @@ void timer_stop(hdg_context* c, Timer& t);
 float timer_ms(Timer& t);
 
 // flag words in d_flags
-enum Flag : int { FLAG_BAD_GEOM = 0, FLAG_SINGULAR = 1, FLAG_DONE = 2, FLAG_ITERS = 3, FLAG_NOT_BOUNDARY = 4, NFLAGS = 8 };
+enum Flag : int { FLAG_BAD_GEOM = 0, FLAG_SINGULAR = 1, FLAG_DONE = 2, FLAG_ITERS = 3, FLAG_NOT_BOUNDARY = 4, FLAG_MG = 5, NFLAGS = 8 };
 
 // ---- per-translation-unit entry points ------------------------------------------------------
 hdg_status upload_tables(hdg_context* c);                       // hdg_element.cu
@@ -207,6 +208,12 @@ void free_mesh(hdg_context* c);
 
 hdg_status apply_dirichlet(hdg_context* c, const double* values);   // hdg_solve.cu
 hdg_status pcg_solve(hdg_context* c, double rtol, int maxit, hdg_solve_info* info);
+
+// hdg_mg.cu: P1-vertex multigrid term of the preconditioner (one GPU, rectangle_mesh)
+hdg_status mg_setup(hdg_context* c);                                              // operators of the current trace matrix
+void mg_apply(hdg_context* c, const double* r, double* z, double* part, int np);   // z += P V(P'r); part = partials of (P'r).V(P'r)
+void mg_free(hdg_context* c);
+int mg_levels(const hdg_context* c);
 
 hdg_status recover(hdg_context* c);                             // hdg_recover.cu
 hdg_status errornorm(hdg_context* c, int exact_id, double* err2);

@@ -35,8 +35,9 @@ constexpr int MAX_PARTIALS = 2048;
 
 // d_scal layout
 enum Scal : int { S_BNORM2 = 0, S_RELRES = 1, S_MEANSUM = 2, S_ERR2 = 3, S_RZ = 4, NSCAL = 8 };
-// d_partials layout: 5 arrays of MAX_PARTIALS
-enum Part : int { P_PAP = 0, P_RZ0 = 1, P_RZ1 = 2, P_RR = 3, P_BB = 4, NPART = 5 };
+// d_partials layout: NPART arrays of MAX_PARTIALS
+// (P_RZC*: the multigrid part of r.z, same parity scheme as P_RZ*)
+enum Part : int { P_PAP = 0, P_RZ0 = 1, P_RZ1 = 2, P_RR = 3, P_BB = 4, P_RZC0 = 5, P_RZC1 = 6, NPART = 7 };
 
 // ---- apply! ----------------------------------------------------------------------------------
 template <int NT>
@@ -156,11 +157,19 @@ struct PcgArgs {
     double* pnext;               // where pcg_dir writes the next direction (p is double-buffered)
     int ghost_mode;              // 0 local ghost segment (NCCL halo), 1 peer p read in place, 2 peer p recomputed on the fly
     int parity;                  // iteration parity (which r.z partial array is current)
+    int mg;                      // r.z = block-Jacobi part (P_RZ*) + multigrid part (P_RZC*)
 };
 
 __device__ __forceinline__ double get_sum(const PcgArgs& a, int which) {
     if (a.gscal) return a.gscal[which];                                   // summed over ranks by NCCL
     return reduce_partials(a.part + which * MAX_PARTIALS, a.np);          // fixed-order, every block identically
+}
+
+// r.z of the parity slot `which` (P_RZ0 / P_RZ1)
+__device__ __forceinline__ double get_rz(const PcgArgs& a, int which) {
+    double s = get_sum(a, which);
+    if (a.mg) s += get_sum(a, which + (P_RZC0 - P_RZ0));
+    return s;
 }
 
 // multi-GPU: local sums of all partial arrays -> gscal slots (then all-reduced in place)
@@ -400,8 +409,8 @@ __global__ void __launch_bounds__(RB) pcg_update(const PcgArgs a, int64_t N, int
 
 __global__ void __launch_bounds__(RB) pcg_dir(const PcgArgs a, int64_t N, int parity, int iter, int z_in_ap) {
     if (*reinterpret_cast<volatile int32_t*>(a.flags + FLAG_DONE)) return;
-    const double rz_old = get_sum(a, parity ? P_RZ1 : P_RZ0);
-    const double rz_new = get_sum(a, parity ? P_RZ0 : P_RZ1);
+    const double rz_old = get_rz(a, parity ? P_RZ1 : P_RZ0);
+    const double rz_new = get_rz(a, parity ? P_RZ0 : P_RZ1);
     const double rr = get_sum(a, P_RR);
     const double bb = a.scal[S_BNORM2];
     const bool conv = rr <= a.rtol * a.rtol * bb;
@@ -502,6 +511,8 @@ __global__ void __launch_bounds__(RB) pcg_init_blk(const PcgArgs a, double* __re
         a.part[P_PAP * MAX_PARTIALS + blockIdx.x] = 0.0;
         a.part[P_RZ1 * MAX_PARTIALS + blockIdx.x] = blockIdx.x == 0 ? 1.0 : 0.0;
         a.part[P_RR * MAX_PARTIALS + blockIdx.x] = 0.0;
+        a.part[P_RZC0 * MAX_PARTIALS + blockIdx.x] = 0.0;
+        a.part[P_RZC1 * MAX_PARTIALS + blockIdx.x] = 0.0;
     }
 }
 
@@ -509,7 +520,7 @@ template <int NT>
 __global__ void __launch_bounds__(RB) pcg_update_blk(const PcgArgs a, const double* __restrict__ binv, int parity) {
     if (*reinterpret_cast<volatile int32_t*>(a.flags + FLAG_DONE)) return;
     constexpr int NT2 = NT * NT;
-    const double alpha = get_sum(a, parity ? P_RZ1 : P_RZ0) / get_sum(a, P_PAP);
+    const double alpha = get_rz(a, parity ? P_RZ1 : P_RZ0) / get_sum(a, P_PAP);
     double rz_new = 0.0, rr = 0.0;
     for (int64_t f = int64_t(blockIdx.x) * RB + threadIdx.x; f < a.nface; f += int64_t(gridDim.x) * RB) {
         double r[NT], p[NT], q[NT], x[NT], B[NT2];
@@ -565,7 +576,8 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
     const bool p2p = multi && comm_p2p(c);
     if (multi && !p2p && c->comm->general_mesh)
         return set_err(c, HDG_ERR_NCCL, "partitioned hdg_set_mesh meshes need the peer-memory path (CUDA IPC between the GPUs)");
-    const bool blockjac = c->precond == 1;
+    const bool mg = c->precond == 2;            // block-Jacobi + P1-vertex multigrid (hdg_mg.cu)
+    const bool blockjac = c->precond >= 1;
     if (!c->d_x) HDG_CUDA(c, cudaMalloc(&c->d_x, sizeof(double) * Nloc));
     if (!c->d_p) {
         // one region [p0 | p1 | r | Dinv], each Nloc long: the neighbouring ranks map it (CUDA IPC) and read all four
@@ -589,6 +601,7 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
     a.x = c->d_x; a.r = c->d_r; a.p = c->d_p; a.pnext = c->d_p + Nloc; a.Ap = c->d_Ap; a.dinv = c->d_dinv;
     a.part = c->d_partials; a.scal = c->d_scal; a.flags = c->d_flags; a.nface = c->nface_own;
     a.gscal = multi ? c->comm->d_gscal : nullptr;
+    a.mg = mg ? 1 : 0;
     // ghost_mode 2 (no barrier between pcg_dir and the next SpMV) needs the point-Jacobi z = Dinv r; with block-Jacobi
     // or the row-wise nt = 5 SpMV the neighbours' finished p is read after a barrier (mode 1)
     const int ghost_mode = !p2p ? 0 : ((blockjac || NT == 5 || getenv("HDG_PCG_BARRIER")) ? 1 : 2);
@@ -621,6 +634,10 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
 
     timer_start(c, c->t_solve);
     HDG_CUDA(c, cudaMemsetAsync(c->d_flags, 0, sizeof(int32_t) * NFLAGS, c->stream));
+    if (mg) {
+        hdg_status st = mg_setup(c);
+        if (st) { timer_stop(c, c->t_solve); return st; }
+    }
     hdg_status cst = HDG_OK;
     auto note = [&](hdg_status s2) { if (s2) cst = s2; };
     auto global_sums = [&](unsigned mask) {   // several GPUs: selected partial arrays -> sums over all ranks (+ inter-GPU barrier)
@@ -633,12 +650,14 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
     };
     if (blockjac) pcg_init_blk<NT><<<G, RB, 0, c->stream>>>(a, c->d_binv);
     else pcg_init<NT><<<G, RB, 0, c->stream>>>(a);
+    if (mg) mg_apply(c, a.r, a.p, c->d_partials + P_RZC0 * MAX_PARTIALS, G);      // p_0 = z_0 = M^-1 r_0
     global_sums((1u << NPART) - 1);
     pcg_init_final<<<1, RB, 0, c->stream>>>(a);
     c->launches += 2;
 
     // one CUDA graph = CHUNK iterations (even, so the rz double-buffer parity restarts at 0)
-    const int CHUNK = 32;
+    // (the multigrid kernels do not test the converged flag: a short chunk bounds the work done after convergence)
+    const int CHUNK = mg ? 4 : 32;
     const bool use_graph = getenv("HDG_NO_GRAPH") == nullptr;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
@@ -651,6 +670,7 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
         global_sums(1u << P_PAP);      // p.Ap; every rank has finished reading the neighbours' vectors
         if (blockjac) pcg_update_blk<NT><<<G, RB, 0, c->stream>>>(ak, c->d_binv, parity);
         else pcg_update<<<G, RB, 0, c->stream>>>(ak, N, parity);
+        if (mg) mg_apply(c, ak.r, ak.Ap, c->d_partials + (parity ? P_RZC0 : P_RZC1) * MAX_PARTIALS, G);   // z (in Ap) += P V(P'r)
         global_sums((1u << (parity ? P_RZ0 : P_RZ1)) | (1u << P_RR));      // r.z, r.r; r complete on every rank
         pcg_dir<<<G, RB, 0, c->stream>>>(ak, N, parity, it + 1, blockjac ? 1 : 0);
         if (ghost_mode == 1) global_sums(0);  // barrier: p complete on every rank before the next SpMV reads it
@@ -671,7 +691,7 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
         } else {
             for (int k = 0; k < chunk; ++k) enqueue_iter(k);
         }
-        c->launches += 3 * chunk;
+        c->launches += int64_t(3 + (mg ? 4 + 5 * (mg_levels(c) - 1) : 0)) * chunk;
         HDG_CUDA(c, cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int32_t) * NFLAGS, cudaMemcpyDeviceToHost, c->stream));
         HDG_CUDA(c, cudaStreamSynchronize(c->stream));
         done = c->h_flags[FLAG_DONE] != 0;

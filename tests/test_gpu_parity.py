@@ -320,6 +320,39 @@ def test_block_jacobi_preconditioner(order, qd):
         assert ib["iterations"] < ij["iterations"]
 
 
+@pytest.mark.parametrize("order,qd,nx,ny", [(1, 2, 10, 10), (1, 2, 64, 32), (1, 2, 51, 27), (2, 4, 33, 20), (3, 6, 24, 24), (4, 9, 12, 9), (1, 2, 3, 2)])
+def test_multigrid_preconditioner(order, qd, nx, ny):
+    """hdg_set_preconditioner(ctx, 2): block-Jacobi + P1-vertex multigrid.  Same solution as Jacobi-PCG (and the oracle's
+    direct solve on the small case), iteration count independent of the mesh size."""
+    mesh = hdg.rectangle_mesh(hdg.TriangleCell, (nx, ny), (0.0, 0.0), (2.0, 1.0))
+    Vh, Wh, Mh = _spaces(mesh, order, qd)
+    K, b, _, _ = hdg.doassemble(Vh, Wh, Mh)
+    hdg.apply_(K, b, hdg.Dirichlet(hdg.TrialFunction(Mh), mesh, "boundary", lambda x: 0))
+    xj, ij = hdg.solve(K, b, rtol=1e-13, precond="jacobi")
+    xm, im = hdg.solve(K, b, rtol=1e-13, precond="mg")
+    xm2, im2 = hdg.solve(K, b, rtol=1e-13, precond="mg")
+    assert relerr(xm.to_numpy(), xj.to_numpy()) < RTOL
+    assert im["converged"] and im["iterations"] <= 60
+    assert np.array_equal(xm.to_numpy(), xm2.to_numpy()) and im["iterations"] == im2["iterations"]   # gather-formulated: reproducible
+    if nx >= 33:
+        assert im["iterations"] < ij["iterations"] // 3
+    if (nx, ny) == (10, 10):
+        ro = orc.run_poisson(orc.rectangle_mesh(nx, ny, (0.0, 0.0), (2.0, 1.0)), order, qd)
+        assert relerr(xm.to_numpy(), ro["uhat"]) < RTOL
+
+
+def test_multigrid_needs_rectangle_mesh():
+    mo = orc.rectangle_mesh(6, 5)
+    mesh = host_mesh_from_oracle(mo)          # same mesh, but passed as arrays: no grid structure known to the library
+    Vh, Wh, Mh = _spaces(mesh, 1, 2)
+    K, b, _, _ = hdg.doassemble(Vh, Wh, Mh)
+    hdg.apply_(K, b, hdg.Dirichlet(hdg.TrialFunction(Mh), mesh, "boundary", lambda x: 0))
+    with pytest.raises(hdg.HDGError):
+        hdg.solve(K, b, precond="mg")
+    x, info = hdg.solve(K, b, precond="block")      # the context stays usable
+    assert info["converged"]
+
+
 def test_maxit_reports_not_converged():
     mesh = hdg.rectangle_mesh(hdg.TriangleCell, (16, 16), (0.0, 0.0), (1.0, 1.0))
     Vh, Wh, Mh = _spaces(mesh, 1, 2)
