@@ -423,11 +423,17 @@ class TrialFunction:
 
 class Dirichlet:
     """Dirichlet(u_hat, mesh, faceset, f) for trace spaces, src/boundary.jl:7-42: prescribed dofs
-    face*nt-nt+i over the set in ascending face order.  Only g == 0 is on the hot path (the
-    reference's projection of non-zero data is inconsistent, SURVEY.md section 0 trap 4), so
-    `f` is sampled at the face end points only to verify that it vanishes."""
+    face*nt-nt+i over the set in ascending face order, values = the reference's face projection of f,
+    restated as it is written there:  values[k] = N with N += qr_weights[q] f(x_q) T_i(q) accumulated over the
+    face's quadrature points - the accumulator N is NOT reset between the nt dofs of a face (:27) and the
+    weights are the first nfq CELL weights (fs.fs.qr_weights, :33), not the face weights.  For f == 0 (the
+    only case the reference's own driver uses) the values are exactly 0.  `corrected=True` gives the L2
+    projection onto the orthonormal Legendre trace basis instead (face weights, accumulator per dof)."""
 
-    def __init__(self, u, mesh, faceset, f):
+    # reference edges of the triangle, src/shapes.jl:19-23
+    _REF_EDGES = np.array([[[1.0, 0.0], [0.0, 1.0]], [[0.0, 1.0], [0.0, 0.0]], [[0.0, 0.0], [1.0, 0.0]]])
+
+    def __init__(self, u, mesh, faceset, f, corrected=False):
         fs = u.fs
         if not isinstance(fs, ScalarTraceFunctionSpace):
             raise NotImplementedError("only trace-space Dirichlet conditions are on the HDG path")
@@ -438,12 +444,33 @@ class Dirichlet:
                 raise AssertionError(f"Face {fi} is not in boundary")   # src/boundary.jl:22
         self.faces = np.array(faces, dtype=np.int64)
         self.prescribed_dofs = (self.faces[:, None] * nt - nt + np.arange(1, nt + 1)[None, :]).reshape(-1)
+        order = fs.fe.order
+        qd = fs.fs.quad_degree
+        T = np.asarray(ref_table(order, qd, "T")).reshape(-1, nt).T        # T[i, q]
+        s_pts = np.asarray(ref_table(order, qd, "fpoints"))
+        w_cell = np.asarray(ref_table(order, qd, "qweights"))
+        w_face = np.asarray(ref_table(order, qd, "fweights"))
+        nfq = s_pts.size
         vals = np.zeros(self.prescribed_dofs.size)
-        if faces:
-            ends = mesh.nodes[mesh.faces[self.faces - 1, :2].reshape(-1) - 1]
-            g = np.array([float(f(p)) for p in ends[: min(len(ends), 64)]])
-            if np.any(g != 0.0):
-                raise NotImplementedError("non-homogeneous Dirichlet data is not on the HDG hot path (g must be 0)")
+        k = 0
+        for fi in faces:
+            cell = int(mesh.faces[fi - 1, 2])
+            lidx = list(mesh.cells[cell - 1, 3:6]).index(fi)
+            ori = face_orientation(mesh, cell, lidx + 1)
+            x = mesh.nodes[mesh.cells[cell - 1, :3] - 1]                  # get_coordinates(cell, mesh)
+            e1, e2 = self._REF_EDGES[lidx]
+            acc = 0.0
+            for i in range(nt):
+                if corrected:
+                    acc = 0.0
+                for q in range(nfq):
+                    qo = q if ori else nfq - 1 - q                        # spatial_coordinate, src/TraceFunctionSpaces.jl:47-57
+                    eta = (1.0 - s_pts[qo]) * e1 + s_pts[qo] * e2
+                    xq = (1.0 - eta[0] - eta[1]) * x[0] + eta[0] * x[1] + eta[1] * x[2]
+                    w = w_face[q] if corrected else w_cell[q]
+                    acc += w * float(f(xq)) * T[i, q]
+                vals[k] = acc
+                k += 1
         self.values = vals
 
 

@@ -284,6 +284,38 @@ def test_nonzero_dirichlet_values_through_abi():
     assert relerr(uhat.to_numpy(), orc.solve_direct(Kb, rb)) < RTOL
 
 
+@pytest.mark.parametrize("order,qd", [(1, 2), (2, 4), (3, 6)])
+def test_nonhomogeneous_dirichlet_driver(order, qd):
+    """Dirichlet data g != 0 through the host mirror.  (a) bug-for-bug: values of src/boundary.jl:11-42
+    -> same trace solution as the oracle with the same values; (b) corrected projection: a linear harmonic function
+    is in the HDG space, so the trace solution is its face projection everywhere."""
+    g = lambda x: 1.0 + x[0] + 2.0 * x[1]
+    mo = orc.rectangle_mesh(5, 4, (0.0, 0.0), (2.0, 1.0))
+    tab = orc.build_tables(order, qd)
+    zero = lambda x: 0.0
+    asm = orc.doassemble(mo, tab, f=zero)
+    dofs, vals = orc.dirichlet(mo, tab, "boundary", g)
+    Kb, rb, _ = orc.apply_dirichlet(asm.K, asm.rhs, dofs, vals)
+    r = _assemble(mo, order, qd, f=zero)
+    mesh, Mh = r["mesh"], r["Mh"]
+    dbc = hdg.Dirichlet(hdg.TrialFunction(Mh), mesh, "boundary", g)
+    hdg.apply_(r["K"], r["b"], dbc)
+    uhat, info = hdg.solve(r["K"], r["b"], rtol=1e-14)
+    assert relerr(uhat.to_numpy(), orc.solve_direct(Kb, rb)) < RTOL
+    # (b)
+    r2 = _assemble(mo, order, qd, f=zero)
+    dbc2 = hdg.Dirichlet(hdg.TrialFunction(r2["Mh"]), r2["mesh"], "boundary", g, corrected=True)
+    hdg.apply_(r2["K"], r2["b"], dbc2)
+    uhat2, _ = hdg.solve(r2["K"], r2["b"], rtol=1e-14)
+    u2 = uhat2.to_numpy().reshape(-1, order + 1)
+    v1, v2 = mo.faces[:, 0] - 1, mo.faces[:, 1] - 1
+    lo, hi = np.minimum(v1, v2), np.maximum(v1, v2)
+    ga, gb = np.array([g(p) for p in mo.nodes[lo]]), np.array([g(p) for p in mo.nodes[hi]])
+    assert np.abs(u2[:, 0] - 0.5 * (ga + gb)).max() < 1e-9                      # Legendre mode 0 = face mean
+    assert np.abs(u2[:, 1] - (gb - ga) / (2.0 * np.sqrt(3.0))).max() < 1e-9      # mode 1 of a linear function
+    assert np.abs(u2[:, 2:]).max(initial=0.0) < 1e-9
+
+
 def test_repeated_solve_and_reassembly_same_context():
     mesh = hdg.rectangle_mesh(hdg.TriangleCell, (12, 9), (0.0, 0.0), (2.0, 1.0))
     Vh, Wh, Mh = _spaces(mesh, 1, 2)

@@ -70,8 +70,9 @@ def test_dirichlet_dofs_and_values():
         dofs, vals = orc.dirichlet(mo, orc.build_tables(order, 2 * order))
         assert np.array_equal(d.prescribed_dofs, dofs) and np.array_equal(d.values, vals)
     assert hdg.getnlocaldofs(Mh) == 3 * (order + 1)
-    with pytest.raises(NotImplementedError):
-        hdg.Dirichlet(hdg.TrialFunction(Mh), m, "boundary", lambda x: 1.0)
+    d1 = hdg.Dirichlet(hdg.TrialFunction(Mh), m, "boundary", lambda x: 1.0)      # g != 0: the reference's projection, restated
+    dofs1, vals1 = orc.dirichlet(mo, orc.build_tables(order, 2 * order), "boundary", lambda x: 1.0)
+    assert np.array_equal(d1.prescribed_dofs, dofs1) and np.abs(d1.values - vals1).max() < 1e-13
 
 
 def test_trial_function_storage():
@@ -109,3 +110,23 @@ def test_c_pcg_matches_direct_solve():
     x, it, rel = occ.pcg(Kb, rb, isbc, 1e-13, 5000, 2)
     xd = orc.solve_direct(Kb, rb)
     assert rel <= 1e-13 and np.abs(x - xd).max() < 1e-11 * np.abs(xd).max()
+
+
+@pytest.mark.parametrize("order,qd", [(1, 2), (2, 4), (2, 3), (3, 6), (4, 9)])
+def test_nonhomogeneous_dirichlet_values_match_the_restated_reference(order, qd):
+    """Dirichlet(u_hat, mesh, "boundary", g) of the host mirror == src/boundary.jl:11-42 as restated in the oracle
+    (accumulator not reset per dof, cell weights) - host-only code, no device."""
+    g = lambda x: 1.0 + x[0] + 2.0 * x[1] * x[1]
+    mo = orc.rectangle_mesh(3, 2, (0.0, 0.0), (2.0, 1.0))
+    tab = orc.build_tables(order, qd)
+    dofs, vals = orc.dirichlet(mo, tab, "boundary", g)
+    mesh = hdg.PolygonalMesh(np.hstack([mo.cells, mo.cell_faces]), mo.nodes, mo.faces, {k: set(v) for k, v in mo.facesets.items()})
+    Wh = hdg.ScalarFunctionSpace(mesh, hdg.GenericFiniteElement(hdg.Dubiner(2, hdg.RefTetrahedron, order)), qd)
+    Mh = hdg.ScalarTraceFunctionSpace(Wh, hdg.GenericFiniteElement(hdg.Legendre(1, hdg.RefTetrahedron, order)))
+    d = hdg.Dirichlet(hdg.TrialFunction(Mh), mesh, "boundary", g)
+    assert np.array_equal(d.prescribed_dofs, dofs)
+    assert np.abs(d.values - vals).max() <= 1e-13 * np.abs(vals).max()
+    # corrected variant: L2 projection on the orthonormal Legendre basis -> mode 0 = face mean of g
+    dc = hdg.Dirichlet(hdg.TrialFunction(Mh), mesh, "boundary", lambda x: 3.0, corrected=True)
+    assert np.allclose(dc.values.reshape(-1, order + 1)[:, 0], 3.0, atol=1e-13)
+    assert np.allclose(dc.values.reshape(-1, order + 1)[:, 1:], 0.0, atol=1e-13)
