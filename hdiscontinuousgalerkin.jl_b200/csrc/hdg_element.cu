@@ -100,10 +100,12 @@ __device__ __forceinline__ void load_geometry(const ElemArgs& a, int64_t c, Cell
 __device__ __forceinline__ double source_value(int source_id, double x, double y) {
     // f of examples/poisson2D_HDG.jl:55
     const double pi = 3.141592653589793;
-#ifdef HDG_USE_SINPI
-    return 2.0 * (pi * pi) * sinpi(x) * sinpi(y);
-#else
+#ifdef HDG_USE_SIN
     return 2.0 * (pi * pi) * sin(pi * x) * sin(pi * y);
+#else
+    // sinpi(x) = sin(pi x) without the rounding of pi*x and with a cheaper argument reduction (measured 1-4 % of the
+    // element kernels at k >= 2); differs from sin(pi * x) by an ulp or two
+    return 2.0 * (pi * pi) * sinpi(x) * sinpi(y);
 #endif
 }
 

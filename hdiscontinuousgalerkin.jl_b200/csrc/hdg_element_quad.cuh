@@ -14,12 +14,14 @@
 //   phase 2  (thread = cell tid%32, warp w = tid/32)  warp w solves the columns w, w+4, ... of [K_e | b_e] for the 32
 //            cells of the tile, CB columns at a time so that one shared-memory load of an L entry feeds CB FMAs.  The
 //            column index is warp-uniform, so reference-matrix operands come from the constant bank, and a store
-//            instruction writes one 256-byte row segment of the tile.  sigma = A^-1(r1 + B u) is formed row by row,
+//            instruction writes one 256-byte row segment of the tile.  (k = 3: the 12 face columns deal evenly; the
+//            load-vector column is solved by every warp and its rows are split 4 ways, see SPLITB.)  sigma = A^-1(r1 + B u) is formed row by row,
 //            stored, and folded into the 3 nt accumulators of the Ate column; products with structural zeros of
 //            Tr, Ts, Fhat are skipped at compile time (hdg_sparsity.h, validated on the host against the tables);
 //   phase 3  the face-diagonal blocks and rhs entries staged in shared memory are paired with the neighbour cell
 //            of the same tile and stored (RED.ADD.F64 only when the neighbour is in another tile), warp w = face w.
 #pragma once
+#include <type_traits>
 
 namespace hdg {
 
@@ -51,7 +53,13 @@ template <int K> struct QuadCfg {
     static constexpr int R = (n + G - 1) / G;         // rows of S per lane (phase 1)
     static constexpr int CC = (t + 1 + G - 1) / G;    // columns per warp (phase 2)
     static constexpr int CB = K == 2 ? QCB2 : (K == 3 ? QCB3 : QCB4);   // columns per batch
-    static constexpr int NB = (CC + CB - 1) / CB;
+#ifndef QSPLITB
+#define QSPLITB 0
+#endif
+    // t = 0 mod 4 (k = 3): the t face columns deal evenly to the 4 warps and the load-vector column t would make warp 0
+    // carry 4 columns against 3; instead every warp solves it and takes the rows i = w mod 4 of sigma / K_e / bte
+    static constexpr bool SPLITB = QSPLITB && (t % 4 == 0) && CB == 1;
+    static constexpr int NB = SPLITB ? t / 4 + 1 : (CC + CB - 1) / CB;
     static constexpr int nL = n * (n - 1) / 2;
     // shared-memory record per cell, stored [entry][cell]
     static constexpr int o_L = 0;                     // strict lower triangle of S, overwritten by L
@@ -60,11 +68,12 @@ template <int K> struct QuadCfg {
     static constexpr int o_status = o_be + n;
     static constexpr int o_diag = o_status + 1;       // staging of the face-diagonal blocks (phases 2-3); partial be sums (phases 0-1)
     static constexpr int o_rhs = o_diag + 3 * nt * nt;
-    static constexpr int o_scr = o_rhs + 3 * nt;      // phase 2: solutions of the 2nd ... CB-th column of a batch, per warp
+    static constexpr int o_scr = o_rhs + (SPLITB ? 4 : 1) * 3 * nt;      // phase 2: solutions of the 2nd ... CB-th column of a batch, per warp
     static constexpr int entries = o_scr + 4 * (CB - 1) * n;
     static_assert(3 * nt * nt + 3 * nt >= 4 * n, "partial load vectors alias the staging area");
     static constexpr size_t smem = sizeof(double) * entries * CS;
     static constexpr int min_blocks = K == 2 ? QMINB2 : (K == 3 ? QMINB3 : QMINB4);
+    static constexpr bool col_sweep = K <= 3;         // ordering of the triangular sweeps, see phase 2
 };
 
 // phase 0, rows i = W, W+4, ... of S = C + B'A^-1 B = tau sum_l |wn_l| Chat_l + detJ (al Prr + be Prs + ga Pss); W is a
@@ -213,7 +222,8 @@ __global__ void __launch_bounds__(QuadCfg<K>::threads, QuadCfg<K>::min_blocks) e
 
 #pragma unroll 1
     for (int b = 0; b < Q::NB; ++b) {
-        const int col0 = w + 4 * CB * b;        // columns col0, col0 + 4, ... (warp-uniform)
+        const bool bpart = Q::SPLITB && b == Q::NB - 1;          // the shared load-vector column: rows i = w mod 4 only
+        const int col0 = bpart ? t : w + 4 * CB * b;             // columns col0, col0 + 4, ... (warp-uniform)
         if (col0 > t) break;
         double u[CB][n];
         // right-hand sides: [-E;F] columns reduced to the u-block  (B'A^-1 E_l = ca_l Qr_l + cb_l Qs_l), or be
@@ -240,29 +250,58 @@ __global__ void __launch_bounds__(QuadCfg<K>::threads, QuadCfg<K>::min_blocks) e
                 for (int i = 0; i < n; ++i) u[cb][i] = 0.0;
             }
         }
-        // S u = r  by L D L', one load of every L entry for the CB columns
+        // S u = r  by L D L'; one load of every L entry serves the CB columns of the batch.  Two orderings of the same
+        // operations: column-oriented (axpy: once u[k] is final the updates of u[k+1..] are independent FMAs) and
+        // row-oriented (dot products).  Measured per order (4 M / 1 M elements): k=2 2.35 vs 2.43 ms, k=3 4.91 vs 4.93 ms,
+        // k=4 4.00 vs 3.62 ms  ->  column-oriented for k <= 3.
+        if constexpr (Q::col_sweep) {
 #pragma unroll
-        for (int i = 1; i < n; ++i)
+            for (int k = 0; k < n - 1; ++k) {
+                double lk[n];
 #pragma unroll
-            for (int k = 0; k < i; ++k) {
-                const double lik = smv[(Q::o_L + tri(i, k)) * CS];
+                for (int i = k + 1; i < n; ++i) lk[i] = smv[(Q::o_L + tri(i, k)) * CS];
 #pragma unroll
-                for (int cb = 0; cb < CB; ++cb) u[cb][i] = fma(-lik, u[cb][k], u[cb][i]);
+                for (int i = k + 1; i < n; ++i)
+#pragma unroll
+                    for (int cb = 0; cb < CB; ++cb) u[cb][i] = fma(-lk[i], u[cb][k], u[cb][i]);
             }
+        } else {
+#pragma unroll
+            for (int i = 1; i < n; ++i)
+#pragma unroll
+                for (int k = 0; k < i; ++k) {
+                    const double lik = smv[(Q::o_L + tri(i, k)) * CS];
+#pragma unroll
+                    for (int cb = 0; cb < CB; ++cb) u[cb][i] = fma(-lik, u[cb][k], u[cb][i]);
+                }
+        }
 #pragma unroll
         for (int i = 0; i < n; ++i) {
             const double di = smv[(Q::o_dinv + i) * CS];
 #pragma unroll
             for (int cb = 0; cb < CB; ++cb) u[cb][i] *= di;
         }
+        if constexpr (Q::col_sweep) {
 #pragma unroll
-        for (int i = n - 2; i >= 0; --i)
+            for (int k = n - 1; k > 0; --k) {
+                double lk[n];
 #pragma unroll
-            for (int k = i + 1; k < n; ++k) {
-                const double lki = smv[(Q::o_L + tri(k, i)) * CS];
+                for (int i = 0; i < k; ++i) lk[i] = smv[(Q::o_L + tri(k, i)) * CS];
 #pragma unroll
-                for (int cb = 0; cb < CB; ++cb) u[cb][i] = fma(-lki, u[cb][k], u[cb][i]);
+                for (int i = 0; i < k; ++i)
+#pragma unroll
+                    for (int cb = 0; cb < CB; ++cb) u[cb][i] = fma(-lk[i], u[cb][k], u[cb][i]);
             }
+        } else {
+#pragma unroll
+            for (int i = n - 2; i >= 0; --i)
+#pragma unroll
+                for (int k = i + 1; k < n; ++k) {
+                    const double lki = smv[(Q::o_L + tri(k, i)) * CS];
+#pragma unroll
+                    for (int cb = 0; cb < CB; ++cb) u[cb][i] = fma(-lki, u[cb][k], u[cb][i]);
+                }
+        }
 
         // per column: sigma = A^-1 (r1 + B u) row by row; column of Ate = [E;F]'K_e - He accumulated on the fly.
         // The columns of a batch are processed one after the other by ONE copy of the code (the solutions of the 2nd,
@@ -275,6 +314,86 @@ __global__ void __launch_bounds__(QuadCfg<K>::threads, QuadCfg<K>::min_blocks) e
         for (int cb = 1; cb < CB; ++cb)
 #pragma unroll
             for (int i = 0; i < n; ++i) scr[((cb - 1) * n + i) * CS] = u[cb][i];
+        // one column: generic lambda so that the row-split variant of the load-vector column (BP = true_type) is a second,
+        // separately scheduled copy of the code instead of a branch inside every row of the common one
+        auto column = [&](auto BP, const int col) {
+            constexpr bool kBP = decltype(BP)::value;
+                const bool isb = col == t;
+                const int l = isb ? 0 : col / nt;
+                const int j = isb ? 0 : col - l * nt;
+                const bool o_l = l == 0 ? o0 : (l == 1 ? o1 : o2);
+                const double scol = (isb || o_l || !(j & 1)) ? 1.0 : -1.0;      // Legendre parity of a reversed face
+                const double dJf_l = l == 0 ? g.dJf[0] : (l == 1 ? g.dJf[1] : g.dJf[2]);
+                const double wnx_l = l == 0 ? g.wn[0][0] : (l == 1 ? g.wn[1][0] : g.wn[2][0]);
+                const double wny_l = l == 0 ? g.wn[0][1] : (l == 1 ? g.wn[1][1] : g.wn[2][1]);
+                const double ex = isb ? 0.0 : wnx_l * idet, ey = isb ? 0.0 : wny_l * idet;
+                const int mcol = isb ? 0 : col;
+                double val[3][nt];
+    #pragma unroll
+                for (int lp = 0; lp < 3; ++lp)
+    #pragma unroll
+                    for (int ip = 0; ip < nt; ++ip) val[lp][ip] = 0.0;
+                double* __restrict__ const Kp = Ke_tile + int64_t(col) * 32;
+    #pragma unroll
+                for (int i = 0; i < n; ++i) {
+                    if (kBP && (i & 3) != w) continue;
+                    double p = 0.0, s = 0.0;
+    #pragma unroll
+                    for (int k = 0; k < n; ++k) {
+                        if ((Sp::tr(i) >> k) & 1u) p = fma(T.Tr[i * n + k], uc[k], p);
+                        if ((Sp::ts(i) >> k) & 1u) s = fma(T.Ts[i * n + k], uc[k], s);
+                    }
+                    const double mf = T.MF[i * t + mcol];
+                    const double sx = fma(g.G00, p, fma(g.G10, s, -ex * mf));
+                    const double sy = fma(g.G01, p, fma(g.G11, s, -ey * mf));
+                    if (active && !dbg) {               // 256-byte row segments of the tile
+                        Kp[int64_t(i * (t + 1)) * 32] = scol * sx;
+                        Kp[int64_t((n + i) * (t + 1)) * 32] = scol * sy;
+                        Kp[int64_t((2 * n + i) * (t + 1)) * 32] = scol * uc[i];
+                    }
+                    const double w0 = fma(g.wn[0][0], sx, fma(g.wn[0][1], sy, cf0 * uc[i]));
+                    const double w1 = fma(g.wn[1][0], sx, fma(g.wn[1][1], sy, cf1 * uc[i]));
+                    const double w2 = fma(g.wn[2][0], sx, fma(g.wn[2][1], sy, cf2 * uc[i]));
+    #pragma unroll
+                    for (int ip = 0; ip < nt; ++ip) {
+                        if ((Sp::fh(i) >> (0 * nt + ip)) & 1u) val[0][ip] = fma(T.Fhat[i * t + 0 * nt + ip], w0, val[0][ip]);
+                        if ((Sp::fh(i) >> (1 * nt + ip)) & 1u) val[1][ip] = fma(T.Fhat[i * t + 1 * nt + ip], w1, val[1][ip]);
+                        if ((Sp::fh(i) >> (2 * nt + ip)) & 1u) val[2][ip] = fma(T.Fhat[i * t + 2 * nt + ip], w2, val[2][ip]);
+                    }
+                }
+    #pragma unroll
+                for (int lp = 0; lp < 3; ++lp) {
+                    const bool o_lp = lp == 0 ? o0 : (lp == 1 ? o1 : o2);
+                    double v[nt];
+    #pragma unroll
+                    for (int ip = 0; ip < nt; ++ip) {
+                        const double srow = (o_lp || !(ip & 1)) ? 1.0 : -1.0;
+                        v[ip] = val[lp][ip] * (srow * scol);
+                    }
+                    if (isb) {                                   // bte = -[E;F]' b_e
+    #pragma unroll
+                        for (int ip = 0; ip < nt; ++ip) {
+                            if (dbg && !Q::SPLITB) { if (active) a.dbg_bt[lp * nt + ip] = -v[ip]; }
+                            else sm[(Q::o_rhs + (Q::SPLITB ? w * 3 * nt : 0) + lp * nt + ip) * CS] = -v[ip];
+                        }
+                    } else if (lp == l) {                        // face-diagonal block, minus He (poisson2D_HDG.jl:144-151)
+    #pragma unroll
+                        for (int ip = 0; ip < nt; ++ip) {
+                            const double h = fma(-dJf_l, T.Hhat[ip * nt + j], v[ip]);
+                            if (dbg) { if (active) a.dbg_At[col * t + lp * nt + ip] = h; }
+                            else sm[(Q::o_diag + (lp * nt + j) * nt + ip) * CS] = h;
+                        }
+                    } else if (dbg) {
+    #pragma unroll
+                        for (int ip = 0; ip < nt; ++ip) if (active) a.dbg_At[col * t + lp * nt + ip] = v[ip];
+                    } else if (active) {                         // off-diagonal block: exactly one contributing cell
+                        const int s = (l - lp + 3) % 3 - 1;
+                        const int64_t f_lp = g.f[lp] & 0x7fffffffu;
+                        const int slot = int(g.f[lp] >> 31) * 2 + s;
+                        store_vec<nt>(a.Ko + (f_lp * 4 + slot) * nt2 + j * nt, v);
+                    }
+                }
+        };
 #pragma unroll 1
         for (int cb = 0; cb < CB; ++cb) {
             const int col = col0 + 4 * cb;
@@ -283,83 +402,19 @@ __global__ void __launch_bounds__(QuadCfg<K>::threads, QuadCfg<K>::min_blocks) e
 #pragma unroll
                 for (int i = 0; i < n; ++i) uc[i] = scr[((cb - 1) * n + i) * CS];
             }
-            const bool isb = col == t;
-            const int l = isb ? 0 : col / nt;
-            const int j = isb ? 0 : col - l * nt;
-            const bool o_l = l == 0 ? o0 : (l == 1 ? o1 : o2);
-            const double scol = (isb || o_l || !(j & 1)) ? 1.0 : -1.0;      // Legendre parity of a reversed face
-            const double dJf_l = l == 0 ? g.dJf[0] : (l == 1 ? g.dJf[1] : g.dJf[2]);
-            const double wnx_l = l == 0 ? g.wn[0][0] : (l == 1 ? g.wn[1][0] : g.wn[2][0]);
-            const double wny_l = l == 0 ? g.wn[0][1] : (l == 1 ? g.wn[1][1] : g.wn[2][1]);
-            const double ex = isb ? 0.0 : wnx_l * idet, ey = isb ? 0.0 : wny_l * idet;
-            const int mcol = isb ? 0 : col;
-            double val[3][nt];
-#pragma unroll
-            for (int lp = 0; lp < 3; ++lp)
-#pragma unroll
-                for (int ip = 0; ip < nt; ++ip) val[lp][ip] = 0.0;
-            double* __restrict__ const Kp = Ke_tile + int64_t(col) * 32;
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-                double p = 0.0, s = 0.0;
-#pragma unroll
-                for (int k = 0; k < n; ++k) {
-                    if ((Sp::tr(i) >> k) & 1u) p = fma(T.Tr[i * n + k], uc[k], p);
-                    if ((Sp::ts(i) >> k) & 1u) s = fma(T.Ts[i * n + k], uc[k], s);
-                }
-                const double mf = T.MF[i * t + mcol];
-                const double sx = fma(g.G00, p, fma(g.G10, s, -ex * mf));
-                const double sy = fma(g.G01, p, fma(g.G11, s, -ey * mf));
-                if (active && !dbg) {               // 256-byte row segments of the tile
-                    Kp[int64_t(i * (t + 1)) * 32] = scol * sx;
-                    Kp[int64_t((n + i) * (t + 1)) * 32] = scol * sy;
-                    Kp[int64_t((2 * n + i) * (t + 1)) * 32] = scol * uc[i];
-                }
-                const double w0 = fma(g.wn[0][0], sx, fma(g.wn[0][1], sy, cf0 * uc[i]));
-                const double w1 = fma(g.wn[1][0], sx, fma(g.wn[1][1], sy, cf1 * uc[i]));
-                const double w2 = fma(g.wn[2][0], sx, fma(g.wn[2][1], sy, cf2 * uc[i]));
-#pragma unroll
-                for (int ip = 0; ip < nt; ++ip) {
-                    if ((Sp::fh(i) >> (0 * nt + ip)) & 1u) val[0][ip] = fma(T.Fhat[i * t + 0 * nt + ip], w0, val[0][ip]);
-                    if ((Sp::fh(i) >> (1 * nt + ip)) & 1u) val[1][ip] = fma(T.Fhat[i * t + 1 * nt + ip], w1, val[1][ip]);
-                    if ((Sp::fh(i) >> (2 * nt + ip)) & 1u) val[2][ip] = fma(T.Fhat[i * t + 2 * nt + ip], w2, val[2][ip]);
-                }
-            }
-#pragma unroll
-            for (int lp = 0; lp < 3; ++lp) {
-                const bool o_lp = lp == 0 ? o0 : (lp == 1 ? o1 : o2);
-                double v[nt];
-#pragma unroll
-                for (int ip = 0; ip < nt; ++ip) {
-                    const double srow = (o_lp || !(ip & 1)) ? 1.0 : -1.0;
-                    v[ip] = val[lp][ip] * (srow * scol);
-                }
-                if (isb) {                                   // bte = -[E;F]' b_e
-#pragma unroll
-                    for (int ip = 0; ip < nt; ++ip) {
-                        if (dbg) { if (active) a.dbg_bt[lp * nt + ip] = -v[ip]; }
-                        else sm[(Q::o_rhs + lp * nt + ip) * CS] = -v[ip];
-                    }
-                } else if (lp == l) {                        // face-diagonal block, minus He (poisson2D_HDG.jl:144-151)
-#pragma unroll
-                    for (int ip = 0; ip < nt; ++ip) {
-                        const double h = fma(-dJf_l, T.Hhat[ip * nt + j], v[ip]);
-                        if (dbg) { if (active) a.dbg_At[col * t + lp * nt + ip] = h; }
-                        else sm[(Q::o_diag + (lp * nt + j) * nt + ip) * CS] = h;
-                    }
-                } else if (dbg) {
-#pragma unroll
-                    for (int ip = 0; ip < nt; ++ip) if (active) a.dbg_At[col * t + lp * nt + ip] = v[ip];
-                } else if (active) {                         // off-diagonal block: exactly one contributing cell
-                    const int s = (l - lp + 3) % 3 - 1;
-                    const int64_t f_lp = g.f[lp] & 0x7fffffffu;
-                    const int slot = int(g.f[lp] >> 31) * 2 + s;
-                    store_vec<nt>(a.Ko + (f_lp * 4 + slot) * nt2 + j * nt, v);
-                }
-            }
+            if (bpart) column(std::true_type{}, col);
+            else column(std::false_type{}, col);
         }
     }
-    if (dbg) return;
+    if (dbg) {
+        if constexpr (Q::SPLITB) {      // bte = sum of the 4 partial vectors
+            __syncthreads();
+            if (w == 0 && active)
+                for (int e = 0; e < 3 * nt; ++e)
+                    a.dbg_bt[e] = ((sm[(Q::o_rhs + e) * CS] + sm[(Q::o_rhs + 3 * nt + e) * CS]) + sm[(Q::o_rhs + 6 * nt + e) * CS]) + sm[(Q::o_rhs + 9 * nt + e) * CS];
+        }
+        return;
+    }
 
     // =========================== phase 3: scatter of the staged blocks, warp w = local face w =================
     __syncthreads();
@@ -374,6 +429,10 @@ __global__ void __launch_bounds__(QuadCfg<K>::threads, QuadCfg<K>::min_blocks) e
         double* const rh = a.rhs + f * nt;
         const double* const sd = sm + (Q::o_diag + l * nt2) * CS;
         const double* const sr = sm + (Q::o_rhs + l * nt) * CS;
+        auto rsum = [&](const double* base, int e) -> double {          // bte entry: one value, or the 4 per-warp partial sums in fixed order
+            if constexpr (Q::SPLITB) return ((base[e * CS] + base[(3 * nt + e) * CS]) + base[(6 * nt + e) * CS]) + base[(9 * nt + e) * CS];
+            else return base[e * CS];
+        };
         if (pb & 0x80u) {
             if (!sec) {
                 const int pl = int(pb & 31u), plf = int((pb >> 5) & 3u);
@@ -383,7 +442,7 @@ __global__ void __launch_bounds__(QuadCfg<K>::threads, QuadCfg<K>::min_blocks) e
 #pragma unroll
                 for (int e = 0; e < nt2; ++e) v[e] = sd[e * CS] + pd[e * CS];
 #pragma unroll
-                for (int e = 0; e < nt; ++e) r[e] = sr[e * CS] + pr[e * CS];
+                for (int e = 0; e < nt; ++e) r[e] = rsum(sr, e) + rsum(pr, e);
                 store_vec<nt2>(kd, v);
                 store_vec<nt>(rh, r);
             }
@@ -392,14 +451,14 @@ __global__ void __launch_bounds__(QuadCfg<K>::threads, QuadCfg<K>::min_blocks) e
 #pragma unroll
             for (int e = 0; e < nt2; ++e) v[e] = sd[e * CS];
 #pragma unroll
-            for (int e = 0; e < nt; ++e) r[e] = sr[e * CS];
+            for (int e = 0; e < nt; ++e) r[e] = rsum(sr, e);
             store_vec<nt2>(kd, v);
             store_vec<nt>(rh, r);
         } else {
 #pragma unroll
             for (int e = 0; e < nt2; ++e) atomicAdd(kd + e, sd[e * CS]);
 #pragma unroll
-            for (int e = 0; e < nt; ++e) atomicAdd(rh + e, sr[e * CS]);
+            for (int e = 0; e < nt; ++e) atomicAdd(rh + e, rsum(sr, e));
         }
     }
 }

@@ -651,7 +651,7 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
     if (blockjac) pcg_init_blk<NT><<<G, RB, 0, c->stream>>>(a, c->d_binv);
     else pcg_init<NT><<<G, RB, 0, c->stream>>>(a);
     if (mg) mg_apply(c, a.r, a.p, c->d_partials + P_RZC0 * MAX_PARTIALS, G);      // p_0 = z_0 = M^-1 r_0
-    global_sums((1u << NPART) - 1);
+    global_sums(0x1fu | (mg ? 0x60u : 0u));
     pcg_init_final<<<1, RB, 0, c->stream>>>(a);
     c->launches += 2;
 
