@@ -213,6 +213,9 @@ hdg_status hdg_comm_pingpong(hdg_context* ctx, int32_t iters, double* usec_per_e
  * named phase: "assemble" (memsets + element kernel), "element_kernel", "apply", "solve",
  * "recover", "errornorm". */
 hdg_status hdg_last_phase_ms(const hdg_context* ctx, const char* phase, double* ms);
+/* FP64 FMA throughput of the context's device (TFLOP/s, best of 3 launches of a register-only DFMA kernel, CUDA events):
+ * the denominator for the FP64 roofline of the k >= 2 element kernels - MEASURED_PEAKS.json holds no FP64 figure. */
+hdg_status hdg_measure_fp64_peak(hdg_context* ctx, double* tflops);
 /* Number of kernel launches issued by this context since creation. */
 int64_t    hdg_launch_count(const hdg_context* ctx);
 

@@ -240,40 +240,51 @@ int hdg_c_doassemble(int n, int nt, int nq, int nfq, const double* N, const doub
     int64_t* fill = (int64_t*)malloc(sizeof(int64_t) * ndof);
     memcpy(fill, start, sizeof(int64_t) * ndof);
     int64_t* key = (int64_t*)malloc(sizeof(int64_t) * ncoo * 2);   /* (row, coo index) pairs */
+    /* With nthreads > 1 the bucket fill and the per-column sort/merge run over all threads (the reference's sparse() is
+       serial; this is the "all host cores" arm).  The result does not depend on the fill order: ties are re-sorted
+       by coo index below. */
+#pragma omp parallel for num_threads(nthreads) schedule(static) if (nthreads > 1)
     for (int64_t k = 0; k < ncoo; ++k) {
-        int64_t p = fill[Jc[k] - 1]++;
+        int64_t p;
+#pragma omp atomic capture
+        p = fill[Jc[k] - 1]++;
         key[2 * p] = I[k] - 1;
         key[2 * p + 1] = k;
     }
-    int64_t nnz = 0;
-    colptr[0] = 0;
+    /* pass 1: sort every column by row, count its distinct rows */
+    int64_t* nuniq = cnt;   /* reuse */
+#pragma omp parallel for num_threads(nthreads) schedule(static) if (nthreads > 1)
     for (int64_t j = 0; j < ndof; ++j) {
-        int64_t a = start[j], b = start[j + 1];
-        qsort(key + 2 * a, (size_t)(b - a), 2 * sizeof(int64_t), cmp_i64);   /* by row; ties keep no order: sum is of <= 2 terms */
+        int64_t a = start[j], b = start[j + 1], u = 0;
+        qsort(key + 2 * a, (size_t)(b - a), 2 * sizeof(int64_t), cmp_i64);
+        for (int64_t p = a; p < b; ++p) u += (p == a || key[2 * p] != key[2 * (p - 1)]);
+        nuniq[j] = u;
+    }
+    colptr[0] = 0;
+    for (int64_t j = 0; j < ndof; ++j) colptr[j + 1] = colptr[j] + nuniq[j];
+    const int64_t nnz = colptr[ndof];
+    /* pass 2: duplicates are summed in COO order (ascending coo index), as sparse() does */
+#pragma omp parallel for num_threads(nthreads) schedule(static) if (nthreads > 1)
+    for (int64_t j = 0; j < ndof; ++j) {
+        int64_t a = start[j], b = start[j + 1], o = colptr[j];
         int64_t p = a;
         while (p < b) {
-            int64_t row = key[2 * p];
-            /* duplicates are summed in COO order (ascending coo index), as sparse() does */
-            int64_t q = p, k0 = key[2 * p + 1], k1 = -1;
-            double s;
+            int64_t row = key[2 * p], q = p;
             while (q + 1 < b && key[2 * (q + 1)] == row) ++q;
-            if (q == p) s = V[k0];
+            double s2;
+            if (q == p) s2 = V[key[2 * p + 1]];
             else {
-                /* general case: gather indices, sort ascending, sum */
-                int64_t cntd = q - p + 1;
-                int64_t idx[8];
+                int64_t cntd = q - p + 1, idx[8];
                 for (int64_t r = 0; r < cntd && r < 8; ++r) idx[r] = key[2 * (p + r) + 1];
                 for (int64_t r = 1; r < cntd && r < 8; ++r) { int64_t v2 = idx[r]; int64_t u = r - 1; while (u >= 0 && idx[u] > v2) { idx[u + 1] = idx[u]; --u; } idx[u + 1] = v2; }
-                s = 0.0;
-                for (int64_t r = 0; r < cntd && r < 8; ++r) s += V[idx[r]];
-                (void)k1;
+                s2 = 0.0;
+                for (int64_t r = 0; r < cntd && r < 8; ++r) s2 += V[idx[r]];
             }
-            rowval[nnz] = row;
-            nzval[nnz] = s;
-            ++nnz;
+            rowval[o] = row;
+            nzval[o] = s2;
+            ++o;
             p = q + 1;
         }
-        colptr[j + 1] = nnz;
     }
     *nnz_out = nnz;
     free(cnt); free(start); free(fill); free(key); free(I); free(Jc); free(V); free(bt_all);
