@@ -127,6 +127,9 @@ struct hdg_context {
     int64_t *d_stage_cells = nullptr, *d_stage_faces = nullptr;           // int64 staging of hdg_set_mesh inputs
     // structured-mesh parameters (0 when the mesh came from hdg_set_mesh)
     int64_t nx = 0, ny = 0;
+    // vertex grid (px x py, node id = iy px + ix) when the triangulation is that of rectangle_mesh - either generated
+    // (hdg_set_rectangle_mesh) or recognised in the arrays of hdg_set_mesh; 0 = none.  Used by the multigrid preconditioner.
+    int64_t grid_px = 0, grid_py = 0;
 
     // source
     double* d_fq = nullptr;          // ncell x nq when source_id == 0
@@ -184,7 +187,7 @@ void timer_stop(hdg_context* c, Timer& t);
 float timer_ms(Timer& t);
 
 // flag words in d_flags
-enum Flag : int { FLAG_BAD_GEOM = 0, FLAG_SINGULAR = 1, FLAG_DONE = 2, FLAG_ITERS = 3, FLAG_NOT_BOUNDARY = 4, FLAG_MG = 5, NFLAGS = 8 };
+enum Flag : int { FLAG_BAD_GEOM = 0, FLAG_SINGULAR = 1, FLAG_DONE = 2, FLAG_ITERS = 3, FLAG_NOT_BOUNDARY = 4, FLAG_MG = 5, FLAG_GRID_PX = 6, FLAG_GRID_BAD = 7, NFLAGS = 8 };
 
 // ---- per-translation-unit entry points ------------------------------------------------------
 hdg_status upload_tables(hdg_context* c);                       // hdg_element.cu

@@ -684,7 +684,7 @@ static hdg_status mesh_from_host_partitioned(hdg_context* c, const int64_t* cell
         ridx.push_back(int32_t(f - F0[q]));
     }
     c->ncell = ncloc; c->ncell_own = ncown; c->nnode = nnode; c->nface = nfloc; c->nface_own = nown;
-    c->nbface = int64_t(bf.size()); c->nx = c->ny = 0;
+    c->nbface = int64_t(bf.size()); c->nx = c->ny = 0; c->grid_px = c->grid_py = 0;
     hdg_status st = alloc_mesh(c);
     if (st) return st;
     HDG_CUDA(c, cudaMemcpyAsync(c->d_cellinfo, cellinfo.data(), sizeof(int32_t) * cellinfo.size(), cudaMemcpyHostToDevice, c->stream));
@@ -714,12 +714,34 @@ static hdg_status mesh_from_host_partitioned(hdg_context* c, const int64_t* cell
     return HDG_OK;
 }
 
+// ---- is this the triangulation of rectangle_mesh?  (hdg_set_mesh arrays; enables the vertex-grid multigrid) ---------------
+// rectangle_mesh numbers the nodes iy (nx+1) + ix and joins (ix,iy) to (ix+1,iy), (ix,iy+1) and (ix+1,iy) to (ix,iy+1)
+// (src/generate_mesh.jl:1-18,101-143).  Node 0 is the lower-left corner: its only neighbours are node 1 and node px.
+__global__ void grid_find_px(const int32_t* __restrict__ facenode, int64_t nface, int32_t* __restrict__ flags) {
+    int64_t f = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (f >= nface) return;
+    const int32_t v1 = facenode[2 * f], v2 = facenode[2 * f + 1];
+    if (min(v1, v2) == 0) atomicMax(&flags[FLAG_GRID_PX], max(v1, v2));
+}
+__global__ void grid_check(const int32_t* __restrict__ facenode, int64_t nface, int64_t nnode, int32_t* __restrict__ flags) {
+    int64_t f = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (f >= nface) return;
+    const int32_t px = flags[FLAG_GRID_PX];
+    if (px < 2 || nnode % px != 0) { if (f == 0) flags[FLAG_GRID_BAD] = 1; return; }
+    const int32_t v1 = facenode[2 * f], v2 = facenode[2 * f + 1];
+    const int32_t lo = min(v1, v2), hi = max(v1, v2);
+    const int dx = hi % px - lo % px, dy = hi / px - lo / px;
+    const bool ok = (dx == 1 && dy == 0) || (dx == 0 && dy == 1) || (dx == -1 && dy == 1);
+    if (!ok) flags[FLAG_GRID_BAD] = 1;
+}
+
 hdg_status mesh_from_host(hdg_context* c, const int64_t* cells, int64_t ncell, const double* nodes, int64_t nnode,
                           const int64_t* faces, int64_t nface, const int64_t* bfaces, int64_t nbface) {
     mg_free(c);   // vertex adjacency / hierarchy of the previous mesh
 
     if (comm_active(c)) return mesh_from_host_partitioned(c, cells, ncell, nodes, nnode, faces, nface, bfaces, nbface);
     c->ncell = c->ncell_own = ncell; c->nnode = nnode; c->nface = c->nface_own = nface; c->nbface = nbface; c->nx = c->ny = 0;
+    c->grid_px = c->grid_py = 0;
     hdg_status st = alloc_mesh(c);
     if (st) return st;
     if (!c->d_stage_cells) HDG_CUDA(c, cudaMalloc(&c->d_stage_cells, sizeof(int64_t) * 6 * ncell));
@@ -759,7 +781,20 @@ hdg_status mesh_from_host(hdg_context* c, const int64_t* cells, int64_t ncell, c
         c->launches += 1;
         HDG_CUDA(c, cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int32_t) * NFLAGS, cudaMemcpyDeviceToHost, c->stream));
     }
+    // rectangle_mesh triangulation passed as arrays?  (two words of the flag array; after the Dirichlet check's reset)
+    HDG_CUDA(c, cudaMemsetAsync(c->d_flags + FLAG_GRID_PX, 0, sizeof(int32_t) * 2, c->stream));
+    grid_find_px<<<(unsigned)ceil_div(nface, B), B, 0, c->stream>>>(c->d_facenode, nface, c->d_flags);
+    grid_check<<<(unsigned)ceil_div(nface, B), B, 0, c->stream>>>(c->d_facenode, nface, nnode, c->d_flags);
+    c->launches += 2;
+    HDG_CUDA(c, cudaMemcpyAsync(c->h_flags + FLAG_GRID_PX, c->d_flags + FLAG_GRID_PX, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, c->stream));
     HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    {
+        const int64_t px = c->h_flags[FLAG_GRID_PX], py = px >= 2 ? nnode / px : 0;
+        if (!c->h_flags[FLAG_GRID_BAD] && px >= 2 && py >= 2 && px * py == nnode &&
+            nface == 3 * (px - 1) * (py - 1) + (px - 1) + (py - 1) && ncell == 2 * (px - 1) * (py - 1)) {
+            c->grid_px = px; c->grid_py = py;
+        }
+    }
     if (c->nbface && c->h_flags[FLAG_NOT_BOUNDARY])
         return set_err(c, HDG_ERR_NOT_BOUNDARY, "Face " + std::to_string(c->h_flags[FLAG_NOT_BOUNDARY]) + " is not in boundary");
     st = alloc_system(c);
@@ -792,6 +827,7 @@ hdg_status mesh_rectangle(hdg_context* c, int64_t nx, int64_t ny, double llx, do
     S.node0 = j0 * (nx + 1);
     const int64_t node_rows = (j1 - j0 + 1) + (j1 < ny ? 1 : 0);
     c->nx = nx; c->ny = ny;
+    c->grid_px = multi ? 0 : nx + 1; c->grid_py = multi ? 0 : ny + 1;
     c->ncell_own = S.ncell_own;
     c->ncell = S.ncell_own + (j1 < ny ? nx : 0);
     c->nnode = node_rows * (nx + 1);

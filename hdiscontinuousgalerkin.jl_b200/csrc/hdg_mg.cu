@@ -354,15 +354,17 @@ void mg_free(hdg_context* c) {
 
 template <int NT> static hdg_status mg_setup_t(hdg_context* c) {
     if (comm_active(c)) return set_err(c, HDG_ERR_INVALID, "the multigrid preconditioner runs on one GPU");
-    if (c->nx <= 0 || c->ny <= 0) return set_err(c, HDG_ERR_INVALID, "the multigrid preconditioner needs a rectangle_mesh (hdg_set_rectangle_mesh)");
+    if (c->grid_px < 2 || c->grid_py < 2)
+        return set_err(c, HDG_ERR_INVALID, "the multigrid preconditioner needs the triangulation of rectangle_mesh (hdg_set_rectangle_mesh, or "
+                                           "hdg_set_mesh with rectangle_mesh's node numbering)");
     MgData* m = static_cast<MgData*>(c->mg);
-    if (m && (m->nnode != c->nnode || m->nface != c->nface || m->nx != c->nx || m->ny != c->ny)) { mg_free(c); m = nullptr; }
+    if (m && (m->nnode != c->nnode || m->nface != c->nface || m->nx != c->grid_px - 1 || m->ny != c->grid_py - 1)) { mg_free(c); m = nullptr; }
     if (!m) {
         m = new MgData();
         c->mg = m;
-        m->nnode = c->nnode; m->nface = c->nface; m->nx = int(c->nx); m->ny = int(c->ny);
+        m->nnode = c->nnode; m->nface = c->nface; m->nx = int(c->grid_px) - 1; m->ny = int(c->grid_py) - 1;
         // grid hierarchy
-        int px = int(c->nx) + 1, py = int(c->ny) + 1;
+        int px = int(c->grid_px), py = int(c->grid_py);
         int64_t total = 0;
         while (true) {
             MgLevel& L = m->lev[m->nlev++];

@@ -373,9 +373,27 @@ def test_multigrid_preconditioner(order, qd, nx, ny):
         assert relerr(xm.to_numpy(), ro["uhat"]) < RTOL
 
 
-def test_multigrid_needs_rectangle_mesh():
-    mo = orc.rectangle_mesh(6, 5)
-    mesh = host_mesh_from_oracle(mo)          # same mesh, but passed as arrays: no grid structure known to the library
+@pytest.mark.parametrize("order,qd,nx,ny", [(1, 2, 6, 5), (2, 4, 40, 24), (1, 2, 1, 1), (1, 2, 7, 1)])
+def test_multigrid_through_set_mesh_arrays(order, qd, nx, ny):
+    """The drop-in path hands rectangle_mesh over as Julia arrays (hdg_set_mesh): the library recognises the grid
+    triangulation in the face table and the multigrid solve is the one of hdg_set_rectangle_mesh, bit for bit."""
+    mo = orc.rectangle_mesh(nx, ny, (0.0, 0.0), (2.0, 1.0))
+    xs = []
+    for rect in (None, (nx, ny, (0.0, 0.0), (2.0, 1.0))):
+        mesh = host_mesh_from_oracle(mo)
+        mesh._rect = rect                       # None: passed as arrays, no grid structure told to the library
+        Vh, Wh, Mh = _spaces(mesh, order, qd)
+        K, b, _, _ = hdg.doassemble(Vh, Wh, Mh)
+        hdg.apply_(K, b, hdg.Dirichlet(hdg.TrialFunction(Mh), mesh, "boundary", lambda x: 0))
+        x, info = hdg.solve(K, b, rtol=1e-13, precond="mg")
+        assert info["converged"] and info["iterations"] <= 60
+        xs.append((x.to_numpy(), info["iterations"]))
+    assert xs[0][1] == xs[1][1] and np.array_equal(xs[0][0], xs[1][0])
+
+
+def test_multigrid_rejects_other_triangulations():
+    mo = orc.parse_mesh_triangle(triangle_root("figure.1"))      # unstructured, 62 cells
+    mesh = host_mesh_from_oracle(mo)
     Vh, Wh, Mh = _spaces(mesh, 1, 2)
     K, b, _, _ = hdg.doassemble(Vh, Wh, Mh)
     hdg.apply_(K, b, hdg.Dirichlet(hdg.TrialFunction(Mh), mesh, "boundary", lambda x: 0))
@@ -383,6 +401,20 @@ def test_multigrid_needs_rectangle_mesh():
         hdg.solve(K, b, precond="mg")
     x, info = hdg.solve(K, b, precond="block")      # the context stays usable
     assert info["converged"]
+    # rectangle_mesh with permuted node ids: same triangulation, but not the grid numbering the hierarchy is built on
+    mo = orc.rectangle_mesh(5, 4)
+    perm = np.random.default_rng(3).permutation(mo.nodes.shape[0])
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(perm.size)
+    tri = inv[mo.cells - 1] + 1
+    nodes = mo.nodes[perm]
+    cell_faces, faces = hdg.api.number_faces(tri)
+    mesh = hdg.PolygonalMesh(np.hstack([tri, cell_faces]), nodes, faces, {"boundary": set(int(f) + 1 for f in np.nonzero(faces[:, 3] == 0)[0])})
+    Vh, Wh, Mh = _spaces(mesh, 1, 2)
+    K, b, _, _ = hdg.doassemble(Vh, Wh, Mh)
+    hdg.apply_(K, b, hdg.Dirichlet(hdg.TrialFunction(Mh), mesh, "boundary", lambda x: 0))
+    with pytest.raises(hdg.HDGError):
+        hdg.solve(K, b, precond="mg")
 
 
 def test_maxit_reports_not_converged():
