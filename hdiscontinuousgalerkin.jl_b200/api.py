@@ -318,6 +318,7 @@ class _Context:
         return s
 
     def set_mesh(self, mesh):
+        self._dirichlet_faces = None     # the library takes the mesh's "boundary" set again
         if mesh._rect is not None and not getattr(mesh, "_modified", False):
             nx, ny, LL, UR = mesh._rect
             check(self.lib.hdg_set_rectangle_mesh(self.h, nx, ny, LL[0], LL[1], UR[0], UR[1]), self.h)
@@ -576,8 +577,13 @@ def apply_(K, b, dbc):
     ctx = K._ctx
     s = ctx.sizes()
     mine = np.array(sorted(ctx.mesh.facesets["boundary"]), dtype=np.int64)
+    if getattr(ctx, "_dirichlet_faces", None) is not None:
+        mine = ctx._dirichlet_faces
     if dbc.faces.size != s.nbface or not np.array_equal(dbc.faces, mine):
-        raise NotImplementedError("the Dirichlet set must be the mesh's \"boundary\" face set")
+        # another named face set ("bottom", "left", ... src/generate_mesh.jl:60-89): the rest of the boundary stays natural
+        faces = np.ascontiguousarray(dbc.faces, dtype=np.int64)
+        check(ctx.lib.hdg_set_dirichlet_faces(ctx.h, i64p(faces), faces.size), ctx.h)
+        ctx._dirichlet_faces = faces
     vals = dbc.values if np.any(dbc.values != 0) else None
     check(ctx.lib.hdg_apply_dirichlet(ctx.h, f64p(vals)), ctx.h)
 
@@ -614,13 +620,21 @@ def errornorm(u_h, u_ex=poisson_exact, norm_type="L2"):
     """errornorm(u_h,u_ex): squared L2 error, src/DiscreteFunctions.jl:97-120."""
     if norm_type != "L2":
         raise ValueError(f"Norm {norm_type} not available")
-    if u_ex is not poisson_exact:
-        raise NotImplementedError("only the manufactured solution sin(pi x) sin(pi y) is built in")
     ctx = u_h._ctx
     if ctx is None:
         raise HDGError(1, "errornorm before get_usigma_")
     e = C.c_double()
-    check(ctx.lib.hdg_errornorm(ctx.h, 1, C.byref(e)), ctx.h)
+    if u_ex is poisson_exact:
+        check(ctx.lib.hdg_errornorm(ctx.h, 1, C.byref(e)), ctx.h)
+        return e.value
+    # any other u_ex: sampled on the host at x_q = sum_g M[g,q] x_g like the source (function_value,
+    # src/DiscreteFunctions.jl:6-24, :108), the quadrature sum runs on the device
+    mesh = u_h.fs.mesh
+    qp = np.asarray(ref_table(u_h.fs.fe.order, u_h.fs.quad_degree, "qpoints")).reshape(-1, 2)
+    M = np.stack([1 - qp[:, 0] - qp[:, 1], qp[:, 0], qp[:, 1]], axis=0)
+    xq = np.einsum("gq,cgd->cqd", M, mesh.nodes[mesh.cells[:, :3] - 1])
+    uq = np.ascontiguousarray(np.vectorize(lambda a, b: u_ex((a, b)))(xq[..., 0], xq[..., 1]), dtype=np.float64)
+    check(ctx.lib.hdg_errornorm_values(ctx.h, f64p(uq), C.byref(e)), ctx.h)
     return e.value
 
 

@@ -158,6 +158,12 @@ hdg_status hdg_set_rectangle_mesh(hdg_context* c, int64_t nx, int64_t ny, double
     return mesh_rectangle(c, nx, ny, llx, lly, urx, ury);
 }
 
+hdg_status hdg_set_dirichlet_faces(hdg_context* c, const int64_t* bfaces, int64_t nbface) {
+    if (!c || nbface < 0 || (nbface > 0 && !bfaces)) return HDG_ERR_INVALID;
+    cudaSetDevice(c->device);
+    return mesh_set_dirichlet(c, bfaces, nbface);
+}
+
 hdg_status hdg_number_faces(hdg_context* c, const int64_t* tri, int64_t ncell, const double* nodes, int64_t nnode,
                             int64_t* cells_out, int64_t* faces_out, int64_t faces_capacity, int64_t* nface_out) {
     if (!c || !tri || !nodes || !nface_out) return HDG_ERR_INVALID;
@@ -327,7 +333,14 @@ hdg_status hdg_errornorm(hdg_context* c, int32_t exact_id, double* err2) {
     if (!c->recovered) return set_err(c, HDG_ERR_INVALID, "hdg_errornorm before hdg_recover");
     if (exact_id != 1) return set_err(c, HDG_ERR_INVALID, "unknown exact_id");
     cudaSetDevice(c->device);
-    return errornorm(c, exact_id, err2);
+    return errornorm(c, exact_id, nullptr, err2);
+}
+
+hdg_status hdg_errornorm_values(hdg_context* c, const double* uex_q, double* err2) {
+    if (!c || !uex_q || !err2) return HDG_ERR_INVALID;
+    if (!c->recovered) return set_err(c, HDG_ERR_INVALID, "hdg_errornorm_values before hdg_recover");
+    cudaSetDevice(c->device);
+    return errornorm(c, 0, uex_q, err2);
 }
 
 hdg_status hdg_get_pattern(hdg_context* c, int64_t* colptr, int64_t* rowval) {

@@ -197,6 +197,7 @@ hdg_status condensed_of_cell(hdg_context* c, int64_t cell, double* At, double* b
 hdg_status mesh_from_host(hdg_context* c, const int64_t* cells, int64_t ncell, const double* nodes,
                           int64_t nnode, const int64_t* faces, int64_t nface, const int64_t* bfaces,
                           int64_t nbface);                      // hdg_mesh.cu
+hdg_status mesh_set_dirichlet(hdg_context* c, const int64_t* bfaces, int64_t nbface);   // hdg_mesh.cu
 hdg_status mesh_rectangle(hdg_context* c, int64_t nx, int64_t ny, double llx, double lly, double urx,
                           double ury);                          // hdg_mesh.cu
 hdg_status mesh_perturb(hdg_context* c, double fraction, uint64_t seed);
@@ -219,7 +220,7 @@ void mg_free(hdg_context* c);
 int mg_levels(const hdg_context* c);
 
 hdg_status recover(hdg_context* c);                             // hdg_recover.cu
-hdg_status errornorm(hdg_context* c, int exact_id, double* err2);
+hdg_status errornorm(hdg_context* c, int exact_id, const double* uex_host, double* err2);
 hdg_status local_download(hdg_context* c, int64_t cell, double* Ke, double* be);
 hdg_status nodal_average(hdg_context* c, double* out);
 

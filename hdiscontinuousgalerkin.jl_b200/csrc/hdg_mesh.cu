@@ -803,6 +803,51 @@ hdg_status mesh_from_host(hdg_context* c, const int64_t* cells, int64_t ncell, c
     return HDG_OK;
 }
 
+// Dirichlet(u_hat, mesh, faceset, g) on another face set than the one given with the mesh (src/boundary.jl:7-42: any named set
+// of boundary faces - "bottom", "left", ... of rectangle_mesh, src/generate_mesh.jl:60-89).  Faces of the boundary that are not
+// in the set keep their natural (flux) condition.
+hdg_status mesh_set_dirichlet(hdg_context* c, const int64_t* bfaces, int64_t nbface) {
+    if (!c->have_mesh) return set_err(c, HDG_ERR_INVALID, "hdg_set_dirichlet_faces before a mesh is set");
+    if (comm_active(c)) return set_err(c, HDG_ERR_INVALID, "hdg_set_dirichlet_faces is single-GPU");
+    if (c->applied) return set_err(c, HDG_ERR_INVALID, "the system was already modified by hdg_apply_dirichlet: call hdg_assemble again first");
+    std::vector<int32_t> bf(nbface);
+    for (int64_t i = 0; i < nbface; ++i) {
+        if (bfaces[i] < 1 || bfaces[i] > c->nface) return set_err(c, HDG_ERR_INVALID, "boundary face id out of range");
+        bf[i] = int32_t(bfaces[i] - 1);
+    }
+    std::sort(bf.begin(), bf.end());
+    bf.erase(std::unique(bf.begin(), bf.end()), bf.end());
+    const int64_t nb = int64_t(bf.size());
+    if (nb > c->cap_nbface) {
+        cudaFree(c->d_bfaces);
+        c->d_bfaces = nullptr;
+        c->cap_nbface = 0;
+        HDG_CUDA(c, cudaMalloc(&c->d_bfaces, sizeof(int32_t) * nb));
+        c->cap_nbface = nb;
+    }
+    mg_free(c);   // the vertex hierarchy fixes the vertices of Dirichlet faces
+    const int B = 256;
+    HDG_CUDA(c, cudaMemsetAsync(c->d_isbc, 0, c->nface, c->stream));
+    c->nbface = 0;
+    c->solved = false;
+    if (nb) {
+        HDG_CUDA(c, cudaMemcpyAsync(c->d_bfaces, bf.data(), sizeof(int32_t) * nb, cudaMemcpyHostToDevice, c->stream));
+        HDG_CUDA(c, cudaMemsetAsync(c->d_flags + FLAG_NOT_BOUNDARY, 0, sizeof(int32_t), c->stream));
+        mark_bfaces<<<(unsigned)ceil_div(nb, B), B, 0, c->stream>>>(c->d_bfaces, nb, c->d_facecell, c->d_isbc, c->d_flags);
+        c->launches += 1;
+        HDG_CUDA(c, cudaMemcpyAsync(c->h_flags + FLAG_NOT_BOUNDARY, c->d_flags + FLAG_NOT_BOUNDARY, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    }
+    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (nb && c->h_flags[FLAG_NOT_BOUNDARY]) {
+        const int bad = c->h_flags[FLAG_NOT_BOUNDARY];
+        cudaMemsetAsync(c->d_isbc, 0, c->nface, c->stream);     // leave an empty set behind, not a half-checked one
+        cudaStreamSynchronize(c->stream);
+        return set_err(c, HDG_ERR_NOT_BOUNDARY, "Face " + std::to_string(bad) + " is not in boundary");
+    }
+    c->nbface = nb;
+    return HDG_OK;
+}
+
 hdg_status mesh_rectangle(hdg_context* c, int64_t nx, int64_t ny, double llx, double lly, double urx, double ury) {
     mg_free(c);   // vertex adjacency / hierarchy of the previous mesh
 

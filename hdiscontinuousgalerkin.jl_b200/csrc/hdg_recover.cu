@@ -78,7 +78,7 @@ hdg_status recover(hdg_context* c) {
 // ---- squared L2 error ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(RB) errornorm_kernel(const double* __restrict__ u, const int32_t* __restrict__ cellinfo,
                                                        const double* __restrict__ nodes, RawTablesDev R, int64_t ncell,
-                                                       int exact_id, double* __restrict__ part) {
+                                                       int exact_id, const double* __restrict__ uexq, double* __restrict__ part) {
     const double pi = 3.141592653589793;
     double acc = 0.0;
     for (int64_t c = int64_t(blockIdx.x) * RB + threadIdx.x; c < ncell; c += int64_t(gridDim.x) * RB) {
@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(RB) errornorm_kernel(const double* __restrict_
             for (int i = 0; i < R.n; ++i) uq += u[c + ncell * i] * R.N[i + R.n * q];
             double xq = R.Mgeo[3 * q] * x[0][0] + R.Mgeo[3 * q + 1] * x[1][0] + R.Mgeo[3 * q + 2] * x[2][0];
             double yq = R.Mgeo[3 * q] * x[0][1] + R.Mgeo[3 * q + 1] * x[1][1] + R.Mgeo[3 * q + 2] * x[2][1];
-            double ex = exact_id == 1 ? sin(pi * xq) * sin(pi * yq) : 0.0;   // u_ex, poisson2D_HDG.jl:216
+            // u_ex: built in (poisson2D_HDG.jl:216) or the caller's values at the cell quadrature points
+            double ex = exact_id == 1 ? sin(pi * xq) * sin(pi * yq) : (uexq ? uexq[c * R.nq + q] : 0.0);
             double d = uq - ex;
             el += d * d * (detJ * R.qw[q]);
         }
@@ -106,17 +107,26 @@ __global__ void __launch_bounds__(RB) errornorm_kernel(const double* __restrict_
     if (threadIdx.x == 0) part[blockIdx.x] = tot;
 }
 
-hdg_status errornorm(hdg_context* c, int exact_id, double* err2) {
+hdg_status errornorm(hdg_context* c, int exact_id, const double* uex_host, double* err2) {
     int np = int(std::min<int64_t>(ceil_div(c->ncell_own, RB), 1024));
+    double* d_uex = nullptr;
+    if (exact_id == 0) {
+        const size_t bytes = sizeof(double) * size_t(c->ncell_own) * c->tab.nq;
+        HDG_CUDA(c, cudaMalloc(&d_uex, bytes));
+        cudaError_t e = cudaMemcpyAsync(d_uex, uex_host, bytes, cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) { cudaFree(d_uex); return set_err(c, HDG_ERR_CUDA, cudaGetErrorString(e)); }
+    }
     timer_start(c, c->t_err);
-    errornorm_kernel<<<np, RB, 0, c->stream>>>(c->d_u, c->d_cellinfo, c->d_nodes, c->raw, c->ncell_own, exact_id, c->d_partials);
+    errornorm_kernel<<<np, RB, 0, c->stream>>>(c->d_u, c->d_cellinfo, c->d_nodes, c->raw, c->ncell_own, exact_id, d_uex, c->d_partials);
     final_sum<<<1, RB, 0, c->stream>>>(c->d_partials, np, c->d_scal + 3);
     c->launches += 2;
     hdg_status st = comm_allreduce_sum(c, c->d_scal + 3, 1);
-    if (st) return st;
+    if (st) { if (d_uex) { cudaStreamSynchronize(c->stream); cudaFree(d_uex); } return st; }
     timer_stop(c, c->t_err);
     HDG_CUDA(c, cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(double) * 8, cudaMemcpyDeviceToHost, c->stream));
-    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaError_t es = cudaStreamSynchronize(c->stream);
+    if (d_uex) cudaFree(d_uex);
+    if (es != cudaSuccess) return set_err(c, HDG_ERR_CUDA, cudaGetErrorString(es));
     *err2 = c->h_scal[3];
     return HDG_OK;
 }

@@ -114,10 +114,14 @@ function Base.Vector(v::TraceVector)
     out
 end
 
-"apply!(K, b, dbc) of src/boundary.jl:121-158 (dbc.values are all zero on the HDG path)."
+"apply!(K, b, dbc) of src/boundary.jl:121-158.  The Dirichlet faces are read back from dbc.prescribed_dofs (nt consecutive
+dofs per face, ascending, src/boundary.jl:19-25), so any named face set works ("left", "bottom", ...)."
 function HDiscontinuousGalerkin.apply!(K::TraceMatrix, b::TraceVector, dbc::Dirichlet)
+    c = K.ctx
+    faces = Int64[(d - 1) ÷ c.nt + 1 for d in dbc.prescribed_dofs[1:c.nt:end]]
+    check(ccall((:hdg_set_dirichlet_faces, lib), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64), c.h, faces, length(faces)), c.h)
     vals = any(!iszero, dbc.values) ? dbc.values : C_NULL
-    check(ccall((:hdg_apply_dirichlet, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}), K.ctx.h, vals), K.ctx.h)
+    check(ccall((:hdg_apply_dirichlet, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}), c.h, vals), c.h)
 end
 
 "û = K \\ b of examples/poisson2D_HDG.jl:195."
@@ -139,6 +143,18 @@ end
 function errornorm_b200(ctx::Context)
     e = Ref{Float64}(0.0)
     check(ccall((:hdg_errornorm, lib), Cint, (Ptr{Cvoid}, Int32, Ref{Float64}), ctx.h, 1, e), ctx.h)
+    e[]
+end
+
+"errornorm(u_h, u_ex) for any u_ex: sampled at the cell quadrature points like `function_value` (src/DiscreteFunctions.jl:108)."
+function errornorm_b200(ctx::Context, Wh, mesh, u_ex::Function)
+    nq = getnquadpoints(Wh)
+    uq = Matrix{Float64}(undef, nq, getncells(mesh))              # uq[q, cell] == C layout uex_q[cell*nq + q]
+    for (ci, cell) in enumerate(CellIterator(mesh)), q in 1:nq
+        uq[q, ci] = function_value(u_ex, Wh, cell, q)
+    end
+    e = Ref{Float64}(0.0)
+    check(ccall((:hdg_errornorm_values, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}), ctx.h, uq, e), ctx.h)
     e[]
 end
 

@@ -110,6 +110,13 @@ hdg_status hdg_set_mesh(hdg_context* ctx,
 hdg_status hdg_set_rectangle_mesh(hdg_context* ctx, int64_t nx, int64_t ny,
                                   double llx, double lly, double urx, double ury);
 
+/* Dirichlet(u_hat, mesh, faceset, g) for another face set than the one handed over with the mesh (src/boundary.jl:7-42 takes
+ * any named set of boundary faces, e.g. "bottom"/"right"/"top"/"left" of rectangle_mesh, src/generate_mesh.jl:60-89): replaces
+ * the Dirichlet face set (1-based ids, any order).  Boundary faces outside the set keep the natural condition.  A face with
+ * two cells gives HDG_ERR_NOT_BOUNDARY (the @assert of src/boundary.jl:22) and leaves an empty set.  Call after the mesh is set
+ * and before hdg_apply_dirichlet; single GPU. */
+hdg_status hdg_set_dirichlet_faces(hdg_context* ctx, const int64_t* bfaces, int64_t nbface);
+
 /* First-encounter face numbering of an arbitrary triangle list on the device - the job of _build_cells
  * (src/generate_mesh.jl:20-46) / parse_cells! (src/triangle_mesh.jl:48-108), which are sequential hash-table
  * inserts in the reference.  tri: ncell x 3 Int64 node ids (1-based, either orientation: clockwise cells get
@@ -164,6 +171,11 @@ hdg_status hdg_recover(hdg_context* ctx);
 /* errornorm(u_h,u_ex) (squared L2, src/DiscreteFunctions.jl:97-120).  exact_id 1:
  * sin(pi x) sin(pi y) (poisson2D_HDG.jl:216). */
 hdg_status hdg_errornorm(hdg_context* ctx, int32_t exact_id, double* err2);
+
+/* errornorm(u_h, u_ex) for any u_ex: uex_q holds u_ex at the cell quadrature points, ncell x nq doubles laid out like the
+ * source values of hdg_set_source_values (uex_q[c*nq+q] = u_ex(spatial_coordinate(Wh,q,coords_c))).  Several GPUs: every
+ * rank passes the values of the cells it owns; the result is the global sum. */
+hdg_status hdg_errornorm_values(hdg_context* ctx, const double* uex_q, double* err2);
 
 /* Asynchronous variant of hdg_assemble for timing loops: enqueues on the context stream and
  * returns; pair with hdg_sync.  hdg_stream returns the cudaStream_t as an integer handle. */

@@ -316,6 +316,60 @@ def test_nonhomogeneous_dirichlet_driver(order, qd):
     assert np.abs(u2[:, 2:]).max(initial=0.0) < 1e-9
 
 
+@pytest.mark.parametrize("order,qd,sets", [(1, 2, ("left",)), (2, 4, ("bottom", "right")), (3, 6, ("top",))])
+def test_dirichlet_on_named_face_sets(order, qd, sets):
+    """Dirichlet(u_hat, mesh, "left", g): any named set of boundary faces (src/boundary.jl:7-42, the sets of
+    src/generate_mesh.jl:60-89); the other boundary faces keep the natural condition.  hdg_set_dirichlet_faces."""
+    mo = orc.rectangle_mesh(6, 5)
+    tab = orc.build_tables(order, qd)
+    asm = orc.doassemble(mo, tab)
+    fset = set().union(*[mo.facesets[s] for s in sets])
+    g = (lambda x: 0.0) if order != 2 else (lambda x: 1.0 + x[0] - 2.0 * x[1])
+    dofs, vals = orc.dirichlet(mo, tab, fset, g)
+    Kb, rb, m = orc.apply_dirichlet(asm.K, asm.rhs, dofs, vals)
+    uo = orc.solve_direct(Kb, rb)
+    mesh = hdg.rectangle_mesh(hdg.TriangleCell, (6, 5), (0.0, 0.0), (1.0, 1.0))
+    Vh, Wh, Mh = _spaces(mesh, order, qd)
+    K, b, K_e, b_e = hdg.doassemble(Vh, Wh, Mh)
+    uhat_h = hdg.TrialFunction(Mh)
+    dbc = hdg.Dirichlet(uhat_h, mesh, sets[0] if len(sets) == 1 else fset, g)
+    assert np.array_equal(dbc.prescribed_dofs, dofs)
+    assert np.abs(dbc.values - vals).max() <= 1e-13 * max(np.abs(vals).max(), 1.0)
+    hdg.apply_(K, b, dbc)
+    assert abs(hdg.meandiag(K) - m) <= 1e-12 * abs(m)
+    assert relerr(K.nzval(), Kb.data) < RTOL and relerr(b.to_numpy(), rb) < RTOL
+    for precond in ("jacobi", "block"):
+        x, info = hdg.solve(K, b, rtol=1e-14, precond=precond)
+        assert info["converged"] and relerr(x.to_numpy(), uo) < 1e-9
+    # the set is part of the context now: a re-assembly on the same context keeps it
+    ctx = K._ctx
+    hdg.check(ctx.lib.hdg_assemble(ctx.h), ctx.h)
+    hdg.apply_(K, b, dbc)
+    x2, _ = hdg.solve(K, b, rtol=1e-14)
+    assert relerr(x2.to_numpy(), uo) < 1e-9
+    # an interior face in the set: the @assert of src/boundary.jl:22, through the ABI
+    interior = int(np.nonzero(mo.faces[:, 3] != 0)[0][0]) + 1
+    hdg.check(ctx.lib.hdg_assemble(ctx.h), ctx.h)
+    bad = np.array([interior], dtype=np.int64)
+    with pytest.raises(hdg.NotBoundaryError):
+        hdg.check(ctx.lib.hdg_set_dirichlet_faces(ctx.h, hdg.api.i64p(bad), 1), ctx.h)
+
+
+def test_errornorm_with_user_exact_solution():
+    """errornorm(u_h, u_ex) for any u_ex (src/DiscreteFunctions.jl:97-120): hdg_errornorm_values."""
+    mo = orc.rectangle_mesh(5, 4)
+    for order, qd in ((1, 2), (3, 6)):
+        ro = orc.run_poisson(mo, order, qd)
+        mesh = hdg.rectangle_mesh(hdg.TriangleCell, (5, 4), (0.0, 0.0), (1.0, 1.0))
+        r = hdg.poisson2D_HDG(mesh, order, qd, rtol=1e-14)
+        u_ex = lambda x: x[0] * (1.0 - x[0]) * np.exp(x[1])
+        eo = orc.errornorm(mo, ro["tab"], ro["u"], u_ex)
+        eg = hdg.errornorm(r["u_h"], u_ex)
+        assert abs(eg - eo) <= 1e-9 * eo
+        same = hdg.errornorm(r["u_h"], lambda x: np.sin(np.pi * x[0]) * np.sin(np.pi * x[1]))
+        assert abs(same - r["err2"]) <= 1e-9 * r["err2"]
+
+
 def test_repeated_solve_and_reassembly_same_context():
     mesh = hdg.rectangle_mesh(hdg.TriangleCell, (12, 9), (0.0, 0.0), (2.0, 1.0))
     Vh, Wh, Mh = _spaces(mesh, 1, 2)
