@@ -37,6 +37,17 @@ namespace hdg {
 #ifndef QMINB2
 #define QMINB2 4
 #endif
+// Stage the off-diagonal trace blocks in shared memory and store them cooperatively in phase 3 (16-byte pieces of the
+// two adjacent blocks a cell owns in a face row, consecutive threads -> consecutive pieces).  Pays when nt is not a
+// multiple of 4: per-lane stores of nt doubles are then split into 8-byte STGs that each touch their own sector
+// (k = 2, ncu: 263 M store sectors where 66 M would do, L1->L2 request path 70 % busy).  k = 3 writes whole 32-byte
+// columns already.
+#ifndef QSTAGE2
+#define QSTAGE2 1
+#endif
+#ifndef QSTAGE4
+#define QSTAGE4 0
+#endif
 #ifndef QMINB3
 #define QMINB3 4
 #endif
@@ -69,9 +80,12 @@ template <int K> struct QuadCfg {
     static constexpr int o_diag = o_status + 1;       // staging of the face-diagonal blocks (phases 2-3); partial be sums (phases 0-1)
     static constexpr int o_rhs = o_diag + 3 * nt * nt;
     static constexpr int o_scr = o_rhs + (SPLITB ? 4 : 1) * 3 * nt;      // phase 2: solutions of the 2nd ... CB-th column of a batch, per warp
-    static constexpr int entries = o_scr + 4 * (CB - 1) * n;
+    static constexpr bool STAGE_OFF = (K == 2 && QSTAGE2) || (K == 4 && QSTAGE4);
+    static constexpr int o_off = o_scr + 4 * (CB - 1) * n;             // staged off-diagonal blocks: [(lp*2 + s)*nt*nt + j*nt + ip]
+    static constexpr int entries = o_off + (STAGE_OFF ? 6 * nt * nt : 0);
     static_assert(3 * nt * nt + 3 * nt >= 4 * n, "partial load vectors alias the staging area");
-    static constexpr size_t smem = sizeof(double) * entries * CS;
+    static constexpr size_t smem_rec = sizeof(double) * entries * CS;
+    static constexpr size_t smem = smem_rec + (STAGE_OFF ? sizeof(uint32_t) * 3 * cells : 0);   // + face words of the tile
     static constexpr int min_blocks = K == 2 ? QMINB2 : (K == 3 ? QMINB3 : QMINB4);
     static constexpr bool col_sweep = K <= 3;         // ordering of the triangular sweeps, see phase 2
 };
@@ -386,6 +400,10 @@ __global__ void __launch_bounds__(QuadCfg<K>::threads, QuadCfg<K>::min_blocks) e
                     } else if (dbg) {
     #pragma unroll
                         for (int ip = 0; ip < nt; ++ip) if (active) a.dbg_At[col * t + lp * nt + ip] = v[ip];
+                    } else if (Q::STAGE_OFF) {                   // off-diagonal block, staged: stored cooperatively in phase 3
+                        const int s = (l - lp + 3) % 3 - 1;
+    #pragma unroll
+                        for (int ip = 0; ip < nt; ++ip) sm[(Q::o_off + ((lp * 2 + s) * nt + j) * nt + ip) * CS] = v[ip];
                     } else if (active) {                         // off-diagonal block: exactly one contributing cell
                         const int s = (l - lp + 3) % 3 - 1;
                         const int64_t f_lp = g.f[lp] & 0x7fffffffu;
@@ -417,7 +435,25 @@ __global__ void __launch_bounds__(QuadCfg<K>::threads, QuadCfg<K>::min_blocks) e
     }
 
     // =========================== phase 3: scatter of the staged blocks, warp w = local face w =================
-    __syncthreads();
+    if constexpr (Q::STAGE_OFF) {
+        // face words of the tile, so that any thread can address any cell's face rows (0xffffffff: nothing to store)
+        uint32_t* const fword = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem) + Q::smem_rec);
+        if (w < 3) fword[3 * ci + w] = active ? (w == 0 ? g.f[0] : (w == 1 ? g.f[1] : g.f[2])) : 0xffffffffu;
+        __syncthreads();
+        // A cell owns, in the row of each of its faces, the two adjacent blocks of its side: 2 nt^2 doubles, 16-byte aligned
+        constexpr int PC = nt * nt;                        // 16-byte pieces per (cell, face) chunk
+        for (int idx = threadIdx.x; idx < 3 * Q::cells * PC; idx += Q::threads) {
+            const int chunk = idx / PC, piece = idx - chunk * PC;
+            const int cell = chunk / 3, lp = chunk - 3 * cell;
+            const uint32_t fw = fword[chunk];
+            if (fw == 0xffffffffu) continue;
+            const double* const src = smem + cell + (Q::o_off + lp * 2 * PC + 2 * piece) * CS;
+            double* const dst = a.Ko + (int64_t(fw & 0x7fffffffu) * 4 + 2 * int64_t(fw >> 31)) * nt2 + 2 * piece;
+            *reinterpret_cast<double2*>(dst) = make_double2(src[0], src[CS]);
+        }
+    } else {
+        __syncthreads();
+    }
     if (!active || w == 3) return;
     {
         const int l = w;

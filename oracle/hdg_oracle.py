@@ -676,3 +676,97 @@ def run_poisson(mesh, order=1, quad_degree=None, tau=1.0):
     err2 = errornorm(mesh, tab, u)
     return dict(tab=tab, asm=asm, dofs=dofs, vals=vals, K_bc=Kb, rhs_bc=rb, meandiag=m,
                 uhat=uhat, sigma=sig, u=u, uhat_h=uh, err2=err2)
+
+
+# --------------------------------------------------------------------------
+# CG side of the exported API: DofHandler, sparsity pattern, Dirichlet on a DofHandler.
+# Integer logic only; loop-faithful to src/dofhandler.jl:80-220 and src/boundary.jl:44-96.
+# Pinned on test/test_handlers.jl:13-19 (tests/test_oracle_goldens.py).
+# --------------------------------------------------------------------------
+def lagrange_topology(order):
+    """gettopology(ContinuousLagrange{2,RefTetrahedron,order}) via get_nodal_points, src/shapes.jl:46-57:
+    dofs on the 3 vertices, on the 3 edges together, in the interior."""
+    return {0: 3, 1: 3 * (order - 1), 2: (order - 1) * (order - 2) // 2}
+
+
+def distribute_dofs(mesh, order=1, ncomponents=1):
+    """_distribute_dofs for ONE field, src/dofhandler.jl:84-152.  Returns (cell_dofs, cell_dofs_offset), 1-based.
+    Restated as written: when an edge with several dofs is met again only `ncomponents` dofs starting at the stored
+    first dof are pushed (:121-124), which is what the reference does for order >= 3."""
+    topo = lagrange_topology(order)
+    geo = {0: 3, 1: 3, 2: 1}                      # gettopology(RefTetrahedron, Val{2}), src/shapes.jl:26-28
+    dicts = {0: {}, 1: {}}
+    cell_dofs, offsets = [], [1]
+    nextdof = 1
+    for c in range(mesh.ncells):
+        for n_el in (0, 1):
+            assert topo[n_el] % geo[n_el] == 0
+            nelementdofs = topo[n_el] // geo[n_el]
+            if nelementdofs == 0:
+                continue
+            elements = mesh.cells[c] if n_el == 0 else mesh.cell_faces[c]     # topology_elements, src/mesh.jl:33-41
+            for el in elements:
+                el = int(el)
+                if el in dicts[n_el]:
+                    reuse = dicts[n_el][el]
+                    for d in range(ncomponents):
+                        cell_dofs.append(reuse + d)
+                else:
+                    for _ in range(nelementdofs):
+                        dicts[n_el][el] = nextdof          # _setindex! overwrites: the LAST first-dof is stored (:127)
+                        for d in range(ncomponents):
+                            cell_dofs.append(nextdof)
+                            nextdof += 1
+        for _ in range(topo[2]):
+            for d in range(ncomponents):
+                cell_dofs.append(nextdof)
+                nextdof += 1
+        offsets.append(len(cell_dofs) + 1)
+    return np.array(cell_dofs, dtype=np.int64), np.array(offsets, dtype=np.int64)
+
+
+def create_sparsity_pattern(cell_dofs, offsets):
+    """_create_sparsity_pattern(dh, false), src/dofhandler.jl:180-216: CSC pattern (colptr, rowval; 1-based) of
+    sparse(I, J, zeros) with all element couplings plus the diagonal."""
+    ncell = offsets.size - 1
+    n = int(offsets[1] - offsets[0])
+    ndofs = int(cell_dofs.max())
+    I, J = [], []
+    for e in range(ncell):
+        g = cell_dofs[offsets[e] - 1: offsets[e] - 1 + n]
+        for j in range(n):
+            for i in range(n):
+                I.append(g[i]); J.append(g[j])
+    for d in range(1, ndofs + 1):
+        I.append(d); J.append(d)
+    K = sp.coo_matrix((np.zeros(len(I)), (np.array(I) - 1, np.array(J) - 1)), shape=(ndofs, ndofs)).tocsc()
+    K.sum_duplicates()
+    K.sort_indices()
+    return K.indptr.astype(np.int64) + 1, K.indices.astype(np.int64) + 1
+
+
+def dirichlet_dofhandler(mesh, cell_dofs, offsets, order=1, faceset="boundary"):
+    """prescribed_dofs of Dirichlet(u, dh, faceset, f), src/boundary.jl:48-96 (sorted; one scalar field)."""
+    fset = mesh.facesets[faceset] if isinstance(faceset, str) else faceset
+    topo = lagrange_topology(order)
+    nel = [topo[0] // 3, topo[1] // 3]
+    edge_nodes = ((2, 3), (3, 1), (1, 2))          # reference_edge_nodes, src/shapes.jl (local faces = node pairs)
+    prescribed = []
+    for face in range(1, mesh.nfaces + 1):
+        if face not in fset:
+            continue
+        assert mesh.faces[face - 1, 3] == 0, f"Face {face} is not in boundary"
+        cell = int(mesh.faces[face - 1, 2]) - 1
+        lidx = list(mesh.cell_faces[cell]).index(face) + 1
+        off = int(offsets[cell]) - 1
+        for j in range(2):
+            lo = edge_nodes[lidx - 1][j]
+            d = int(cell_dofs[off + lo - 1])
+            if d not in prescribed:
+                prescribed.append(d)
+        for j in range(1, nel[1] + 1):
+            lo = topo[0] + nel[1] * (lidx - 1) + j
+            d = int(cell_dofs[off + lo - 1])
+            if d not in prescribed:
+                prescribed.append(d)
+    return np.array(sorted(prescribed), dtype=np.int64)

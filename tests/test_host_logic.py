@@ -130,3 +130,36 @@ def test_nonhomogeneous_dirichlet_values_match_the_restated_reference(order, qd)
     dc = hdg.Dirichlet(hdg.TrialFunction(Mh), mesh, "boundary", lambda x: 3.0, corrected=True)
     assert np.allclose(dc.values.reshape(-1, order + 1)[:, 0], 3.0, atol=1e-13)
     assert np.allclose(dc.values.reshape(-1, order + 1)[:, 1:], 0.0, atol=1e-13)
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_cg_dofhandler_host_mirror(order):
+    """DofHandler / create_sparsity_pattern / Dirichlet(u, dh, ...) of the host mirror (sort-based first-encounter ranking)
+    == the reference's sequential dictionary walk as restated in the oracle; goldens of test/test_handlers.jl:13-19."""
+    from fixtures_util import triangle_root
+    for mo in (orc.rectangle_mesh(2, 2), orc.rectangle_mesh(7, 5), orc.parse_mesh_triangle(triangle_root("figure.1"))):
+        mesh = hdg.PolygonalMesh(np.hstack([mo.cells, mo.cell_faces]), mo.nodes, mo.faces, {k: set(v) for k, v in mo.facesets.items()})
+        u = hdg.LagrangeField(hdg.ContinuousLagrange(2, hdg.RefTetrahedron, order), mesh)
+        dh = hdg.DofHandler([u], mesh)
+        cd, off = orc.distribute_dofs(mo, order)
+        assert np.array_equal(dh.cell_dofs, cd) and np.array_equal(dh.cell_dofs_offset, off)
+        assert hdg.ndofs(dh) == cd.max() and hdg.ndofs_per_cell(dh) == (3 if order == 1 else 6)
+        assert hdg.dof_range(dh, u) == range(1, (3 if order == 1 else 6) + 1)
+        cp, rv = orc.create_sparsity_pattern(cd, off)
+        cp2, rv2 = hdg.create_sparsity_pattern(dh)
+        assert np.array_equal(cp, cp2) and np.array_equal(rv, rv2)
+        dbc = hdg.DirichletCG(u, dh, "boundary", lambda x: x[0] + 2.0 * x[1])
+        assert np.array_equal(dbc.prescribed_dofs, orc.dirichlet_dofhandler(mo, cd, off, order))
+        # values of a linear function at the dof nodes; reconstruct! puts them back per cell
+        uvec = np.zeros(hdg.ndofs(dh))
+        uvec[dbc.prescribed_dofs - 1] = dbc.values
+        hdg.reconstruct_(u, uvec, dh)
+        xv = mesh.nodes[mesh.cells[:, :3] - 1]
+        onb = np.isin(dh.cell_dofs.reshape(mo.ncells, -1)[:, :3], dbc.prescribed_dofs)
+        assert np.allclose(u.m_values[:, :3][onb], (xv[..., 0] + 2.0 * xv[..., 1])[onb], atol=1e-14)
+    mo = orc.rectangle_mesh(2, 2)
+    mesh = hdg.PolygonalMesh(np.hstack([mo.cells, mo.cell_faces]), mo.nodes, mo.faces, {k: set(v) for k, v in mo.facesets.items()})
+    if order == 1:
+        dh = hdg.DofHandler([hdg.LagrangeField(hdg.ContinuousLagrange(2, hdg.RefTetrahedron, 1), mesh)], mesh)
+        assert dh.cell_dofs.tolist() == [1, 2, 3, 2, 4, 3, 2, 5, 4, 5, 6, 4, 3, 4, 7, 4, 8, 7, 4, 6, 8, 6, 9, 8]
+    assert hdg.getcells_matrix(mesh).shape == (8, 3) and hdg.get_vertices_matrix(mesh).shape == (9, 2)

@@ -203,3 +203,14 @@ def test_convergence_rates():
     for k, qd, lo in ((1, 2, 12.0), (2, 4, 50.0)):
         e = [orc.run_poisson(orc.rectangle_mesh(n, n), k, qd)["err2"] for n in (4, 8)]
         assert e[0] / e[1] > lo
+
+
+def test_dofhandler_goldens():
+    """test/test_handlers.jl:13-19: P1 DofHandler on rectangle_mesh(TriangleCell,(2,2)) and its Dirichlet dofs."""
+    mo = orc.rectangle_mesh(2, 2)
+    cell_dofs, offsets = orc.distribute_dofs(mo, 1)
+    assert cell_dofs.tolist() == [1, 2, 3, 2, 4, 3, 2, 5, 4, 5, 6, 4, 3, 4, 7, 4, 8, 7, 4, 6, 8, 6, 9, 8]
+    assert offsets.tolist() == [1, 4, 7, 10, 13, 16, 19, 22, 25]
+    assert orc.dirichlet_dofhandler(mo, cell_dofs, offsets).tolist() == [1, 2, 3, 5, 6, 7, 8, 9]
+    colptr, rowval = orc.create_sparsity_pattern(cell_dofs, offsets)
+    assert colptr[-1] - 1 == rowval.size == 9 + 2 * 16      # 9 vertices + 16 edges, both directions

@@ -97,6 +97,11 @@ def main():
                 d = np.abs(A[name] - B[name]).max() / max(np.abs(A[name]).max(), 1e-300)
                 print(f"    max |v1 - quad| / max|v1|  {name}: {d:.3e}  finite={bool(np.isfinite(B[name]).all())}")
             print(f"    speed-up quad vs v1: {res['v1']['ms_med'] / res['quad']['ms_med']:.2f}x", flush=True)
+        for nm in [x for x in a.libs.split(",") if x]:          # variant libraries against the default build
+            if nm in res and "quad" in res:
+                A, B = np.load(f"/tmp/ab_{k}_quad.npz"), np.load(f"/tmp/ab_{k}_{nm}.npz")
+                d = max(np.abs(A[name] - B[name]).max() / max(np.abs(A[name]).max(), 1e-300) for name in ("rhs", "nz", "loc"))
+                print(f"    {nm}: max rel diff vs default {d:.3e}; default/{nm} time {res['quad']['ms_med'] / res[nm]['ms_med']:.3f}", flush=True)
 
 
 if __name__ == "__main__":
