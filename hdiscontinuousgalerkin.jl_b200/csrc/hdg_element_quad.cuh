@@ -48,6 +48,12 @@ namespace hdg {
 #ifndef QSTAGE4
 #define QSTAGE4 0
 #endif
+// QINV: phase 1 inverts S in place (Gauss-Jordan without pivoting on the SPD matrix, rows dealt to the 4 lanes of a cell,
+// pivot rows by shuffle) and phase 2 applies S^-1 as a symmetric matrix-vector product: n(n+1)/2 shared-memory loads and n^2
+// INDEPENDENT FMAs per column instead of two triangular sweeps (n(n-1) loads, serial dependency chains of length 2n).
+#ifndef QINV
+#define QINV 0
+#endif
 #ifndef QMINB3
 #define QMINB3 4
 #endif
@@ -81,6 +87,7 @@ template <int K> struct QuadCfg {
     static constexpr int o_rhs = o_diag + 3 * nt * nt;
     static constexpr int o_scr = o_rhs + (SPLITB ? 4 : 1) * 3 * nt;      // phase 2: solutions of the 2nd ... CB-th column of a batch, per warp
     static constexpr bool STAGE_OFF = (K == 2 && QSTAGE2) || (K == 4 && QSTAGE4);
+    static constexpr bool INV = ((QINV >> (K - 2)) & 1) != 0;          // bit 0: k = 2, bit 1: k = 3, bit 2: k = 4
     static constexpr int o_off = o_scr + 4 * (CB - 1) * n;             // staged off-diagonal blocks: [(lp*2 + s)*nt*nt + j*nt + ip]
     static constexpr int entries = o_off + (STAGE_OFF ? 6 * nt * nt : 0);
     static_assert(3 * nt * nt + 3 * nt >= 4 * n, "partial load vectors alias the staging area");
@@ -169,9 +176,54 @@ __global__ void __launch_bounds__(QuadCfg<K>::threads, QuadCfg<K>::min_blocks) e
         const int q = threadIdx.x & 3, pc = threadIdx.x >> 2;
         const unsigned lane = threadIdx.x & 31u;
         double* const sp = smem + pc;           // record of cell pc
+        bool spd = true;
+        if constexpr (Q::INV) {
+        // lane q owns rows q, q+4, ... of the full symmetric matrix, in registers
+        double A[R][n];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = q + 4 * r;
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                A[r][j] = 0.0;
+                if (i < n) A[r][j] = sp[(i == j ? Q::o_dinv + j : (i > j ? Q::o_L + i * (i - 1) / 2 + j : Q::o_L + j * (j - 1) / 2 + i)) * CS];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < n; ++k) {
+            double prow[n];
+#pragma unroll
+            for (int j = 0; j < n; ++j) prow[j] = __shfl_sync(0xffffffffu, A[k >> 2][j], (lane & ~3u) | unsigned(k & 3));
+            const double dk = prow[k];
+            spd = spd && (dk > 0.0);
+            const double dinv = 1.0 / dk;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (4 * r >= n) continue;
+                const bool own = (r == (k >> 2)) && (q == (k & 3));       // this lane holds the pivot row in slot r
+                const double f = A[r][k] * dinv;
+#pragma unroll
+                for (int j = 0; j < n; ++j) {
+                    if (j == k) continue;
+                    A[r][j] = own ? prow[j] * dinv : fma(-f, prow[j], A[r][j]);
+                }
+                A[r][k] = own ? dinv : -f;
+            }
+        }
+        // S^-1 (lower triangle + diagonal) overwrites S
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = q + 4 * r;
+            if (i < n) {
+#pragma unroll
+                for (int j = 0; j < n; ++j)
+                    if (j <= i) sp[(i == j ? Q::o_dinv + j : Q::o_L + i * (i - 1) / 2 + j) * CS] = A[r][j];
+            }
+        }
+        __syncwarp();
+        } else {
         // lane q owns rows q, q+4, ...; its rows of L stay in registers, the pivot row is read from shared memory
         double Lr[R][n], dd[n];
-        bool spd = true;
 #pragma unroll
         for (int j = 0; j < n; ++j) {
             double ljd[n];
@@ -206,6 +258,7 @@ __global__ void __launch_bounds__(QuadCfg<K>::threads, QuadCfg<K>::min_blocks) e
                 }
             }
             __syncwarp();
+        }
         }
         // be = sum of the 4 partial vectors (fixed order)
 #pragma unroll
@@ -268,6 +321,32 @@ __global__ void __launch_bounds__(QuadCfg<K>::threads, QuadCfg<K>::min_blocks) e
         // operations: column-oriented (axpy: once u[k] is final the updates of u[k+1..] are independent FMAs) and
         // row-oriented (dot products).  Measured per order (4 M / 1 M elements): k=2 2.35 vs 2.43 ms, k=3 4.91 vs 4.93 ms,
         // k=4 4.00 vs 3.62 ms  ->  column-oriented for k <= 3.
+        if constexpr (Q::INV) {
+            double x[CB][n];
+#pragma unroll
+            for (int cb = 0; cb < CB; ++cb)
+#pragma unroll
+                for (int i = 0; i < n; ++i) x[cb][i] = 0.0;
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                const double ajj = smv[(Q::o_dinv + j) * CS];
+#pragma unroll
+                for (int cb = 0; cb < CB; ++cb) x[cb][j] = fma(ajj, u[cb][j], x[cb][j]);
+#pragma unroll
+                for (int i = 0; i < j; ++i) {
+                    const double aji = smv[(Q::o_L + tri(j, i)) * CS];
+#pragma unroll
+                    for (int cb = 0; cb < CB; ++cb) {
+                        x[cb][j] = fma(aji, u[cb][i], x[cb][j]);
+                        x[cb][i] = fma(aji, u[cb][j], x[cb][i]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int cb = 0; cb < CB; ++cb)
+#pragma unroll
+                for (int i = 0; i < n; ++i) u[cb][i] = x[cb][i];
+        } else {
         if constexpr (Q::col_sweep) {
 #pragma unroll
             for (int k = 0; k < n - 1; ++k) {
@@ -317,6 +396,7 @@ __global__ void __launch_bounds__(QuadCfg<K>::threads, QuadCfg<K>::min_blocks) e
                 }
         }
 
+        }
         // per column: sigma = A^-1 (r1 + B u) row by row; column of Ate = [E;F]'K_e - He accumulated on the fly.
         // The columns of a batch are processed one after the other by ONE copy of the code (the solutions of the 2nd,
         // 3rd ... column wait in a per-thread shared-memory scratch), so the register need is that of a single column.

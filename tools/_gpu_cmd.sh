@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu2.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/pytest_gpu2.log
-timeout 300 python tools/ab_elem.py --orders 2,4 --libs base0,s4 --reps 20 > gpurun_out/ab_stage.txt 2>&1; cat gpurun_out/ab_stage.txt
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py > gpurun_out/multi_gpu_check_n2.log 2>&1; echo "multi_gpu_check exit $?"; tail -12 gpurun_out/multi_gpu_check_n2.log
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "bench n2 exit $?"; tail -c 1500 gpurun_out/bench_n2.json
