@@ -113,6 +113,16 @@ def cpu_port_elements_per_s(order, qd, sample, nthreads, passes=1):
     return mesh.ncells / dt, dt, mesh.ncells
 
 
+def host_threads(occ):
+    """All host threads this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers, which would turn the
+    "all cores" arm into a single-threaded one, so the CPU affinity mask decides, not the OpenMP default (the count is
+    handed to the C port explicitly: `num_threads` clauses)."""
+    try:
+        return max(len(os.sched_getaffinity(0)), 1)
+    except Exception:
+        return max(os.cpu_count() or 1, occ.max_threads())
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  Julia cannot run here
     (DESIGN.md), so this is the loop-faithful C port (oracle/hdg_oracle.c) with all host threads."""
@@ -123,7 +133,7 @@ def run_reference(args):
     import hdg_oracle_c as occ
     order = args.order
     qd = args.quad_degree or QD_FOR_ORDER[order]
-    cores = occ.max_threads()
+    cores = host_threads(occ)
     sample = (400, 200) if order == 1 else ((200, 100) if order == 2 else (100, 50))
     for _ in range(args.warmup):
         cpu_port_elements_per_s(order, qd, (40, 20), cores)
@@ -343,11 +353,13 @@ def main():
                     hdg.check(lib.hdg_errornorm(ctx2.h, 1, C.byref(err_d)), ctx2.h)
 
                 driver_step()
-                t0 = time.perf_counter()
+                tsteps = []
                 for _ in range(3):
+                    t0 = time.perf_counter()
                     driver_step()
-                dtd = (time.perf_counter() - t0) / 3
-                e2e["driver"] = {"value": ncell / dtd, "unit": "elements/s", "ms_per_step": dtd * 1e3, "steps": 3,
+                    tsteps.append(time.perf_counter() - t0)
+                dtd = sum(tsteps) / len(tsteps)
+                e2e["driver"] = {"value": ncell / dtd, "unit": "elements/s", "ms_per_step": dtd * 1e3, "steps": 3, "ms_steps": [round(t * 1e3, 3) for t in tsteps],
                                  "pcg_iterations": info_d.iterations, "err2": err_d.value,
                                  "d2h_bytes_per_step": int(rhs_out.nbytes + sig_out.nbytes + u_out.nbytes),
                                  "what": "e2e step + hdg_apply_dirichlet + hdg_solve (block-Jacobi + P1-vertex multigrid, grid recognised in "
@@ -420,7 +432,7 @@ def main():
         v1, dt1, n1 = cpu_port_elements_per_s(order, qd, sample, 1, passes=3 if order == 1 else 1)
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import hdg_oracle_c as occ
-        cores = occ.max_threads()
+        cores = host_threads(occ)
         vN, dtN, _ = cpu_port_elements_per_s(order, qd, sample, cores, passes=3 if order == 1 else 1)
         cpu = {"value": v1, "unit": "elements/s", "cores": 1, "kind": "port",
                "sample": f"C port of doassemble (oracle/hdg_oracle.c), rectangle_mesh {sample[0]}x{sample[1]} = {n1} elements, "
