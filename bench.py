@@ -309,21 +309,32 @@ def main():
         ctxh.close()
         ctx2 = hdg._Context(order, qd, 1.0, 1, local_rank, args.local_solver)
 
+        parts = [0.0, 0.0, 0.0]      # seconds in hdg_set_mesh / hdg_assemble / hdg_get_rhs (each call returns synchronised)
+
         def e2e_step():
+            t_a = time.perf_counter()
             hdg.check(lib.hdg_set_mesh(ctx2.h, hdg.api.i64p(cells), ncell, hdg.api.f64p(nodes), nnode_s,
                                        hdg.api.i64p(faces) if args.e2e_faces else None, nface_s, hdg.api.i64p(bfaces), nbf_s), ctx2.h)
+            t_b = time.perf_counter()
             hdg.check(lib.hdg_assemble(ctx2.h), ctx2.h)
+            t_c = time.perf_counter()
             hdg.check(lib.hdg_get_rhs(ctx2.h, hdg.api.f64p(rhs_out)), ctx2.h)
+            t_d = time.perf_counter()
+            parts[0] += t_b - t_a
+            parts[1] += t_c - t_b
+            parts[2] += t_d - t_c
 
         ke2e = max(3, min(K, 10))
         for _ in range(2):
             e2e_step()
         barrier()
+        parts[:] = [0.0, 0.0, 0.0]
         t0 = time.perf_counter()
         for _ in range(ke2e):
             e2e_step()
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / ke2e
+        parts_ms = [1e3 * p_ / ke2e for p_ in parts]
         if dist is not None:
             tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -331,6 +342,9 @@ def main():
         h2d = cells.nbytes + nodes.nbytes + (faces.nbytes if args.e2e_faces else 0) + bfaces.nbytes
         e2e = {"value": ncell * world / dt, "unit": "elements/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(rhs_out.nbytes), "ms_per_step": dt * 1e3, "steps": ke2e,
+               "breakdown_ms": {"hdg_set_mesh (h2d + device-side face table / adjacency)": parts_ms[0], "hdg_assemble": parts_ms[1],
+                                "hdg_get_rhs (d2h)": parts_ms[2], "h2d_GBps": h2d / max(parts_ms[0], 1e-9) / 1e6,
+                                "d2h_GBps": rhs_out.nbytes / max(parts_ms[2], 1e-9) / 1e6},
                "what": "hdg_set_mesh(pinned host arrays in the Julia layouts: cells, nodes, boundary set"
                        + (", faces" if args.e2e_faces else "; mesh.faces is rebuilt on the device") + ") + hdg_assemble + hdg_get_rhs(host)"}
         # the whole driver through the C ABI with host buffers (N=1): mesh arrays in, multigrid-PCG solve, recovery,

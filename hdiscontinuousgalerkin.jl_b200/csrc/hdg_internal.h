@@ -218,6 +218,7 @@ hdg_status mg_setup(hdg_context* c);                                            
 void mg_apply(hdg_context* c, const double* r, double* z, double* part, int np);   // z += P V(P'r); part = partials of (P'r).V(P'r)
 void mg_free(hdg_context* c);
 int mg_levels(const hdg_context* c);
+int mg_launches_per_apply(const hdg_context* c);
 
 hdg_status recover(hdg_context* c);                             // hdg_recover.cu
 hdg_status errornorm(hdg_context* c, int exact_id, const double* uex_host, double* err2);

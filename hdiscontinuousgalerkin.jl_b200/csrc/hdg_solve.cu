@@ -691,7 +691,7 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
         } else {
             for (int k = 0; k < chunk; ++k) enqueue_iter(k);
         }
-        c->launches += int64_t(3 + (mg ? 4 + 5 * (mg_levels(c) - 1) : 0)) * chunk;
+        c->launches += int64_t(3 + (mg ? mg_launches_per_apply(c) : 0)) * chunk;
         HDG_CUDA(c, cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int32_t) * NFLAGS, cudaMemcpyDeviceToHost, c->stream));
         HDG_CUDA(c, cudaStreamSynchronize(c->stream));
         done = c->h_flags[FLAG_DONE] != 0;
