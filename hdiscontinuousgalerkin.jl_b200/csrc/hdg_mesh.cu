@@ -872,7 +872,7 @@ hdg_status mesh_rectangle(hdg_context* c, int64_t nx, int64_t ny, double llx, do
     S.node0 = j0 * (nx + 1);
     const int64_t node_rows = (j1 - j0 + 1) + (j1 < ny ? 1 : 0);
     c->nx = nx; c->ny = ny;
-    c->grid_px = multi ? 0 : nx + 1; c->grid_py = multi ? 0 : ny + 1;
+    c->grid_px = nx + 1; c->grid_py = ny + 1;      // the global vertex grid, also on a strip
     c->ncell_own = S.ncell_own;
     c->ncell = S.ncell_own + (j1 < ny ? nx : 0);
     c->nnode = node_rows * (nx + 1);

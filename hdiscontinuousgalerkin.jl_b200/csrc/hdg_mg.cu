@@ -11,7 +11,11 @@
 // that triangulation (stays 7-point), down to <= 64 points, which are solved with a dense inverse.  Vertices on
 // Dirichlet faces carry no coarse unknown.  Everything is gather-formulated (no atomics): bitwise reproducible.
 // Measured in the scipy prototype (tools/mg_prototype.py): 34-40 PCG iterations to 1e-12 for k = 1..4, independent of h.
-// One GPU, rectangle_mesh only (a general mesh needs an algebraic hierarchy for A_c - next).
+// rectangle_mesh triangulations only (a general mesh needs an algebraic hierarchy for A_c - next).  On several GPUs (strips of
+// hdg_set_rectangle_mesh) the vertex hierarchy is replicated: every rank builds the rows of A_c of the faces it owns and
+// restricts the residual of its own faces, the partial level-0 stencils (once per solve) and vertex residuals (once per
+// iteration) are summed with ncclAllReduce, and every rank runs the same V-cycle on the whole vertex grid (1 vertex per 2
+// cells and 1 double each: small against the trace system).  The PCG then runs without CUDA-graph capture.
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
@@ -61,22 +65,30 @@ struct MgData {
     int nx = 0, ny = 0;
     int lf = 0;                      // first level of the fused tail (levels lf .. nlev-1 run in mg_fused_vcycle)
     bool adjacency_ok = false;
+    // several GPUs (strips of rectangle_mesh): the vertex hierarchy is REPLICATED on every rank over the global vertex grid;
+    // a rank contributes the rows of the faces it owns and the partial vertex vectors / stencils are all-reduced
+    bool multi = false;
+    int64_t node0 = 0;               // global id of local node 0
+    int64_t nface_rows = 0;          // owned faces (rows of the trace system held by this rank)
 };
 
 // ---- vertex -> faces adjacency ------------------------------------------------------------------------------------
-__global__ void mg_adj_fill(const int32_t* __restrict__ facenode, int64_t nface, int32_t* __restrict__ vcnt, int32_t* __restrict__ vface,
-                            int32_t* __restrict__ flags) {
+__global__ void mg_adj_fill(const int32_t* __restrict__ facenode, int64_t nface, int64_t node0, int32_t* __restrict__ vcnt,
+                            int32_t* __restrict__ vface, int32_t* __restrict__ flags) {
     int64_t f = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (f >= nface) return;
-    const int32_t v1 = facenode[2 * f], v2 = facenode[2 * f + 1];
-    const int32_t lo = min(v1, v2), hi = max(v1, v2);
+    const int64_t v1 = facenode[2 * f] + node0, v2 = facenode[2 * f + 1] + node0;
+    const int64_t lo = min(v1, v2), hi = max(v1, v2);
     int k = atomicAdd(&vcnt[lo], 1);
-    if (k < MG_MAXVAL) vface[int64_t(lo) * MG_MAXVAL + k] = int32_t(f); else atomicExch(&flags[FLAG_MG], 1);
+    if (k < MG_MAXVAL) vface[lo * MG_MAXVAL + k] = int32_t(f); else atomicExch(&flags[FLAG_MG], 1);
     k = atomicAdd(&vcnt[hi], 1);
-    if (k < MG_MAXVAL) vface[int64_t(hi) * MG_MAXVAL + k] = int32_t(uint32_t(f) | 0x80000000u); else atomicExch(&flags[FLAG_MG], 1);
+    if (k < MG_MAXVAL) vface[hi * MG_MAXVAL + k] = int32_t(uint32_t(f) | 0x80000000u); else atomicExch(&flags[FLAG_MG], 1);
 }
 
-__global__ void mg_adj_sort(int64_t nnode, int32_t* __restrict__ vcnt, int32_t* __restrict__ vface, const uint8_t* __restrict__ isbc) {
+// sorts the incident faces; fc[v] = 1 if the vertex touches a Dirichlet face, fc[nnode + v] = number of incident faces
+// (doubles: summed over the ranks by an all-reduce when the mesh is distributed)
+__global__ void mg_adj_sort(int64_t nnode, const int32_t* __restrict__ vcnt, int32_t* __restrict__ vface, const uint8_t* __restrict__ isbc,
+                            double* __restrict__ fc) {
     int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (v >= nnode) return;
     const int cnt = min(vcnt[v], MG_MAXVAL);
@@ -93,26 +105,27 @@ __global__ void mg_adj_sort(int64_t nnode, int32_t* __restrict__ vcnt, int32_t* 
         a[j + 1] = key;
     }
     for (int k = 0; k < cnt; ++k) vface[v * MG_MAXVAL + k] = a[k];
-    if (fixed || cnt == 0) vcnt[v] = -1;
+    fc[v] = fixed ? 1.0 : 0.0;
+    fc[nnode + v] = double(cnt);
+}
+// a vertex carries no coarse unknown if it touches a Dirichlet face (on any rank) or has no face at all
+__global__ void mg_adj_fix(int64_t nnode, int32_t* __restrict__ vcnt, const double* __restrict__ fc) {
+    int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (v >= nnode) return;
+    if (fc[v] > 0.0 || fc[nnode + v] == 0.0) vcnt[v] = -1;
 }
 
 // ---- A_c = P'AP on the vertex grid, gathered per vertex ---------------------------------------------------------------
 template <int NT>
 __global__ void mg_vertex_operator(const double* __restrict__ Kd, const double* __restrict__ Ko, const int32_t* __restrict__ kcol,
-                                   const uint8_t* __restrict__ isbc, const int32_t* __restrict__ facenode,
+                                   const uint8_t* __restrict__ isbc, const int32_t* __restrict__ facenode, int64_t node0,
                                    const int32_t* __restrict__ vcnt, const int32_t* __restrict__ vface, int px, int64_t nnode,
-                                   double* __restrict__ st, double* __restrict__ dinv) {
+                                   double* __restrict__ st) {
     constexpr int NT2 = NT * NT;
     int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (v >= nnode) return;
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-    const int cnt = vcnt[v];
-    if (cnt < 0) {
-        st[v] = 1.0;
-        for (int k = 1; k < 7; ++k) st[k * nnode + v] = 0.0;
-        dinv[v] = 0.0;
-        return;
-    }
+    const int cnt = vcnt[v];        // < 0: fixed vertex (identity row, written by mg_finalize_rows)
     const int vx = int(v % px), vy = int(v / px);
     for (int k = 0; k < cnt; ++k) {
         const int32_t e = vface[v * MG_MAXVAL + k];
@@ -125,24 +138,30 @@ __global__ void mg_vertex_operator(const double* __restrict__ Kd, const double* 
             // t_b = - sum_a pf_a K[a][b]   (A = -K on free rows), b = 0, 1
             const double t0 = -(pf0 * blk[0] + pf1 * blk[1]);
             const double t1 = -(pf0 * blk[NT] + pf1 * blk[NT + 1]);
-            const int32_t g1 = facenode[2 * g], g2 = facenode[2 * g + 1];
-            const int32_t lo = min(g1, g2), hi = max(g1, g2);
+            const int64_t g1 = facenode[2 * g] + node0, g2 = facenode[2 * g + 1] + node0;
+            const int64_t lo = min(g1, g2), hi = max(g1, g2);
             if (vcnt[lo] >= 0) {
-                const int sl = mg_slot(lo % px - vx, lo / px - vy);
+                const int sl = mg_slot(int(lo % px) - vx, int(lo / px) - vy);
                 if (sl >= 0) acc[sl] += 0.5 * t0 - MG_C1 * t1;
             }
             if (vcnt[hi] >= 0) {
-                const int sl = mg_slot(hi % px - vx, hi / px - vy);
+                const int sl = mg_slot(int(hi % px) - vx, int(hi / px) - vy);
                 if (sl >= 0) acc[sl] += 0.5 * t0 + MG_C1 * t1;
             }
         }
     }
     for (int k = 0; k < 7; ++k) st[k * nnode + v] = acc[k];
-    dinv[v] = acc[0] > 0.0 ? 1.0 / acc[0] : 0.0;
-    if (!(acc[0] > 0.0)) {
-        st[v] = 1.0;
-        for (int k = 1; k < 7; ++k) st[k * nnode + v] = 0.0;
-    }
+}
+// after the rows are complete (all-reduced over the ranks on a distributed mesh): inverse diagonal, identity rows at the
+// fixed vertices and wherever the diagonal is not positive
+__global__ void mg_finalize_rows(const int32_t* __restrict__ vcnt, int64_t nnode, double* __restrict__ st, double* __restrict__ dinv) {
+    int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (v >= nnode) return;
+    const double d = st[v];
+    if (vcnt[v] >= 0 && d > 0.0) { dinv[v] = 1.0 / d; return; }
+    st[v] = 1.0;
+    for (int k = 1; k < 7; ++k) st[k * nnode + v] = 0.0;
+    dinv[v] = 0.0;
 }
 
 // ---- Galerkin coarse operator: A_c[I][J] = sum_p sum_q R[I,p] A[p,q] P[q,J], gathered per coarse point -----------------
@@ -390,21 +409,22 @@ __global__ void mg_restrict_trace(const double* __restrict__ r, const int32_t* _
 }
 // z += P e
 template <int NT>
-__global__ void __launch_bounds__(RB) mg_prolong_trace(const double* __restrict__ e, const int32_t* __restrict__ facenode, const uint8_t* __restrict__ isbc,
-                                                       int64_t nface, double* __restrict__ z) {
+__global__ void __launch_bounds__(RB) mg_prolong_trace(const double* __restrict__ e, const int32_t* __restrict__ facenode, int64_t node0,
+                                                       const uint8_t* __restrict__ isbc, int64_t nface, double* __restrict__ z) {
     for (int64_t f = int64_t(blockIdx.x) * RB + threadIdx.x; f < nface; f += int64_t(gridDim.x) * RB) {
         if (isbc[f]) continue;
-        const int32_t v1 = facenode[2 * f], v2 = facenode[2 * f + 1];
+        const int64_t v1 = facenode[2 * f] + node0, v2 = facenode[2 * f + 1] + node0;
         const double a = e[min(v1, v2)], b = e[max(v1, v2)];
         z[f * NT] += 0.5 * (a + b);
         z[f * NT + 1] += MG_C1 * (b - a);
     }
 }
-__global__ void __launch_bounds__(RB) mg_dot(const double* __restrict__ a, const double* __restrict__ b, int64_t n, double* __restrict__ part) {
+// scale = 0 on the ranks > 0 of a distributed mesh: the vertex vectors are replicated, their dot product counts once
+__global__ void __launch_bounds__(RB) mg_dot(const double* __restrict__ a, const double* __restrict__ b, int64_t n, double scale, double* __restrict__ part) {
     double s = 0.0;
     for (int64_t i = int64_t(blockIdx.x) * RB + threadIdx.x; i < n; i += int64_t(gridDim.x) * RB) s = fma(a[i], b[i], s);
     const double tot = block_sum(s);
-    if (threadIdx.x == 0) part[blockIdx.x] = tot;
+    if (threadIdx.x == 0) part[blockIdx.x] = scale * tot;
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
@@ -422,16 +442,22 @@ void mg_free(hdg_context* c) {
 }
 
 template <int NT> static hdg_status mg_setup_t(hdg_context* c) {
-    if (comm_active(c)) return set_err(c, HDG_ERR_INVALID, "the multigrid preconditioner runs on one GPU");
+    const bool multi = comm_active(c);
+    if (multi && c->comm->general_mesh)
+        return set_err(c, HDG_ERR_INVALID, "on several GPUs the multigrid preconditioner needs hdg_set_rectangle_mesh (strip partition)");
     if (c->grid_px < 2 || c->grid_py < 2)
         return set_err(c, HDG_ERR_INVALID, "the multigrid preconditioner needs the triangulation of rectangle_mesh (hdg_set_rectangle_mesh, or "
                                            "hdg_set_mesh with rectangle_mesh's node numbering)");
     MgData* m = static_cast<MgData*>(c->mg);
-    if (m && (m->nnode != c->nnode || m->nface != c->nface || m->nx != c->grid_px - 1 || m->ny != c->grid_py - 1)) { mg_free(c); m = nullptr; }
+    const int64_t nnode_g = c->grid_px * c->grid_py;       // the GLOBAL vertex grid (== the local one on a single GPU)
+    if (m && (m->nnode != nnode_g || m->nface != c->nface || m->nx != c->grid_px - 1 || m->ny != c->grid_py - 1)) { mg_free(c); m = nullptr; }
     if (!m) {
         m = new MgData();
         c->mg = m;
-        m->nnode = c->nnode; m->nface = c->nface; m->nx = int(c->grid_px) - 1; m->ny = int(c->grid_py) - 1;
+        m->nnode = nnode_g; m->nface = c->nface; m->nx = int(c->grid_px) - 1; m->ny = int(c->grid_py) - 1;
+        m->multi = multi;
+        m->node0 = multi ? c->comm->j0 * c->grid_px : 0;    // local node ids are global ids minus j0 (nx+1), see Strip
+        m->nface_rows = c->nface_own;
         // grid hierarchy
         int px = int(c->grid_px), py = int(c->grid_py);
         int64_t total = 0;
@@ -460,25 +486,37 @@ template <int NT> static hdg_status mg_setup_t(hdg_context* c) {
             L.t = q; q += L.n;
         }
         HDG_CUDA(c, cudaMalloc(&m->ainv, sizeof(double) * last.n * last.n));
-        HDG_CUDA(c, cudaMalloc(&m->vface, sizeof(int32_t) * c->nnode * MG_MAXVAL));
-        HDG_CUDA(c, cudaMalloc(&m->vcnt, sizeof(int32_t) * c->nnode));
+        HDG_CUDA(c, cudaMalloc(&m->vface, sizeof(int32_t) * nnode_g * MG_MAXVAL));
+        HDG_CUDA(c, cudaMalloc(&m->vcnt, sizeof(int32_t) * nnode_g));
     }
+    MgLevel& L0 = m->lev[0];
     if (!m->adjacency_ok) {
-        HDG_CUDA(c, cudaMemsetAsync(m->vcnt, 0, sizeof(int32_t) * c->nnode, c->stream));
+        // vertex -> OWNED faces (a face row is counted by exactly one rank); the "fixed" flags are global
+        double* fc = L0.st;      // 2 n doubles of scratch (the stencil array is filled below)
+        HDG_CUDA(c, cudaMemsetAsync(m->vcnt, 0, sizeof(int32_t) * nnode_g, c->stream));
         HDG_CUDA(c, cudaMemsetAsync(c->d_flags + FLAG_MG, 0, sizeof(int32_t), c->stream));
-        mg_adj_fill<<<nblk(c->nface), 256, 0, c->stream>>>(c->d_facenode, c->nface, m->vcnt, m->vface, c->d_flags);
-        mg_adj_sort<<<nblk(c->nnode), 256, 0, c->stream>>>(c->nnode, m->vcnt, m->vface, c->d_isbc);
-        c->launches += 2;
+        mg_adj_fill<<<nblk(m->nface_rows), 256, 0, c->stream>>>(c->d_facenode, m->nface_rows, m->node0, m->vcnt, m->vface, c->d_flags);
+        mg_adj_sort<<<nblk(nnode_g), 256, 0, c->stream>>>(nnode_g, m->vcnt, m->vface, c->d_isbc, fc);
+        if (multi) {
+            hdg_status st = comm_allreduce_sum(c, fc, int(2 * nnode_g));
+            if (st) return st;
+        }
+        mg_adj_fix<<<nblk(nnode_g), 256, 0, c->stream>>>(nnode_g, m->vcnt, fc);
+        c->launches += 3;
         HDG_CUDA(c, cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int32_t) * NFLAGS, cudaMemcpyDeviceToHost, c->stream));
         HDG_CUDA(c, cudaStreamSynchronize(c->stream));
         if (c->h_flags[FLAG_MG]) return set_err(c, HDG_ERR_INVALID, "a vertex has more than 8 faces");
         m->adjacency_ok = true;
     }
     // operators (every solve: the matrix may have changed)
-    MgLevel& L0 = m->lev[0];
-    mg_vertex_operator<NT><<<nblk(L0.n), 256, 0, c->stream>>>(c->d_Kd, c->d_Ko, c->d_kcol, c->d_isbc, c->d_facenode, m->vcnt, m->vface,
-                                                              L0.px, L0.n, L0.st, L0.dinv);
-    c->launches += 1;
+    mg_vertex_operator<NT><<<nblk(L0.n), 256, 0, c->stream>>>(c->d_Kd, c->d_Ko, c->d_kcol, c->d_isbc, c->d_facenode, m->node0, m->vcnt,
+                                                              m->vface, L0.px, L0.n, L0.st);
+    if (multi) {     // rows of the faces of the other ranks
+        hdg_status st = comm_allreduce_sum(c, L0.st, int(7 * L0.n));
+        if (st) return st;
+    }
+    mg_finalize_rows<<<nblk(L0.n), 256, 0, c->stream>>>(m->vcnt, L0.n, L0.st, L0.dinv);
+    c->launches += 2;
     for (int l = 0; l + 1 < m->nlev; ++l) {
         MgLevel &F = m->lev[l], &C = m->lev[l + 1];
         mg_rap<<<nblk(C.n), 256, 0, c->stream>>>(F.st, F.dinv, F.px, F.py, C.px, C.py, C.st, C.dinv);
@@ -508,6 +546,7 @@ template <int NT> static void mg_apply_t(hdg_context* c, const double* r, double
     cudaStream_t s = c->stream;
     MgLevel& L0 = m->lev[0];
     mg_restrict_trace<NT><<<nblk(L0.n), 256, 0, s>>>(r, m->vcnt, m->vface, L0.n, L0.r);
+    if (m->multi) comm_allreduce_sum(c, L0.r, int(L0.n));     // P'r summed over the ranks; the V-cycle below is replicated
     const int nl = m->nlev, lf = m->lf;
     for (int l = 0; l < lf; ++l) {
         MgLevel &F = m->lev[l], &C = m->lev[l + 1];
@@ -533,8 +572,8 @@ template <int NT> static void mg_apply_t(hdg_context* c, const double* r, double
         mg_prolong_add<<<nblk(F.n), 256, 0, s>>>(C.t, C.px, C.py, F.dinv, F.x, F.px, F.py);
         mg_smooth<<<nblk(F.n), 256, 0, s>>>(F.st, F.dinv, F.r, F.x, F.t, F.px, F.py);
     }
-    mg_dot<<<np, RB, 0, s>>>(L0.r, L0.t, L0.n, part);
-    mg_prolong_trace<NT><<<np, RB, 0, s>>>(L0.t, c->d_facenode, c->d_isbc, c->nface_own, z);
+    mg_dot<<<np, RB, 0, s>>>(L0.r, L0.t, L0.n, (m->multi && c->comm->rank != 0) ? 0.0 : 1.0, part);
+    mg_prolong_trace<NT><<<np, RB, 0, s>>>(L0.t, c->d_facenode, m->node0, c->d_isbc, c->nface_own, z);
 }
 
 void mg_apply(hdg_context* c, const double* r, double* z, double* part, int np) {

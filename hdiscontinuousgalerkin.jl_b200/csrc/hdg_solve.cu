@@ -658,7 +658,8 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
     // one CUDA graph = CHUNK iterations (even, so the rz double-buffer parity restarts at 0)
     // (the multigrid kernels do not test the converged flag: a short chunk bounds the work done after convergence)
     const int CHUNK = mg ? 4 : 32;
-    const bool use_graph = getenv("HDG_NO_GRAPH") == nullptr;
+    // multigrid on several GPUs puts an ncclAllReduce into every iteration: launched directly, not captured
+    const bool use_graph = getenv("HDG_NO_GRAPH") == nullptr && !(mg && multi);
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
     auto enqueue_iter = [&](int it) {
@@ -671,7 +672,7 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
         if (blockjac) pcg_update_blk<NT><<<G, RB, 0, c->stream>>>(ak, c->d_binv, parity);
         else pcg_update<<<G, RB, 0, c->stream>>>(ak, N, parity);
         if (mg) mg_apply(c, ak.r, ak.Ap, c->d_partials + (parity ? P_RZC0 : P_RZC1) * MAX_PARTIALS, G);   // z (in Ap) += P V(P'r)
-        global_sums((1u << (parity ? P_RZ0 : P_RZ1)) | (1u << P_RR));      // r.z, r.r; r complete on every rank
+        global_sums((1u << (parity ? P_RZ0 : P_RZ1)) | (1u << P_RR) | (mg ? 1u << (parity ? P_RZC0 : P_RZC1) : 0u));   // r.z (+ its vertex-space part), r.r; r complete on every rank
         pcg_dir<<<G, RB, 0, c->stream>>>(ak, N, parity, it + 1, blockjac ? 1 : 0);
         if (ghost_mode == 1) global_sums(0);  // barrier: p complete on every rank before the next SpMV reads it
     };

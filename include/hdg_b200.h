@@ -162,9 +162,11 @@ hdg_status hdg_apply_dirichlet(hdg_context* ctx, const double* values);
 hdg_status hdg_solve(hdg_context* ctx, double rtol, int32_t maxit, hdg_solve_info* info);
 /* Preconditioner of hdg_solve: 0 = Jacobi (default), 1 = block-Jacobi with the nt x nt face-diagonal blocks
  * (fewer iterations for k >= 2; identical to Jacobi for k = 1 where the blocks are diagonal), 2 = block-Jacobi plus a
- * geometric multigrid V-cycle on the P1 vertex space (35-40 iterations independent of h and k; one GPU; the mesh must be
- * the triangulation of rectangle_mesh - from hdg_set_rectangle_mesh, or handed over as arrays through hdg_set_mesh, where
- * the grid numbering is recognised in the face table; any other configuration makes hdg_solve return HDG_ERR_INVALID). */
+ * geometric multigrid V-cycle on the P1 vertex space (35-45 iterations independent of h and k).  The mesh must be the
+ * triangulation of rectangle_mesh: from hdg_set_rectangle_mesh (one GPU, or strips over several GPUs - the vertex hierarchy
+ * is then replicated and the partial stencils / vertex residuals are all-reduced), or handed over as arrays through
+ * hdg_set_mesh on one GPU, where the grid numbering is recognised in the face table; any other configuration makes hdg_solve
+ * return HDG_ERR_INVALID. */
 hdg_status hdg_set_preconditioner(hdg_context* ctx, int32_t id);
 /* get_uσ!(σ_h,u_h,û_h,û,K_e,b_e,mesh), poisson2D_HDG.jl:197-212 (nt-general). */
 hdg_status hdg_recover(hdg_context* ctx);

@@ -17,8 +17,9 @@ sys.path.insert(0, ROOT)
 import hdg_b200 as hdg  # noqa: E402
 
 
-def solve(ctx, nx, ny, rtol, host_mesh=None):
+def solve(ctx, nx, ny, rtol, host_mesh=None, precond=0):
     lib = ctx.lib
+    hdg.check(lib.hdg_set_preconditioner(ctx.h, precond), ctx.h)
     if host_mesh is None:
         hdg.check(lib.hdg_set_rectangle_mesh(ctx.h, nx, ny, 0.0, 0.0, 2.0, 1.0), ctx.h)
     else:   # hdg_set_mesh: every rank passes the whole mesh, the library keeps a contiguous cell range + ghosts
@@ -47,6 +48,31 @@ def main():
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     ok = True
+    # ---- multigrid preconditioner on strips: replicated vertex hierarchy, all-reduced stencils / vertex residuals
+    for order, qd, nx, ny in ((1, 2, 48, 37), (2, 4, 40, 24), (3, 6, 33, 20), (1, 2, 7, 2 * world)):
+        ctx = hdg._Context(order, qd, 1.0, 1, lr)
+        ctx.comm_init(dist, device=torch.device("cuda", lr))
+        x, u, err2, iters, md = solve(ctx, nx, ny, 1e-13, precond=2)
+        part = ctx.partition()
+        xs = [None] * world
+        dist.all_gather_object(xs, (part["face_begin"], x))
+        ctx.close()
+        if rank == 0:
+            ref = hdg._Context(order, qd, 1.0, 1, lr)
+            xr, ur, e1, it1, md1 = solve(ref, nx, ny, 1e-13, precond=2)
+            ref.close()
+            xg = np.concatenate([p[1] for p in sorted(xs, key=lambda p: p[0])])
+            ex = np.abs(xg - xr).max() / np.abs(xr).max()
+            good = ex < 1e-10 and abs(err2 - e1) <= 1e-9 * e1 and abs(iters - it1) <= 1 and iters <= 60
+            ok &= good
+            print(f"multigrid k={order} {nx}x{ny} on {world} GPUs: iters {iters} (1 GPU: {it1})  relerr(uhat)={ex:.2e} "
+                  f"err2 {err2:.12e} vs {e1:.12e}  {'OK' if good else 'FAIL'}", flush=True)
+    if "--mg-only" in sys.argv:
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.broadcast(flag, src=0)
+        dist.barrier()
+        dist.destroy_process_group()
+        sys.exit(0 if flag.item() else 1)
     for order, qd, nx, ny in ((1, 2, 48, 37), (2, 4, 24, 16), (3, 6, 16, 11)):
         ctx = hdg._Context(order, qd, 1.0, 1, lr)
         ctx.comm_init(dist, device=torch.device("cuda", lr))
