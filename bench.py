@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--pcg", default="all", choices=["all", "mg"], help="mg: time only the multigrid-preconditioned solve (large single-GPU problems)")
     ap.add_argument("--ly", type=float, default=0.0, help="height of the global domain [0,2]x[0,ly] (default: number of GPUs)")
     ap.add_argument("--lx", type=float, default=2.0, help="width of the global domain [0,lx]x[0,ly] (C5 sweep: --lx 1 --ly 1 with square meshes)")
+    ap.add_argument("--mg-multi", action="store_true", help="with --pcg all on several GPUs: also time the multigrid-preconditioned solve")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--local-solver", type=int, default=0, help="1: literal quadrature + dense LU element kernel")
     ap.add_argument("--e2e-faces", action="store_true", help="also upload mesh.faces in the e2e step (it is rebuilt on the device otherwise)")
@@ -421,7 +422,9 @@ def main():
             pcg["block_jacobi"] = {"iterations": info2.iterations, "converged": bool(info2.converged), "solve_s": info2.solve_ms * 1e-3,
                                    "ms_per_iter": info2.solve_ms / max(info2.iterations, 1), "relres": info2.relres}
             hdg.check(lib.hdg_set_preconditioner(ctx.h, 0), ctx.h)
-        if world == 1 and args.pcg == "all":   # block-Jacobi + P1-vertex multigrid (one GPU, rectangle_mesh) on the same system
+        # block-Jacobi + P1-vertex multigrid on the same system; on several GPUs (replicated vertex
+        # hierarchy, an ncclAllReduce per iteration) only on request: --mg-multi
+        if args.pcg == "all" and (world == 1 or args.mg_multi):
             hdg.check(lib.hdg_set_preconditioner(ctx.h, 2), ctx.h)
             info3 = hdg.api.SolveInfo()
             best = None
