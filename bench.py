@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--ly", type=float, default=0.0, help="height of the global domain [0,2]x[0,ly] (default: number of GPUs)")
     ap.add_argument("--lx", type=float, default=2.0, help="width of the global domain [0,lx]x[0,ly] (C5 sweep: --lx 1 --ly 1 with square meshes)")
     ap.add_argument("--mg-multi", action="store_true", help="with --pcg all on several GPUs: also time the multigrid-preconditioned solve")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (quick solver experiments)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--local-solver", type=int, default=0, help="1: literal quadrature + dense LU element kernel")
     ap.add_argument("--e2e-faces", action="store_true", help="also upload mesh.faces in the e2e step (it is rebuilt on the device otherwise)")
@@ -293,7 +294,7 @@ def main():
 
     # ---------------- end to end through the C ABI with HOST buffers ----------------
     e2e = None
-    if rank == 0 or world > 1:
+    if (rank == 0 or world > 1) and not args.no_e2e:
         nnode_s, nface_s, nbf_s = (nx + 1) * (ny + 1), 3 * nx * ny + nx + ny, 2 * (nx + ny)
         cells = torch.empty((ncell, 6), dtype=torch.int64).pin_memory().numpy()
         nodes = torch.empty((nnode_s, 2), dtype=torch.float64).pin_memory().numpy()
