@@ -215,7 +215,7 @@ hdg_status pcg_solve(hdg_context* c, double rtol, int maxit, hdg_solve_info* inf
 
 // hdg_mg.cu: P1-vertex multigrid term of the preconditioner (one GPU, rectangle_mesh)
 hdg_status mg_setup(hdg_context* c);                                              // operators of the current trace matrix
-void mg_apply(hdg_context* c, const double* r, double* z, double* part, int np);   // z += P V(P'r); part = partials of (P'r).V(P'r)
+hdg_status mg_apply(hdg_context* c, const double* r, double* z, double* part, int np);   // z += P V(P'r); part = partials of (P'r).V(P'r)
 void mg_free(hdg_context* c);
 int mg_levels(const hdg_context* c);
 int mg_launches_per_apply(const hdg_context* c);

@@ -338,14 +338,6 @@ __global__ void mg_dense_inverse(const double* __restrict__ st, int px, int py, 
     }
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) ainv[e] = A[e];
 }
-__global__ void mg_dense_solve(const double* __restrict__ ainv, const double* __restrict__ r, double* __restrict__ t, int n) {
-    const int i = threadIdx.x;
-    if (i >= n) return;
-    double s = 0.0;
-    for (int j = 0; j < n; ++j) s = fma(ainv[i * n + j], r[j], s);
-    t[i] = s;
-}
-
 // ---- the coarse tail of the V-cycle in one kernel ----------------------------------------------------------------------
 // The smallest levels are pure launch latency (five kernels for a microsecond of work each).  The levels with at most
 // MG_FUSE_MAX points run inside one block: the same point-wise operations in the same order (results are bitwise those of the
@@ -541,12 +533,15 @@ hdg_status mg_setup(hdg_context* c) {
 }
 
 // z += P V(P' r);  part[0..np) = partial sums of (P' r) . V(P' r).  Enqueued on c->stream (capturable).
-template <int NT> static void mg_apply_t(hdg_context* c, const double* r, double* z, double* part, int np) {
+template <int NT> static hdg_status mg_apply_t(hdg_context* c, const double* r, double* z, double* part, int np) {
     MgData* m = static_cast<MgData*>(c->mg);
     cudaStream_t s = c->stream;
     MgLevel& L0 = m->lev[0];
     mg_restrict_trace<NT><<<nblk(L0.n), 256, 0, s>>>(r, m->vcnt, m->vface, L0.n, L0.r);
-    if (m->multi) comm_allreduce_sum(c, L0.r, int(L0.n));     // P'r summed over the ranks; the V-cycle below is replicated
+    if (m->multi) {     // P'r summed over the ranks; the V-cycle below is replicated
+        hdg_status st = comm_allreduce_sum(c, L0.r, int(L0.n));
+        if (st) return st;
+    }
     const int nl = m->nlev, lf = m->lf;
     for (int l = 0; l < lf; ++l) {
         MgLevel &F = m->lev[l], &C = m->lev[l + 1];
@@ -574,15 +569,17 @@ template <int NT> static void mg_apply_t(hdg_context* c, const double* r, double
     }
     mg_dot<<<np, RB, 0, s>>>(L0.r, L0.t, L0.n, (m->multi && c->comm->rank != 0) ? 0.0 : 1.0, part);
     mg_prolong_trace<NT><<<np, RB, 0, s>>>(L0.t, c->d_facenode, m->node0, c->d_isbc, c->nface_own, z);
+    return HDG_OK;
 }
 
-void mg_apply(hdg_context* c, const double* r, double* z, double* part, int np) {
+hdg_status mg_apply(hdg_context* c, const double* r, double* z, double* part, int np) {
     switch (c->tab.nt) {
-        case 2: mg_apply_t<2>(c, r, z, part, np); break;
-        case 3: mg_apply_t<3>(c, r, z, part, np); break;
-        case 4: mg_apply_t<4>(c, r, z, part, np); break;
-        case 5: mg_apply_t<5>(c, r, z, part, np); break;
+        case 2: return mg_apply_t<2>(c, r, z, part, np);
+        case 3: return mg_apply_t<3>(c, r, z, part, np);
+        case 4: return mg_apply_t<4>(c, r, z, part, np);
+        case 5: return mg_apply_t<5>(c, r, z, part, np);
     }
+    return HDG_OK;
 }
 
 int mg_levels(const hdg_context* c) { return c->mg ? static_cast<const MgData*>(c->mg)->nlev : 0; }

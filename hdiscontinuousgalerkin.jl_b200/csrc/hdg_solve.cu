@@ -650,7 +650,7 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
     };
     if (blockjac) pcg_init_blk<NT><<<G, RB, 0, c->stream>>>(a, c->d_binv);
     else pcg_init<NT><<<G, RB, 0, c->stream>>>(a);
-    if (mg) mg_apply(c, a.r, a.p, c->d_partials + P_RZC0 * MAX_PARTIALS, G);      // p_0 = z_0 = M^-1 r_0
+    if (mg) note(mg_apply(c, a.r, a.p, c->d_partials + P_RZC0 * MAX_PARTIALS, G));      // p_0 = z_0 = M^-1 r_0
     global_sums(0x1fu | (mg ? 0x60u : 0u));
     pcg_init_final<<<1, RB, 0, c->stream>>>(a);
     c->launches += 2;
@@ -671,7 +671,7 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
         global_sums(1u << P_PAP);      // p.Ap; every rank has finished reading the neighbours' vectors
         if (blockjac) pcg_update_blk<NT><<<G, RB, 0, c->stream>>>(ak, c->d_binv, parity);
         else pcg_update<<<G, RB, 0, c->stream>>>(ak, N, parity);
-        if (mg) mg_apply(c, ak.r, ak.Ap, c->d_partials + (parity ? P_RZC0 : P_RZC1) * MAX_PARTIALS, G);   // z (in Ap) += P V(P'r)
+        if (mg) note(mg_apply(c, ak.r, ak.Ap, c->d_partials + (parity ? P_RZC0 : P_RZC1) * MAX_PARTIALS, G));   // z (in Ap) += P V(P'r)
         global_sums((1u << (parity ? P_RZ0 : P_RZ1)) | (1u << P_RR) | (mg ? 1u << (parity ? P_RZC0 : P_RZC1) : 0u));   // r.z (+ its vertex-space part), r.r; r complete on every rank
         pcg_dir<<<G, RB, 0, c->stream>>>(ak, N, parity, it + 1, blockjac ? 1 : 0);
         if (ghost_mode == 1) global_sums(0);  // barrier: p complete on every rank before the next SpMV reads it

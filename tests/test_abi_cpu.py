@@ -93,3 +93,6 @@ def test_null_context_is_rejected():
     assert lib.hdg_assemble(None) == 1
     assert lib.hdg_solve(None, 1e-8, 10, None) == 1
     assert lib.hdg_launch_count(None) == 0
+    assert lib.hdg_set_dirichlet_faces(None, None, 0) == 1
+    assert lib.hdg_errornorm_values(None, None, None) == 1
+    assert lib.hdg_measure_fp64_peak(None, None) == 1
