@@ -414,6 +414,15 @@ def main():
                "recover_roofline": {"bound": "hbm", "achieved": RECOVER_BYTES[order] * ncell / (rec_ms * 1e-3) / 1e9, "peak": peak,
                                     "unit": "GB/s", "frac": RECOVER_BYTES[order] * ncell / (rec_ms * 1e-3) / 1e9 / peak},
                "err2": err2.value}
+        try:      # measured DRAM traffic of one Jacobi-PCG iteration / one recovery pass (ncu captures under profiles/), scaled to this size
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+                tj = json.load(fh)
+            if tj.get(f"pcg_k{order}_iteration") and args.pcg == "all":
+                pcg["roofline"]["traffic"] = tj[f"pcg_k{order}_iteration"] * int(s.ndof) / tj[f"pcg_k{order}_dofs"]
+            if tj.get(f"recover_k{order}"):
+                pcg["recover_roofline"]["traffic"] = tj[f"recover_k{order}"] * ncell / tj[f"recover_k{order}_elements"]
+        except Exception:
+            pass
         if order >= 2 and args.pcg == "all":   # block-Jacobi (nt x nt face blocks) on the same system
             hdg.check(lib.hdg_set_preconditioner(ctx.h, 1), ctx.h)
             info2 = hdg.api.SolveInfo()
