@@ -109,6 +109,73 @@ def getfaceset(mesh, name):
     return mesh.getfaceset(name)
 
 
+# small mesh queries of src/mesh.jl (host-side, 1-based indices like the reference)
+def n_faces_per_cell(mesh):
+    return 3                                                    # src/mesh.jl:70
+
+
+def n_nodes_per_cell(mesh):
+    return 3                                                    # src/mesh.jl:71
+
+
+def reference_edge_nodes():
+    return ((2, 3), (3, 1), (1, 2))                             # src/shapes.jl:24
+
+
+def getnodeset(mesh, name):
+    """getnodeset(mesh, name), src/mesh.jl:76: the nodes of the faces of the face set of that name
+    (_get_rectangular_boundary_sets, src/generate_mesh.jl:60-89, builds both from the same faces)."""
+    f = np.array(sorted(mesh.facesets[name]), dtype=np.int64) - 1
+    return set(np.unique(mesh.faces[f, :2]).tolist())
+
+
+def getnodesets(mesh):
+    return {k: getnodeset(mesh, k) for k in mesh.facesets}
+
+
+def get_coordinates(item, mesh):
+    """get_coordinates(cell, mesh) / get_coordinates(face::Int, mesh), src/mesh.jl:83-119: vertex coordinates of a cell
+    (pass the 1-based cell index as ("cell", i), or a row of mesh.cells) or of a face (1-based face index)."""
+    if isinstance(item, tuple) and item[0] == "cell":
+        return mesh.nodes[mesh.cells[item[1] - 1, :3] - 1].copy()
+    if np.ndim(item) == 0:
+        return mesh.nodes[mesh.faces[int(item) - 1, :2] - 1].copy()
+    return mesh.nodes[np.asarray(item)[:3] - 1].copy()
+
+
+def get_cell_coordinates(cell_idx, mesh):
+    return mesh.nodes[mesh.cells[cell_idx - 1, :3] - 1].copy()   # src/mesh.jl:101-107
+
+
+def volume(coords):
+    """volume(verts) of a polygon given by its vertices (shoelace formula, src/shapes.jl / src/mesh.jl:148-152)."""
+    x = np.asarray(coords, dtype=np.float64)
+    xn = np.roll(x, -1, axis=0)
+    return 0.5 * abs(np.sum(x[:, 0] * xn[:, 1] - xn[:, 0] * x[:, 1]))
+
+
+def cell_volume(mesh, cell_idx):
+    return volume(get_cell_coordinates(cell_idx, mesh))         # src/mesh.jl:148-152
+
+
+def cell_centroid(mesh, cell_idx):
+    """src/mesh.jl:154-161."""
+    x = get_cell_coordinates(cell_idx, mesh)
+    xn = np.roll(x, -1, axis=0)
+    cr = x[:, 0] * xn[:, 1] - xn[:, 0] * x[:, 1]
+    ve = cell_volume(mesh, cell_idx)
+    return np.array([np.sum(cr * (x[:, 0] + xn[:, 0])), np.sum(cr * (x[:, 1] + xn[:, 1]))]) / (6.0 * ve)
+
+
+def cell_diameter(mesh, cell_idx):
+    """cell_diameter(mesh, idx), src/mesh.jl:121-129: the longest face of the cell."""
+    h = 0.0
+    for f in mesh.cells[cell_idx - 1, 3:6]:
+        a, b = mesh.nodes[mesh.faces[f - 1, 0] - 1], mesh.nodes[mesh.faces[f - 1, 1] - 1]
+        h = max(h, float(np.linalg.norm(b - a)))
+    return h
+
+
 def face_orientation(mesh, cell_idx, face_idx):
     """src/mesh.jl:51-54 (1-based cell / local face)."""
     k1, k2 = ((2, 3), (3, 1), (1, 2))[face_idx - 1]

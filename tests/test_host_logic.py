@@ -163,3 +163,30 @@ def test_cg_dofhandler_host_mirror(order):
         dh = hdg.DofHandler([hdg.LagrangeField(hdg.ContinuousLagrange(2, hdg.RefTetrahedron, 1), mesh)], mesh)
         assert dh.cell_dofs.tolist() == [1, 2, 3, 2, 4, 3, 2, 5, 4, 5, 6, 4, 3, 4, 7, 4, 8, 7, 4, 6, 8, 6, 9, 8]
     assert hdg.getcells_matrix(mesh).shape == (8, 3) and hdg.get_vertices_matrix(mesh).shape == (9, 2)
+
+
+def test_mesh_queries_match_reference_goldens():
+    """test/test_mesh.jl:9-24 (figure2.1) and :27-43 (rectangle_mesh 2x2) for the host-side mesh helpers."""
+    from fixtures_util import triangle_root
+    mesh = hdg.parse_mesh_triangle(triangle_root("figure2.1"))
+    assert hdg.getncells(mesh) == 4 and hdg.getnnodes(mesh) == 5 and hdg.n_faces_per_cell(mesh) == 3
+    for c in range(1, 5):
+        assert abs(hdg.cell_volume(mesh, c) - 0.25) < 1e-15
+        assert abs(hdg.volume(hdg.get_coordinates(mesh.cells[c - 1], mesh)) - 0.25) < 1e-15
+    assert hdg.getcells_matrix(mesh).tolist() == [[2, 3, 5], [4, 1, 5], [5, 3, 4], [1, 2, 5]]
+    assert hdg.get_vertices_matrix(mesh).tolist() == [[0.0, 0.0], [1.0, 0.0], [1.0, 1.0], [0.0, 1.0], [0.5, 0.5]]
+    assert mesh.cells[0].tolist() == [2, 3, 5, 1, 2, 3]
+    assert [hdg.face_orientation(mesh, 1, i) for i in (1, 2, 3)] == [True, False, True]
+    assert hdg.cell_diameter(mesh, 1) == 1.0
+    assert hdg.getfaceset(mesh, "boundary") == {3, 6, 7, 8}
+    assert hdg.get_coordinates(1, mesh).tolist() == [[1.0, 1.0], [0.5, 0.5]]
+    assert np.allclose(hdg.cell_centroid(mesh, 1), mesh.nodes[[1, 2, 4]].mean(axis=0))
+    mo = orc.rectangle_mesh(2, 2)
+    mesh = hdg.PolygonalMesh(np.hstack([mo.cells, mo.cell_faces]), mo.nodes, mo.faces, {k: set(v) for k, v in mo.facesets.items()})
+    for c in range(1, 9):
+        assert abs(hdg.cell_volume(mesh, c) - 0.125) < 1e-15
+    assert hdg.getcells_matrix(mesh).tolist() == [[1, 2, 4], [2, 5, 4], [2, 3, 5], [3, 6, 5], [4, 5, 7], [5, 8, 7], [5, 6, 8], [6, 9, 8]]
+    assert hdg.cell_diameter(mesh, 1) == np.sqrt(2) / 2
+    assert hdg.getfaceset(mesh, "boundary") == {3, 7, 9, 16, 2, 11, 12, 15}
+    assert hdg.getnodeset(mesh, "boundary") == {1, 2, 3, 4, 6, 7, 8, 9}
+    assert hdg.n_nodes_per_cell(mesh) == 3 and hdg.reference_edge_nodes() == ((2, 3), (3, 1), (1, 2))
