@@ -16,7 +16,7 @@ import re
 import numpy as np
 
 from . import _lib
-from ._lib import HDGError, Params, Sizes, SolveInfo, check, f64p, i64p
+from ._lib import BadGeometryError, HDGError, Params, Sizes, SolveInfo, check, f64p, i64p
 
 # ----------------------------------------------------------------------------------------------
 # element / basis descriptors (src/basis.jl, src/FiniteElement.jl) - tables are built by the library
@@ -439,6 +439,69 @@ class ScalarFunctionSpace:
     def getnquadpoints(self):
         return self._tables()["qweights"].size
 
+    # ---- per-cell data and accessors (src/ScalarFunctionSpaces.jl:101-161), 1-based indices like the reference.  The hot
+    # path does not go through these (hdg_assemble forms the blocks on the device); they are the inspection / hand-written
+    # loop interface of the reference, served from the SAME reference tables the kernels consume (hdg_ref_table).
+    def _arrays(self):
+        if getattr(self, "_arr", None) is None:
+            t, n = self._tables(), self.fe.basis.getnbasefunctions()
+            nq, nfq = t["qweights"].size, t["fweights"].size
+            self._arr = dict(N=t["N"].reshape(nq, n).T, dN=t["dNdxi"].reshape(nq, n, 2).transpose(1, 0, 2),
+                             E=t["E"].reshape(3, nfq, n).transpose(2, 1, 0), qp=t["qpoints"].reshape(nq, 2), qw=t["qweights"],
+                             fw=t["fweights"], n=n, nq=nq, nfq=nfq)
+        return self._arr
+
+    def reinit_(self, x):
+        """reinit!(fs, x): x = (3,2) vertex coordinates (or a row of mesh.cells).  det(J) <= 0 raises like :110."""
+        x = np.asarray(x, dtype=np.float64)
+        if x.ndim == 1:
+            x = self.mesh.nodes[x[:3].astype(np.int64) - 1]
+        a = self._arrays()
+        J = np.stack([x[1] - x[0], x[2] - x[0]], axis=1)            # sum_j x_j (x) dM_j/dxi, P1 geometry
+        detJ = J[0, 0] * J[1, 1] - J[0, 1] * J[1, 0]
+        if not detJ > 0.0:
+            raise BadGeometryError(2, f"det(J) is not positive: det(J) = {detJ}")
+        self.detJ = detJ
+        self.Jinv = np.array([[J[1, 1], -J[0, 1]], [-J[1, 0], J[0, 0]]]) / detJ
+        self.dNdx = a["dN"] @ self.Jinv                              # dNdxi . Jinv, :116
+        wn = np.array([[-(J[1, 0] - J[1, 1]), J[0, 0] - J[0, 1]], [-J[1, 1], J[0, 1]], [J[1, 0], -J[0, 0]]])   # src/shapes.jl:80-87
+        self.detJf = np.linalg.norm(wn, axis=1)
+        self.normals = wn / self.detJf[:, None]
+        self._x = x
+
+    def getdetJdV(self, q):
+        return self.detJ * self._arrays()["qw"][q - 1]
+
+    def shape_value(self, *a):
+        """shape_value(fs, q, i)  or  shape_value(fs, face, q, i, orientation=True)  (:138, :153)."""
+        A = self._arrays()
+        if len(a) == 2:
+            return A["N"][a[1] - 1, a[0] - 1]
+        face, q, i = a[0], a[1], a[2]
+        ori = a[3] if len(a) > 3 else True
+        return A["E"][i - 1, (q - 1) if ori else (A["nfq"] - q), face - 1]
+
+    def shape_gradient(self, q, i):
+        return self.dNdx[i - 1, q - 1]
+
+    def getnfacequadpoints(self):
+        return self._arrays()["nfq"]
+
+    def getfacedetJdS(self, face, q):
+        return self.detJf[face - 1] * self._arrays()["fw"][q - 1]
+
+    def get_normal(self, face):
+        return self.normals[face - 1]
+
+    def spatial_coordinate(self, q, x=None):
+        """spatial_coordinate(fs, q, x): x_q = sum_g M[g,q] x_g (src/DiscreteFunctions.jl:15-24)."""
+        x = self._x if x is None else np.asarray(x, dtype=np.float64)
+        r, s_ = self._arrays()["qp"][q - 1]
+        return (1.0 - r - s_) * x[0] + r * x[1] + s_ * x[2]
+
+    def function_value(self, f, q, x=None):
+        return f(self.spatial_coordinate(q, x))
+
 
 class VectorFunctionSpace(ScalarFunctionSpace):
     """VectorFunctionSpace(mesh, fe; quad_degree), src/VectorFunctionSpaces.jl:10-18."""
@@ -448,6 +511,19 @@ class VectorFunctionSpace(ScalarFunctionSpace):
         return 2 * self.fe.basis.getnbasefunctions()
 
     getnlocaldofs = getnbasefunctions
+
+    def shape_value(self, *a):
+        """Vector-valued: dof i lives in component (i-1) div n with scalar function (i-1) mod n (:28-34, :49-57)."""
+        n = self._arrays()["n"]
+        i = a[1] if len(a) == 2 else a[2]
+        out = np.zeros(2)
+        sc = (i - 1) % n + 1
+        out[(i - 1) // n] = ScalarFunctionSpace.shape_value(self, *((a[0], sc) if len(a) == 2 else (a[0], a[1], sc) + tuple(a[3:])))
+        return out
+
+    def shape_divergence(self, q, i):
+        n = self._arrays()["n"]
+        return self.dNdx[(i - 1) % n, q - 1, (i - 1) // n]             # tr(shape_gradient), :45-48
 
 
 class ScalarTraceFunctionSpace:
@@ -462,6 +538,17 @@ class ScalarTraceFunctionSpace:
 
     def getnlocaldofs(self):
         return 3 * self.getnbasefunctions()
+
+    # src/TraceFunctionSpaces.jl:31-57
+    def getnquadpoints(self):
+        return self.fs._arrays()["nfq"]
+
+    def shape_value(self, q, i):
+        nt = self.getnbasefunctions()
+        return ref_table(self.fe.order, self.fs.quad_degree, "T").reshape(-1, nt)[q - 1, i - 1]
+
+    def getfacedetJdS(self, face, q):
+        return self.fs.getfacedetJdS(face, q)
 
 
 def getnbasefunctions(x):

@@ -190,3 +190,63 @@ def test_mesh_queries_match_reference_goldens():
     assert hdg.getfaceset(mesh, "boundary") == {3, 7, 9, 16, 2, 11, 12, 15}
     assert hdg.getnodeset(mesh, "boundary") == {1, 2, 3, 4, 6, 7, 8, 9}
     assert hdg.n_nodes_per_cell(mesh) == 3 and hdg.reference_edge_nodes() == ((2, 3), (3, 1), (1, 2))
+
+
+def test_function_space_accessors_reproduce_the_reference_test_loop():
+    """The loop of test/test_FunctionSpace.jl:97-178 and the checks of test/test_ScalarFuncSp.jl:15-32, transcribed onto
+    the host mirror's accessors (reinit_, getdetJdV, shape_value, shape_divergence, getfacedetJdS, get_normal).  The
+    accessors read the reference tables the device kernels consume (hdg_ref_table), so this pins those tables directly
+    on the reference's golden blocks Ae, Be, Ce, Ee, He."""
+    from fixtures_util import triangle_root
+    from test_oracle_goldens import Be_ex, Ce_ex, Ee_ex, He_ex
+    sq2 = np.sqrt(2.0)
+    mesh = hdg.parse_mesh_triangle(triangle_root("figure2.1"))
+    fe = hdg.GenericFiniteElement(hdg.Dubiner(2, hdg.RefTetrahedron, 1))
+    Wh = hdg.ScalarFunctionSpace(mesh, fe)
+    Vh = hdg.VectorFunctionSpace(mesh, fe)
+    Mh = hdg.ScalarTraceFunctionSpace(Wh, hdg.GenericFiniteElement(hdg.Legendre(1, hdg.RefTetrahedron, 1)))
+    assert (hdg.getnlocaldofs(Vh), hdg.getnlocaldofs(Wh), hdg.getnlocaldofs(Mh)) == (6, 3, 6)          # :30-32
+    invs = ([[1.0, 1.0], [-2.0, 0.0]], [[-1.0, -1.0], [2.0, 0.0]], [[1.0, 1.0], [-1.0, 1.0]], [[1.0, -1.0], [0.0, 2.0]])
+    detsJf = ([sq2 / 2, sq2 / 2, 1], [sq2 / 2, sq2 / 2, 1], [1, sq2 / 2, sq2 / 2], [sq2 / 2, sq2 / 2, 1])
+    nv, ns, nt, tau = 6, 3, 2, 1.0
+    for c in range(4):
+        cell = mesh.cells[c]
+        Wh.reinit_(cell)
+        Vh.reinit_(cell)
+        assert abs(Wh.detJ - 0.5) < 1e-15 and abs(Wh.getdetJdV(1) / Wh._arrays()["qw"][0] - 0.5) < 1e-15   # test_ScalarFuncSp.jl:25-26
+        assert np.allclose(Wh.Jinv, invs[c], atol=1e-14) and np.allclose(Wh.detJf, detsJf[c], atol=1e-14)
+        if c == 0:
+            assert np.allclose(Wh.normals, [[-sq2 / 2, sq2 / 2], [-sq2 / 2, -sq2 / 2], [1.0, 0.0]], atol=1e-14)
+        Ae, Be, Ce = np.zeros((nv, nv)), np.zeros((nv, ns)), np.zeros((ns, ns))
+        Ee, He = np.zeros((nv, 3 * nt)), np.zeros((3 * nt, 3 * nt))
+        for q in range(1, Vh.getnquadpoints() + 1):
+            dO = Vh.getdetJdV(q)
+            for i in range(1, nv + 1):
+                vh, div_vh = Vh.shape_value(q, i), Vh.shape_divergence(q, i)
+                for j in range(1, nv + 1):
+                    Ae[i - 1, j - 1] += (Vh.shape_value(q, j) @ vh) * dO
+                for j in range(1, ns + 1):
+                    Be[i - 1, j - 1] += Wh.shape_value(q, j) * div_vh * dO
+        for face in (1, 2, 3):
+            ori = hdg.face_orientation(mesh, c + 1, face)
+            for q in range(1, Wh.getnfacequadpoints() + 1):
+                dS = Wh.getfacedetJdS(face, q)
+                for i in range(1, ns + 1):
+                    w = Wh.shape_value(face, q, i)
+                    for j in range(1, ns + 1):
+                        Ce[i - 1, j - 1] += tau * Wh.shape_value(face, q, j) * w * dS
+                dS = Mh.getfacedetJdS(face, q)
+                n = Vh.get_normal(face)
+                for i in range(1, nv + 1):
+                    v = Vh.shape_value(face, q, i, ori)
+                    for j in range(1, nt + 1):
+                        Ee[i - 1, nt * (face - 1) + j - 1] += Mh.shape_value(q, j) * (v @ n) * dS
+                for i in range(1, nt + 1):
+                    for j in range(1, nt + 1):
+                        He[nt * (face - 1) + i - 1, nt * (face - 1) + j - 1] += Mh.shape_value(q, j) * Mh.shape_value(q, i) * dS
+        assert np.allclose(Ae, 0.5 * np.eye(6), atol=1e-14)                   # :125
+        assert np.allclose(Be, Be_ex[c], atol=1e-13)                          # :126
+        assert np.allclose(Ce, Ce_ex[c], atol=1e-13) and np.allclose(Ee, Ee_ex[c], atol=1e-13) and np.allclose(He, He_ex[c], atol=1e-13)   # :176-178
+    assert np.allclose([Mh.getfacedetJdS(f, 1) for f in (1, 2, 3)], [sq2 / 4, sq2 / 4, 0.5])                # :39-41 (state after the loop)
+    with pytest.raises(hdg.BadGeometryError):
+        Wh.reinit_(mesh.nodes[mesh.cells[0, [0, 2, 1]] - 1])                  # clockwise cell: det(J) is not positive
