@@ -94,6 +94,7 @@ SIGNATURES = {
     "hdg_set_preconditioner": (C.c_int, [_P, C.c_int32]),
     "hdg_recover": (C.c_int, [_P]),
     "hdg_errornorm": (C.c_int, [_P, C.c_int32, _F64P]),
+    "hdg_basis_value": (C.c_int, [C.c_int32, C.c_int32, _F64P, _F64P, _F64P]),
     "hdg_errornorm_values": (C.c_int, [_P, _F64P, _F64P]),
     "hdg_set_dirichlet_faces": (C.c_int, [_P, _I64P, C.c_int64]),
     "hdg_assemble_async": (C.c_int, [_P]),

@@ -47,6 +47,23 @@ class Legendre:
         return self.order + 1
 
 
+def value(ip, j, xi):
+    """value(ip, j, xi), src/basis.jl:65-86 (Dubiner) / :351-354 (Legendre): evaluated by the library's table builder."""
+    x = np.atleast_1d(np.asarray(xi, dtype=np.float64)).copy()
+    v = C.c_double()
+    check(_lib.load().hdg_basis_value(0 if isinstance(ip, Dubiner) else 1, int(j), f64p(x), C.byref(v), None))
+    return v.value
+
+
+def gradient_value(ip, j, xi):
+    """gradient_value(ip, j, xi), src/basis.jl:88-110."""
+    x = np.atleast_1d(np.asarray(xi, dtype=np.float64)).copy()
+    v = C.c_double()
+    g = np.zeros(2)
+    check(_lib.load().hdg_basis_value(0 if isinstance(ip, Dubiner) else 1, int(j), f64p(x), C.byref(v), f64p(g)))
+    return g if isinstance(ip, Dubiner) else g[:1]
+
+
 class GenericFiniteElement:
     """GenericFiniteElement(func_basis), src/FiniteElement.jl:8-27 (order-1 Lagrange geometry)."""
 

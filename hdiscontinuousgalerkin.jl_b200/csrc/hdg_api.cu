@@ -248,6 +248,28 @@ hdg_status hdg_ref_table(int32_t order, int32_t quad_degree, const char* name, d
     return HDG_OK;
 }
 
+hdg_status hdg_basis_value(int32_t kind, int32_t j, const double* xi, double* value, double* grad) {
+    if (!xi || !value) return HDG_ERR_INVALID;
+    if (kind == 0) {            // Dubiner on the reference triangle, src/basis.jl:65-86
+        if (j < 1 || j > 15 || !(xi[0] >= -1e-12 && xi[1] >= -1e-12)) return set_err(nullptr, HDG_ERR_INVALID, "Dubiner: 1 <= j <= 15 (order <= 4)");
+        double v, dr, ds;
+        dubiner_eval(j, xi[0], xi[1], &v, &dr, &ds);
+        *value = v;
+        if (grad) { grad[0] = dr; grad[1] = ds; }
+        return HDG_OK;
+    }
+    if (kind == 1) {            // orthonormal Legendre on (0,1), src/basis.jl:351-354
+        if (j < 1 || j > 5) return set_err(nullptr, HDG_ERR_INVALID, "Legendre: 1 <= j <= 5 (order <= 4)");
+        *value = legendre01_eval(j, xi[0]);
+        if (grad) {             // central difference of the polynomial (table building never needs the derivative)
+            const double h = 1e-6;
+            grad[0] = (legendre01_eval(j, xi[0] + h) - legendre01_eval(j, xi[0] - h)) / (2.0 * h);
+        }
+        return HDG_OK;
+    }
+    return set_err(nullptr, HDG_ERR_INVALID, "unknown basis kind");
+}
+
 hdg_status hdg_set_source_values(hdg_context* c, const double* fq) {
     if (!c || !fq) return HDG_ERR_INVALID;
     if (!c->have_mesh) return set_err(c, HDG_ERR_INVALID, "hdg_set_source_values before a mesh is set");

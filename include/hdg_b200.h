@@ -145,6 +145,11 @@ hdg_status hdg_get_table(const hdg_context* ctx, const char* name, double* buf, 
 /* Same tables without a context (host-only table builder; needs no device). */
 hdg_status hdg_ref_table(int32_t order, int32_t quad_degree, const char* name, double* buf, int64_t* count);
 
+/* value(ip, j, xi) / gradient_value(ip, j, xi) of the bases the tables are built from (src/basis.jl:65-86 Dubiner on the
+ * reference triangle, kind 0, xi = (r, s); :351-354 orthonormal Legendre on (0,1), kind 1, xi = (x)); j is 1-based.  grad may
+ * be NULL.  Host-only (needs no device): lets the reference's basis tests run against the library's own evaluation. */
+hdg_status hdg_basis_value(int32_t kind, int32_t j, const double* xi, double* value, double* grad);
+
 /* ---- source -------------------------------------------------------------------------------
  * Pre-evaluated f(x_q): ncell x nq doubles, fq[c*nq+q] = f(spatial_coordinate(Wh,q,coords_c))
  * (function_value, src/DiscreteFunctions.jl:6-24).  Required when source_id == 0. */

@@ -96,3 +96,44 @@ def test_null_context_is_rejected():
     assert lib.hdg_set_dirichlet_faces(None, None, 0) == 1
     assert lib.hdg_errornorm_values(None, None, None) == 1
     assert lib.hdg_measure_fp64_peak(None, None) == 1
+
+
+def test_library_basis_values_match_the_reference_closed_forms():
+    """test/test_basis.jl:6-12 and :62-93 against the LIBRARY's own basis evaluation (hdg_basis_value, the functions its
+    table builder uses): Dubiner values equal the reference's closed forms dubiner_basis at the Strang(5) points, gradients
+    match their central differences, the Legendre functions equal the closed forms at the 3-point Gauss rule."""
+    import math
+    from test_oracle_goldens import _dubiner_closed
+    dub, leg = hdg.Dubiner(2, hdg.RefTetrahedron, 4), hdg.Legendre(1, hdg.RefTetrahedron, 3)
+    pts = hdg.ref_table(4, 5, "qpoints").reshape(-1, 2)          # Strang(5), src/StrangQuad.jl
+    assert pts.shape == (7, 2)
+    h = 1e-6
+    for j in [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 13, 14, 15]:
+        for r, s in pts:
+            assert abs(hdg.value(dub, j, (r, s)) - _dubiner_closed(j, r, s)) < 2e-13
+            g = hdg.gradient_value(dub, j, (r, s))
+            gx = (_dubiner_closed(j, r + h, s) - _dubiner_closed(j, r - h, s)) / (2 * h)
+            gy = (_dubiner_closed(j, r, s + h) - _dubiner_closed(j, r, s - h)) / (2 * h)
+            assert abs(g[0] - gx) < 2e-6 * max(1, abs(gx)) and abs(g[1] - gy) < 2e-6 * max(1, abs(gy))
+    ref = [lambda x: 1.0, lambda x: math.sqrt(3) * (2 * x - 1), lambda x: math.sqrt(5) * (6 * x * x - 6 * x + 1),
+           lambda x: math.sqrt(7) * (2 * x - 1) * (10 * x * x - 10 * x + 1)]
+    dref = [lambda x: 0.0, lambda x: math.sqrt(3) * 2, lambda x: math.sqrt(5) * (12 * x - 6), lambda x: math.sqrt(7) * 12 * (5 * x * x - 5 * x + 1)]
+    for x in hdg.ref_table(2, 3, "fpoints"):                     # 3-point Gauss-Legendre on (0,1)
+        for i in range(4):
+            assert abs(hdg.value(leg, i + 1, x) - ref[i](x)) < 1e-14
+            assert abs(hdg.gradient_value(leg, i + 1, x)[0] - dref[i](x)) < 1e-7
+    with pytest.raises(hdg.HDGError):
+        hdg.value(dub, 16, (0.2, 0.2))
+
+
+def test_library_quadrature_rules():
+    """test/test_quadrature.jl:16-25 on the library's rules: cell weights sum to the area of the reference triangle, the
+    1-D Gauss rule to 1; point counts of the default rules (src/quadrature.jl:17-39)."""
+    counts = {2: 3, 3: 6, 4: 6, 5: 7, 6: 12, 9: 35}
+    for qd, npts in counts.items():
+        w = hdg.ref_table(1, qd, "qweights")
+        assert w.size == npts and abs(w.sum() - 0.5) < 1e-14
+        fw, fp = hdg.ref_table(1, qd, "fweights"), hdg.ref_table(1, qd, "fpoints")
+        assert fw.size == qd and abs(fw.sum() - 1.0) < 1e-14 and np.all(np.diff(fp) > 0) and 0.0 < fp[0] and fp[-1] < 1.0
+        p = hdg.ref_table(1, qd, "qpoints").reshape(-1, 2)
+        assert np.all(p > 0) and np.all(p.sum(axis=1) < 1)               # interior points
