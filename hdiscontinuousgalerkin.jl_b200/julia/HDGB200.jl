@@ -124,8 +124,14 @@ function HDiscontinuousGalerkin.apply!(K::TraceMatrix, b::TraceVector, dbc::Diri
     check(ccall((:hdg_apply_dirichlet, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}), c.h, vals), c.h)
 end
 
-"û = K \\ b of examples/poisson2D_HDG.jl:195."
-function Base.:\(K::TraceMatrix, b::TraceVector; rtol = 1e-13, maxit = 200_000)
+"û = K \\ b of examples/poisson2D_HDG.jl:195 (Jacobi-PCG).  `solve(K, b; precond = :mg)` selects the block-Jacobi + P1-vertex
+multigrid preconditioner (rectangle_mesh triangulations: recognised in the arrays passed by doassemble), `:block` the
+face-block Jacobi one."
+Base.:\(K::TraceMatrix, b::TraceVector) = solve(K, b)
+
+function solve(K::TraceMatrix, b::TraceVector; rtol = 1e-13, maxit = 200_000, precond::Symbol = :jacobi)
+    id = Dict(:jacobi => 0, :block => 1, :mg => 2)[precond]
+    check(ccall((:hdg_set_preconditioner, lib), Cint, (Ptr{Cvoid}, Int32), K.ctx.h, id), K.ctx.h)
     info = Ref(SolveInfo(0, 0, 0.0, 0.0, 0.0))
     check(ccall((:hdg_solve, lib), Cint, (Ptr{Cvoid}, Float64, Int32, Ref{SolveInfo}), K.ctx.h, rtol, maxit, info), K.ctx.h)
     TraceVector(K.ctx, :trace)
