@@ -33,3 +33,13 @@ def test_bench_refuses_to_run_without_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_reference_arm_ignores_torchrun_omp_limit():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the "all host threads" arm must still use the CPU affinity mask."""
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-1500:]
+    d = json.loads([ln for ln in out.stdout.splitlines() if ln.strip()][0])
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
