@@ -214,3 +214,37 @@ def test_dofhandler_goldens():
     assert orc.dirichlet_dofhandler(mo, cell_dofs, offsets).tolist() == [1, 2, 3, 5, 6, 7, 8, 9]
     colptr, rowval = orc.create_sparsity_pattern(cell_dofs, offsets)
     assert colptr[-1] - 1 == rowval.size == 9 + 2 * 16      # 9 vertices + 16 edges, both directions
+
+
+def test_condensation_against_extended_precision_on_the_golden_blocks(fig21):
+    """K_e, b_e, Ate, bte have no golden in the reference.  What can be pinned: the condensation
+    (examples/poisson2D_HDG.jl:155-174) applied to the reference's GOLDEN blocks A = I/2, Be, Ce, Ee, He
+    (test/test_FunctionSpace.jl:49-72) in 40-digit arithmetic must give the oracle's K_e and Ate; only Fe and be (no golden)
+    are taken from the restatement itself."""
+    import mpmath as mp
+    mp.mp.dps = 40
+    tab = orc.build_tables(1)
+    ori = orc.orientations(fig21)
+    for c in range(4):
+        blk = orc.local_blocks(tab, fig21.nodes[fig21.cells[c] - 1], ori[c])
+        K_e, b_e, At, bt = orc.condense(blk)
+        A = 0.5 * np.eye(6)
+        B, Cm, E, H = (np.asarray(M, dtype=float) for M in (Be_ex[c], Ce_ex[c], Ee_ex[c], He_ex[c]))
+        F, be = blk["F"], blk["be"]
+        Me = mp.matrix(np.block([[A, -B], [B.T, Cm]]).tolist())                # doubles in, 40-digit arithmetic from here
+        EF = mp.matrix(np.vstack([-E, F]).tolist())
+        G = mp.matrix(np.vstack([E, F]).tolist())
+        cols = [mp.lu_solve(Me, EF[:, j]) for j in range(6)]                   # lu_solve takes one right-hand side
+        Kx = mp.matrix(9, 6)
+        for j in range(6):
+            for i in range(9):
+                Kx[i, j] = cols[j][i]
+        Atx = G.T * Kx - mp.matrix(H.tolist())
+        bx = mp.lu_solve(Me, mp.matrix(np.concatenate([np.zeros(6), be]).reshape(-1, 1).tolist()))
+        btx = -(G.T * bx)
+        tonp = lambda M: np.array([[float(M[i, j]) for j in range(M.cols)] for i in range(M.rows)])
+        assert np.abs(tonp(Kx) - K_e).max() < 5e-13 * np.abs(K_e).max()
+        assert np.abs(tonp(Atx) - At).max() < 5e-13 * np.abs(At).max()
+        assert np.abs(tonp(bx)[:, 0] - b_e).max() < 5e-13 * np.abs(b_e).max()
+        assert np.abs(tonp(btx)[:, 0] - bt).max() < 5e-13 * np.abs(bt).max()
+        assert np.abs(At - At.T).max() < 1e-13                                 # symmetric to rounding
