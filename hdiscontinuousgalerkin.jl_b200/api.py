@@ -819,8 +819,9 @@ def nodal_avg(u_h):
     return out
 
 
-def poisson2D_HDG(mesh=None, order=1, quad_degree=None, tau=1.0, rtol=1e-13, maxit=200000):
-    """The driver examples/poisson2D_HDG.jl:37-218 end to end.  Returns a dict of results."""
+def poisson2D_HDG(mesh=None, order=1, quad_degree=None, tau=1.0, rtol=1e-13, maxit=200000, precond="jacobi"):
+    """The driver examples/poisson2D_HDG.jl:37-218 end to end.  Returns a dict of results.
+    precond: "jacobi" (default), "block", or "mg" (rectangle_mesh triangulations), see `solve`."""
     if mesh is None:
         mesh = rectangle_mesh(TriangleCell, (10, 10), (0.0, 0.0), (1.0, 1.0))
     fe = GenericFiniteElement(Dubiner(2, RefTetrahedron, order))
@@ -831,7 +832,7 @@ def poisson2D_HDG(mesh=None, order=1, quad_degree=None, tau=1.0, rtol=1e-13, max
     dbc = Dirichlet(uhat_h, mesh, "boundary", lambda x: 0)
     K, b, K_e, b_e = doassemble(Vh, Wh, Mh, tau)
     apply_(K, b, dbc)
-    uhat, info = solve(K, b, rtol, maxit)
+    uhat, info = solve(K, b, rtol, maxit, precond)
     get_usigma_(sigma_h, u_h, uhat_h, uhat, K_e, b_e, mesh)
     err2 = errornorm(u_h, poisson_exact)
     return dict(K=K, b=b, K_e=K_e, b_e=b_e, uhat=uhat, sigma_h=sigma_h, u_h=u_h, uhat_h=uhat_h,
