@@ -38,3 +38,4 @@ __device__ __forceinline__ double mg_prolong_pt(const double* ec, int cx, int cy
 }
 }  // namespace hdg
 #include "experimental/mg_persistent.cuh"
+#include "experimental/mg_general.cuh"
