@@ -63,7 +63,11 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, double a, d
 
 extern "C" {
 
+#ifdef HDG_MG_GENERAL
+const char* hdg_version(void) { return "hdg_b200 0.1 (sm_100a) +mg_general"; }
+#else
 const char* hdg_version(void) { return "hdg_b200 0.1 (sm_100a)"; }
+#endif
 
 const char* hdg_last_error(const hdg_context* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 

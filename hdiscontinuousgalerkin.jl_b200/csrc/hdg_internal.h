@@ -154,6 +154,9 @@ struct hdg_context {
     double* d_binv = nullptr;        // block-Jacobi: inverted face-diagonal blocks
     int precond = 0;                 // 0 Jacobi, 1 block-Jacobi, 2 block-Jacobi + P1-vertex multigrid (hdg_mg.cu)
     void* mg = nullptr;              // hdg::MgData
+#ifdef HDG_MG_GENERAL
+    void* mg_general = nullptr;      // MgGeneral (round-2 candidate, hdg_mg.cu)
+#endif
     double* d_partials = nullptr;    // reduction partials
     double* d_scal = nullptr;        // device scalars
     int32_t* d_flags = nullptr;      // error / convergence flags

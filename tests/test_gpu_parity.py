@@ -445,7 +445,43 @@ def test_multigrid_through_set_mesh_arrays(order, qd, nx, ny):
     assert xs[0][1] == xs[1][1] and np.array_equal(xs[0][0], xs[1][0])
 
 
+# round-2 candidate: built only with `make EXTRA=-DHDG_MG_GENERAL=1` (csrc/hdg_mg.cu); the default library rejects such meshes
+_MG_GENERAL = b"mg_general" in hdg.load().hdg_version()
+
+
+@pytest.mark.skipif(not _MG_GENERAL, reason="library built without -DHDG_MG_GENERAL (round-2 candidate)")
+@pytest.mark.parametrize("order,qd", [(1, 2), (2, 4), (3, 6)])
+def test_multigrid_term_on_unstructured_meshes(order, qd):
+    """Hierarchy-free vertex-space term (Chebyshev on the ELL vertex operator) on meshes without grid structure."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(11)
+    m = 24
+    g = np.linspace(0.0, 1.0, m + 1)
+    X, Y = np.meshgrid(g, g)
+    nodes = np.c_[X.ravel(), Y.ravel()]
+    inner = (nodes[:, 0] > 0) & (nodes[:, 0] < 1) & (nodes[:, 1] > 0) & (nodes[:, 1] < 1)
+    nodes[inner] += rng.uniform(-0.3 / m, 0.3 / m, size=(inner.sum(), 2))
+    tri = Delaunay(nodes).simplices.astype(np.int64) + 1
+    pts = nodes[tri - 1]
+    a, b = pts[:, 1] - pts[:, 0], pts[:, 2] - pts[:, 0]
+    flip = (a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]) < 0
+    tri[flip] = tri[flip][:, [0, 2, 1]]
+    cf, faces = hdg.number_faces(tri)
+    mesh = hdg.PolygonalMesh(np.hstack([tri, cf]), nodes, faces, {"boundary": set((np.flatnonzero(faces[:, 3] == 0) + 1).tolist())})
+    Vh, Wh, Mh = _spaces(mesh, order, qd)
+    K, b_, _, _ = hdg.doassemble(Vh, Wh, Mh)
+    hdg.apply_(K, b_, hdg.Dirichlet(hdg.TrialFunction(Mh), mesh, "boundary", lambda x: 0))
+    xb, ib = hdg.solve(K, b_, rtol=1e-13, precond="block")
+    xm, im = hdg.solve(K, b_, rtol=1e-13, precond="mg")
+    xm2, im2 = hdg.solve(K, b_, rtol=1e-13, precond="mg")
+    assert relerr(xm.to_numpy(), xb.to_numpy()) < RTOL
+    assert im["converged"] and im["iterations"] < ib["iterations"] // 2
+    assert np.array_equal(xm.to_numpy(), xm2.to_numpy()) and im["iterations"] == im2["iterations"]
+
+
 def test_multigrid_rejects_other_triangulations():
+    if _MG_GENERAL:
+        pytest.skip("this build carries the general-mesh vertex term")
     mo = orc.parse_mesh_triangle(triangle_root("figure.1"))      # unstructured, 62 cells
     mesh = host_mesh_from_oracle(mo)
     Vh, Wh, Mh = _spaces(mesh, 1, 2)
