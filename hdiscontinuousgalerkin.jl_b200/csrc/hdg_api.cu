@@ -63,8 +63,12 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, double a, d
 
 extern "C" {
 
-#ifdef HDG_MG_GENERAL
+#if defined(HDG_MG_GENERAL) && defined(HDG_ZERO_ASYNC)
+const char* hdg_version(void) { return "hdg_b200 0.1 (sm_100a) +mg_general +zero_async"; }
+#elif defined(HDG_MG_GENERAL)
 const char* hdg_version(void) { return "hdg_b200 0.1 (sm_100a) +mg_general"; }
+#elif defined(HDG_ZERO_ASYNC)
+const char* hdg_version(void) { return "hdg_b200 0.1 (sm_100a) +zero_async"; }
 #else
 const char* hdg_version(void) { return "hdg_b200 0.1 (sm_100a)"; }
 #endif
@@ -132,6 +136,11 @@ void hdg_destroy(hdg_context* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_mesh(c);
+#ifdef HDG_ZERO_ASYNC
+    if (c->zstream) cudaStreamDestroy(c->zstream);
+    if (c->ev_main) cudaEventDestroy(c->ev_main);
+    if (c->ev_zero) cudaEventDestroy(c->ev_zero);
+#endif
     comm_destroy(c);
     if (c->d_rawtab) cudaFree(c->d_rawtab);
     if (c->d_flags) cudaFree(c->d_flags);

@@ -23,6 +23,7 @@
 // contributing cell -> plain stores.  Face-diagonal blocks and rhs entries have at most two
 // contributions -> RED.ADD.F64 onto zeroed storage, which is bitwise deterministic because a
 // two-term IEEE sum is commutative.
+#include <utility>
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -1008,7 +1009,25 @@ static hdg_status launch_elements(hdg_context* c, ElemArgs a) {
 
 hdg_status launch_element_kernels(hdg_context* c) {
     const int nt = c->tab.nt;
+#ifdef HDG_ZERO_ASYNC
+    const size_t zbytes = sizeof(double) * c->nface * (nt * nt + nt);
+    if (!c->zstream) {
+        HDG_CUDA(c, cudaStreamCreateWithFlags(&c->zstream, cudaStreamNonBlocking));
+        HDG_CUDA(c, cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+        HDG_CUDA(c, cudaEventCreateWithFlags(&c->ev_zero, cudaEventDisableTiming));
+    }
+    if (!c->d_Kd_alt) { HDG_CUDA(c, cudaMalloc(&c->d_Kd_alt, zbytes)); c->alt_ready = false; }
+    HDG_CUDA(c, cudaEventRecord(c->ev_main, c->stream));      // everything enqueued so far may still read the current buffers
+    if (c->alt_ready) {                                       // the spare buffer was zeroed in the background: flip
+        HDG_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_zero, 0));
+        std::swap(c->d_Kd, c->d_Kd_alt);
+        c->d_rhs = c->d_Kd + c->nface * nt * nt;
+    } else {
+        HDG_CUDA(c, cudaMemsetAsync(c->d_Kd, 0, zbytes, c->stream));
+    }
+#else
     HDG_CUDA(c, cudaMemsetAsync(c->d_Kd, 0, sizeof(double) * c->nface * (nt * nt + nt), c->stream));   // Kd and rhs (contiguous)
+#endif
     ElemArgs a{};
     a.cellinfo = c->d_cellinfo; a.nodes = c->d_nodes; a.fq = c->d_fq;
     a.Ke = c->d_Ke; a.Kd = c->d_Kd; a.Ko = c->d_Ko; a.rhs = c->d_rhs; a.flags = c->d_flags;
@@ -1017,6 +1036,14 @@ hdg_status launch_element_kernels(hdg_context* c) {
     timer_start(c, c->t_elem);
     hdg_status st = launch_elements(c, a);
     timer_stop(c, c->t_elem);
+#ifdef HDG_ZERO_ASYNC
+    // zero the other buffer for the NEXT assembly: behind everything the main stream held before this call (its last
+    // readers), concurrently with the element kernel just launched
+    HDG_CUDA(c, cudaStreamWaitEvent(c->zstream, c->ev_main, 0));
+    HDG_CUDA(c, cudaMemsetAsync(c->d_Kd_alt, 0, zbytes, c->zstream));
+    HDG_CUDA(c, cudaEventRecord(c->ev_zero, c->zstream));
+    c->alt_ready = true;
+#endif
     return st;
 }
 

@@ -141,6 +141,14 @@ struct hdg_context {
 
     // trace system, block-ELL: diagonal blocks + 4 off-diagonal blocks per face, blocks column-major nt x nt
     double* d_Kd = nullptr;          // nface * nt*nt
+#ifdef HDG_ZERO_ASYNC
+    // round-2 candidate (make EXTRA=-DHDG_ZERO_ASYNC=1): a second Kd+rhs buffer is zeroed on a side stream while the element
+    // kernel of the current assembly runs; hdg_assemble flips the two, so the 72 MB memset leaves the critical path
+    double* d_Kd_alt = nullptr;
+    cudaStream_t zstream = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_zero = nullptr;
+    bool alt_ready = false;
+#endif
     double* d_Ko = nullptr;          // nface * 4 * nt*nt
     double* d_rhs = nullptr;         // ndof
     double* d_Ke = nullptr;          // ncell * ke  ([K_e | b_e])

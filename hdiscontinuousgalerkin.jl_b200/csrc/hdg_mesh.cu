@@ -529,6 +529,11 @@ void free_mesh(hdg_context* c) {
     F(c->d_cellinfo); F(c->d_nodes); F(c->d_facecell); F(c->d_facenode); F(c->d_bfaces); F(c->d_isbc);
     F(c->d_kcol); F(c->d_fq); F(c->d_Kd); F(c->d_Ko); F(c->d_Ke); F(c->d_bcval);
     c->d_rhs = nullptr;   // lives behind d_Kd (one allocation, one memset per assembly)
+#ifdef HDG_ZERO_ASYNC
+    if (c->zstream) cudaStreamSynchronize(c->zstream);
+    F(c->d_Kd_alt);
+    c->alt_ready = false;
+#endif
     if (c->d_p) comm_unshare_vectors(c);   // close the neighbours' mappings before the vectors go away
     F(c->d_x); F(c->d_p); F(c->d_Ap);
     c->d_r = c->d_dinv = nullptr;          // r and Dinv live inside the d_p region
