@@ -113,6 +113,7 @@ SIGNATURES = {
     "hdg_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "hdg_comm_init": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]),
     "hdg_get_partition": (C.c_int, [_P, _I64P]),
+    "hdg_get_ghost_cells": (C.c_int, [_P, _I64P]),
     "hdg_comm_pingpong": (C.c_int, [_P, C.c_int32, _F64P]),
     "hdg_last_phase_ms": (C.c_int, [_P, C.c_char_p, _F64P]),
     "hdg_measure_fp64_peak": (C.c_int, [_P, _F64P]),

@@ -63,15 +63,7 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, double a, d
 
 extern "C" {
 
-#if defined(HDG_MG_GENERAL) && defined(HDG_ZERO_ASYNC)
-const char* hdg_version(void) { return "hdg_b200 0.1 (sm_100a) +mg_general +zero_async"; }
-#elif defined(HDG_MG_GENERAL)
-const char* hdg_version(void) { return "hdg_b200 0.1 (sm_100a) +mg_general"; }
-#elif defined(HDG_ZERO_ASYNC)
-const char* hdg_version(void) { return "hdg_b200 0.1 (sm_100a) +zero_async"; }
-#else
-const char* hdg_version(void) { return "hdg_b200 0.1 (sm_100a)"; }
-#endif
+const char* hdg_version(void) { return "hdg_b200 0.2 (sm_100a)"; }
 
 const char* hdg_last_error(const hdg_context* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
@@ -136,11 +128,7 @@ void hdg_destroy(hdg_context* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_mesh(c);
-#ifdef HDG_ZERO_ASYNC
-    if (c->zstream) cudaStreamDestroy(c->zstream);
-    if (c->ev_main) cudaEventDestroy(c->ev_main);
-    if (c->ev_zero) cudaEventDestroy(c->ev_zero);
-#endif
+    release_tables(c);
     comm_destroy(c);
     if (c->d_rawtab) cudaFree(c->d_rawtab);
     if (c->d_flags) cudaFree(c->d_flags);
@@ -412,7 +400,12 @@ hdg_status hdg_set_trace(hdg_context* c, const double* uhat) {
     if (!c || !uhat) return HDG_ERR_INVALID;
     if (!c->have_mesh) return set_err(c, HDG_ERR_INVALID, "no mesh");
     cudaSetDevice(c->device);
-    if (!c->d_x) HDG_CUDA(c, cudaMalloc(&c->d_x, sizeof(double) * c->nface * c->tab.nt));
+    if (comm_active(c) && c->comm->general_mesh)      // ghost entries live on arbitrary ranks there: only hdg_solve fills them
+        return set_err(c, HDG_ERR_INVALID, "hdg_set_trace is not available on a partitioned hdg_set_mesh mesh");
+    if (!c->d_x) {
+        HDG_CUDA(c, cudaMalloc(&c->d_x, sizeof(double) * c->nface * c->tab.nt));
+        HDG_CUDA(c, cudaMemsetAsync(c->d_x, 0, sizeof(double) * c->nface * c->tab.nt, c->stream));
+    }
     HDG_CUDA(c, cudaMemcpyAsync(c->d_x, uhat, sizeof(double) * c->nface_own * c->tab.nt, cudaMemcpyHostToDevice, c->stream));
     hdg_status st = comm_halo_exchange(c, c->d_x, c->tab.nt);
     if (st) return st;

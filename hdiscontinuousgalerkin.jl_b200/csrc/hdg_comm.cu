@@ -399,6 +399,14 @@ hdg_status hdg_comm_pingpong(hdg_context* c, int32_t iters, double* usec_per_exc
     return HDG_OK;
 }
 
+hdg_status hdg_get_ghost_cells(const hdg_context* c, int64_t* ids) {
+    if (!c || !ids) return HDG_ERR_INVALID;
+    if (!c->have_mesh) return set_err(const_cast<hdg_context*>(c), HDG_ERR_INVALID, "no mesh");
+    if (c->comm && c->comm->nranks > 1)
+        for (size_t i = 0; i < c->comm->ghost_cells.size(); ++i) ids[i] = c->comm->ghost_cells[i];
+    return HDG_OK;
+}
+
 hdg_status hdg_get_partition(const hdg_context* c, int64_t out[8]) {
     if (!c || !out) return HDG_ERR_INVALID;
     if (!c->have_mesh) return set_err(const_cast<hdg_context*>(c), HDG_ERR_INVALID, "no mesh");

@@ -896,10 +896,23 @@ template <int K> static bool sparsity_matches(const DevTables<K>& D) {
     return true;
 }
 
+// The constant tables are per (device, order), shared by every context of that order on the device.  Whoever uploaded last
+// owns them: a context re-uploads when another one (e.g. a different quad_degree) has used them since; hdg_destroy releases.
+constexpr int MAX_DEVICES = 16;
+static const hdg_context* g_table_owner[MAX_DEVICES][MAX_ORDER + 1] = {};
+static const hdg_context*& table_owner(const hdg_context* c) { return g_table_owner[c->device & (MAX_DEVICES - 1)][c->tab.order]; }
+void release_tables(const hdg_context* c) {
+    if (c->tab.order >= 1 && c->tab.order <= MAX_ORDER && table_owner(c) == c) table_owner(c) = nullptr;
+}
+
 template <int K, typename Sym> static hdg_status upload_dev_tables(hdg_context* c, const Sym& symbol) {
     static DevTables<K> D;
     fill_dev_tables<K>(c->tab, D);
+    // the tables are shared by every context of this order on this device: kernels of the previous owner may still be
+    // running on its (non-blocking) stream, and from here on the tables are this context's
+    HDG_CUDA(c, cudaDeviceSynchronize());
     HDG_CUDA(c, cudaMemcpyToSymbol(symbol, &D, sizeof(D)));
+    table_owner(c) = c;
     c->quad_ok = sparsity_matches<K>(D);
     return HDG_OK;
 }
@@ -930,9 +943,6 @@ hdg_status upload_tables(hdg_context* c) {
     return HDG_OK;
 }
 
-// The constant tables are per order, shared by every context of that order in the process.
-// Re-upload when another context (different quad_degree) used them last.
-static const hdg_context* g_table_owner[MAX_ORDER + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 
 template <int K> static hdg_status launch_schur(hdg_context* c, const ElemArgs& a) {
     constexpr int B = SchurCfg<K>::threads;
@@ -985,11 +995,9 @@ static hdg_status launch_elements(hdg_context* c, ElemArgs a) {
         HDG_CUDA(c, cudaGetLastError());
         return HDG_OK;
     }
-    if (g_table_owner[c->tab.order] != c) {
-        HDG_CUDA(c, cudaDeviceSynchronize());
-        hdg_status st = upload_tables(c);
+    if (table_owner(c) != c) {
+        hdg_status st = upload_tables(c);      // synchronises the device and takes ownership
         if (st) return st;
-        g_table_owner[c->tab.order] = c;
     }
     if (use_quad_kernel(c)) {
         switch (c->tab.order) {
@@ -1009,25 +1017,7 @@ static hdg_status launch_elements(hdg_context* c, ElemArgs a) {
 
 hdg_status launch_element_kernels(hdg_context* c) {
     const int nt = c->tab.nt;
-#ifdef HDG_ZERO_ASYNC
-    const size_t zbytes = sizeof(double) * c->nface * (nt * nt + nt);
-    if (!c->zstream) {
-        HDG_CUDA(c, cudaStreamCreateWithFlags(&c->zstream, cudaStreamNonBlocking));
-        HDG_CUDA(c, cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
-        HDG_CUDA(c, cudaEventCreateWithFlags(&c->ev_zero, cudaEventDisableTiming));
-    }
-    if (!c->d_Kd_alt) { HDG_CUDA(c, cudaMalloc(&c->d_Kd_alt, zbytes)); c->alt_ready = false; }
-    HDG_CUDA(c, cudaEventRecord(c->ev_main, c->stream));      // everything enqueued so far may still read the current buffers
-    if (c->alt_ready) {                                       // the spare buffer was zeroed in the background: flip
-        HDG_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_zero, 0));
-        std::swap(c->d_Kd, c->d_Kd_alt);
-        c->d_rhs = c->d_Kd + c->nface * nt * nt;
-    } else {
-        HDG_CUDA(c, cudaMemsetAsync(c->d_Kd, 0, zbytes, c->stream));
-    }
-#else
     HDG_CUDA(c, cudaMemsetAsync(c->d_Kd, 0, sizeof(double) * c->nface * (nt * nt + nt), c->stream));   // Kd and rhs (contiguous)
-#endif
     ElemArgs a{};
     a.cellinfo = c->d_cellinfo; a.nodes = c->d_nodes; a.fq = c->d_fq;
     a.Ke = c->d_Ke; a.Kd = c->d_Kd; a.Ko = c->d_Ko; a.rhs = c->d_rhs; a.flags = c->d_flags;
@@ -1036,14 +1026,6 @@ hdg_status launch_element_kernels(hdg_context* c) {
     timer_start(c, c->t_elem);
     hdg_status st = launch_elements(c, a);
     timer_stop(c, c->t_elem);
-#ifdef HDG_ZERO_ASYNC
-    // zero the other buffer for the NEXT assembly: behind everything the main stream held before this call (its last
-    // readers), concurrently with the element kernel just launched
-    HDG_CUDA(c, cudaStreamWaitEvent(c->zstream, c->ev_main, 0));
-    HDG_CUDA(c, cudaMemsetAsync(c->d_Kd_alt, 0, zbytes, c->zstream));
-    HDG_CUDA(c, cudaEventRecord(c->ev_zero, c->zstream));
-    c->alt_ready = true;
-#endif
     return st;
 }
 

@@ -93,6 +93,7 @@ struct Comm {
     int32_t* d_ghost_ridx = nullptr;        // for every ghost face: its local face index on the owning rank
     int32_t* d_ghost_owner = nullptr;       // ... and the owning rank
     bool general_mesh = false;              // partition of an hdg_set_mesh mesh (no NCCL halo lists)
+    std::vector<int64_t> ghost_cells;       // global 0-based ids of the ghost cells, in local order (hdg_get_ghost_cells)
     std::vector<void*> ipc_opened;
 };
 constexpr int MAILW = 8;   // doubles per mailbox slot: epoch word + up to 7 values
@@ -141,14 +142,6 @@ struct hdg_context {
 
     // trace system, block-ELL: diagonal blocks + 4 off-diagonal blocks per face, blocks column-major nt x nt
     double* d_Kd = nullptr;          // nface * nt*nt
-#ifdef HDG_ZERO_ASYNC
-    // round-2 candidate (make EXTRA=-DHDG_ZERO_ASYNC=1): a second Kd+rhs buffer is zeroed on a side stream while the element
-    // kernel of the current assembly runs; hdg_assemble flips the two, so the 72 MB memset leaves the critical path
-    double* d_Kd_alt = nullptr;
-    cudaStream_t zstream = nullptr;
-    cudaEvent_t ev_main = nullptr, ev_zero = nullptr;
-    bool alt_ready = false;
-#endif
     double* d_Ko = nullptr;          // nface * 4 * nt*nt
     double* d_rhs = nullptr;         // ndof
     double* d_Ke = nullptr;          // ncell * ke  ([K_e | b_e])
@@ -162,9 +155,7 @@ struct hdg_context {
     double* d_binv = nullptr;        // block-Jacobi: inverted face-diagonal blocks
     int precond = 0;                 // 0 Jacobi, 1 block-Jacobi, 2 block-Jacobi + P1-vertex multigrid (hdg_mg.cu)
     void* mg = nullptr;              // hdg::MgData
-#ifdef HDG_MG_GENERAL
     void* mg_general = nullptr;      // MgGeneral (round-2 candidate, hdg_mg.cu)
-#endif
     double* d_partials = nullptr;    // reduction partials
     double* d_scal = nullptr;        // device scalars
     int32_t* d_flags = nullptr;      // error / convergence flags
@@ -198,10 +189,11 @@ void timer_stop(hdg_context* c, Timer& t);
 float timer_ms(Timer& t);
 
 // flag words in d_flags
-enum Flag : int { FLAG_BAD_GEOM = 0, FLAG_SINGULAR = 1, FLAG_DONE = 2, FLAG_ITERS = 3, FLAG_NOT_BOUNDARY = 4, FLAG_MG = 5, FLAG_GRID_PX = 6, FLAG_GRID_BAD = 7, NFLAGS = 8 };
+enum Flag : int { FLAG_BAD_GEOM = 0, FLAG_SINGULAR = 1, FLAG_DONE = 2, FLAG_ITERS = 3, FLAG_NOT_BOUNDARY = 4, FLAG_MG = 5, FLAG_GRID_PX = 6, FLAG_GRID_BAD = 7, FLAG_BAD_ID = 8, NFLAGS = 12 };
 
 // ---- per-translation-unit entry points ------------------------------------------------------
 hdg_status upload_tables(hdg_context* c);                       // hdg_element.cu
+void release_tables(const hdg_context* c);                      // hdg_element.cu: gives up the __constant__ tables on destroy
 hdg_status launch_element_kernels(hdg_context* c);              // hdg_element.cu
 hdg_status condensed_of_cell(hdg_context* c, int64_t cell, double* At, double* bt);  // hdg_element.cu
 

@@ -110,6 +110,26 @@ static hdg_status exclusive_scan(hdg_context* c, const int32_t* in, int64_t n, i
 // ------------------------------------------------------------------------------------------
 // mesh from host arrays (Julia layouts, 1-based int64)
 // ------------------------------------------------------------------------------------------
+// Range check of the 1-based ids handed over by hdg_set_mesh (the reference would throw a BoundsError at the first use):
+// node ids in [1, nnode], face ids in [1, nface], cell ids of the face table in [0, ncell].  flag = 1 + first offender kind.
+__global__ void check_mesh_ids(const int64_t* __restrict__ cells, int64_t ncell, int64_t nnode, const int64_t* __restrict__ faces,
+                               int64_t nface, int32_t* __restrict__ flag) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < ncell) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int64_t v = cells[6 * i + k], f = cells[6 * i + 3 + k];
+            if (v < 1 || v > nnode) atomicCAS(flag, 0, 1);
+            if (f < 1 || f > nface) atomicCAS(flag, 0, 2);
+        }
+    }
+    if (faces && i < nface) {
+        const int64_t v1 = faces[i], v2 = faces[i + nface], c1 = faces[i + 2 * nface], c2 = faces[i + 3 * nface];
+        if (v1 < 1 || v1 > nnode || v2 < 1 || v2 > nnode) atomicCAS(flag, 0, 3);
+        if (c1 < 1 || c1 > ncell || c2 < 0 || c2 > ncell) atomicCAS(flag, 0, 4);
+    }
+}
+
 __global__ void convert_faces(const int64_t* __restrict__ faces, int64_t nface, int32_t* __restrict__ facecell,
                               int32_t* __restrict__ facenode) {
     int64_t f = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -529,11 +549,6 @@ void free_mesh(hdg_context* c) {
     F(c->d_cellinfo); F(c->d_nodes); F(c->d_facecell); F(c->d_facenode); F(c->d_bfaces); F(c->d_isbc);
     F(c->d_kcol); F(c->d_fq); F(c->d_Kd); F(c->d_Ko); F(c->d_Ke); F(c->d_bcval);
     c->d_rhs = nullptr;   // lives behind d_Kd (one allocation, one memset per assembly)
-#ifdef HDG_ZERO_ASYNC
-    if (c->zstream) cudaStreamSynchronize(c->zstream);
-    F(c->d_Kd_alt);
-    c->alt_ready = false;
-#endif
     if (c->d_p) comm_unshare_vectors(c);   // close the neighbours' mappings before the vectors go away
     F(c->d_x); F(c->d_p); F(c->d_Ap);
     c->d_r = c->d_dinv = nullptr;          // r and Dinv live inside the d_p region
@@ -546,6 +561,9 @@ void free_mesh(hdg_context* c) {
 // Device buffers are kept across hdg_set_mesh / hdg_set_rectangle_mesh calls with unchanged sizes
 // (cudaMalloc / cudaFree of ~1 GB costs far more than re-uploading the mesh).
 static bool same_capacity(const hdg_context* c, int64_t ncell, int64_t nnode, int64_t nface, int64_t nbface) {
+    // several GPUs: the decision would have to be collective (a neighbour whose sizes did change frees the vector region this
+    // rank has mapped and re-shares it in its next solve) - every mesh change goes through free_mesh / re-share there
+    if (comm_active(c)) return false;
     return c->d_cellinfo && c->d_Ke && c->cap_ncell == ncell && c->cap_nnode == nnode && c->cap_nface == nface &&
            c->cap_nbface >= nbface;
 }
@@ -710,6 +728,7 @@ static hdg_status mesh_from_host_partitioned(hdg_context* c, const int64_t* cell
     m->cell_begin = cb; m->face_begin = fb; m->ncell_global = ncell; m->nface_global = nface;
     m->nbelow = m->nabove = 0;
     m->general_mesh = true;
+    m->ghost_cells = gcells;
     comm_free_halo(c);
     st = comm_set_ghosts(c, ridx, owner);
     if (st) return st;
@@ -756,6 +775,17 @@ hdg_status mesh_from_host(hdg_context* c, const int64_t* cells, int64_t ncell, c
     if (faces) HDG_CUDA(c, cudaMemcpyAsync(d_faces, faces, sizeof(int64_t) * 4 * nface, cudaMemcpyHostToDevice, c->stream));
     HDG_CUDA(c, cudaMemcpyAsync(c->d_nodes, nodes, sizeof(double) * 2 * nnode, cudaMemcpyHostToDevice, c->stream));
     const int B = 256;
+    {   // ids are used as device indices from here on: reject a malformed (e.g. 0-based) mesh first
+        HDG_CUDA(c, cudaMemsetAsync(c->d_flags + FLAG_BAD_ID, 0, sizeof(int32_t), c->stream));
+        check_mesh_ids<<<(unsigned)ceil_div(std::max(ncell, nface), B), B, 0, c->stream>>>(d_cells, ncell, nnode, faces ? d_faces : nullptr, nface,
+                                                                                         c->d_flags + FLAG_BAD_ID);
+        c->launches += 1;
+        HDG_CUDA(c, cudaMemcpyAsync(c->h_flags + FLAG_BAD_ID, c->d_flags + FLAG_BAD_ID, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+        static const char* what[] = {"", "node id of a cell", "face id of a cell", "node id of a face", "cell id of a face"};
+        const int bad = c->h_flags[FLAG_BAD_ID];
+        if (bad) return set_err(c, HDG_ERR_INVALID, std::string("mesh arrays: ") + what[bad & 7] + " out of range (ids are 1-based: nodes 1..nnode, faces 1..nface, cells 1..ncell)");
+    }
     if (faces) {
         convert_faces<<<(unsigned)ceil_div(nface, B), B, 0, c->stream>>>(d_faces, nface, c->d_facecell, c->d_facenode);
     } else {
@@ -949,6 +979,8 @@ hdg_status mesh_rectangle(hdg_context* c, int64_t nx, int64_t ny, double llx, do
             }
         }
         m->general_mesh = false;
+        m->ghost_cells.clear();      // the lower-left triangles of the quad row above the strip
+        if (j1 < ny) for (int64_t i = 0; i < nx; ++i) m->ghost_cells.push_back(2 * (j1 * nx + i));
         st = comm_set_ghosts(c, ridx, owner);
         if (st) return st;
     }

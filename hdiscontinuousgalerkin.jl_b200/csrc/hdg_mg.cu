@@ -420,15 +420,13 @@ __global__ void __launch_bounds__(RB) mg_dot(const double* __restrict__ a, const
     if (threadIdx.x == 0) part[blockIdx.x] = scale * tot;
 }
 
-#ifdef HDG_MG_GENERAL
 // ======================================================================================================================
-// ROUND-2 CANDIDATE, compiled only with -DHDG_MG_GENERAL (make EXTRA=-DHDG_MG_GENERAL=1); the default library does not
-// contain it (same object code as without this block).  Meshes without grid structure: hierarchy-free vertex-space term
-// z += P C_m(A_c) P' r with the kernels of experimental/mg_general.cuh (bodies checked on the CPU: tools/check_mg_general.py).
-// The host wiring below has NOT run on a GPU.
+// Meshes without grid structure (parse_mesh_triangle input, permuted node ids, Delaunay meshes): hierarchy-free vertex-space
+// term  z += P C_m(A_c) P' r  with the kernels of hdg_mg_general.cuh (ELL vertex operator, Jacobi-scaled Chebyshev polynomial;
+// bodies also checked on the CPU against scipy: tools/check_mg_general.py).  A fixed polynomial, so plain CG still applies.
 // ======================================================================================================================
 }  // namespace hdg
-#include "experimental/mg_general.cuh"
+#include "hdg_mg_general.cuh"
 namespace hdg {
 
 constexpr int MGX_CHEB_STEPS = 16;          // tools/cheb_prototype.py: m = 16, alpha = 100
@@ -561,18 +559,13 @@ static hdg_status mgx_apply(hdg_context* c, const double* r, double* z, double* 
     mgx_prolong<<<(unsigned)ceil_div(c->nface_own, 256), 256, 0, s>>>(c->nface_own, NT, c->d_facenode, c->d_isbc, g->x, z);
     return HDG_OK;
 }
-#endif  // HDG_MG_GENERAL
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
 static inline unsigned nblk(int64_t n, int b = 256) { return (unsigned)ceil_div(n, b); }
 
-#ifdef HDG_MG_GENERAL
 static void mgx_free(hdg_context* c);
-#endif
 void mg_free(hdg_context* c) {
-#ifdef HDG_MG_GENERAL
     mgx_free(c);
-#endif
     MgData* m = static_cast<MgData*>(c->mg);
     if (!m) return;
     if (m->pool) cudaFree(m->pool);
@@ -587,13 +580,8 @@ template <int NT> static hdg_status mg_setup_t(hdg_context* c) {
     const bool multi = comm_active(c);
     if (multi && c->comm->general_mesh)
         return set_err(c, HDG_ERR_INVALID, "on several GPUs the multigrid preconditioner needs hdg_set_rectangle_mesh (strip partition)");
-#ifdef HDG_MG_GENERAL
-    if (c->grid_px < 2 || c->grid_py < 2) return mgx_setup(c);        // no grid structure: hierarchy-free vertex term (round-2 candidate)
+    if (c->grid_px < 2 || c->grid_py < 2) return mgx_setup(c);        // no grid structure: hierarchy-free vertex term
     mgx_free(c);
-#endif
-    if (c->grid_px < 2 || c->grid_py < 2)
-        return set_err(c, HDG_ERR_INVALID, "the multigrid preconditioner needs the triangulation of rectangle_mesh (hdg_set_rectangle_mesh, or "
-                                           "hdg_set_mesh with rectangle_mesh's node numbering)");
     MgData* m = static_cast<MgData*>(c->mg);
     const int64_t nnode_g = c->grid_px * c->grid_py;       // the GLOBAL vertex grid (== the local one on a single GPU)
     if (m && (m->nnode != nnode_g || m->nface != c->nface || m->nx != c->grid_px - 1 || m->ny != c->grid_py - 1)) { mg_free(c); m = nullptr; }
@@ -727,9 +715,7 @@ template <int NT> static hdg_status mg_apply_t(hdg_context* c, const double* r, 
 }
 
 hdg_status mg_apply(hdg_context* c, const double* r, double* z, double* part, int np) {
-#ifdef HDG_MG_GENERAL
     if (c->mg_general) return mgx_apply(c, r, z, part, np);
-#endif
     switch (c->tab.nt) {
         case 2: return mg_apply_t<2>(c, r, z, part, np);
         case 3: return mg_apply_t<3>(c, r, z, part, np);
@@ -742,9 +728,7 @@ hdg_status mg_apply(hdg_context* c, const double* r, double* z, double* part, in
 int mg_levels(const hdg_context* c) { return c->mg ? static_cast<const MgData*>(c->mg)->nlev : 0; }
 // kernels one mg_apply enqueues: restrict_trace, fused tail, dot, prolong_trace + 5 per unfused level
 int mg_launches_per_apply(const hdg_context* c) {
-#ifdef HDG_MG_GENERAL
     if (c->mg_general) return 3 + 2 * MGX_CHEB_STEPS;
-#endif
     return c->mg ? 4 + 5 * static_cast<const MgData*>(c->mg)->lf : 0;
 }
 

@@ -1,5 +1,3 @@
-// EXPERIMENTAL - NOT compiled into libhdg_b200.so and NOT run on a GPU yet (round-2 candidate).
-//
 // Vertex-space term of the multigrid preconditioner for meshes WITHOUT grid structure, hierarchy-free variant
 // (tools/cheb_prototype.py):   z += P C_m(A_c) P' r,   A_c = P'AP in ELL form on the vertex graph,
 // C_m = m steps of the Jacobi-scaled Chebyshev iteration on [lmax/alpha, lmax], lmax from the Gershgorin bound.

@@ -152,7 +152,9 @@ hdg_status hdg_basis_value(int32_t kind, int32_t j, const double* xi, double* va
 
 /* ---- source -------------------------------------------------------------------------------
  * Pre-evaluated f(x_q): ncell x nq doubles, fq[c*nq+q] = f(spatial_coordinate(Wh,q,coords_c))
- * (function_value, src/DiscreteFunctions.jl:6-24).  Required when source_id == 0. */
+ * (function_value, src/DiscreteFunctions.jl:6-24).  Required when source_id == 0.
+ * Several GPUs: the rows are this rank's LOCAL cells - the owned cells in id order (hdg_get_partition out[0..1]) followed by
+ * the ghost cells it recomputes, in the order of hdg_get_ghost_cells (out[6] of them): (ncell_own + nghost) x nq doubles. */
 hdg_status hdg_set_source_values(hdg_context* ctx, const double* fq);
 
 /* ---- hot path -----------------------------------------------------------------------------
@@ -225,6 +227,9 @@ hdg_status hdg_comm_init(hdg_context* ctx, int32_t rank, int32_t nranks, const u
  * ncell_global, nface_global, ghost cells held, ghost faces held}.  Cell and face ids are the reference's
  * global numbering minus one; trace dofs of face f are nt*f .. nt*f+nt-1. */
 hdg_status hdg_get_partition(const hdg_context* ctx, int64_t out[8]);
+/* Global 0-based ids of the ghost cells this rank holds (out[6] of hdg_get_partition), in local order: the cells of other
+ * ranks that touch an owned face and are recomputed here instead of exchanged. */
+hdg_status hdg_get_ghost_cells(const hdg_context* ctx, int64_t* ids);
 /* Measurement helper: mean latency (microseconds) of one all-to-all mailbox exchange over peer memory. */
 hdg_status hdg_comm_pingpong(hdg_context* ctx, int32_t iters, double* usec_per_exchange);
 

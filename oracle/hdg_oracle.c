@@ -349,6 +349,128 @@ int hdg_c_pcg(int64_t ndof, const int64_t* colptr, const int64_t* rowval, const 
     return it > maxit ? maxit : it;
 }
 
+/*
+ * rectangle_mesh(TriangleCell,(nx,ny),LL,UR), src/generate_mesh.jl:101-143: nodes by _generate_2d_nodes! (:1-18, the same
+ * floating-point expression), two triangles per quad made counter-clockwise by _check_node_data (:49-57), and the sequential
+ * first-encounter face numbering of _build_cells (:20-46) - the reference's Dict{(min,max) => face} is an open-addressing hash
+ * table here.  Outputs (1-based, the numpy oracle's layouts): cells ncell x 3, cell_faces ncell x 3, nodes nnode x 2,
+ * faces nface x 4 row-major (v1 v2 cell1 cell2|0).  Returns the number of faces.  Sequential like the reference.
+ */
+__attribute__((optimize("fp-contract=off")))
+static void ccw(const double* nodes, int64_t n1, int64_t n2, int64_t n3, int64_t out[3]) {
+    const double ax = nodes[2 * (n2 - 1)] - nodes[2 * (n1 - 1)], ay = nodes[2 * (n2 - 1) + 1] - nodes[2 * (n1 - 1) + 1];
+    const double bx = nodes[2 * (n3 - 1)] - nodes[2 * (n1 - 1)], by = nodes[2 * (n3 - 1) + 1] - nodes[2 * (n1 - 1) + 1];
+    out[0] = n1;
+    if (ax * by - ay * bx < 0) { out[1] = n3; out[2] = n2; } else { out[1] = n2; out[2] = n3; }
+}
+
+/* no FMA contraction: the coordinates must be the reference's separately rounded products and sums, bit for bit */
+__attribute__((optimize("fp-contract=off")))
+int64_t hdg_c_rectangle_mesh(int64_t nx, int64_t ny, double llx, double lly, double urx, double ury, int64_t* cells,
+                             int64_t* cell_faces, double* nodes, int64_t* faces) {
+    const int64_t nnx = nx + 1, nny = ny + 1;
+    const double LRx = urx, LRy = lly, ULx = llx, ULy = ury;
+    int64_t p = 0;
+    for (int64_t i = 0; i < nny; ++i) {
+        const double rb = (double)i / (double)(nny - 1);
+        const double x0 = llx * (1 - rb) + rb * ULx, x1 = LRx * (1 - rb) + rb * urx;
+        const double y0 = lly * (1 - rb) + rb * ULy, y1 = LRy * (1 - rb) + rb * ury;
+        for (int64_t j = 0; j < nnx; ++j) {
+            const double r = (double)j / (double)(nnx - 1);
+            nodes[2 * p] = x0 * (1 - r) + r * x1;
+            nodes[2 * p + 1] = y0 * (1 - r) + r * y1;
+            ++p;
+        }
+    }
+    const int64_t ncell = 2 * nx * ny;
+    /* hash table: key = (min << 32 | max), value = face id */
+    uint64_t cap = 16;
+    while (cap < (uint64_t)(3 * ncell) * 2) cap <<= 1;
+    uint64_t* keys = (uint64_t*)calloc(cap, sizeof(uint64_t));
+    int64_t* vals = (int64_t*)malloc(cap * sizeof(int64_t));
+    static const int EN[3][2] = {{1, 2}, {2, 0}, {0, 1}};   /* reference_edge_nodes ((2,3),(3,1),(1,2)), src/shapes.jl:14 */
+    int64_t face_idx = 0, n_el = 0;
+    for (int64_t j = 1; j <= ny; ++j)
+        for (int64_t i = 1; i <= nx; ++i)
+            for (int half = 0; half < 2; ++half) {
+                int64_t el[3];
+#define NA(I, J) ((I) + ((J) - 1) * nnx)
+                if (half == 0) ccw(nodes, NA(i, j), NA(i + 1, j), NA(i, j + 1), el);
+                else ccw(nodes, NA(i + 1, j), NA(i + 1, j + 1), NA(i, j + 1), el);
+#undef NA
+                ++n_el;
+                for (int e = 0; e < 3; ++e) {
+                    const int64_t v1 = el[EN[e][0]], v2 = el[EN[e][1]];
+                    const uint64_t lo = (uint64_t)(v1 < v2 ? v1 : v2), hi = (uint64_t)(v1 < v2 ? v2 : v1);
+                    const uint64_t key = (lo << 32) | hi;
+                    uint64_t h = (key * 0x9E3779B97F4A7C15ull) & (cap - 1);
+                    while (keys[h] != 0 && keys[h] != key) h = (h + 1) & (cap - 1);
+                    if (keys[h] == key) {
+                        const int64_t fid = vals[h];
+                        cell_faces[3 * (n_el - 1) + e] = fid;
+                        if (n_el != faces[4 * (fid - 1) + 3]) faces[4 * (fid - 1) + 3] = n_el;
+                    } else {
+                        ++face_idx;
+                        keys[h] = key; vals[h] = face_idx;
+                        faces[4 * (face_idx - 1)] = v1; faces[4 * (face_idx - 1) + 1] = v2;
+                        faces[4 * (face_idx - 1) + 2] = n_el; faces[4 * (face_idx - 1) + 3] = 0;
+                        cell_faces[3 * (n_el - 1) + e] = face_idx;
+                    }
+                }
+                cells[3 * (n_el - 1)] = el[0]; cells[3 * (n_el - 1) + 1] = el[1]; cells[3 * (n_el - 1) + 2] = el[2];
+            }
+    free(keys); free(vals);
+    return face_idx;
+}
+
+/*
+ * get_u_sigma!(sigma_h, u_h, uhat_h, uhat, K_e, b_e, mesh), examples/poisson2D_HDG.jl:197-212 (the hard-coded nt = 2 slice of
+ * :205-206 generalised to nt): per cell gather uhat_e in local-face order, dof = K_e uhat_e + b_e.  Outputs are the m_values
+ * arrays as the numpy oracle returns them: sigma ncell x 2n, u ncell x n (row-major).
+ */
+void hdg_c_recover(int n, int nt, int64_t ncell, const int64_t* cell_faces, const double* Ke, const double* be,
+                   const double* uhat, int nthreads, double* sigma, double* u) {
+    const int m = 3 * n, t = 3 * nt;
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+    for (int64_t c = 0; c < ncell; ++c) {
+        double ue[15];
+        for (int k = 0; k < 3; ++k)
+            for (int a = 0; a < nt; ++a) ue[k * nt + a] = uhat[nt * (cell_faces[3 * c + k] - 1) + a];
+        for (int i = 0; i < m; ++i) {
+            double s = 0.0;
+            for (int j = 0; j < t; ++j) s += Ke[(c * m + i) * t + j] * ue[j];
+            s += be[c * m + i];
+            if (i < 2 * n) sigma[c * 2 * n + i] = s; else u[c * n + (i - 2 * n)] = s;
+        }
+    }
+}
+
+/* errornorm(u_h, u_ex) with u_ex = sin(pi x) sin(pi y) (examples/poisson2D_HDG.jl:216), src/DiscreteFunctions.jl:97-120:
+ * squared L2 error with the cell rule.  N[n][nq], M[3][nq], qw[nq]; u ncell x n row-major. */
+double hdg_c_errornorm(int n, int nq, const double* N, const double* M, const double* qw, int64_t ncell, const int64_t* cells,
+                       const double* nodes, const double* u, int nthreads) {
+    const double pi = 3.141592653589793;
+    double tot = 0.0;
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for num_threads(nthreads) schedule(static) reduction(+ : tot)
+    for (int64_t c = 0; c < ncell; ++c) {
+        double x[3][2];
+        for (int g = 0; g < 3; ++g) { x[g][0] = nodes[2 * (cells[3 * c + g] - 1)]; x[g][1] = nodes[2 * (cells[3 * c + g] - 1) + 1]; }
+        const double detJ = (x[1][0] - x[0][0]) * (x[2][1] - x[0][1]) - (x[2][0] - x[0][0]) * (x[1][1] - x[0][1]);
+        double el = 0.0;
+        for (int q = 0; q < nq; ++q) {
+            double uq = 0.0, xq = 0.0, yq = 0.0;
+            for (int i = 0; i < n; ++i) uq += u[c * n + i] * N[i * nq + q];
+            for (int g = 0; g < 3; ++g) { xq += M[g * nq + q] * x[g][0]; yq += M[g * nq + q] * x[g][1]; }
+            const double d = uq - sin(pi * xq) * sin(pi * yq);
+            el += d * d * (detJ * qw[q]);
+        }
+        tot += el;
+    }
+    return tot;
+}
+
 int hdg_c_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -445,11 +445,6 @@ def test_multigrid_through_set_mesh_arrays(order, qd, nx, ny):
     assert xs[0][1] == xs[1][1] and np.array_equal(xs[0][0], xs[1][0])
 
 
-# round-2 candidate: built only with `make EXTRA=-DHDG_MG_GENERAL=1` (csrc/hdg_mg.cu); the default library rejects such meshes
-_MG_GENERAL = b"mg_general" in hdg.load().hdg_version()
-
-
-@pytest.mark.skipif(not _MG_GENERAL, reason="library built without -DHDG_MG_GENERAL (round-2 candidate)")
 @pytest.mark.parametrize("order,qd", [(1, 2), (2, 4), (3, 6)])
 def test_multigrid_term_on_unstructured_meshes(order, qd):
     """Hierarchy-free vertex-space term (Chebyshev on the ELL vertex operator) on meshes without grid structure."""
@@ -479,20 +474,21 @@ def test_multigrid_term_on_unstructured_meshes(order, qd):
     assert np.array_equal(xm.to_numpy(), xm2.to_numpy()) and im["iterations"] == im2["iterations"]
 
 
-def test_multigrid_rejects_other_triangulations():
-    if _MG_GENERAL:
-        pytest.skip("this build carries the general-mesh vertex term")
+def test_multigrid_on_other_triangulations():
+    """precond="mg" on meshes without grid structure (the reference solves any mesh with K \\ b, examples/poisson2D_HDG.jl:195):
+    the reference's unstructured fixture and rectangle_mesh with permuted node ids take the general vertex term."""
     mo = orc.parse_mesh_triangle(triangle_root("figure.1"))      # unstructured, 62 cells
     mesh = host_mesh_from_oracle(mo)
     Vh, Wh, Mh = _spaces(mesh, 1, 2)
     K, b, _, _ = hdg.doassemble(Vh, Wh, Mh)
     hdg.apply_(K, b, hdg.Dirichlet(hdg.TrialFunction(Mh), mesh, "boundary", lambda x: 0))
-    with pytest.raises(hdg.HDGError):
-        hdg.solve(K, b, precond="mg")
-    x, info = hdg.solve(K, b, precond="block")      # the context stays usable
-    assert info["converged"]
-    # rectangle_mesh with permuted node ids: same triangulation, but not the grid numbering the hierarchy is built on
-    mo = orc.rectangle_mesh(5, 4)
+    xb, ib = hdg.solve(K, b, rtol=1e-13, precond="block")
+    xm, im = hdg.solve(K, b, rtol=1e-13, precond="mg")
+    assert im["converged"] and relerr(xm.to_numpy(), xb.to_numpy()) < RTOL
+    ro = orc.run_poisson(mo, 1, 2)
+    assert relerr(xm.to_numpy(), ro["uhat"]) < RTOL
+    # rectangle_mesh with permuted node ids: same triangulation, but not the grid numbering the geometric hierarchy is built on
+    mo = orc.rectangle_mesh(12, 10)
     perm = np.random.default_rng(3).permutation(mo.nodes.shape[0])
     inv = np.empty_like(perm)
     inv[perm] = np.arange(perm.size)
@@ -503,8 +499,9 @@ def test_multigrid_rejects_other_triangulations():
     Vh, Wh, Mh = _spaces(mesh, 1, 2)
     K, b, _, _ = hdg.doassemble(Vh, Wh, Mh)
     hdg.apply_(K, b, hdg.Dirichlet(hdg.TrialFunction(Mh), mesh, "boundary", lambda x: 0))
-    with pytest.raises(hdg.HDGError):
-        hdg.solve(K, b, precond="mg")
+    xb, ib = hdg.solve(K, b, rtol=1e-13, precond="block")
+    xm, im = hdg.solve(K, b, rtol=1e-13, precond="mg")
+    assert im["converged"] and im["iterations"] < ib["iterations"] and relerr(xm.to_numpy(), xb.to_numpy()) < RTOL
 
 
 def test_maxit_reports_not_converged():
@@ -636,4 +633,59 @@ def test_c2_size_properties():
     # k=1: err^2 ~ C h^4; 10x10 on the unit square gives 5.36e-5 at h=0.1  ->  h=0.002 gives ~8.6e-12
     assert 1e-12 < e.value < 5e-11, e.value
     assert rhs.shape == bb.shape
+    ctx.close()
+
+
+# ---------------------------------------------------------------------------------- robustness (round-1 advisor findings)
+def test_two_contexts_of_one_order_do_not_share_stale_tables():
+    """The __constant__ reference tables are per order; creating a second context of the same order with another cell rule
+    between two assemblies of the first must not change the first one's load vector."""
+    mo = orc.rectangle_mesh(6, 5)
+    mesh = host_mesh_from_oracle(mo)
+    a = hdg._Context(1, 2)
+    a.set_mesh(mesh)
+    hdg.check(a.lib.hdg_assemble(a.h), a.h)
+    rhs0 = np.empty(a.sizes().ndof)
+    hdg.check(a.lib.hdg_get_rhs(a.h, hdg.api.f64p(rhs0)), a.h)
+    b = hdg._Context(1, 5)                 # same order, 7-point rule: re-uploads the shared tables
+    b.set_mesh(mesh)
+    hdg.check(b.lib.hdg_assemble(b.h), b.h)
+    rhsb = np.empty(b.sizes().ndof)
+    hdg.check(b.lib.hdg_get_rhs(b.h, hdg.api.f64p(rhsb)), b.h)
+    for _ in range(2):                     # a again, with b alive and after b is gone
+        hdg.check(a.lib.hdg_assemble(a.h), a.h)
+        rhs1 = np.empty_like(rhs0)
+        hdg.check(a.lib.hdg_get_rhs(a.h, hdg.api.f64p(rhs1)), a.h)
+        assert np.array_equal(rhs0, rhs1)
+        Ate, bte = np.empty((6, 6), order="F"), np.empty(6)
+        hdg.check(a.lib.hdg_get_condensed(a.h, 3, hdg.api.f64p(Ate), hdg.api.f64p(bte)), a.h)
+        ro = orc.doassemble(mo, orc.build_tables(1, 2))
+        assert relerr(rhs1, ro.rhs) < RTOL
+        b.close()
+    assert not np.array_equal(rhs0, rhsb)  # the two rules do integrate f differently
+    a.close()
+
+
+@pytest.mark.parametrize("what", ["zero_based_nodes", "face_id_too_large", "face_table_cell", "face_table_node"])
+def test_malformed_mesh_ids_are_rejected(what):
+    """Ids are device indices once the mesh is set: a 0-based / out-of-range mesh gets HDG_ERR_INVALID (the reference would
+    throw a BoundsError), not out-of-bounds device writes; the context stays usable."""
+    mo = orc.rectangle_mesh(4, 3)
+    cells = np.hstack([mo.cells, mo.cell_faces]).astype(np.int64)
+    faces = np.asfortranarray(mo.faces.astype(np.int64))
+    if what == "zero_based_nodes":
+        cells[:, :3] -= 1
+    elif what == "face_id_too_large":
+        cells[5, 4] = faces.shape[0] + 1
+    elif what == "face_table_cell":
+        faces[2, 3] = cells.shape[0] + 7
+    else:
+        faces[1, 0] = 0
+    bad = hdg.PolygonalMesh(cells, mo.nodes, faces, {"boundary": set(mo.facesets["boundary"])})
+    ctx = hdg._Context(1, 2)
+    with pytest.raises(hdg.HDGError) as ei:
+        ctx.set_mesh(bad)
+    assert ei.value.status == 1 and "out of range" in str(ei.value)
+    ctx.set_mesh(host_mesh_from_oracle(mo))           # still usable
+    hdg.check(ctx.lib.hdg_assemble(ctx.h), ctx.h)
     ctx.close()

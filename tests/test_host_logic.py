@@ -250,3 +250,29 @@ def test_function_space_accessors_reproduce_the_reference_test_loop():
     assert np.allclose([Mh.getfacedetJdS(f, 1) for f in (1, 2, 3)], [sq2 / 4, sq2 / 4, 0.5])                # :39-41 (state after the loop)
     with pytest.raises(hdg.BadGeometryError):
         Wh.reinit_(mesh.nodes[mesh.cells[0, [0, 2, 1]] - 1])                  # clockwise cell: det(J) is not positive
+
+
+# ---- the C oracle's full-size helpers (used by tests/test_full_size_parity.py and bench.py) against the numpy oracle ----
+@pytest.mark.parametrize("nx,ny,LL,UR", [(1, 1, (0, 0), (1, 1)), (7, 5, (0.0, 0.0), (2.0, 1.0)), (10, 10, (0, 0), (1, 1)),
+                                         (3, 17, (-1.0, 0.5), (2.0, 3.0)), (40, 1, (0.0, 0.0), (1.0, 1.0))])
+def test_c_rectangle_mesh_is_the_numpy_oracles_bit_for_bit(nx, ny, LL, UR):
+    a, b = orc.rectangle_mesh(nx, ny, LL, UR), occ.rectangle_mesh(nx, ny, LL, UR)
+    assert np.array_equal(a.cells, b.cells) and np.array_equal(a.cell_faces, b.cell_faces)
+    assert np.array_equal(a.faces, b.faces) and np.array_equal(a.nodes, b.nodes)       # coordinates bit for bit
+    assert a.facesets["boundary"] == b.facesets["boundary"]
+
+
+@pytest.mark.parametrize("order,qd", [(1, 2), (3, 6)])
+def test_c_recover_errornorm_apply_match_numpy_oracle(order, qd):
+    mesh = orc.rectangle_mesh(6, 5, (0.0, 0.0), (2.0, 1.0))
+    r = orc.run_poisson(mesh, order, qd)
+    tab, asm = r["tab"], r["asm"]
+    sig, u = occ.recover(mesh, tab, r["uhat"], asm.K_e, asm.b_e, nthreads=2)
+    assert np.abs(sig - r["sigma"]).max() < 1e-13 * np.abs(r["sigma"]).max()
+    assert np.abs(u - r["u"]).max() < 1e-13 * np.abs(r["u"]).max()
+    assert abs(occ.errornorm(mesh, tab, r["u"], nthreads=2) - r["err2"]) < 1e-12 * r["err2"]
+    K2, f2, m2, dset = occ.apply_dirichlet_homogeneous(asm.K, asm.rhs, r["dofs"])
+    assert m2 == pytest.approx(r["meandiag"], rel=1e-15)
+    assert np.array_equal(K2.indptr, r["K_bc"].indptr) and np.array_equal(K2.indices, r["K_bc"].indices)
+    assert np.array_equal(K2.data, r["K_bc"].data) and np.array_equal(f2, r["rhs_bc"])
+    assert dset.sum() == len(r["dofs"])

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Host emulation of csrc/experimental/mg_general.cuh (round-2 candidate, not part of the library): the kernel bodies are
+"""Host emulation of csrc/hdg_mg_general.cuh: the kernel bodies are
 compiled for the CPU (-DHDG_HOST_EMU), run in serial loops over their index, and checked against scipy:
   * the ELL vertex operator equals P'AP,
   * restrict -> m Chebyshev steps -> prolong equals the numpy formulation of tools/cheb_prototype.py,
@@ -24,7 +24,7 @@ from mg_prototype import block_jacobi, pcg, prolongation  # noqa: E402
 
 SRC = r'''
 #define HDG_HOST_EMU 1
-#include "experimental/mg_general.cuh"
+#include "hdg_mg_general.cuh"
 using namespace hdg;
 extern "C" {
 int emu_maxval() { return MGX_MAXVAL; }
