@@ -562,22 +562,29 @@ def main():
                 info_d = hdg.api.SolveInfo()
                 err_d = C.c_double()
 
+                dparts = [0.0] * 6      # seconds per call of the driver (every call returns synchronised)
+
                 def driver_step():
-                    e2e_step()
-                    hdg.check(lib.hdg_apply_dirichlet(ctx2.h, None), ctx2.h)
-                    hdg.check(lib.hdg_solve(ctx2.h, args.rtol, args.maxit, C.byref(info_d)), ctx2.h)
-                    hdg.check(lib.hdg_recover(ctx2.h), ctx2.h)
-                    hdg.check(lib.hdg_get_mvalues(ctx2.h, hdg.api.f64p(sig_out), hdg.api.f64p(u_out), None), ctx2.h)
-                    hdg.check(lib.hdg_errornorm(ctx2.h, 1, C.byref(err_d)), ctx2.h)
+                    t = [time.perf_counter()]
+                    e2e_step(); t.append(time.perf_counter())
+                    hdg.check(lib.hdg_apply_dirichlet(ctx2.h, None), ctx2.h); t.append(time.perf_counter())
+                    hdg.check(lib.hdg_solve(ctx2.h, args.rtol, args.maxit, C.byref(info_d)), ctx2.h); t.append(time.perf_counter())
+                    hdg.check(lib.hdg_recover(ctx2.h), ctx2.h); t.append(time.perf_counter())
+                    hdg.check(lib.hdg_get_mvalues(ctx2.h, hdg.api.f64p(sig_out), hdg.api.f64p(u_out), None), ctx2.h); t.append(time.perf_counter())
+                    hdg.check(lib.hdg_errornorm(ctx2.h, 1, C.byref(err_d)), ctx2.h); t.append(time.perf_counter())
+                    for i in range(6):
+                        dparts[i] += t[i + 1] - t[i]
 
                 driver_step()
                 env.barrier()
+                dparts[:] = [0.0] * 6
                 t0 = time.perf_counter()
                 for _ in range(3):
                     driver_step()
                 dtd = env.maxf((time.perf_counter() - t0) / 3)
                 e2e.update({"driver_ms_per_step": dtd * 1e3, "driver_elements_per_s": ncell_l * world / dtd, "driver_pcg_iterations": int(info_d.iterations),
-                            "driver_err2": err_d.value, "driver_d2h_bytes_per_step": int(rhs_out.nbytes + sig_out.nbytes + u_out.nbytes),
+                            "driver_err2": err_d.value, "driver_solve_device_ms": float(info_d.solve_ms),
+                            **{f"driver_{nm}_ms": 1e3 * dparts[i] / 3 for i, nm in enumerate(("e2e_step", "apply", "solve", "recover", "get_mvalues", "errornorm"))}, "driver_d2h_bytes_per_step": int(rhs_out.nbytes + sig_out.nbytes + u_out.nbytes),
                             "driver_what": "e2e step + hdg_apply_dirichlet + hdg_solve (multigrid PCG) + hdg_recover + hdg_get_mvalues(host) + hdg_errornorm; "
                                            "several GPUs: every rank its own strip problem"})
             except Exception as ex:      # keep the headline line even if this extra leg fails

@@ -12,6 +12,7 @@
 #include <cstring>
 
 #include "hdg_internal.h"
+#include "hdg_xgpu.cuh"
 
 namespace hdg {
 
@@ -223,6 +224,43 @@ hdg_status comm_share_vectors(hdg_context* c, void* region, int64_t ndof_own) {
     return HDG_OK;
 }
 
+hdg_status comm_share_buffer(hdg_context* c, void* mine, unsigned rank_mask, void* peers[MAXR]) {
+    Comm* m = c->comm;
+    for (int q = 0; q < MAXR; ++q) peers[q] = nullptr;
+    IpcRecord rec{};
+    HDG_CUDA(c, cudaIpcGetMemHandle(&rec.handle, mine));
+    std::vector<IpcRecord> all;
+    hdg_status st = allgather_records(c, rec, all);
+    if (st) return st;
+    for (int q = 0; q < m->nranks && q < MAXR; ++q) {
+        if (q == m->rank) { peers[q] = mine; continue; }
+        if (!((rank_mask >> q) & 1u)) continue;
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, all[q].handle, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return set_err(c, HDG_ERR_CUDA, std::string("cudaIpcOpenMemHandle(buffer): ") + cudaGetErrorString(e));
+        }
+        peers[q] = p;
+    }
+    return HDG_OK;
+}
+
+void comm_close_buffer(hdg_context* c, void* peers[MAXR]) {
+    const int me = c->comm ? c->comm->rank : -1;
+    for (int q = 0; q < MAXR; ++q) {
+        if (peers[q] && q != me) cudaIpcCloseMemHandle(peers[q]);
+        peers[q] = nullptr;
+    }
+}
+
+void comm_xg(const hdg_context* c, XgComm* out) {
+    *out = XgComm{};
+    if (!comm_p2p(c)) return;
+    const Comm* m = c->comm;
+    out->peer_mail = m->d_peer_mail; out->my_mail = m->d_mail; out->epoch = m->d_epoch; out->rank = m->rank; out->nranks = m->nranks;
+}
+
 hdg_status comm_set_ghosts(hdg_context* c, const std::vector<int32_t>& ridx, const std::vector<int32_t>& owner) {
     Comm* m = c->comm;
     if (m->d_ghost_ridx) { cudaFree(m->d_ghost_ridx); m->d_ghost_ridx = nullptr; }
@@ -240,6 +278,7 @@ hdg_status comm_set_ghosts(hdg_context* c, const std::vector<int32_t>& ridx, con
     return HDG_OK;
 }
 
+static_assert(XG_MAILW == MAILW, "mailbox slot width");
 constexpr int XG_THREADS = 256;
 constexpr int XG_MAXPART = 2048;   // == MAX_PARTIALS of hdg_solve.cu
 

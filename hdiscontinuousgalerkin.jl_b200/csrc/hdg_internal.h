@@ -238,6 +238,12 @@ void comm_destroy(hdg_context* c);
 bool comm_p2p(const hdg_context* c);
 hdg_status comm_share_vectors(hdg_context* c, void* region, int64_t ndof_own);              // maps the neighbours' regions
 void comm_unshare_vectors(hdg_context* c);
+// generic: all-gathers the IPC handle of `mine` (a cudaMalloc base pointer) and maps the regions of the ranks in `rank_mask`
+// into peers[q] (peers[rank] = mine); collective.  comm_close_buffer unmaps them.
+hdg_status comm_share_buffer(hdg_context* c, void* mine, unsigned rank_mask, void* peers[MAXR]);
+void comm_close_buffer(hdg_context* c, void* peers[MAXR]);
+struct XgComm;
+void comm_xg(const hdg_context* c, XgComm* out);                 // mailbox handles for in-kernel barriers (hdg_xgpu.cuh)
 hdg_status comm_p2p_allreduce(hdg_context* c, const double* d_partials, int np, unsigned slot_mask);   // selected partial arrays -> d_gscal, all ranks (mask 0: barrier only)
 hdg_status comm_set_ghosts(hdg_context* c, const std::vector<int32_t>& ridx, const std::vector<int32_t>& owner);
 

@@ -10,7 +10,7 @@ layout, the 64-bit offsets and the grid-stride loops are actually exercised:
   nzval, rhs                  1e-10       (max-norm, relative to the largest entry)
   K_e, b_e of sampled cells   1e-10
   K, b after apply!, meandiag 1e-10 / 1e-13
-  u_hat                       residual of the GPU solution in the ORACLE's system  ||b - K_oracle u|| / ||b|| <= 2e-12, and
+  u_hat                       backward error of the GPU solution in the ORACLE's system  ||b - K u|| / || |K||u| + |b| || <= 2e-14, and
                               (C2) max-norm distance to the port's own Jacobi-PCG solution (see the tolerance note there)
   sigma_h, u_h of ALL cells   1e-10       vs the port's get_u_sigma! applied to the port's K_e, b_e (so every K_e, b_e is covered)
   err2                        1e-9        vs the port's errornorm
@@ -101,15 +101,18 @@ def _full_size(order, qd, nx, ny, cpu_pcg):
     assert info.converged and info.iterations <= 80
     x = np.empty(s.ndof)
     hdg.check(lib.hdg_get_trace(ctx.h, hdg.api.f64p(x)), ctx.h)
+    # normwise backward error: ||K|| ||x|| is ~1e6 ||b|| here (K ~ 16, x ~ 1, b ~ 4e-5), so ||b - K x|| / ||b|| of ANY computed
+    # solution sits at ~1e-10..1e-9 (sparse direct solve 8e-11, the port's PCG 1.1e-9); the meaningful scale is |K||x| + |b|
+    # (direct solve: 1.0e-16, the port's PCG at rtol 1e-13: 1.4e-15)
     res = f2 - K2 @ x
-    assert np.linalg.norm(res) / np.linalg.norm(f2) < 2e-12
+    assert np.linalg.norm(res) / np.linalg.norm(abs(K2) @ np.abs(x) + np.abs(f2)) < 2e-14
     if cpu_pcg:
-        # the port's own Jacobi-PCG (same sign-fixed system, same stopping rule).  Two iterative solutions of a system whose
-        # Jacobi-scaled condition number is ~1e6 at this size, each stopped at ||r|| <= 1e-13 ||b||: their distance is bounded
-        # by cond * 2e-13, observed ~1e-10 (the port's solution differs from a sparse direct solve by as much).
+        # the port's own Jacobi-PCG (same sign-fixed system, same stopping rule, rtol 1e-13).  Measured once on this system: the
+        # port's solution is 3.7e-12 (max-norm, relative) away from a sparse direct solve (scipy SuperLU, 300 s) - so the
+        # 1e-10 bar of the north-star applies to two iterative solutions as well
         xo, it, rel = occ.pcg(K2, f2, dset, rtol=1e-13, maxit=100000, nthreads=nth)
         assert rel <= 1e-13
-        assert _maxrel(x, xo) < 2e-8
+        assert _maxrel(x, xo) < RTOL
     # ---- get_u_sigma! for every cell: the port's recovery on the port's K_e, b_e with the same trace
     hdg.check(lib.hdg_recover(ctx.h), ctx.h)
     sig = np.empty((2 * n, s.ncell))
