@@ -375,7 +375,7 @@ def parity_leg(env):
     hdg, world = env.hdg, env.world
     worst, iters_ok, err_ok, cases = 0.0, True, True, []
     for order, qd, precond in ((1, 2, 0), (1, 2, 2), (3, 6, 0), (3, 6, 2)):
-        nx, ny = 64, 64 * world
+        nx, ny = 256, 128 * world      # level 0 of the vertex hierarchy is distributed, the rest replicated
         res = []
         for multi in (True, False):
             ctx = env.context(order, qd, comm=multi)
@@ -404,7 +404,7 @@ def parity_leg(env):
         err_ok = err_ok and abs(em - e1) <= 1e-9 * e1
         cases.append({"order": order, "precond": precond, "max_rel": rel, "iters": [itm, it1], "err2": [em, e1]})
     return {"max_rel": worst, "iters_equal": bool(iters_ok), "err2_equal": bool(err_ok), "cases": cases,
-            "what": f"64 x {64*world} mesh on {world} GPUs vs the same mesh on one GPU; Jacobi and multigrid PCG, k=1 and k=3, rtol 1e-13"}
+            "what": f"256 x {128*world} mesh on {world} GPUs vs the same mesh on one GPU; Jacobi and multigrid PCG, k=1 and k=3, rtol 1e-13"}
 
 
 def main():

@@ -117,6 +117,7 @@ SIGNATURES = {
     "hdg_comm_pingpong": (C.c_int, [_P, C.c_int32, _F64P]),
     "hdg_last_phase_ms": (C.c_int, [_P, C.c_char_p, _F64P]),
     "hdg_measure_fp64_peak": (C.c_int, [_P, _F64P]),
+    "hdg_mg_trace": (C.c_int32, [_P, _F64P, C.c_int32]),
     "hdg_launch_count": (C.c_int64, [_P]),
 }
 

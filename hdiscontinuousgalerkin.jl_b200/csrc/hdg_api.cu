@@ -504,6 +504,13 @@ hdg_status hdg_measure_fp64_peak(hdg_context* c, double* tflops) {
     return HDG_OK;
 }
 
+int32_t hdg_mg_trace(hdg_context* c, double* usec, int32_t capacity) {
+    if (!c || !usec) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    return mg_trace(c, usec, capacity);
+}
+
 int64_t hdg_launch_count(const hdg_context* c) { return c ? c->launches : 0; }
 
 }  // extern "C"

@@ -220,7 +220,9 @@ hdg_status pcg_solve(hdg_context* c, double rtol, int maxit, hdg_solve_info* inf
 hdg_status mg_setup(hdg_context* c);                                              // operators of the current trace matrix
 hdg_status mg_apply(hdg_context* c, const double* r, double* z, double* part, int np);   // z += P V(P'r); part = partials of (P'r).V(P'r)
 void mg_free(hdg_context* c);
+void mg_invalidate(hdg_context* c);                             // keep the buffers, rebuild adjacency / flags at the next solve
 int mg_levels(const hdg_context* c);
+int mg_trace(hdg_context* c, double* us, int cap);                // HDG_MG_TRACE=1: barrier timestamps of the last V-cycle
 int mg_launches_per_apply(const hdg_context* c);
 
 hdg_status recover(hdg_context* c);                             // hdg_recover.cu

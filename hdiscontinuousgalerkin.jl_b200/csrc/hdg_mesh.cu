@@ -761,7 +761,7 @@ __global__ void grid_check(const int32_t* __restrict__ facenode, int64_t nface, 
 
 hdg_status mesh_from_host(hdg_context* c, const int64_t* cells, int64_t ncell, const double* nodes, int64_t nnode,
                           const int64_t* faces, int64_t nface, const int64_t* bfaces, int64_t nbface) {
-    mg_free(c);   // vertex adjacency / hierarchy of the previous mesh
+    mg_invalidate(c);   // vertex adjacency of the previous mesh (buffers are kept while the sizes fit)
 
     if (comm_active(c)) return mesh_from_host_partitioned(c, cells, ncell, nodes, nnode, faces, nface, bfaces, nbface);
     c->ncell = c->ncell_own = ncell; c->nnode = nnode; c->nface = c->nface_own = nface; c->nbface = nbface; c->nx = c->ny = 0;
@@ -860,7 +860,7 @@ hdg_status mesh_set_dirichlet(hdg_context* c, const int64_t* bfaces, int64_t nbf
         HDG_CUDA(c, cudaMalloc(&c->d_bfaces, sizeof(int32_t) * nb));
         c->cap_nbface = nb;
     }
-    mg_free(c);   // the vertex hierarchy fixes the vertices of Dirichlet faces
+    mg_invalidate(c);   // the vertex hierarchy fixes the vertices of Dirichlet faces
     const int B = 256;
     HDG_CUDA(c, cudaMemsetAsync(c->d_isbc, 0, c->nface, c->stream));
     c->nbface = 0;
@@ -884,7 +884,7 @@ hdg_status mesh_set_dirichlet(hdg_context* c, const int64_t* bfaces, int64_t nbf
 }
 
 hdg_status mesh_rectangle(hdg_context* c, int64_t nx, int64_t ny, double llx, double lly, double urx, double ury) {
-    mg_free(c);   // vertex adjacency / hierarchy of the previous mesh
+    mg_invalidate(c);   // vertex adjacency of the previous mesh (buffers are kept while the sizes fit)
 
     if (nx < 1 || ny < 1 || !(urx > llx) || !(ury > lly)) return set_err(c, HDG_ERR_INVALID, "rectangle_mesh: need nx,ny >= 1 and UR > LL");
     // strip of quad rows owned by this rank (whole mesh on one GPU)

@@ -10,12 +10,24 @@
 // from (i+1,j) to (i,j+1)) as a 7-point stencil; the coarser operators are Galerkin products with the P1 interpolation of
 // that triangulation (stays 7-point), down to <= 64 points, which are solved with a dense inverse.  Vertices on
 // Dirichlet faces carry no coarse unknown.  Everything is gather-formulated (no atomics): bitwise reproducible.
-// Measured in the scipy prototype (tools/mg_prototype.py): 34-40 PCG iterations to 1e-12 for k = 1..4, independent of h.
-// rectangle_mesh triangulations only (a general mesh needs an algebraic hierarchy for A_c - next).  On several GPUs (strips of
-// hdg_set_rectangle_mesh) the vertex hierarchy is replicated: every rank builds the rows of A_c of the faces it owns and
-// restricts the residual of its own faces, the partial level-0 stencils (once per solve) and vertex residuals (once per
-// iteration) are summed with ncclAllReduce, and every rank runs the same V-cycle on the whole vertex grid (1 vertex per 2
-// cells and 1 double each: small against the trace system).  The PCG then runs without CUDA-graph capture.
+//
+// ONE V-cycle = ONE persistent cooperative kernel (mg_vcycle_kernel): the stages are separated by grid barriers instead of
+// kernel boundaries (the ~30 launches of 3-5 us each were 2/3 of a multigrid-PCG iteration), and the two sweeps of a level are
+// fused into one stage each way - the smoothed iterate x = omega Dinv r (+ P e on the way up) is recomputed at the neighbours
+// from r, Dinv (and the coarse correction) instead of being stored and re-read:
+//     down, level l:  r_{l+1} = R (r_l - A_l (omega Dinv_l r_l))                     one stage, gathers over a 2-ring
+//     up,   level l:  t_l = x + omega Dinv_l (r_l - A_l x),  x = omega Dinv_l r_l + P t_{l+1}     one stage
+// Same operations in the same order as the unfused kernels, so the iterates are bitwise those of the launch-per-stage version.
+//
+// SEVERAL GPUs (strips of hdg_set_rectangle_mesh): the hierarchy is DISTRIBUTED.  A rank owns the vertex rows of its quad
+// rows (level 0: rows [j0, j1), the last rank also row ny; level l+1: the rows Y with 2Y owned on level l).  Level arrays hold
+// the owned rows (+1); the rows of the two neighbouring ranks a stage needs (<= 2 on each side) are READ IN PLACE from the
+// neighbours' memory (CUDA IPC over NVLink, like the SpMV of the PCG) - no ghost copies, no pack/send/recv.  P'r and the
+// level-0 stencil rows of the vertex row shared by two strips are formed as partial sums by both ranks and added up by the
+// owner.  The grid barrier between two stages then carries a barrier across the GPUs (xg_barrier_thread: mailbox flags over
+// peer memory, ~3 us), executed by the last block to arrive.  Levels with <= MG_REP_MAX points (and all levels of a mesh too
+// small for two rows per rank) are REPLICATED: the owners compute their rows of the first such level, every rank gathers the
+// others' rows once, and everything below runs redundantly on every GPU with local barriers only.  No NCCL call in the solve.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -23,22 +35,30 @@
 
 #include "hdg_internal.h"
 #include "hdg_reduce.cuh"
+#include "hdg_xgpu.cuh"
 
 namespace hdg {
 
+// general-mesh term (hdg_mgx.cu)
+hdg_status mgx_setup(hdg_context* c);
+hdg_status mgx_apply(hdg_context* c, const double* r, double* z, double* part, int np);
+void mgx_free(hdg_context* c);
+void mgx_invalidate(hdg_context* c);
+bool mgx_active(const hdg_context* c);
+int mgx_launches_per_apply();
+
 constexpr int MG_MAXVAL = 8;        // faces per vertex (6 on rectangle_mesh)
 constexpr int MG_DENSE = 64;        // the coarsest grid has at most this many points
-constexpr int MG_MAXLEV = 24;
-#ifndef MG_FUSE_MAX
-#define MG_FUSE_MAX 640            // levels with at most this many points run inside ONE single-block kernel (mg_fused_vcycle)
-#endif
-constexpr int MG_FUSE_LEVELS = 8;   // capacity of the argument struct (640 -> 160 -> 40: 3 fused levels by default)
+constexpr int MG_MAXLEV = 16;       // 2^16 vertices per direction
+constexpr int MG_TAIL_MAX = 640;    // levels with at most this many points run inside ONE block (block barriers)
+constexpr int MG_REP_MAX = 32768;   // several GPUs: levels with at most this many points are replicated on every rank
 constexpr double MG_OMEGA = 0.8;    // damped Jacobi on the vertex grids
 constexpr double MG_C1 = 0.28867513459481287;   // 1 / (2 sqrt 3)
+constexpr int MG_THREADS = 256;
 
 // stencil slots: centre, E, W, N, S, SE, NW  (the neighbours of a vertex in the triangulation)
-__device__ __constant__ int MG_DX[7] = {0, 1, -1, 0, 0, 1, -1};
-__device__ __constant__ int MG_DY[7] = {0, 0, 0, 1, -1, -1, 1};
+__device__ constexpr int MG_DX[7] = {0, 1, -1, 0, 0, 1, -1};
+__device__ constexpr int MG_DY[7] = {0, 0, 0, 1, -1, -1, 1};
 __device__ __forceinline__ int mg_slot(int dx, int dy) {
     if (dy == 0) return dx == 0 ? 0 : (dx == 1 ? 1 : (dx == -1 ? 2 : -1));
     if (dx == 0) return dy == 1 ? 3 : (dy == -1 ? 4 : -1);
@@ -47,51 +67,150 @@ __device__ __forceinline__ int mg_slot(int dx, int dy) {
     return -1;
 }
 
-struct MgLevel {
-    int px = 0, py = 0;
-    int64_t n = 0;
-    double* st = nullptr;     // 7 x n, slot-major
-    double* dinv = nullptr;   // 1/diagonal, 0 at fixed points (identity rows)
-    double *r = nullptr, *x = nullptr, *t = nullptr;
+// One level as the kernels see it.  Rows [oy0, oy1) are owned by this rank; the arrays hold rows [rb, rb + rows) with
+// rb = oy0 on a distributed level (one spare row: the partial sums of the row shared with the rank above) and rb = 0 on a
+// replicated level (all rows, valid everywhere once gathered).  Rows below oy0 / from oy1 on of a distributed level are read
+// from the neighbouring ranks' arrays (same layout with their own rb).
+struct LvDev {
+    int px, py;
+    int rb, oy0, oy1;
+    int rep;
+    int64_t n;                  // stored points = rows * px: the stride between the 7 stencil slots
+    double *st, *dinv, *r, *t, *x;
+    const double *b_st, *b_dinv, *b_r, *b_t;  int64_t b_n;  int b_rb;     // rank below
+    int a_rb;
+    const double *a_st, *a_dinv, *a_r, *a_t;  int64_t a_n;                // rank above
 };
 
-struct MgData {
-    int nlev = 0;
-    MgLevel lev[MG_MAXLEV];
-    double* pool = nullptr;          // one allocation for all levels
-    double* ainv = nullptr;          // dense inverse of the coarsest operator
-    int32_t* vface = nullptr;        // nnode x MG_MAXVAL: incident faces ascending, bit 31 = the vertex is the face's hi vertex
-    int32_t* vcnt = nullptr;         // nnode: number of incident faces, -1 = fixed (touches a Dirichlet face)
-    int64_t nnode = 0, nface = 0;
-    int nx = 0, ny = 0;
-    int lf = 0;                      // first level of the fused tail (levels lf .. nlev-1 run in mg_fused_vcycle)
-    bool adjacency_ok = false;
-    // several GPUs (strips of rectangle_mesh): the vertex hierarchy is REPLICATED on every rank over the global vertex grid;
-    // a rank contributes the rows of the faces it owns and the partial vertex vectors / stencils are all-reduced
-    bool multi = false;
-    int64_t node0 = 0;               // global id of local node 0
-    int64_t nface_rows = 0;          // owned faces (rows of the trace system held by this rank)
-};
+enum MgArr : int { AR_DINV = 0, AR_R = 1, AR_T = 2 };
 
-// ---- vertex -> faces adjacency ------------------------------------------------------------------------------------
-__global__ void mg_adj_fill(const int32_t* __restrict__ facenode, int64_t nface, int64_t node0, int32_t* __restrict__ vcnt,
+// vector entry (x, y) of a level, wherever the row lives.  Dynamic vectors (r, t) are written by other SMs / GPUs inside the
+// same launch: L2-coherent loads (ld.global.cg) for them, plain loads for the operators (constant during a solve).  Pointer and
+// row base are SELECTED (no branches), so that the loads of a whole stencil can be in flight together: the persistent kernel
+// runs 512 threads per SM and lives on memory-level parallelism inside a thread.  DIST = false (one GPU, replicated levels):
+// every row is local and the access is a plain 32-bit index (levels have < 2^31 points).
+template <int W, bool DIST> __device__ __forceinline__ double lv(const LvDev& L, int x, int y) {
+    const double* pm = W == AR_DINV ? L.dinv : (W == AR_R ? L.r : L.t);
+    if constexpr (!DIST) {
+        const int off = (y - L.rb) * L.px + x;
+        return W == AR_DINV ? pm[off] : __ldcg(pm + off);
+    } else {
+        const bool mine = L.rep | ((y >= L.oy0) & (y < L.oy1)), below = !mine & (y < L.oy0);
+        const double* pb = W == AR_DINV ? L.b_dinv : (W == AR_R ? L.b_r : L.b_t);
+        const double* pa = W == AR_DINV ? L.a_dinv : (W == AR_R ? L.a_r : L.a_t);
+        const double* p = mine ? pm : (below ? pb : pa);
+        const int rb = mine ? L.rb : (below ? L.b_rb : L.a_rb);
+        const int off = (y - rb) * L.px + x;
+        return W == AR_DINV ? p[off] : __ldcg(p + off);
+    }
+}
+template <bool DIST> __device__ __forceinline__ double lv_st(const LvDev& L, int k, int x, int y) {
+    if constexpr (!DIST) return L.st[k * L.n + (y - L.rb) * L.px + x];
+    else {
+        const bool mine = L.rep | ((y >= L.oy0) & (y < L.oy1)), below = !mine & (y < L.oy0);
+        const double* p = mine ? L.st : (below ? L.b_st : L.a_st);
+        const int64_t n = mine ? L.n : (below ? L.b_n : L.a_n);
+        const int rb = mine ? L.rb : (below ? L.b_rb : L.a_rb);
+        return p[k * n + (y - rb) * L.px + x];
+    }
+}
+__device__ __forceinline__ int lv_idx(const LvDev& L, int x, int y) { return (y - L.rb) * L.px + x; }
+
+// ---- the point-wise operations of the V-cycle ---------------------------------------------------------------------------
+// Neighbours outside the grid are handled by MASKS, not branches: the address is clamped to the centre point and the value
+// replaced by 0 (their stencil coefficients are 0 as well), which leaves every sum bit-identical to the skipping version.
+
+// x = omega Dinv r (first sweep from a zero start) at (qx, qy), 0 outside the grid; (cx, cy) is a point inside
+template <bool DIST> __device__ __forceinline__ double mg_x0(const LvDev& L, int qx, int qy, int cx, int cy) {
+    const bool in = (qx >= 0) & (qy >= 0) & (qx < L.px) & (qy < L.py);
+    const int sx = in ? qx : cx, sy = in ? qy : cy;
+    const double v = MG_OMEGA * lv<AR_DINV, DIST>(L, sx, sy) * lv<AR_R, DIST>(L, sx, sy);
+    return in ? v : 0.0;
+}
+
+// P e at the fine point (x, y), e = t of the coarse level: the mean of two coarse values (twice the same one at a coarse twin)
+template <bool DIST> __device__ __forceinline__ double mg_prolong_pt(const LvDev& C, int x, int y) {
+    const int a2 = x & 1, b2 = y & 1, hx = x >> 1, hy = y >> 1;
+    const int x1 = hx + (a2 & b2), y1 = hy, x2 = hx + (a2 & (b2 ^ 1)), y2 = hy + b2;
+    const bool in1 = (x1 < C.px) & (y1 < C.py), in2 = (x2 < C.px) & (y2 < C.py);
+    const double g1 = lv<AR_T, DIST>(C, in1 ? x1 : hx, in1 ? y1 : hy), g2 = lv<AR_T, DIST>(C, in2 ? x2 : hx, in2 ? y2 : hy);
+    return 0.5 * ((in1 ? g1 : 0.0) + (in2 ? g2 : 0.0));
+}
+// x after the coarse correction at (qx, qy): omega Dinv r + P e at the free points; 0 outside the grid
+template <bool DF, bool DC> __device__ __forceinline__ double mg_x1(const LvDev& F, const LvDev& C, int qx, int qy, int cx, int cy) {
+    const bool in = (qx >= 0) & (qy >= 0) & (qx < F.px) & (qy < F.py);
+    const int sx = in ? qx : cx, sy = in ? qy : cy;
+    const double di = lv<AR_DINV, DF>(F, sx, sy);
+    const double pe = mg_prolong_pt<DC>(C, sx, sy);
+    const double v = MG_OMEGA * di * lv<AR_R, DF>(F, sx, sy) + (di != 0.0 ? pe : 0.0);
+    return in ? v : 0.0;
+}
+
+// down: r_C(I) = sum_d w_d (r - A x0)(fine neighbour d of 2I), 0 at fixed coarse points; coarse rows [cy0, cy1).
+// The 7 residuals need x0 on the 19 points of the 2-ring around 2I: loaded once into a 5 x 5 window.
+template <bool DIST> __device__ void mg_stage_down(const LvDev& F, const LvDev& C, int cy0, int cy1, int tid, int T) {
+    const int cnt = (cy1 - cy0) * C.px;
+    for (int i = tid; i < cnt; i += T) {
+        const int Iy = cy0 + i / C.px, Ix = i - (Iy - cy0) * C.px;
+        double s = 0.0;
+        if (C.dinv[lv_idx(C, Ix, Iy)] != 0.0) {
+            const int cx = 2 * Ix, cy = 2 * Iy;
+            double xw[5][5];
+#pragma unroll
+            for (int dy = -2; dy <= 2; ++dy)
+#pragma unroll
+                for (int dx = -2; dx <= 2; ++dx)
+                    if (dx + dy >= -2 && dx + dy <= 2) xw[dy + 2][dx + 2] = mg_x0<DIST>(F, cx + dx, cy + dy, cx, cy);
+#pragma unroll
+            for (int d = 0; d < 7; ++d) {
+                const int fx = cx + MG_DX[d], fy = cy + MG_DY[d];
+                const bool in = (fx >= 0) & (fy >= 0) & (fx < F.px) & (fy < F.py);
+                const int sx = in ? fx : cx, sy = in ? fy : cy;
+                double a = lv_st<DIST>(F, 0, sx, sy) * xw[MG_DY[d] + 2][MG_DX[d] + 2];
+#pragma unroll
+                for (int k = 1; k < 7; ++k) a = fma(lv_st<DIST>(F, k, sx, sy), xw[MG_DY[d] + MG_DY[k] + 2][MG_DX[d] + MG_DX[k] + 2], a);
+                const double t = lv<AR_R, DIST>(F, sx, sy) - a;
+                s += in ? (d == 0 ? 1.0 : 0.5) * t : 0.0;
+            }
+        }
+        C.r[lv_idx(C, Ix, Iy)] = s;
+    }
+}
+
+// up: t_F = x1 + omega Dinv (r - A x1); fine rows [fy0, fy1)
+template <bool DF, bool DC> __device__ void mg_stage_up(const LvDev& F, const LvDev& C, int fy0, int fy1, int tid, int T) {
+    const int cnt = (fy1 - fy0) * F.px;
+    for (int i = tid; i < cnt; i += T) {
+        const int y = fy0 + i / F.px, x = i - (y - fy0) * F.px;
+        double xq[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) xq[k] = mg_x1<DF, DC>(F, C, x + MG_DX[k], y + MG_DY[k], x, y);
+        double s = lv_st<DF>(F, 0, x, y) * xq[0];
+#pragma unroll
+        for (int k = 1; k < 7; ++k) s = fma(lv_st<DF>(F, k, x, y), xq[k], s);
+        F.t[lv_idx(F, x, y)] = fma(MG_OMEGA * F.dinv[lv_idx(F, x, y)], lv<AR_R, DF>(F, x, y) - s, xq[0]);
+    }
+}
+
+// ---- vertex <-> trace adjacency ---------------------------------------------------------------------------------------------
+// vertex -> OWNED faces (a face row of K is counted by exactly one rank), local node ids (row - j0) px + x
+__global__ void mg_adj_fill(const int32_t* __restrict__ facenode, int64_t nface, int32_t* __restrict__ vcnt,
                             int32_t* __restrict__ vface, int32_t* __restrict__ flags) {
     int64_t f = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (f >= nface) return;
-    const int64_t v1 = facenode[2 * f] + node0, v2 = facenode[2 * f + 1] + node0;
+    const int64_t v1 = facenode[2 * f], v2 = facenode[2 * f + 1];
     const int64_t lo = min(v1, v2), hi = max(v1, v2);
     int k = atomicAdd(&vcnt[lo], 1);
     if (k < MG_MAXVAL) vface[lo * MG_MAXVAL + k] = int32_t(f); else atomicExch(&flags[FLAG_MG], 1);
     k = atomicAdd(&vcnt[hi], 1);
     if (k < MG_MAXVAL) vface[hi * MG_MAXVAL + k] = int32_t(uint32_t(f) | 0x80000000u); else atomicExch(&flags[FLAG_MG], 1);
 }
-
-// sorts the incident faces; fc[v] = 1 if the vertex touches a Dirichlet face, fc[nnode + v] = number of incident faces
-// (doubles: summed over the ranks by an all-reduce when the mesh is distributed)
-__global__ void mg_adj_sort(int64_t nnode, const int32_t* __restrict__ vcnt, int32_t* __restrict__ vface, const uint8_t* __restrict__ isbc,
-                            double* __restrict__ fc) {
+// sorts the incident faces (the atomic append order is arbitrary); partial "touches a Dirichlet face" flag and face count of
+// the local vertex rows into two level-0 scratch vectors - the row shared by two strips is summed by its owner afterwards
+__global__ void mg_adj_sort(int64_t nv, int32_t* __restrict__ vcnt, int32_t* __restrict__ vface, const uint8_t* __restrict__ isbc,
+                            double* __restrict__ flag, double* __restrict__ count) {
     int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (v >= nnode) return;
+    if (v >= nv) return;
     const int cnt = min(vcnt[v], MG_MAXVAL);
     int32_t a[MG_MAXVAL];
     bool fixed = false;
@@ -99,35 +218,68 @@ __global__ void mg_adj_sort(int64_t nnode, const int32_t* __restrict__ vcnt, int
         a[k] = vface[v * MG_MAXVAL + k];
         fixed = fixed || isbc[a[k] & 0x7fffffff];
     }
-    for (int i = 1; i < cnt; ++i) {     // insertion sort by face id: the atomic append order is arbitrary
+    for (int i = 1; i < cnt; ++i) {
         const int32_t key = a[i];
         int j = i - 1;
         while (j >= 0 && (a[j] & 0x7fffffff) > (key & 0x7fffffff)) { a[j + 1] = a[j]; --j; }
         a[j + 1] = key;
     }
     for (int k = 0; k < cnt; ++k) vface[v * MG_MAXVAL + k] = a[k];
-    fc[v] = fixed ? 1.0 : 0.0;
-    fc[nnode + v] = double(cnt);
+    vcnt[v] = cnt;
+    flag[v] = fixed ? 1.0 : 0.0;
+    count[v] = double(cnt);
 }
-// a vertex carries no coarse unknown if it touches a Dirichlet face (on any rank) or has no face at all
-__global__ void mg_adj_fix(int64_t nnode, int32_t* __restrict__ vcnt, const double* __restrict__ fc) {
+// the owner of the shared vertex row adds the partial sums the rank below formed in its spare row: narr arrays, one row each
+__global__ void mg_add_shared_row(double* __restrict__ mine, int64_t stride, const double* __restrict__ below, int64_t bstride, int narr, int px) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= px) return;
+    for (int k = 0; k < narr; ++k) mine[k * stride + i] += __ldcg(below + k * bstride + i);
+}
+// a vertex carries no coarse unknown (fx = 1) if it touches a Dirichlet face on any rank or has no face at all
+__global__ void mg_fix_flags(int64_t cnt, const double* __restrict__ flag, const double* __restrict__ count, double* __restrict__ fx) {
     int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (v >= nnode) return;
-    if (fc[v] > 0.0 || fc[nnode + v] == 0.0) vcnt[v] = -1;
+    if (v < cnt) fx[v] = (flag[v] > 0.0 || count[v] == 0.0) ? 1.0 : 0.0;
 }
 
-// ---- A_c = P'AP on the vertex grid, gathered per vertex ---------------------------------------------------------------
+// every rank copies the rows of a replicated array it does not own from their owners: narr arrays of stride n each
+struct GatherArgs {
+    const double* src[MAXR];      // the same array on every rank (replicated levels share one layout)
+    int ry0[MAXR + 1];            // owned rows of rank q: [ry0[q], ry0[q+1])
+    int nranks, rank;
+};
+__device__ void mg_gather_rows_dev(const GatherArgs& g, double* dst, int64_t n, int narr, int px, int64_t tid, int64_t T) {
+    for (int q = 0; q < g.nranks; ++q) {
+        if (q == g.rank) continue;
+        const int64_t o = int64_t(g.ry0[q]) * px, cnt = int64_t(g.ry0[q + 1] - g.ry0[q]) * px;
+        for (int k = 0; k < narr; ++k)
+            for (int64_t i = tid; i < cnt; i += T) dst[k * n + o + i] = __ldcg(g.src[q] + k * n + o + i);
+    }
+}
+__global__ void mg_gather_rows(const GatherArgs g, double* dst, int64_t n, int narr, int px) {
+    mg_gather_rows_dev(g, dst, n, narr, px, int64_t(blockIdx.x) * blockDim.x + threadIdx.x, int64_t(gridDim.x) * blockDim.x);
+}
+
+// ---- A_c = P'AP on the vertex grid: partial rows from the owned faces of the local vertex rows ---------------------------
+// fixed flags in the level-0 layout; the rows from oy1 on are read from the rank above
+struct FxView {
+    const double* mine; const double* above;
+    int rb, oy1, a_rb, rep;
+};
+__device__ __forceinline__ bool mg_fixed(const FxView& f, int px, int x, int y) {
+    if (f.rep || y < f.oy1) return f.mine[int64_t(y - f.rb) * px + x] != 0.0;
+    return f.above[int64_t(y - f.a_rb) * px + x] != 0.0;
+}
 template <int NT>
 __global__ void mg_vertex_operator(const double* __restrict__ Kd, const double* __restrict__ Ko, const int32_t* __restrict__ kcol,
-                                   const uint8_t* __restrict__ isbc, const int32_t* __restrict__ facenode, int64_t node0,
-                                   const int32_t* __restrict__ vcnt, const int32_t* __restrict__ vface, int px, int64_t nnode,
-                                   double* __restrict__ st) {
+                                   const uint8_t* __restrict__ isbc, const int32_t* __restrict__ facenode, int node_row0,
+                                   const int32_t* __restrict__ vcnt, const int32_t* __restrict__ vface, const FxView fxv, int px,
+                                   int64_t nv, double* __restrict__ st, int64_t stride) {
     constexpr int NT2 = NT * NT;
-    int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (v >= nnode) return;
+    int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;      // local node id = (row - node_row0) px + x
+    if (v >= nv) return;
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-    const int cnt = vcnt[v];        // < 0: fixed vertex (identity row, written by mg_finalize_rows)
-    const int vx = int(v % px), vy = int(v / px);
+    const int vx = int(v % px), vy = int(v / px) + node_row0;
+    const int cnt = mg_fixed(fxv, px, vx, vy) ? 0 : vcnt[v];
     for (int k = 0; k < cnt; ++k) {
         const int32_t e = vface[v * MG_MAXVAL + k];
         const int64_t f = e & 0x7fffffff;
@@ -139,172 +291,91 @@ __global__ void mg_vertex_operator(const double* __restrict__ Kd, const double* 
             // t_b = - sum_a pf_a K[a][b]   (A = -K on free rows), b = 0, 1
             const double t0 = -(pf0 * blk[0] + pf1 * blk[1]);
             const double t1 = -(pf0 * blk[NT] + pf1 * blk[NT + 1]);
-            const int64_t g1 = facenode[2 * g] + node0, g2 = facenode[2 * g + 1] + node0;
+            const int64_t g1 = facenode[2 * g], g2 = facenode[2 * g + 1];
             const int64_t lo = min(g1, g2), hi = max(g1, g2);
-            if (vcnt[lo] >= 0) {
-                const int sl = mg_slot(int(lo % px) - vx, int(lo / px) - vy);
+            const int lox = int(lo % px), loy = int(lo / px) + node_row0, hix = int(hi % px), hiy = int(hi / px) + node_row0;
+            if (!mg_fixed(fxv, px, lox, loy)) {
+                const int sl = mg_slot(lox - vx, loy - vy);
                 if (sl >= 0) acc[sl] += 0.5 * t0 - MG_C1 * t1;
             }
-            if (vcnt[hi] >= 0) {
-                const int sl = mg_slot(int(hi % px) - vx, int(hi / px) - vy);
+            if (!mg_fixed(fxv, px, hix, hiy)) {
+                const int sl = mg_slot(hix - vx, hiy - vy);
                 if (sl >= 0) acc[sl] += 0.5 * t0 + MG_C1 * t1;
             }
         }
     }
-    for (int k = 0; k < 7; ++k) st[k * nnode + v] = acc[k];
+    for (int k = 0; k < 7; ++k) st[k * stride + v] = acc[k];
 }
-// after the rows are complete (all-reduced over the ranks on a distributed mesh): inverse diagonal, identity rows at the
-// fixed vertices and wherever the diagonal is not positive
-__global__ void mg_finalize_rows(const int32_t* __restrict__ vcnt, int64_t nnode, double* __restrict__ st, double* __restrict__ dinv) {
+// complete rows -> inverse diagonal; identity rows at the fixed vertices and wherever the diagonal is not positive
+__global__ void mg_finalize_rows(const double* __restrict__ fx, int64_t cnt, double* __restrict__ st, int64_t stride, double* __restrict__ dinv) {
     int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (v >= nnode) return;
+    if (v >= cnt) return;
     const double d = st[v];
-    if (vcnt[v] >= 0 && d > 0.0) { dinv[v] = 1.0 / d; return; }
+    if (fx[v] == 0.0 && d > 0.0) { dinv[v] = 1.0 / d; return; }
     st[v] = 1.0;
-    for (int k = 1; k < 7; ++k) st[k * nnode + v] = 0.0;
+    for (int k = 1; k < 7; ++k) st[k * stride + v] = 0.0;
     dinv[v] = 0.0;
 }
 
-// ---- Galerkin coarse operator: A_c[I][J] = sum_p sum_q R[I,p] A[p,q] P[q,J], gathered per coarse point -----------------
-__global__ void mg_rap(const double* __restrict__ stf, const double* __restrict__ dinvf, int px, int py, int cx, int cy,
-                       double* __restrict__ stc, double* __restrict__ dinvc) {
-    const int64_t nc = int64_t(cx) * cy, nf = int64_t(px) * py;
-    int64_t I = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (I >= nc) return;
-    const int Ix = int(I % cx), Iy = int(I / cx);
+// ---- Galerkin coarse operator: A_c[I][J] = sum_p sum_q R[I,p] A[p,q] P[q,J], gathered per coarse point; coarse rows [cy0, cy1)
+__global__ void mg_rap(const LvDev F, const LvDev C, int cy0, int cy1) {
+    const int64_t cnt = int64_t(cy1 - cy0) * C.px;
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    const int Ix = int(i % C.px), Iy = cy0 + int(i / C.px);
+    const int px = F.px, py = F.py, cx = C.px, cy = C.py;
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-    const bool free_twin = dinvf[int64_t(2 * Iy) * px + 2 * Ix] != 0.0;
+    const bool free_twin = lv<AR_DINV, true>(F, 2 * Ix, 2 * Iy) != 0.0;
     if (free_twin) {
         for (int d = 0; d < 7; ++d) {
             const int fx = 2 * Ix + MG_DX[d], fy = 2 * Iy + MG_DY[d];
             if (fx < 0 || fy < 0 || fx >= px || fy >= py) continue;
-            const int64_t p = int64_t(fy) * px + fx;
-            if (dinvf[p] == 0.0) continue;
+            if (lv<AR_DINV, true>(F, fx, fy) == 0.0) continue;
             const double wr = d == 0 ? 1.0 : 0.5;
             for (int e = 0; e < 7; ++e) {
                 const int qx = fx + MG_DX[e], qy = fy + MG_DY[e];
                 if (qx < 0 || qy < 0 || qx >= px || qy >= py) continue;
-                const int64_t q = int64_t(qy) * px + qx;
-                if (dinvf[q] == 0.0) continue;
-                const double aw = wr * stf[e * nf + p];
+                if (lv<AR_DINV, true>(F, qx, qy) == 0.0) continue;
+                const double aw = wr * lv_st<true>(F, e, fx, fy);
                 if (aw == 0.0) continue;
                 const int a2 = qx & 1, b2 = qy & 1, hx = qx >> 1, hy = qy >> 1;
-                int jx[2], jy[2], cnt;
+                int jx[2], jy[2], cn;
                 double wp;
-                if (!a2 && !b2) { jx[0] = hx; jy[0] = hy; cnt = 1; wp = 1.0; }
-                else if (a2 && !b2) { jx[0] = hx; jy[0] = hy; jx[1] = hx + 1; jy[1] = hy; cnt = 2; wp = 0.5; }
-                else if (!a2 && b2) { jx[0] = hx; jy[0] = hy; jx[1] = hx; jy[1] = hy + 1; cnt = 2; wp = 0.5; }
-                else { jx[0] = hx + 1; jy[0] = hy; jx[1] = hx; jy[1] = hy + 1; cnt = 2; wp = 0.5; }
-                for (int m = 0; m < cnt; ++m) {
+                if (!a2 && !b2) { jx[0] = hx; jy[0] = hy; cn = 1; wp = 1.0; }
+                else if (a2 && !b2) { jx[0] = hx; jy[0] = hy; jx[1] = hx + 1; jy[1] = hy; cn = 2; wp = 0.5; }
+                else if (!a2 && b2) { jx[0] = hx; jy[0] = hy; jx[1] = hx; jy[1] = hy + 1; cn = 2; wp = 0.5; }
+                else { jx[0] = hx + 1; jy[0] = hy; jx[1] = hx; jy[1] = hy + 1; cn = 2; wp = 0.5; }
+                for (int m = 0; m < cn; ++m) {
                     if (jx[m] >= cx || jy[m] >= cy) continue;
-                    if (dinvf[int64_t(2 * jy[m]) * px + 2 * jx[m]] == 0.0) continue;     // fixed coarse point
+                    if (lv<AR_DINV, true>(F, 2 * jx[m], 2 * jy[m]) == 0.0) continue;     // fixed coarse point
                     const int sl = mg_slot(jx[m] - Ix, jy[m] - Iy);
                     if (sl >= 0) acc[sl] += aw * wp;
                 }
             }
         }
     }
+    const int64_t I = lv_idx(C, Ix, Iy);
     if (free_twin && acc[0] > 0.0) {
-        for (int k = 0; k < 7; ++k) stc[k * nc + I] = acc[k];
-        dinvc[I] = 1.0 / acc[0];
+        for (int k = 0; k < 7; ++k) C.st[k * C.n + I] = acc[k];
+        C.dinv[I] = 1.0 / acc[0];
     } else {
-        stc[I] = 1.0;
-        for (int k = 1; k < 7; ++k) stc[k * nc + I] = 0.0;
-        dinvc[I] = 0.0;
+        C.st[I] = 1.0;
+        for (int k = 1; k < 7; ++k) C.st[k * C.n + I] = 0.0;
+        C.dinv[I] = 0.0;
     }
 }
-
 // a coarse point whose fine twin is free but whose own diagonal vanished is fixed as well: drop the couplings to it
-__global__ void mg_drop_fixed(double* __restrict__ st, const double* __restrict__ dinv, int px, int py) {
-    const int64_t n = int64_t(px) * py;
-    int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (p >= n || dinv[p] == 0.0) return;
-    const int x = int(p % px), y = int(p / px);
+__global__ void mg_drop_fixed(const LvDev C, int cy0, int cy1) {
+    const int64_t cnt = int64_t(cy1 - cy0) * C.px;
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    const int x = int(i % C.px), y = cy0 + int(i / C.px);
+    const int64_t p = lv_idx(C, x, y);
+    if (C.dinv[p] == 0.0) return;
     for (int k = 1; k < 7; ++k) {
         const int qx = x + MG_DX[k], qy = y + MG_DY[k];
-        if (qx < 0 || qy < 0 || qx >= px || qy >= py || dinv[int64_t(qy) * px + qx] == 0.0) st[k * n + p] = 0.0;
+        if (qx < 0 || qy < 0 || qx >= C.px || qy >= C.py || lv<AR_DINV, true>(C, qx, qy) == 0.0) C.st[k * C.n + p] = 0.0;
     }
-}
-
-// ---- V-cycle kernels --------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double mg_apply_row(const double* __restrict__ st, const double* __restrict__ x, int64_t p, int px, int py, int64_t n) {
-    const int ix = int(p % px), iy = int(p / px);
-    double s = st[p] * x[p];
-#pragma unroll
-    for (int k = 1; k < 7; ++k) {
-        const int qx = ix + MG_DX[k], qy = iy + MG_DY[k];
-        if (qx < 0 || qy < 0 || qx >= px || qy >= py) continue;
-        s = fma(st[k * n + p], x[int64_t(qy) * px + qx], s);
-    }
-    return s;
-}
-
-// the same row product without __restrict__: inside mg_fused_vcycle the vectors are written and read within one launch, so the
-// loads must not be routed through the non-coherent read-only path
-__device__ __forceinline__ double mg_apply_row_rw(const double* st, const double* x, int64_t p, int px, int py, int64_t n) {
-    const int ix = int(p % px), iy = int(p / px);
-    double s = st[p] * x[p];
-#pragma unroll
-    for (int k = 1; k < 7; ++k) {
-        const int qx = ix + MG_DX[k], qy = iy + MG_DY[k];
-        if (qx < 0 || qy < 0 || qx >= px || qy >= py) continue;
-        s = fma(st[k * n + p], x[int64_t(qy) * px + qx], s);
-    }
-    return s;
-}
-__device__ __forceinline__ double mg_restrict_pt(const double* tf, int px, int py, const double* dinvc, int64_t I, int cx) {
-    double s = 0.0;
-    if (dinvc[I] != 0.0) {
-        const int Ix = int(I % cx), Iy = int(I / cx);
-#pragma unroll
-        for (int d = 0; d < 7; ++d) {
-            const int fx = 2 * Ix + MG_DX[d], fy = 2 * Iy + MG_DY[d];
-            if (fx < 0 || fy < 0 || fx >= px || fy >= py) continue;
-            s += (d == 0 ? 1.0 : 0.5) * tf[int64_t(fy) * px + fx];
-        }
-    }
-    return s;
-}
-__device__ __forceinline__ double mg_prolong_pt(const double* ec, int cx, int cy, int64_t p, int px) {
-    const int ix = int(p % px), iy = int(p / px);
-    const int a2 = ix & 1, b2 = iy & 1, hx = ix >> 1, hy = iy >> 1;
-    auto get = [&](int jx, int jy) { return (jx < cx && jy < cy) ? ec[int64_t(jy) * cx + jx] : 0.0; };
-    if (!a2 && !b2) return get(hx, hy);
-    if (a2 && !b2) return 0.5 * (get(hx, hy) + get(hx + 1, hy));
-    if (!a2 && b2) return 0.5 * (get(hx, hy) + get(hx, hy + 1));
-    return 0.5 * (get(hx + 1, hy) + get(hx, hy + 1));
-}
-
-// x = omega Dinv r ; t = r - A x needs the neighbours of x, hence two kernels
-__global__ void mg_smooth0(const double* __restrict__ dinv, const double* __restrict__ r, double* __restrict__ x, int64_t n) {
-    int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (p < n) x[p] = MG_OMEGA * dinv[p] * r[p];
-}
-__global__ void mg_residual(const double* __restrict__ st, const double* __restrict__ r, const double* __restrict__ x, double* __restrict__ t,
-                            int px, int py) {
-    const int64_t n = int64_t(px) * py;
-    int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (p < n) t[p] = r[p] - mg_apply_row(st, x, p, px, py, n);
-}
-// t = x + omega Dinv (r - A x)
-__global__ void mg_smooth(const double* __restrict__ st, const double* __restrict__ dinv, const double* __restrict__ r,
-                          const double* __restrict__ x, double* __restrict__ t, int px, int py) {
-    const int64_t n = int64_t(px) * py;
-    int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (p < n) t[p] = fma(MG_OMEGA * dinv[p], r[p] - mg_apply_row(st, x, p, px, py, n), x[p]);
-}
-// r_c = R t_f (transpose of the P1 interpolation), 0 at fixed coarse points
-__global__ void mg_restrict(const double* __restrict__ tf, int px, int py, const double* __restrict__ dinvc, double* __restrict__ rc, int cx, int cy) {
-    const int64_t nc = int64_t(cx) * cy;
-    int64_t I = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (I < nc) rc[I] = mg_restrict_pt(tf, px, py, dinvc, I, cx);
-}
-// x_f += P e_c at the free fine points
-__global__ void mg_prolong_add(const double* __restrict__ ec, int cx, int cy, const double* __restrict__ dinvf, double* __restrict__ x, int px, int py) {
-    const int64_t n = int64_t(px) * py;
-    int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (p >= n || dinvf[p] == 0.0) return;
-    x[p] += mg_prolong_pt(ec, cx, cy, p, px);
 }
 
 // coarsest grid: dense inverse by Gauss-Jordan without pivoting (SPD + identity rows), one block
@@ -339,241 +410,355 @@ __global__ void mg_dense_inverse(const double* __restrict__ st, int px, int py, 
     }
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) ainv[e] = A[e];
 }
-// ---- the coarse tail of the V-cycle in one kernel ----------------------------------------------------------------------
-// The smallest levels are pure launch latency (five kernels for a microsecond of work each).  The levels with at most
-// MG_FUSE_MAX points run inside one block: the same point-wise operations in the same order (results are bitwise those of the
-// per-level kernels), separated by block barriers instead of kernel boundaries.  Measured (k=1, 1 M elements, same box):
-// threshold 640 -> 0.297 ms per PCG iteration against 0.312 unfused; 2304 and 8192 are no faster than unfused (one SM cannot
-// keep up with a few thousand points per stage), so the gain is small - inside a CUDA graph the tiny kernels cost ~1-2 us each.
-struct MgFused {
-    int nl;                                        // fused levels; lev 0 = finest fused, lev nl-1 = the dense one
-    int px[MG_FUSE_LEVELS], py[MG_FUSE_LEVELS];
-    double *st[MG_FUSE_LEVELS], *dinv[MG_FUSE_LEVELS], *r[MG_FUSE_LEVELS], *x[MG_FUSE_LEVELS], *t[MG_FUSE_LEVELS];
+
+// ---- the V-cycle kernel ---------------------------------------------------------------------------------------------------
+struct VcArgs {
+    int nlev;          // all levels; the last one is the dense one
+    int lrep;          // several GPUs: levels [0, lrep) are distributed over the ranks, [lrep, nlev) replicated
+    int lt;            // levels [lt, nlev) run inside block 0 (tail); lrep <= lt
+    LvDev lev[MG_MAXLEV];
     const double* ainv;
+    // trace side
+    const double* r;   // trace residual (nt entries per owned face)
+    double* z;         // z += P V(P'r)
+    double* part;      // partial sums of (P'r).V(P'r), np entries
+    int np;
+    int64_t nface;     // owned faces
+    const int32_t *vcnt, *vface, *facenode;
+    const uint8_t* isbc;
+    int node_row0;     // global vertex row of local node row 0 (j0 of the strip) == first owned row of level 0
+    int prows;         // local vertex rows with (partial) P'r: the owned rows + the row shared with the rank above
+    const double* fx;  // level-0 fixed flags of the owned rows
+    // grid barrier + cross-GPU barrier
+    unsigned* bar_count;
+    volatile unsigned* bar_gen;
+    XgComm xg;
+    GatherArgs gather;     // r of level lrep
+    unsigned long long* trace;   // measurement: globaltimer (ns) of block 0 at every barrier of the last V-cycle, [0] = count
 };
 
-__global__ void __launch_bounds__(1024) mg_fused_vcycle(const MgFused A) {
+// all blocks of the grid; with `cross` the last block to arrive also runs the barrier across the GPUs before releasing
+__device__ __forceinline__ unsigned long long mg_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void mg_grid_barrier(const VcArgs& A, bool cross) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (A.trace && blockIdx.x == 0) { const unsigned long long k = A.trace[0] + 1; if (k < 62) { A.trace[k] = mg_now(); A.trace[0] = k; } }
+        const unsigned g = *A.bar_gen;
+        __threadfence();
+        if (atomicAdd(A.bar_count, 1u) + 1u == gridDim.x) {
+            *A.bar_count = 0u;
+            if (cross && A.xg.nranks > 1) xg_barrier_thread(A.xg);
+            __threadfence();
+            *A.bar_gen = g + 1u;
+        } else {
+            while (*A.bar_gen == g) { }
+            __threadfence();
+        }
+        if (A.trace && blockIdx.x == 0) { const unsigned long long k = A.trace[0] + 1; if (k < 62) { A.trace[k] = mg_now(); A.trace[0] = k; } }
+    }
+    __syncthreads();
+}
+
+// tail: the smallest levels inside one block, in SHARED memory (operators copied in at kernel start, while the other blocks
+// form P'r), unfused sweeps with stored x and block barriers between them
+struct TailLv { int px, py, n; double *st, *dinv, *r, *t, *x; };
+__device__ __forceinline__ TailLv mg_tail_level(const VcArgs& A, double* sm, int l) {
+    int o = 0;
+    for (int k = A.lt; k < l; ++k) o += 11 * int(A.lev[k].n);
+    const int n = int(A.lev[l].n);
+    return TailLv{A.lev[l].px, A.lev[l].py, n, sm + o, sm + o + 7 * n, sm + o + 8 * n, sm + o + 9 * n, sm + o + 10 * n};
+}
+__device__ void mg_tail_load(const VcArgs& A, double* sm) {      // st | dinv of every tail level (adjacent in the pool as well)
+    for (int l = A.lt; l < A.nlev; ++l) {
+        const TailLv L = mg_tail_level(A, sm, l);
+        const double* __restrict__ src = A.lev[l].st;
+        constexpr int U = 8;      // independent loads in flight per thread: one block fetches ~60 kB here
+        for (int i0 = threadIdx.x; i0 < 8 * L.n; i0 += blockDim.x * U) {
+            double v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) { const int i = i0 + u * blockDim.x; v[u] = i < 8 * L.n ? src[i] : 0.0; }
+#pragma unroll
+            for (int u = 0; u < U; ++u) { const int i = i0 + u * blockDim.x; if (i < 8 * L.n) L.st[i] = v[u]; }
+        }
+    }
+}
+__device__ void mg_tail(const VcArgs& A, double* sm) {
     const int T = blockDim.x, tid = threadIdx.x;
-    for (int l = 0; l + 1 < A.nl; ++l) {
-        const int px = A.px[l], py = A.py[l], cx = A.px[l + 1], cy = A.py[l + 1];
-        const int64_t n = int64_t(px) * py, nc = int64_t(cx) * cy;
-        for (int64_t p = tid; p < n; p += T) A.x[l][p] = MG_OMEGA * A.dinv[l][p] * A.r[l][p];
-        __syncthreads();
-        for (int64_t p = tid; p < n; p += T) A.t[l][p] = A.r[l][p] - mg_apply_row_rw(A.st[l], A.x[l], p, px, py, n);
-        __syncthreads();
-        for (int64_t I = tid; I < nc; I += T) A.r[l + 1][I] = mg_restrict_pt(A.t[l], px, py, A.dinv[l + 1], I, cx);
+    auto row = [](const TailLv& L, const double* x, int p) {
+        const int iy = p / L.px, ix = p - iy * L.px;
+        double s = L.st[p] * x[p];
+#pragma unroll
+        for (int k = 1; k < 7; ++k) {
+            const int qx = ix + MG_DX[k], qy = iy + MG_DY[k];
+            const bool in = (qx >= 0) & (qy >= 0) & (qx < L.px) & (qy < L.py);
+            s = fma(L.st[k * L.n + p], in ? x[in ? qy * L.px + qx : p] : 0.0, s);
+        }
+        return s;
+    };
+    {
+        const TailLv F = mg_tail_level(A, sm, A.lt);
+        for (int p = tid; p < F.n; p += T) F.r[p] = __ldcg(A.lev[A.lt].r + p);
         __syncthreads();
     }
-    {
-        const int l = A.nl - 1, n = A.px[l] * A.py[l];
-        for (int i = tid; i < n; i += T) {
+    for (int l = A.lt; l + 1 < A.nlev; ++l) {
+        const TailLv F = mg_tail_level(A, sm, l), C = mg_tail_level(A, sm, l + 1);
+        for (int p = tid; p < F.n; p += T) F.x[p] = MG_OMEGA * F.dinv[p] * F.r[p];
+        __syncthreads();
+        for (int p = tid; p < F.n; p += T) F.t[p] = F.r[p] - row(F, F.x, p);
+        __syncthreads();
+        for (int I = tid; I < C.n; I += T) {
             double s = 0.0;
-            for (int j = 0; j < n; ++j) s = fma(A.ainv[i * n + j], A.r[l][j], s);
-            A.t[l][i] = s;
+            if (C.dinv[I] != 0.0) {
+                const int Iy = I / C.px, Ix = I - Iy * C.px;
+#pragma unroll
+                for (int d = 0; d < 7; ++d) {
+                    const int fx = 2 * Ix + MG_DX[d], fy = 2 * Iy + MG_DY[d];
+                    if (fx < 0 || fy < 0 || fx >= F.px || fy >= F.py) continue;
+                    s += (d == 0 ? 1.0 : 0.5) * F.t[fy * F.px + fx];
+                }
+            }
+            C.r[I] = s;
         }
         __syncthreads();
     }
-    for (int l = A.nl - 2; l >= 0; --l) {
-        const int px = A.px[l], py = A.py[l], cx = A.px[l + 1], cy = A.py[l + 1];
-        const int64_t n = int64_t(px) * py;
-        for (int64_t p = tid; p < n; p += T)
-            if (A.dinv[l][p] != 0.0) A.x[l][p] += mg_prolong_pt(A.t[l + 1], cx, cy, p, px);
+    {
+        // dense coarsest solve t = Ainv r (n <= 64): one warp per row, lanes over the columns, fixed-order shuffle tree
+        const TailLv L = mg_tail_level(A, sm, A.nlev - 1);
+        const int lane = tid & 31, w = tid >> 5, nw = T >> 5;
+        for (int i = w; i < L.n; i += nw) {
+            double s = 0.0;
+            for (int j = lane; j < L.n; j += 32) s = fma(A.ainv[i * L.n + j], L.r[j], s);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) L.t[i] = s;
+        }
         __syncthreads();
-        for (int64_t p = tid; p < n; p += T)
-            A.t[l][p] = fma(MG_OMEGA * A.dinv[l][p], A.r[l][p] - mg_apply_row_rw(A.st[l], A.x[l], p, px, py, n), A.x[l][p]);
+    }
+    for (int l = A.nlev - 2; l >= A.lt; --l) {
+        const TailLv F = mg_tail_level(A, sm, l), C = mg_tail_level(A, sm, l + 1);
+        for (int p = tid; p < F.n; p += T)
+            if (F.dinv[p] != 0.0) {
+                const int y = p / F.px, x = p - y * F.px;
+                const int a2 = x & 1, b2 = y & 1, hx = x >> 1, hy = y >> 1;
+                const int x1 = hx + (a2 & b2), y1 = hy, x2 = hx + (a2 & (b2 ^ 1)), y2 = hy + b2;
+                const double g1 = (x1 < C.px && y1 < C.py) ? C.t[y1 * C.px + x1] : 0.0, g2 = (x2 < C.px && y2 < C.py) ? C.t[y2 * C.px + x2] : 0.0;
+                F.x[p] += 0.5 * (g1 + g2);
+            }
+        __syncthreads();
+        for (int p = tid; p < F.n; p += T) F.t[p] = fma(MG_OMEGA * F.dinv[p], F.r[p] - row(F, F.x, p), F.x[p]);
         __syncthreads();
     }
+    {
+        const TailLv F = mg_tail_level(A, sm, A.lt);
+        for (int p = tid; p < F.n; p += T) A.lev[A.lt].t[p] = F.t[p];
+    }
 }
 
-// ---- transfers between the trace space and the vertex grid ----------------------------------------------------------------
 template <int NT>
-__global__ void mg_restrict_trace(const double* __restrict__ r, const int32_t* __restrict__ vcnt, const int32_t* __restrict__ vface, int64_t nnode,
-                                  double* __restrict__ rc) {
-    int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (v >= nnode) return;
-    const int cnt = vcnt[v];
-    double s = 0.0;
-    for (int k = 0; k < cnt; ++k) {      // cnt < 0: fixed vertex
-        const int32_t e = vface[v * MG_MAXVAL + k];
-        const int64_t f = e & 0x7fffffff;
-        s += 0.5 * r[f * NT] + ((e < 0) ? MG_C1 : -MG_C1) * r[f * NT + 1];
+__global__ void __launch_bounds__(MG_THREADS, 2) mg_vcycle_kernel(const VcArgs A) {
+    const int64_t T = int64_t(gridDim.x) * blockDim.x, tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const bool multi = A.xg.nranks > 1;
+    const LvDev& L0 = A.lev[0];
+    const int64_t o0 = int64_t(L0.oy0 - L0.rb) * L0.px;            // first owned row == local node row 0 inside the level-0 arrays
+    const int64_t nown = int64_t(L0.oy1 - L0.oy0) * L0.px;
+    extern __shared__ double mg_sm[];
+    if (A.trace && tid == 0) { A.trace[0] = 1; A.trace[1] = mg_now(); }
+    if (blockIdx.x == 0) mg_tail_load(A, mg_sm);
+    // ---- P'r at the local vertex rows: sums over the OWNED faces (partial in the row shared with the rank above); fixed vertices 0
+    {
+        const int64_t cnt = int64_t(A.prows) * L0.px;
+        for (int64_t v = tid; v < cnt; v += T) {
+            const int c = A.vcnt[v];
+            const int4 e0 = *reinterpret_cast<const int4*>(A.vface + v * MG_MAXVAL), e1 = *reinterpret_cast<const int4*>(A.vface + v * MG_MAXVAL + 4);
+            const int32_t e[MG_MAXVAL] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+            double r0[MG_MAXVAL], r1[MG_MAXVAL];
+#pragma unroll
+            for (int k = 0; k < MG_MAXVAL; ++k) {      // all gathers in flight together; slots beyond the count read face 0
+                const int64_t f = k < c ? (e[k] & 0x7fffffff) : 0;
+                r0[k] = A.r[f * NT]; r1[k] = A.r[f * NT + 1];
+            }
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < MG_MAXVAL; ++k)
+                if (k < c) s += 0.5 * r0[k] + ((e[k] < 0) ? MG_C1 : -MG_C1) * r1[k];
+            if (v < nown && A.fx[v] != 0.0) s = 0.0;
+            L0.r[o0 + v] = s;
+        }
     }
-    rc[v] = s;
-}
-// z += P e
-template <int NT>
-__global__ void __launch_bounds__(RB) mg_prolong_trace(const double* __restrict__ e, const int32_t* __restrict__ facenode, int64_t node0,
-                                                       const uint8_t* __restrict__ isbc, int64_t nface, double* __restrict__ z) {
-    for (int64_t f = int64_t(blockIdx.x) * RB + threadIdx.x; f < nface; f += int64_t(gridDim.x) * RB) {
-        if (isbc[f]) continue;
-        const int64_t v1 = facenode[2 * f] + node0, v2 = facenode[2 * f + 1] + node0;
-        const double a = e[min(v1, v2)], b = e[max(v1, v2)];
-        z[f * NT] += 0.5 * (a + b);
-        z[f * NT + 1] += MG_C1 * (b - a);
+    mg_grid_barrier(A, true);
+    if (multi) {
+        // the owner of the shared row adds the partial sums of the rank below (its spare row)
+        const double* below = L0.rep ? A.gather.src[A.xg.rank > 0 ? A.xg.rank - 1 : 0] : L0.b_r;     // lrep == 0: gather.src = the ranks' level-0 r
+        if (A.xg.rank > 0 && below) {
+            const int64_t bo = int64_t(L0.oy0 - (L0.rep ? 0 : L0.b_rb)) * L0.px;
+            for (int64_t i = tid; i < L0.px; i += T)
+                if (A.fx[i] == 0.0) L0.r[o0 + i] += __ldcg(below + bo + i);
+        }
+        mg_grid_barrier(A, true);
+        if (A.lrep == 0) {      // the whole hierarchy is replicated: collect the rows of the other ranks
+            mg_gather_rows_dev(A.gather, L0.r, L0.n, 1, L0.px, tid, T);
+            mg_grid_barrier(A, false);
+        }
     }
-}
-// scale = 0 on the ranks > 0 of a distributed mesh: the vertex vectors are replicated, their dot product counts once
-__global__ void __launch_bounds__(RB) mg_dot(const double* __restrict__ a, const double* __restrict__ b, int64_t n, double scale, double* __restrict__ part) {
-    double s = 0.0;
-    for (int64_t i = int64_t(blockIdx.x) * RB + threadIdx.x; i < n; i += int64_t(gridDim.x) * RB) s = fma(a[i], b[i], s);
-    const double tot = block_sum(s);
-    if (threadIdx.x == 0) part[blockIdx.x] = scale * tot;
-}
-
-// ======================================================================================================================
-// Meshes without grid structure (parse_mesh_triangle input, permuted node ids, Delaunay meshes): hierarchy-free vertex-space
-// term  z += P C_m(A_c) P' r  with the kernels of hdg_mg_general.cuh (ELL vertex operator, Jacobi-scaled Chebyshev polynomial;
-// bodies also checked on the CPU against scipy: tools/check_mg_general.py).  A fixed polynomial, so plain CG still applies.
-// ======================================================================================================================
-}  // namespace hdg
-#include "hdg_mg_general.cuh"
-namespace hdg {
-
-constexpr int MGX_CHEB_STEPS = 16;          // tools/cheb_prototype.py: m = 16, alpha = 100
-constexpr double MGX_ALPHA = 100.0;
-
-struct MgGeneral {
-    int64_t nnode = 0, nface = 0;
-    int32_t *vcnt = nullptr, *vface = nullptr, *nbr = nullptr;
-    double *val = nullptr, *diag = nullptr, *dinv = nullptr, *rc = nullptr, *x = nullptr, *res = nullptr, *d = nullptr, *fc = nullptr;
-    unsigned long long* lmax_bits = nullptr;
-    double lmax = 0.0;
-    bool adjacency_ok = false;
-};
-
-__global__ void mgx_adj_fill(const int32_t* __restrict__ facenode, int64_t nface, int32_t* __restrict__ vcnt, int32_t* __restrict__ vface,
-                             int32_t* __restrict__ flags) {
-    int64_t f = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (f >= nface) return;
-    const int64_t v1 = facenode[2 * f], v2 = facenode[2 * f + 1];
-    const int64_t lo = min(v1, v2), hi = max(v1, v2);
-    int k = atomicAdd(&vcnt[lo], 1);
-    if (k < MGX_MAXVAL) vface[lo * MGX_MAXVAL + k] = int32_t(f); else atomicExch(&flags[FLAG_MG], 1);
-    k = atomicAdd(&vcnt[hi], 1);
-    if (k < MGX_MAXVAL) vface[hi * MGX_MAXVAL + k] = int32_t(uint32_t(f) | 0x80000000u); else atomicExch(&flags[FLAG_MG], 1);
-}
-__global__ void mgx_adj_sort(int64_t nnode, int32_t* __restrict__ vcnt, int32_t* __restrict__ vface, const uint8_t* __restrict__ isbc) {
-    int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (v >= nnode) return;
-    const int cnt = min(vcnt[v], MGX_MAXVAL);
-    int32_t a[MGX_MAXVAL];
-    bool fixed = false;
-    for (int k = 0; k < cnt; ++k) {
-        a[k] = vface[v * MGX_MAXVAL + k];
-        fixed = fixed || isbc[a[k] & 0x7fffffff];
+    // ---- down
+    for (int l = 0; l < A.lt; ++l) {
+        const LvDev &F = A.lev[l], &C = A.lev[l + 1];
+        const bool own_rows = multi && l + 1 <= A.lrep;            // coarse level distributed, or the first replicated one
+        if (F.rep) mg_stage_down<false>(F, C, own_rows ? C.oy0 : 0, own_rows ? C.oy1 : C.py, int(tid), int(T));
+        else mg_stage_down<true>(F, C, own_rows ? C.oy0 : 0, own_rows ? C.oy1 : C.py, int(tid), int(T));
+        mg_grid_barrier(A, own_rows);
+        if (multi && l + 1 == A.lrep) {
+            mg_gather_rows_dev(A.gather, C.r, C.n, 1, C.px, tid, T);
+            mg_grid_barrier(A, false);
+        }
     }
-    for (int i = 1; i < cnt; ++i) {
-        const int32_t key = a[i];
-        int j = i - 1;
-        while (j >= 0 && (a[j] & 0x7fffffff) > (key & 0x7fffffff)) { a[j + 1] = a[j]; --j; }
-        a[j + 1] = key;
+    // ---- tail (block 0; the others wait at the barrier)
+    if (blockIdx.x == 0) mg_tail(A, mg_sm);
+    mg_grid_barrier(A, false);
+    // ---- up
+    for (int l = A.lt - 1; l >= 0; --l) {
+        const LvDev &F = A.lev[l], &C = A.lev[l + 1];
+        const bool dist = multi && l < A.lrep;
+        if (F.rep) mg_stage_up<false, false>(F, C, 0, F.py, int(tid), int(T));
+        else if (C.rep) mg_stage_up<true, false>(F, C, F.oy0, F.oy1, int(tid), int(T));
+        else mg_stage_up<true, true>(F, C, F.oy0, F.oy1, int(tid), int(T));
+        mg_grid_barrier(A, dist);
     }
-    for (int k = 0; k < cnt; ++k) vface[v * MGX_MAXVAL + k] = a[k];
-    vcnt[v] = (fixed || cnt == 0) ? -1 : cnt;
-}
-// rc = P'r, res = rc, x = 0, d = Dinv res / theta
-__global__ void mgx_cheb_start(int64_t n, int NT, const int32_t* __restrict__ vcnt, const int32_t* __restrict__ vface, const double* __restrict__ r,
-                               const double* __restrict__ dinv, double inv_theta, double* __restrict__ rc, double* __restrict__ res,
-                               double* __restrict__ x, double* __restrict__ d) {
-    int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (v >= n) return;
-    const double s = mgx_restrict_row(v, NT, vcnt, vface, r);
-    rc[v] = s; res[v] = s; x[v] = 0.0;
-    d[v] = dinv[v] * s * inv_theta;
-}
-
-static void mgx_free(hdg_context* c) {
-    MgGeneral* g = static_cast<MgGeneral*>(c->mg_general);
-    if (!g) return;
-    void* ptrs[] = {g->vcnt, g->vface, g->nbr, g->val, g->diag, g->dinv, g->rc, g->x, g->res, g->d, g->lmax_bits};
-    for (void* q : ptrs) if (q) cudaFree(q);
-    delete g;
-    c->mg_general = nullptr;
-}
-
-static hdg_status mgx_setup(hdg_context* c) {
-    if (comm_active(c)) return set_err(c, HDG_ERR_INVALID, "the general-mesh multigrid term runs on one GPU");
-    const int NT = c->tab.nt;
-    MgGeneral* g = static_cast<MgGeneral*>(c->mg_general);
-    if (g && (g->nnode != c->nnode || g->nface != c->nface)) { mgx_free(c); g = nullptr; }
-    const int64_t n = c->nnode;
-    if (!g) {
-        g = new MgGeneral();
-        c->mg_general = g;
-        g->nnode = n; g->nface = c->nface;
-        HDG_CUDA(c, cudaMalloc(&g->vcnt, sizeof(int32_t) * n));
-        HDG_CUDA(c, cudaMalloc(&g->vface, sizeof(int32_t) * n * MGX_MAXVAL));
-        HDG_CUDA(c, cudaMalloc(&g->nbr, sizeof(int32_t) * n * MGX_MAXVAL));
-        HDG_CUDA(c, cudaMalloc(&g->val, sizeof(double) * n * MGX_MAXVAL));
-        HDG_CUDA(c, cudaMalloc(&g->diag, sizeof(double) * n));
-        HDG_CUDA(c, cudaMalloc(&g->dinv, sizeof(double) * n));
-        HDG_CUDA(c, cudaMalloc(&g->rc, sizeof(double) * n));
-        HDG_CUDA(c, cudaMalloc(&g->x, sizeof(double) * n));
-        HDG_CUDA(c, cudaMalloc(&g->res, sizeof(double) * n));
-        HDG_CUDA(c, cudaMalloc(&g->d, sizeof(double) * n));
-        HDG_CUDA(c, cudaMalloc(&g->lmax_bits, sizeof(unsigned long long)));
+    // ---- (P'r).V(P'r) over the owned rows, z += P t on the owned faces
+    {
+        double s = 0.0;
+        for (int64_t i = tid; i < nown; i += T) s = fma(__ldcg(L0.r + o0 + i), __ldcg(L0.t + o0 + i), s);
+        const double tot = block_sum(s);
+        if (threadIdx.x == 0) A.part[blockIdx.x] = tot;
+        if (blockIdx.x == 0)
+            for (int i = gridDim.x + threadIdx.x; i < A.np; i += blockDim.x) A.part[i] = 0.0;
+        constexpr int U = 4;      // faces per trip: the vertex loads of all of them are issued before the first update of z
+        for (int64_t f0 = tid; f0 < A.nface; f0 += T * U) {
+            double a[U], b[U], z0[U], z1[U];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t f = f0 + u * T;
+                ok[u] = f < A.nface;
+                const int64_t fs = ok[u] ? f : 0;
+                const int2 vv = *reinterpret_cast<const int2*>(A.facenode + 2 * fs);
+                const int lo = min(vv.x, vv.y), hi = max(vv.x, vv.y);
+                a[u] = lv<AR_T, true>(L0, lo % L0.px, lo / L0.px + A.node_row0);
+                b[u] = lv<AR_T, true>(L0, hi % L0.px, hi / L0.px + A.node_row0);
+                z0[u] = A.z[fs * NT]; z1[u] = A.z[fs * NT + 1];
+                ok[u] = ok[u] && !A.isbc[fs];
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (ok[u]) {
+                    const int64_t f = f0 + u * T;
+                    A.z[f * NT] = z0[u] + 0.5 * (a[u] + b[u]);
+                    A.z[f * NT + 1] = z1[u] + MG_C1 * (b[u] - a[u]);
+                }
+        }
+        if (A.trace && tid == 0) { const unsigned long long k = A.trace[0] + 1; if (k < 62) { A.trace[k] = mg_now(); A.trace[0] = k; } }
     }
-    const unsigned nb = (unsigned)ceil_div(n, 256);
-    if (!g->adjacency_ok) {
-        HDG_CUDA(c, cudaMemsetAsync(g->vcnt, 0, sizeof(int32_t) * n, c->stream));
-        HDG_CUDA(c, cudaMemsetAsync(c->d_flags + FLAG_MG, 0, sizeof(int32_t), c->stream));
-        mgx_adj_fill<<<(unsigned)ceil_div(c->nface, 256), 256, 0, c->stream>>>(c->d_facenode, c->nface, g->vcnt, g->vface, c->d_flags);
-        mgx_adj_sort<<<nb, 256, 0, c->stream>>>(n, g->vcnt, g->vface, c->d_isbc);
-        mgx_neighbours<<<nb, 256, 0, c->stream>>>(n, g->vcnt, g->vface, c->d_facenode, g->nbr);
-        c->launches += 3;
-        HDG_CUDA(c, cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int32_t) * NFLAGS, cudaMemcpyDeviceToHost, c->stream));
-        HDG_CUDA(c, cudaStreamSynchronize(c->stream));
-        if (c->h_flags[FLAG_MG]) return set_err(c, HDG_ERR_INVALID, "a vertex has more than 16 faces");
-        g->adjacency_ok = true;
-    }
-    // operator (every solve: the matrix may have changed), inverse diagonal, Gershgorin bound of D^-1 A_c
-    mgx_operator<<<nb, 256, 0, c->stream>>>(n, NT, c->d_Kd, c->d_Ko, c->d_kcol, c->d_isbc, c->d_facenode, g->vcnt, g->vface, g->nbr, g->diag, g->val);
-    HDG_CUDA(c, cudaMemsetAsync(g->lmax_bits, 0, sizeof(unsigned long long), c->stream));
-    mgx_dinv<<<nb, 256, 0, c->stream>>>(n, g->vcnt, g->diag, g->val, g->dinv, g->lmax_bits);
-    c->launches += 2;
-    unsigned long long bits = 0;
-    HDG_CUDA(c, cudaMemcpyAsync(&bits, g->lmax_bits, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
-    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
-    std::memcpy(&g->lmax, &bits, sizeof(double));
-    if (!(g->lmax > 0.0)) g->lmax = 2.0;      // no free vertex at all: the term vanishes anyway
-    return HDG_OK;
-}
-
-static hdg_status mgx_apply(hdg_context* c, const double* r, double* z, double* part, int np) {
-    MgGeneral* g = static_cast<MgGeneral*>(c->mg_general);
-    cudaStream_t s = c->stream;
-    const int NT = c->tab.nt;
-    const int64_t n = g->nnode;
-    const unsigned nb = (unsigned)ceil_div(n, 256);
-    const double lmax = g->lmax, lmin = lmax / MGX_ALPHA;
-    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
-    double rho = 1.0 / sigma;
-    mgx_cheb_start<<<nb, 256, 0, s>>>(n, NT, g->vcnt, g->vface, r, g->dinv, 1.0 / theta, g->rc, g->res, g->x, g->d);
-    for (int i = 0; i < MGX_CHEB_STEPS; ++i) {
-        mgx_cheb_residual<<<nb, 256, 0, s>>>(n, g->vcnt, g->nbr, g->diag, g->val, g->d, g->x, g->res);
-        const double rho_new = 1.0 / (2.0 * sigma - rho);
-        mgx_cheb_direction<<<nb, 256, 0, s>>>(n, g->dinv, g->res, rho_new * rho, 2.0 * rho_new / delta, g->d);
-        rho = rho_new;
-    }
-    mg_dot<<<np, RB, 0, s>>>(g->rc, g->x, n, 1.0, part);
-    mgx_prolong<<<(unsigned)ceil_div(c->nface_own, 256), 256, 0, s>>>(c->nface_own, NT, c->d_facenode, c->d_isbc, g->x, z);
-    return HDG_OK;
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
-static inline unsigned nblk(int64_t n, int b = 256) { return (unsigned)ceil_div(n, b); }
+struct MgLevelHost {
+    int px = 0, py = 0;
+    bool rep = false;
+    int oy0[MAXR + 1] = {};          // owned rows of rank q: [oy0[q], oy0[q+1])
+    int64_t off[MAXR] = {};          // offset of the level's arrays in rank q's pool (doubles)
+    int64_t n[MAXR] = {};            // stored points on rank q
+};
 
-static void mgx_free(hdg_context* c);
+struct MgData {
+    int nlev = 0, lrep = 0, lt = 0;
+    MgLevelHost lev[MG_MAXLEV];
+    int R = 1, rank = 0;
+    double* pool = nullptr;          // one allocation for all levels (+ the level-0 fixed flags behind them)
+    int64_t pool_doubles = 0;
+    int64_t fx_off[MAXR] = {};       // where the fixed flags start in rank q's pool
+    void* peer_pool[MAXR] = {};      // the pools of all ranks, mapped (peer_pool[rank] = pool)
+    double* ainv = nullptr;          // dense inverse of the coarsest operator
+    int32_t* vface = nullptr;        // local nodes x MG_MAXVAL: incident owned faces ascending, bit 31 = the vertex is the face's hi vertex
+    int32_t* vcnt = nullptr;
+    unsigned* bar = nullptr;         // grid barrier words: count, generation
+    unsigned long long* trace = nullptr;   // 64 words, only with HDG_MG_TRACE=1 (hdg_mg_trace)
+    int64_t nnode_local = 0, nface = 0;
+    int nx = 0, ny = 0;
+    bool adjacency_ok = false;
+    int grid_blocks = 0;
+    size_t tail_smem = 0;            // shared memory of the V-cycle kernel: the tail levels
+    VcArgs args{};                   // everything but r / z / part
+};
+
+static inline unsigned nblk(int64_t n, int b = 256) { return (unsigned)std::max<int64_t>(1, ceil_div(n, b)); }
+
+// arrays of one level inside a pool: st (7 n) | dinv | r | t | x
+static void level_pointers(double* base, int64_t n, double*& st, double*& dinv, double*& r, double*& t, double*& x) {
+    st = base; dinv = base + 7 * n; r = base + 8 * n; t = base + 9 * n; x = base + 10 * n;
+}
+
+static LvDev level_dev(const MgData* m, int l) {
+    const MgLevelHost& H = m->lev[l];
+    const int q = m->rank;
+    LvDev L{};
+    L.px = H.px; L.py = H.py; L.rep = H.rep ? 1 : 0;
+    L.oy0 = H.oy0[q]; L.oy1 = H.oy0[q + 1];
+    L.rb = H.rep ? 0 : L.oy0;
+    L.n = H.n[q];
+    level_pointers(m->pool + H.off[q], L.n, L.st, L.dinv, L.r, L.t, L.x);
+    if (!H.rep && m->R > 1) {
+        double *st, *dinv, *r, *t, *x;
+        if (q > 0) {
+            level_pointers(static_cast<double*>(m->peer_pool[q - 1]) + H.off[q - 1], H.n[q - 1], st, dinv, r, t, x);
+            L.b_st = st; L.b_dinv = dinv; L.b_r = r; L.b_t = t; L.b_rb = H.oy0[q - 1]; L.b_n = H.n[q - 1];
+        }
+        if (q + 1 < m->R) {
+            level_pointers(static_cast<double*>(m->peer_pool[q + 1]) + H.off[q + 1], H.n[q + 1], st, dinv, r, t, x);
+            L.a_st = st; L.a_dinv = dinv; L.a_r = r; L.a_t = t; L.a_rb = H.oy0[q + 1]; L.a_n = H.n[q + 1];
+        }
+    }
+    return L;
+}
+
+// the array at offset `which` x n of a REPLICATED level on every rank (0: st followed by dinv, 8: r)
+static GatherArgs gather_args(const MgData* m, int l, int which) {
+    GatherArgs g{};
+    g.nranks = m->R; g.rank = m->rank;
+    const MgLevelHost& H = m->lev[l];
+    for (int q = 0; q <= m->R; ++q) g.ry0[q] = H.oy0[q];
+    for (int q = 0; q < m->R; ++q) g.src[q] = static_cast<const double*>(m->peer_pool[q]) + H.off[q] + which * H.n[q];
+    return g;
+}
+
 void mg_free(hdg_context* c) {
     mgx_free(c);
     MgData* m = static_cast<MgData*>(c->mg);
     if (!m) return;
+    if (m->R > 1) comm_close_buffer(c, m->peer_pool);
     if (m->pool) cudaFree(m->pool);
     if (m->ainv) cudaFree(m->ainv);
     if (m->vface) cudaFree(m->vface);
     if (m->vcnt) cudaFree(m->vcnt);
+    if (m->bar) cudaFree(m->bar);
+    if (m->trace) cudaFree(m->trace);
     delete m;
     c->mg = nullptr;
+}
+
+// the mesh or the Dirichlet set changed: the buffers stay (if the sizes still fit at the next solve), the adjacency is rebuilt
+void mg_invalidate(hdg_context* c) {
+    mgx_invalidate(c);
+    MgData* m = static_cast<MgData*>(c->mg);
+    if (m) m->adjacency_ok = false;
+}
+
+static hdg_status xbarrier(hdg_context* c) {      // stream-ordered barrier across the GPUs (set-up only)
+    if (!comm_active(c)) return HDG_OK;
+    return comm_p2p_allreduce(c, c->d_partials, 1, 0u);
 }
 
 template <int NT> static hdg_status mg_setup_t(hdg_context* c) {
@@ -582,85 +767,202 @@ template <int NT> static hdg_status mg_setup_t(hdg_context* c) {
         return set_err(c, HDG_ERR_INVALID, "on several GPUs the multigrid preconditioner needs hdg_set_rectangle_mesh (strip partition)");
     if (c->grid_px < 2 || c->grid_py < 2) return mgx_setup(c);        // no grid structure: hierarchy-free vertex term
     mgx_free(c);
+    if (multi && !comm_p2p(c))
+        return set_err(c, HDG_ERR_INVALID, "the distributed multigrid preconditioner needs peer access between the GPUs (CUDA IPC)");
+    const int R = multi ? c->comm->nranks : 1, rank = multi ? c->comm->rank : 0;
     MgData* m = static_cast<MgData*>(c->mg);
-    const int64_t nnode_g = c->grid_px * c->grid_py;       // the GLOBAL vertex grid (== the local one on a single GPU)
-    if (m && (m->nnode != nnode_g || m->nface != c->nface || m->nx != c->grid_px - 1 || m->ny != c->grid_py - 1)) { mg_free(c); m = nullptr; }
+    if (m && (m->nnode_local != c->nnode || m->nface != c->nface || m->nx != c->grid_px - 1 || m->ny != c->grid_py - 1 || m->R != R)) { mg_free(c); m = nullptr; }
     if (!m) {
         m = new MgData();
         c->mg = m;
-        m->nnode = nnode_g; m->nface = c->nface; m->nx = int(c->grid_px) - 1; m->ny = int(c->grid_py) - 1;
-        m->multi = multi;
-        m->node0 = multi ? c->comm->j0 * c->grid_px : 0;    // local node ids are global ids minus j0 (nx+1), see Strip
-        m->nface_rows = c->nface_own;
-        // grid hierarchy
+        m->nnode_local = c->nnode; m->nface = c->nface; m->nx = int(c->grid_px) - 1; m->ny = int(c->grid_py) - 1;
+        m->R = R; m->rank = rank;
+        // grid hierarchy (global) and the rows every rank owns
         int px = int(c->grid_px), py = int(c->grid_py);
-        int64_t total = 0;
         while (true) {
-            MgLevel& L = m->lev[m->nlev++];
-            L.px = px; L.py = py; L.n = int64_t(px) * py;
-            total += 11 * L.n;
-            if (L.n <= MG_DENSE || std::min(px, py) < 3 || m->nlev == MG_MAXLEV) break;
+            MgLevelHost& H = m->lev[m->nlev++];
+            H.px = px; H.py = py;
+            if (int64_t(px) * py <= MG_DENSE || std::min(px, py) < 3 || m->nlev == MG_MAXLEV) break;
             px = (px + 1) / 2; py = (py + 1) / 2;
         }
-        const MgLevel& last = m->lev[m->nlev - 1];
-        if (last.n > MG_DENSE) { mg_free(c); return set_err(c, HDG_ERR_INVALID, "mesh too anisotropic for the multigrid preconditioner"); }
-        // fused tail: the levels with at most MG_FUSE_MAX points (always includes the dense one)
-        m->lf = m->nlev - 1;
-        int64_t fuse_max = MG_FUSE_MAX;
-        if (const char* e = getenv("HDG_MG_FUSE_MAX")) fuse_max = atoll(e);      // tuning knob
-        while (m->lf > 0 && m->lev[m->lf - 1].n <= fuse_max && m->nlev - (m->lf - 1) <= MG_FUSE_LEVELS) --m->lf;
-        HDG_CUDA(c, cudaMalloc(&m->pool, sizeof(double) * total));
-        double* q = m->pool;
+        const MgLevelHost& last = m->lev[m->nlev - 1];
+        if (int64_t(last.px) * last.py > MG_DENSE) { mg_free(c); return set_err(c, HDG_ERR_INVALID, "mesh too anisotropic for the multigrid preconditioner"); }
+        int64_t rep_max = MG_REP_MAX;
+        if (const char* e = getenv("HDG_MG_REP_MAX")) rep_max = atoll(e);      // test / tuning knob
+        const int64_t ny = m->ny;
+        m->lrep = R > 1 ? m->nlev : 0;
         for (int l = 0; l < m->nlev; ++l) {
-            MgLevel& L = m->lev[l];
-            L.st = q; q += 7 * L.n;
-            L.dinv = q; q += L.n;
-            L.r = q; q += L.n;
-            L.x = q; q += L.n;
-            L.t = q; q += L.n;
+            MgLevelHost& H = m->lev[l];
+            int minrows = H.py;
+            for (int q = 0; q <= R; ++q) {
+                if (l == 0) H.oy0[q] = q == R ? H.py : int(ny * q / R);         // strips of quad rows (mesh_rectangle); the last rank also owns row ny
+                else H.oy0[q] = q == R ? H.py : (m->lev[l - 1].oy0[q] + 1) / 2;
+                if (q > 0) minrows = std::min(minrows, H.oy0[q] - H.oy0[q - 1]);
+            }
+            if (R > 1 && m->lrep == m->nlev && (int64_t(H.px) * H.py <= rep_max || minrows < 2)) m->lrep = l;
         }
-        HDG_CUDA(c, cudaMalloc(&m->ainv, sizeof(double) * last.n * last.n));
-        HDG_CUDA(c, cudaMalloc(&m->vface, sizeof(int32_t) * nnode_g * MG_MAXVAL));
-        HDG_CUDA(c, cudaMalloc(&m->vcnt, sizeof(int32_t) * nnode_g));
-    }
-    MgLevel& L0 = m->lev[0];
-    if (!m->adjacency_ok) {
-        // vertex -> OWNED faces (a face row is counted by exactly one rank); the "fixed" flags are global
-        double* fc = L0.st;      // 2 n doubles of scratch (the stencil array is filled below)
-        HDG_CUDA(c, cudaMemsetAsync(m->vcnt, 0, sizeof(int32_t) * nnode_g, c->stream));
-        HDG_CUDA(c, cudaMemsetAsync(c->d_flags + FLAG_MG, 0, sizeof(int32_t), c->stream));
-        mg_adj_fill<<<nblk(m->nface_rows), 256, 0, c->stream>>>(c->d_facenode, m->nface_rows, m->node0, m->vcnt, m->vface, c->d_flags);
-        mg_adj_sort<<<nblk(nnode_g), 256, 0, c->stream>>>(nnode_g, m->vcnt, m->vface, c->d_isbc, fc);
-        if (multi) {
-            hdg_status st = comm_allreduce_sum(c, fc, int(2 * nnode_g));
+        // tail: the levels with at most MG_TAIL_MAX points (always includes the dense one)
+        m->lt = m->nlev - 1;
+        int64_t tail_max = MG_TAIL_MAX;
+        if (const char* e = getenv("HDG_MG_FUSE_MAX")) tail_max = std::min<int64_t>(MG_TAIL_MAX, atoll(e));      // the tail lives in shared memory
+        while (m->lt > 0 && int64_t(m->lev[m->lt - 1].px) * m->lev[m->lt - 1].py <= tail_max) --m->lt;
+        if (R > 1) m->lrep = std::min(m->lrep, m->lt);       // the tail runs on replicated levels
+        // pool layout of every rank: replicated levels first (identical offsets everywhere), then the distributed ones
+        for (int q = 0; q < R; ++q) {
+            int64_t o = 0;
+            for (int pass = 0; pass < 2; ++pass)
+                for (int l = 0; l < m->nlev; ++l) {
+                    MgLevelHost& H = m->lev[l];
+                    H.rep = R == 1 || l >= m->lrep;
+                    if ((pass == 0) != H.rep) continue;
+                    H.n[q] = H.rep ? int64_t(H.px) * H.py : int64_t(H.oy0[q + 1] - H.oy0[q] + 1) * H.px;
+                    H.off[q] = o;
+                    o += 11 * H.n[q];
+                }
+            m->fx_off[q] = o;
+            if (q == rank) m->pool_doubles = o + m->lev[0].n[q];
+        }
+        HDG_CUDA(c, cudaMalloc(&m->pool, sizeof(double) * m->pool_doubles));
+        HDG_CUDA(c, cudaMemsetAsync(m->pool, 0, sizeof(double) * m->pool_doubles, c->stream));
+        HDG_CUDA(c, cudaMalloc(&m->ainv, sizeof(double) * int64_t(last.px) * last.py * last.px * last.py));
+        HDG_CUDA(c, cudaMalloc(&m->vface, sizeof(int32_t) * c->nnode * MG_MAXVAL));
+        HDG_CUDA(c, cudaMalloc(&m->vcnt, sizeof(int32_t) * c->nnode));
+        HDG_CUDA(c, cudaMalloc(&m->bar, sizeof(unsigned) * 2));
+        HDG_CUDA(c, cudaMemsetAsync(m->bar, 0, sizeof(unsigned) * 2, c->stream));
+        if (getenv("HDG_MG_TRACE")) {
+            HDG_CUDA(c, cudaMalloc(&m->trace, sizeof(unsigned long long) * 64));
+            HDG_CUDA(c, cudaMemsetAsync(m->trace, 0, sizeof(unsigned long long) * 64, c->stream));
+        }
+        m->peer_pool[rank] = m->pool;
+        if (R > 1) {     // neighbours for the distributed levels, everybody for the gather of the first replicated one (collective)
+            HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+            hdg_status st = comm_share_buffer(c, m->pool, (1u << R) - 1u, m->peer_pool);
             if (st) return st;
         }
-        mg_adj_fix<<<nblk(nnode_g), 256, 0, c->stream>>>(nnode_g, m->vcnt, fc);
-        c->launches += 3;
+        int dev = 0, sms = 148, occ = 1;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        for (int l = m->lt; l < m->nlev; ++l) m->tail_smem += sizeof(double) * 11 * size_t(m->lev[l].px) * m->lev[l].py;
+        if (m->tail_smem > 48 * 1024)
+            HDG_CUDA(c, cudaFuncSetAttribute(mg_vcycle_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(m->tail_smem)));
+        HDG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mg_vcycle_kernel<NT>, MG_THREADS, m->tail_smem));
+        m->grid_blocks = sms * std::max(1, std::min(occ, 2));
+    }
+    const int q = rank;
+    const MgLevelHost& H0 = m->lev[0];
+    const LvDev L0 = level_dev(m, 0);
+    double* fx = m->pool + m->fx_off[q];                    // level-0 layout: rows [rb, ...)
+    const int j0 = H0.oy0[q];                               // global vertex row of local node row 0
+    const int own_rows = H0.oy0[q + 1] - H0.oy0[q];
+    const int prows = own_rows + (q + 1 < R ? 1 : 0);       // + the row shared with the rank above (partial sums)
+    const int64_t lo = int64_t(j0 - L0.rb) * L0.px;         // local node 0 inside the level-0 arrays
+    const int64_t pcount = int64_t(prows) * L0.px, ocount = int64_t(own_rows) * L0.px;
+    if (multi && j0 != int(c->comm->j0)) return set_err(c, HDG_ERR_INVALID, "internal: strip rows of the multigrid hierarchy and of the mesh differ");
+    // the same row of the rank below: its spare row (distributed layout) or its copy of the row (replicated layout)
+    const int64_t bo = q > 0 ? int64_t(j0 - (H0.rep ? 0 : H0.oy0[q - 1])) * H0.px : 0;
+    const double* below0 = q > 0 ? static_cast<const double*>(m->peer_pool[q - 1]) + H0.off[q - 1] : nullptr;
+    FxView fxv{};
+    fxv.mine = fx; fxv.rb = L0.rb; fxv.oy1 = H0.oy0[q + 1]; fxv.rep = H0.rep ? 1 : 0;
+    if (!H0.rep && q + 1 < R) {
+        fxv.above = static_cast<const double*>(m->peer_pool[q + 1]) + m->fx_off[q + 1];
+        fxv.a_rb = H0.oy0[q + 1];
+    }
+    hdg_status st = HDG_OK;
+    if (!m->adjacency_ok) {
+        HDG_CUDA(c, cudaMemsetAsync(m->vcnt, 0, sizeof(int32_t) * c->nnode, c->stream));
+        HDG_CUDA(c, cudaMemsetAsync(c->d_flags + FLAG_MG, 0, sizeof(int32_t), c->stream));
+        mg_adj_fill<<<nblk(c->nface_own), 256, 0, c->stream>>>(c->d_facenode, c->nface_own, m->vcnt, m->vface, c->d_flags);
+        // partial flags / counts of the local rows into the scratch vectors t / x of level 0 (adjacent arrays, stride n)
+        mg_adj_sort<<<nblk(pcount), 256, 0, c->stream>>>(pcount, m->vcnt, m->vface, c->d_isbc, L0.t + lo, L0.x + lo);
+        c->launches += 2;
+        if (multi) {
+            if ((st = xbarrier(c))) return st;
+            if (q > 0) {
+                mg_add_shared_row<<<nblk(H0.px), 256, 0, c->stream>>>(L0.t + lo, L0.n, below0 + 9 * H0.n[q - 1] + bo, H0.n[q - 1], 2, H0.px);
+                c->launches += 1;
+            }
+        }
+        mg_fix_flags<<<nblk(ocount), 256, 0, c->stream>>>(ocount, L0.t + lo, L0.x + lo, fx + lo);
+        c->launches += 1;
+        if (multi) {
+            if ((st = xbarrier(c))) return st;
+            if (H0.rep) {    // replicated level 0: every rank needs all flags
+                GatherArgs g{};
+                g.nranks = R; g.rank = q;
+                for (int k = 0; k <= R; ++k) g.ry0[k] = H0.oy0[k];
+                for (int k = 0; k < R; ++k) g.src[k] = static_cast<const double*>(m->peer_pool[k]) + m->fx_off[k];
+                mg_gather_rows<<<nblk(H0.n[q]), 256, 0, c->stream>>>(g, fx, H0.n[q], 1, H0.px);
+                c->launches += 1;
+                if ((st = xbarrier(c))) return st;
+            }
+        }
         HDG_CUDA(c, cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int32_t) * NFLAGS, cudaMemcpyDeviceToHost, c->stream));
         HDG_CUDA(c, cudaStreamSynchronize(c->stream));
         if (c->h_flags[FLAG_MG]) return set_err(c, HDG_ERR_INVALID, "a vertex has more than 8 faces");
         m->adjacency_ok = true;
     }
-    // operators (every solve: the matrix may have changed)
-    mg_vertex_operator<NT><<<nblk(L0.n), 256, 0, c->stream>>>(c->d_Kd, c->d_Ko, c->d_kcol, c->d_isbc, c->d_facenode, m->node0, m->vcnt,
-                                                              m->vface, L0.px, L0.n, L0.st);
-    if (multi) {     // rows of the faces of the other ranks
-        hdg_status st = comm_allreduce_sum(c, L0.st, int(7 * L0.n));
-        if (st) return st;
+    // ---- operators (every solve: the matrix may have changed)
+    mg_vertex_operator<NT><<<nblk(pcount), 256, 0, c->stream>>>(c->d_Kd, c->d_Ko, c->d_kcol, c->d_isbc, c->d_facenode, j0, m->vcnt, m->vface,
+                                                                fxv, L0.px, pcount, L0.st + lo, L0.n);
+    c->launches += 1;
+    if (multi) {
+        if ((st = xbarrier(c))) return st;
+        if (q > 0) {
+            mg_add_shared_row<<<nblk(H0.px), 256, 0, c->stream>>>(L0.st + lo, L0.n, below0 + bo, H0.n[q - 1], 7, H0.px);
+            c->launches += 1;
+        }
     }
-    mg_finalize_rows<<<nblk(L0.n), 256, 0, c->stream>>>(m->vcnt, L0.n, L0.st, L0.dinv);
-    c->launches += 2;
+    mg_finalize_rows<<<nblk(ocount), 256, 0, c->stream>>>(fx + lo, ocount, L0.st + lo, L0.n, L0.dinv + lo);
+    c->launches += 1;
+    auto complete_level = [&](int l) -> hdg_status {      // operators of level l written by their owners: make them readable everywhere
+        if (!multi) return HDG_OK;
+        hdg_status s2 = xbarrier(c);
+        if (s2) return s2;
+        if (m->lev[l].rep && l == m->lrep) {               // first replicated level: collect the other ranks' rows (st + dinv)
+            const LvDev L = level_dev(m, l);
+            const GatherArgs g = gather_args(m, l, 0);
+            mg_gather_rows<<<nblk(L.n), 256, 0, c->stream>>>(g, L.st, L.n, 8, L.px);
+            c->launches += 1;
+            s2 = xbarrier(c);
+        }
+        return s2;
+    };
+    if ((st = complete_level(0))) return st;
     for (int l = 0; l + 1 < m->nlev; ++l) {
-        MgLevel &F = m->lev[l], &C = m->lev[l + 1];
-        mg_rap<<<nblk(C.n), 256, 0, c->stream>>>(F.st, F.dinv, F.px, F.py, C.px, C.py, C.st, C.dinv);
-        mg_drop_fixed<<<nblk(C.n), 256, 0, c->stream>>>(C.st, C.dinv, C.px, C.py);
-        c->launches += 2;
+        const LvDev F = level_dev(m, l), C = level_dev(m, l + 1);
+        const bool own = multi && l + 1 <= m->lrep;          // coarse rows computed by their owners
+        const int cy0 = own ? C.oy0 : 0, cy1 = own ? C.oy1 : C.py;
+        const int64_t cnt = int64_t(cy1 - cy0) * C.px;
+        mg_rap<<<nblk(cnt), 256, 0, c->stream>>>(F, C, cy0, cy1);
+        c->launches += 1;
+        if (own && m->lev[l + 1].rep) {                      // first replicated level: gather, then drop on all rows
+            if ((st = complete_level(l + 1))) return st;
+            mg_drop_fixed<<<nblk(C.n), 256, 0, c->stream>>>(C, 0, C.py);
+        } else {
+            if (own && (st = xbarrier(c))) return st;        // drop_fixed reads the neighbours' dinv
+            mg_drop_fixed<<<nblk(cnt), 256, 0, c->stream>>>(C, cy0, cy1);
+            if (own && (st = xbarrier(c))) return st;
+        }
+        c->launches += 1;
     }
-    const MgLevel& last = m->lev[m->nlev - 1];
+    const LvDev last = level_dev(m, m->nlev - 1);
     mg_dense_inverse<<<1, 256, sizeof(double) * last.n * last.n, c->stream>>>(last.st, last.px, last.py, m->ainv);
     c->launches += 1;
     HDG_CUDA(c, cudaGetLastError());
+    // ---- arguments of the V-cycle kernel
+    VcArgs& A = m->args;
+    A = VcArgs{};
+    A.nlev = m->nlev; A.lrep = multi ? m->lrep : m->nlev; A.lt = m->lt;
+    for (int l = 0; l < m->nlev; ++l) A.lev[l] = level_dev(m, l);
+    A.ainv = m->ainv;
+    A.nface = c->nface_own;
+    A.vcnt = m->vcnt; A.vface = m->vface; A.facenode = c->d_facenode; A.isbc = c->d_isbc;
+    A.node_row0 = j0; A.prows = prows;
+    A.fx = fx + lo;
+    A.bar_count = m->bar; A.bar_gen = m->bar + 1;
+    comm_xg(c, &A.xg);
+    if (multi) A.gather = gather_args(m, m->lrep, 8);       // r of the first replicated level
+    A.trace = m->trace;
     return HDG_OK;
 }
 
@@ -674,48 +976,19 @@ hdg_status mg_setup(hdg_context* c) {
     return set_err(c, HDG_ERR_INVALID, "unsupported order");
 }
 
-// z += P V(P' r);  part[0..np) = partial sums of (P' r) . V(P' r).  Enqueued on c->stream (capturable).
+// z += P V(P' r);  part[0..np) = partial sums of (P' r) . V(P' r).  One cooperative launch on c->stream (capturable).
 template <int NT> static hdg_status mg_apply_t(hdg_context* c, const double* r, double* z, double* part, int np) {
     MgData* m = static_cast<MgData*>(c->mg);
-    cudaStream_t s = c->stream;
-    MgLevel& L0 = m->lev[0];
-    mg_restrict_trace<NT><<<nblk(L0.n), 256, 0, s>>>(r, m->vcnt, m->vface, L0.n, L0.r);
-    if (m->multi) {     // P'r summed over the ranks; the V-cycle below is replicated
-        hdg_status st = comm_allreduce_sum(c, L0.r, int(L0.n));
-        if (st) return st;
-    }
-    const int nl = m->nlev, lf = m->lf;
-    for (int l = 0; l < lf; ++l) {
-        MgLevel &F = m->lev[l], &C = m->lev[l + 1];
-        mg_smooth0<<<nblk(F.n), 256, 0, s>>>(F.dinv, F.r, F.x, F.n);
-        mg_residual<<<nblk(F.n), 256, 0, s>>>(F.st, F.r, F.x, F.t, F.px, F.py);
-        mg_restrict<<<nblk(C.n), 256, 0, s>>>(F.t, F.px, F.py, C.dinv, C.r, C.px, C.py);
-    }
-    {   // levels lf .. nl-1 in one block (mg_fused_vcycle); the solution of level lf ends up in lev[lf].t
-        MgFused A{};
-        A.nl = nl - lf;
-        for (int l = lf; l < nl; ++l) {
-            MgLevel& L = m->lev[l];
-            const int k = l - lf;
-            A.px[k] = L.px; A.py[k] = L.py; A.st[k] = L.st; A.dinv[k] = L.dinv; A.r[k] = L.r; A.x[k] = L.x; A.t[k] = L.t;
-        }
-        A.ainv = m->ainv;
-        const int64_t nmax = m->lev[lf].n;
-        const int threads = int(std::min<int64_t>(1024, std::max<int64_t>(64, (nmax + 31) / 32 * 32)));
-        mg_fused_vcycle<<<1, threads, 0, s>>>(A);
-    }
-    for (int l = lf - 1; l >= 0; --l) {
-        MgLevel &F = m->lev[l], &C = m->lev[l + 1];
-        mg_prolong_add<<<nblk(F.n), 256, 0, s>>>(C.t, C.px, C.py, F.dinv, F.x, F.px, F.py);
-        mg_smooth<<<nblk(F.n), 256, 0, s>>>(F.st, F.dinv, F.r, F.x, F.t, F.px, F.py);
-    }
-    mg_dot<<<np, RB, 0, s>>>(L0.r, L0.t, L0.n, (m->multi && c->comm->rank != 0) ? 0.0 : 1.0, part);
-    mg_prolong_trace<NT><<<np, RB, 0, s>>>(L0.t, c->d_facenode, m->node0, c->d_isbc, c->nface_own, z);
+    VcArgs A = m->args;
+    A.r = r; A.z = z; A.part = part; A.np = np;
+    const int grid = std::max(1, std::min(m->grid_blocks, np));
+    void* args[] = {&A};
+    HDG_CUDA(c, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(mg_vcycle_kernel<NT>), dim3(grid), dim3(MG_THREADS), args, m->tail_smem, c->stream));
     return HDG_OK;
 }
 
 hdg_status mg_apply(hdg_context* c, const double* r, double* z, double* part, int np) {
-    if (c->mg_general) return mgx_apply(c, r, z, part, np);
+    if (mgx_active(c)) return mgx_apply(c, r, z, part, np);
     switch (c->tab.nt) {
         case 2: return mg_apply_t<2>(c, r, z, part, np);
         case 3: return mg_apply_t<3>(c, r, z, part, np);
@@ -725,11 +998,21 @@ hdg_status mg_apply(hdg_context* c, const double* r, double* z, double* part, in
     return HDG_OK;
 }
 
+// measurement (HDG_MG_TRACE=1): microseconds since the kernel start at every barrier entry / exit of the last V-cycle
+int mg_trace(hdg_context* c, double* us, int cap) {
+    MgData* m = static_cast<MgData*>(c->mg);
+    if (!m || !m->trace) return 0;
+    unsigned long long h[64];
+    if (cudaMemcpy(h, m->trace, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    const int n = int(std::min<unsigned long long>(h[0], 62));
+    for (int i = 0; i < n && i < cap; ++i) us[i] = double(h[1 + i] - h[1]) * 1e-3;
+    return std::min(n, cap);
+}
+
 int mg_levels(const hdg_context* c) { return c->mg ? static_cast<const MgData*>(c->mg)->nlev : 0; }
-// kernels one mg_apply enqueues: restrict_trace, fused tail, dot, prolong_trace + 5 per unfused level
 int mg_launches_per_apply(const hdg_context* c) {
-    if (c->mg_general) return 3 + 2 * MGX_CHEB_STEPS;
-    return c->mg ? 4 + 5 * static_cast<const MgData*>(c->mg)->lf : 0;
+    if (mgx_active(c)) return mgx_launches_per_apply();
+    return c->mg ? 1 : 0;
 }
 
 }  // namespace hdg

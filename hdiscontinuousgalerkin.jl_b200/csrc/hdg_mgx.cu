@@ -151,6 +151,9 @@ hdg_status mgx_apply(hdg_context* c, const double* r, double* z, double* part, i
 }
 
 bool mgx_active(const hdg_context* c) { return c->mg_general != nullptr; }
+void mgx_invalidate(hdg_context* c) {      // same-size mesh change: keep the buffers, rebuild the adjacency
+    if (c->mg_general) static_cast<MgGeneral*>(c->mg_general)->adjacency_ok = false;
+}
 int mgx_launches_per_apply() { return 3 + 2 * MGX_CHEB_STEPS; }
 
 }  // namespace hdg

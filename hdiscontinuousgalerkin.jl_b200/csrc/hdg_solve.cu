@@ -658,8 +658,7 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
     // one CUDA graph = CHUNK iterations (even, so the rz double-buffer parity restarts at 0)
     // (the multigrid kernels do not test the converged flag: a short chunk bounds the work done after convergence)
     const int CHUNK = mg ? 4 : 32;
-    // multigrid on several GPUs puts an ncclAllReduce into every iteration: launched directly, not captured
-    const bool use_graph = getenv("HDG_NO_GRAPH") == nullptr && !(mg && multi);
+    bool use_graph = getenv("HDG_NO_GRAPH") == nullptr && !(multi && !p2p);      // the NCCL fallback path is launched directly
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
     auto enqueue_iter = [&](int it) {
@@ -685,8 +684,17 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
             if (!gexec) {
                 HDG_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
                 for (int k = 0; k < CHUNK; ++k) enqueue_iter(k);
-                HDG_CUDA(c, cudaStreamEndCapture(c->stream, &graph));
-                HDG_CUDA(c, cudaGraphInstantiate(&gexec, graph, 0));
+                cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+                if (ce == cudaSuccess) ce = cudaGraphInstantiate(&gexec, graph, 0);
+                if (ce != cudaSuccess || cst != HDG_OK) {      // e.g. a launch kind the driver cannot capture: run the iterations directly
+                    cudaGetLastError();
+                    if (graph) { cudaGraphDestroy(graph); graph = nullptr; }
+                    gexec = nullptr;
+                    use_graph = false;
+                    cst = HDG_OK;
+                    c->err.clear();
+                    continue;
+                }
             }
             HDG_CUDA(c, cudaGraphLaunch(gexec, c->stream));
         } else {

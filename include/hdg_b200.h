@@ -241,6 +241,9 @@ hdg_status hdg_last_phase_ms(const hdg_context* ctx, const char* phase, double* 
 /* FP64 FMA throughput of the context's device (TFLOP/s, best of 3 launches of a register-only DFMA kernel, CUDA events):
  * the denominator for the FP64 roofline of the k >= 2 element kernels - MEASURED_PEAKS.json holds no FP64 figure. */
 hdg_status hdg_measure_fp64_peak(hdg_context* ctx, double* tflops);
+/* Stage timing of the multigrid V-cycle kernel (library loaded with HDG_MG_TRACE=1 in the environment): microseconds since the
+ * kernel start at the entry and exit of every grid barrier of the LAST V-cycle; returns the number of values written. */
+int32_t    hdg_mg_trace(hdg_context* ctx, double* usec, int32_t capacity);
 /* Number of kernel launches issued by this context since creation. */
 int64_t    hdg_launch_count(const hdg_context* ctx);
 

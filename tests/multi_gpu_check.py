@@ -48,8 +48,16 @@ def main():
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     ok = True
-    # ---- multigrid preconditioner on strips: replicated vertex hierarchy, all-reduced stencils / vertex residuals
-    for order, qd, nx, ny in ((1, 2, 48, 37), (2, 4, 40, 24), (3, 6, 33, 20), (1, 2, 7, 2 * world)):
+    # ---- multigrid preconditioner on strips: distributed vertex hierarchy (rows of the neighbouring ranks read over peer memory,
+    # cross-GPU barriers inside the V-cycle kernel), replicated below MG_REP_MAX points.  rep_max = 0 forces every level that has
+    # two rows per rank to be distributed (odd row counts, tiny strips); the 300 x 260 mesh takes the default thresholds.
+    for rep_max, order, qd, nx, ny in ((None, 1, 2, 48, 37), (None, 2, 4, 40, 24), (None, 3, 6, 33, 20), (None, 1, 2, 7, 2 * world),
+                                       ("0", 1, 2, 48, 37), ("0", 2, 4, 40, 24), ("0", 3, 6, 33, 20), ("0", 4, 9, 21, 8 * world + 3),
+                                       ("0", 1, 2, 7, 2 * world), (None, 1, 2, 300, 260), ("2000", 2, 4, 130, 141)):
+        if rep_max is None:
+            os.environ.pop("HDG_MG_REP_MAX", None)
+        else:
+            os.environ["HDG_MG_REP_MAX"] = rep_max
         ctx = hdg._Context(order, qd, 1.0, 1, lr)
         ctx.comm_init(dist, device=torch.device("cuda", lr))
         x, u, err2, iters, md = solve(ctx, nx, ny, 1e-13, precond=2)
@@ -65,8 +73,9 @@ def main():
             ex = np.abs(xg - xr).max() / np.abs(xr).max()
             good = ex < 1e-10 and abs(err2 - e1) <= 1e-9 * e1 and abs(iters - it1) <= 1 and iters <= 60
             ok &= good
-            print(f"multigrid k={order} {nx}x{ny} on {world} GPUs: iters {iters} (1 GPU: {it1})  relerr(uhat)={ex:.2e} "
+            print(f"multigrid k={order} {nx}x{ny} rep_max={rep_max} on {world} GPUs: iters {iters} (1 GPU: {it1})  relerr(uhat)={ex:.2e} "
                   f"err2 {err2:.12e} vs {e1:.12e}  {'OK' if good else 'FAIL'}", flush=True)
+    os.environ.pop("HDG_MG_REP_MAX", None)
     if "--mg-only" in sys.argv:
         flag = torch.tensor([1 if ok else 0], device="cuda")
         dist.broadcast(flag, src=0)
