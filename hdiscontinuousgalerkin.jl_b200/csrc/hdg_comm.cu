@@ -308,13 +308,10 @@ __global__ void __launch_bounds__(XG_THREADS) xgpu_allreduce(const double* __res
         volatile double* dst = peer_mail[threadIdx.x] + size_t(buf * nranks + rank) * MAILW;
         for (int w = 0; w < MAILW - 1; ++w)
             if ((slot_mask >> w) & 1u) dst[1 + w] = loc[w];
-        __threadfence_system();
-        *reinterpret_cast<volatile unsigned long long*>(dst) = e;
+        xg_st_release_sys(reinterpret_cast<unsigned long long*>(const_cast<double*>(dst)), e);      // values first, then the epoch word
         // wait for rank `threadIdx.x`'s contribution to arrive in my mailbox
-        volatile unsigned long long* flag =
-            reinterpret_cast<volatile unsigned long long*>(my_mail + size_t(buf * nranks + threadIdx.x) * MAILW);
-        while (*flag != e) { }
-        __threadfence_system();
+        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(my_mail + size_t(buf * nranks + threadIdx.x) * MAILW);
+        while (xg_ld_acquire_sys(flag) != e) { }
     }
     __syncthreads();
     if (threadIdx.x < MAILW - 1 && ((slot_mask >> threadIdx.x) & 1u)) {

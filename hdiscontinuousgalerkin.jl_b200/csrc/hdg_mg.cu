@@ -21,13 +21,15 @@
 //
 // SEVERAL GPUs (strips of hdg_set_rectangle_mesh): the hierarchy is DISTRIBUTED.  A rank owns the vertex rows of its quad
 // rows (level 0: rows [j0, j1), the last rank also row ny; level l+1: the rows Y with 2Y owned on level l).  Level arrays hold
-// the owned rows (+1); the rows of the two neighbouring ranks a stage needs (<= 2 on each side) are READ IN PLACE from the
-// neighbours' memory (CUDA IPC over NVLink, like the SpMV of the PCG) - no ghost copies, no pack/send/recv.  P'r and the
-// level-0 stencil rows of the vertex row shared by two strips are formed as partial sums by both ranks and added up by the
-// owner.  The grid barrier between two stages then carries a barrier across the GPUs (xg_barrier_thread: mailbox flags over
-// peer memory, ~3 us), executed by the last block to arrive.  Levels with <= MG_REP_MAX points (and all levels of a mesh too
-// small for two rows per rank) are REPLICATED: the owners compute their rows of the first such level, every rank gathers the
-// others' rows once, and everything below runs redundantly on every GPU with local barriers only.  No NCCL call in the solve.
+// the owned rows plus TWO GHOST ROWS on each side - what a fused stage reads.  Ghost rows are PUSHED: the stage that produces a
+// vector stores the first / last two owned rows also into the neighbouring ranks' arrays (plain stores over NVLink into CUDA IPC
+// mappings), so every load of a stage is local and no stage waits on a remote load (a first version that read the neighbours'
+// rows in place spent 30-40 us per stage in the few threads of the boundary rows).  The operators' ghost rows are copied once
+// per solve.  P'r and the level-0 stencil rows of the vertex row shared by two strips are formed as partial sums by both ranks
+// and added up by the owner.  The grid barrier between two stages then carries a barrier across the GPUs (xg_barrier_thread:
+// mailbox flags over peer memory), executed by the last block to arrive.  Levels with <= MG_REP_MAX points (and all levels of a
+// mesh too small for two rows per rank) are REPLICATED: the owners store their rows of the first such level into every rank's
+// copy, and everything below runs redundantly on every GPU with local barriers only.  No NCCL call in the solve.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -67,129 +69,104 @@ __device__ __forceinline__ int mg_slot(int dx, int dy) {
     return -1;
 }
 
-// One level as the kernels see it.  Rows [oy0, oy1) are owned by this rank; the arrays hold rows [rb, rb + rows) with
-// rb = oy0 on a distributed level (one spare row: the partial sums of the row shared with the rank above) and rb = 0 on a
-// replicated level (all rows, valid everywhere once gathered).  Rows below oy0 / from oy1 on of a distributed level are read
-// from the neighbouring ranks' arrays (same layout with their own rb).
+constexpr int MG_GHOST = 2;         // ghost rows on each side of the owned rows of a distributed level
+
+// One level as the kernels see it.  Rows [oy0, oy1) are owned by this rank; the arrays hold rows [rb, rb + n / px): on a
+// distributed level the owned rows and MG_GHOST ghost rows on each side (clipped to the grid), on a replicated level all rows.
+// b_* / a_*: the same vector on the rank below / above (distributed levels) - where the producer pushes its boundary rows.
 struct LvDev {
     int px, py;
     int rb, oy0, oy1;
     int rep;
-    int64_t n;                  // stored points = rows * px: the stride between the 7 stencil slots
+    int n;                      // stored points: the stride between the 7 stencil slots (levels have < 2^31 points)
     double *st, *dinv, *r, *t, *x;
-    const double *b_st, *b_dinv, *b_r, *b_t;  int64_t b_n;  int b_rb;     // rank below
-    int a_rb;
-    const double *a_st, *a_dinv, *a_r, *a_t;  int64_t a_n;                // rank above
+    double *b_r, *b_t, *b_x;  int b_rb;
+    double *a_r, *a_t, *a_x;  int a_rb;
 };
 
-enum MgArr : int { AR_DINV = 0, AR_R = 1, AR_T = 2 };
+enum MgArr : int { AR_R = 1, AR_T = 2, AR_X = 3 };
 
-// vector entry (x, y) of a level, wherever the row lives.  Dynamic vectors (r, t) are written by other SMs / GPUs inside the
-// same launch: L2-coherent loads (ld.global.cg) for them, plain loads for the operators (constant during a solve).  Pointer and
-// row base are SELECTED (no branches), so that the loads of a whole stencil can be in flight together: the persistent kernel
-// runs 512 threads per SM and lives on memory-level parallelism inside a thread.  DIST = false (one GPU, replicated levels):
-// every row is local and the access is a plain 32-bit index (levels have < 2^31 points).
-template <int W, bool DIST> __device__ __forceinline__ double lv(const LvDev& L, int x, int y) {
-    const double* pm = W == AR_DINV ? L.dinv : (W == AR_R ? L.r : L.t);
-    if constexpr (!DIST) {
-        const int off = (y - L.rb) * L.px + x;
-        return W == AR_DINV ? pm[off] : __ldcg(pm + off);
-    } else {
-        const bool mine = L.rep | ((y >= L.oy0) & (y < L.oy1)), below = !mine & (y < L.oy0);
-        const double* pb = W == AR_DINV ? L.b_dinv : (W == AR_R ? L.b_r : L.b_t);
-        const double* pa = W == AR_DINV ? L.a_dinv : (W == AR_R ? L.a_r : L.a_t);
-        const double* p = mine ? pm : (below ? pb : pa);
-        const int rb = mine ? L.rb : (below ? L.b_rb : L.a_rb);
-        const int off = (y - rb) * L.px + x;
-        return W == AR_DINV ? p[off] : __ldcg(p + off);
-    }
-}
-template <bool DIST> __device__ __forceinline__ double lv_st(const LvDev& L, int k, int x, int y) {
-    if constexpr (!DIST) return L.st[k * L.n + (y - L.rb) * L.px + x];
-    else {
-        const bool mine = L.rep | ((y >= L.oy0) & (y < L.oy1)), below = !mine & (y < L.oy0);
-        const double* p = mine ? L.st : (below ? L.b_st : L.a_st);
-        const int64_t n = mine ? L.n : (below ? L.b_n : L.a_n);
-        const int rb = mine ? L.rb : (below ? L.b_rb : L.a_rb);
-        return p[k * n + (y - rb) * L.px + x];
-    }
-}
 __device__ __forceinline__ int lv_idx(const LvDev& L, int x, int y) { return (y - L.rb) * L.px + x; }
+// Dynamic vectors (r, t) are written by other SMs / GPUs inside the same launch: L2-coherent loads (ld.global.cg) for them,
+// plain loads for the operators (constant during a solve).
+__device__ __forceinline__ double lv_r(const LvDev& L, int x, int y) { return __ldcg(L.r + lv_idx(L, x, y)); }
+__device__ __forceinline__ double lv_t(const LvDev& L, int x, int y) { return __ldcg(L.t + lv_idx(L, x, y)); }
+// store into the own array and, for the first / last MG_GHOST owned rows of a distributed level, into the ghost rows of the neighbours
+template <int W> __device__ __forceinline__ void lv_store(const LvDev& L, int x, int y, double v) {
+    double* own = W == AR_R ? L.r : (W == AR_T ? L.t : L.x);
+    own[lv_idx(L, x, y)] = v;
+    double* b = W == AR_R ? L.b_r : (W == AR_T ? L.b_t : L.b_x);
+    double* a = W == AR_R ? L.a_r : (W == AR_T ? L.a_t : L.a_x);
+    if (b && y < L.oy0 + MG_GHOST) b[(y - L.b_rb) * L.px + x] = v;
+    if (a && y >= L.oy1 - MG_GHOST) a[(y - L.a_rb) * L.px + x] = v;
+}
 
 // ---- the point-wise operations of the V-cycle ---------------------------------------------------------------------------
 // Neighbours outside the grid are handled by MASKS, not branches: the address is clamped to the centre point and the value
-// replaced by 0 (their stencil coefficients are 0 as well), which leaves every sum bit-identical to the skipping version.
+// replaced by 0 (their stencil coefficients are 0 as well), which leaves every sum bit-identical to a skipping version and lets
+// the loads of a whole stencil be in flight together - the persistent kernel runs 512 threads per SM and lives on memory-level
+// parallelism inside a thread.
 
 // x = omega Dinv r (first sweep from a zero start) at (qx, qy), 0 outside the grid; (cx, cy) is a point inside
-template <bool DIST> __device__ __forceinline__ double mg_x0(const LvDev& L, int qx, int qy, int cx, int cy) {
+__device__ __forceinline__ double mg_x0(const LvDev& L, int qx, int qy, int cx, int cy) {
     const bool in = (qx >= 0) & (qy >= 0) & (qx < L.px) & (qy < L.py);
     const int sx = in ? qx : cx, sy = in ? qy : cy;
-    const double v = MG_OMEGA * lv<AR_DINV, DIST>(L, sx, sy) * lv<AR_R, DIST>(L, sx, sy);
+    const double v = MG_OMEGA * L.dinv[lv_idx(L, sx, sy)] * lv_r(L, sx, sy);
     return in ? v : 0.0;
 }
 
 // P e at the fine point (x, y), e = t of the coarse level: the mean of two coarse values (twice the same one at a coarse twin)
-template <bool DIST> __device__ __forceinline__ double mg_prolong_pt(const LvDev& C, int x, int y) {
+__device__ __forceinline__ double mg_prolong_pt(const LvDev& C, int x, int y) {
     const int a2 = x & 1, b2 = y & 1, hx = x >> 1, hy = y >> 1;
     const int x1 = hx + (a2 & b2), y1 = hy, x2 = hx + (a2 & (b2 ^ 1)), y2 = hy + b2;
     const bool in1 = (x1 < C.px) & (y1 < C.py), in2 = (x2 < C.px) & (y2 < C.py);
-    const double g1 = lv<AR_T, DIST>(C, in1 ? x1 : hx, in1 ? y1 : hy), g2 = lv<AR_T, DIST>(C, in2 ? x2 : hx, in2 ? y2 : hy);
+    const double g1 = lv_t(C, in1 ? x1 : hx, in1 ? y1 : hy), g2 = lv_t(C, in2 ? x2 : hx, in2 ? y2 : hy);
     return 0.5 * ((in1 ? g1 : 0.0) + (in2 ? g2 : 0.0));
 }
 // x after the coarse correction at (qx, qy): omega Dinv r + P e at the free points; 0 outside the grid
-template <bool DF, bool DC> __device__ __forceinline__ double mg_x1(const LvDev& F, const LvDev& C, int qx, int qy, int cx, int cy) {
+__device__ __forceinline__ double mg_x1(const LvDev& F, const LvDev& C, int qx, int qy, int cx, int cy) {
     const bool in = (qx >= 0) & (qy >= 0) & (qx < F.px) & (qy < F.py);
     const int sx = in ? qx : cx, sy = in ? qy : cy;
-    const double di = lv<AR_DINV, DF>(F, sx, sy);
-    const double pe = mg_prolong_pt<DC>(C, sx, sy);
-    const double v = MG_OMEGA * di * lv<AR_R, DF>(F, sx, sy) + (di != 0.0 ? pe : 0.0);
+    const double di = F.dinv[lv_idx(F, sx, sy)];
+    const double pe = mg_prolong_pt(C, sx, sy);
+    const double v = MG_OMEGA * di * lv_r(F, sx, sy) + (di != 0.0 ? pe : 0.0);
     return in ? v : 0.0;
 }
 
-// down: r_C(I) = sum_d w_d (r - A x0)(fine neighbour d of 2I), 0 at fixed coarse points; coarse rows [cy0, cy1).
+// down: r_C(I) = sum_d w_d (r - A x0)(fine neighbour d of 2I), 0 at fixed coarse points.
 // The 7 residuals need x0 on the 19 points of the 2-ring around 2I: loaded once into a 5 x 5 window.
-template <bool DIST> __device__ void mg_stage_down(const LvDev& F, const LvDev& C, int cy0, int cy1, int tid, int T) {
-    const int cnt = (cy1 - cy0) * C.px;
-    for (int i = tid; i < cnt; i += T) {
-        const int Iy = cy0 + i / C.px, Ix = i - (Iy - cy0) * C.px;
-        double s = 0.0;
-        if (C.dinv[lv_idx(C, Ix, Iy)] != 0.0) {
-            const int cx = 2 * Ix, cy = 2 * Iy;
-            double xw[5][5];
+__device__ __forceinline__ double mg_down_point(const LvDev& F, int Ix, int Iy) {
+    const int cx = 2 * Ix, cy = 2 * Iy;
+    double xw[5][5];
 #pragma unroll
-            for (int dy = -2; dy <= 2; ++dy)
+    for (int dy = -2; dy <= 2; ++dy)
 #pragma unroll
-                for (int dx = -2; dx <= 2; ++dx)
-                    if (dx + dy >= -2 && dx + dy <= 2) xw[dy + 2][dx + 2] = mg_x0<DIST>(F, cx + dx, cy + dy, cx, cy);
+        for (int dx = -2; dx <= 2; ++dx)
+            if (dx + dy >= -2 && dx + dy <= 2) xw[dy + 2][dx + 2] = mg_x0(F, cx + dx, cy + dy, cx, cy);
+    double s = 0.0;
 #pragma unroll
-            for (int d = 0; d < 7; ++d) {
-                const int fx = cx + MG_DX[d], fy = cy + MG_DY[d];
-                const bool in = (fx >= 0) & (fy >= 0) & (fx < F.px) & (fy < F.py);
-                const int sx = in ? fx : cx, sy = in ? fy : cy;
-                double a = lv_st<DIST>(F, 0, sx, sy) * xw[MG_DY[d] + 2][MG_DX[d] + 2];
+    for (int d = 0; d < 7; ++d) {
+        const int fx = cx + MG_DX[d], fy = cy + MG_DY[d];
+        const bool in = (fx >= 0) & (fy >= 0) & (fx < F.px) & (fy < F.py);
+        const int p = in ? lv_idx(F, fx, fy) : lv_idx(F, cx, cy);
+        double a = F.st[p] * xw[MG_DY[d] + 2][MG_DX[d] + 2];
 #pragma unroll
-                for (int k = 1; k < 7; ++k) a = fma(lv_st<DIST>(F, k, sx, sy), xw[MG_DY[d] + MG_DY[k] + 2][MG_DX[d] + MG_DX[k] + 2], a);
-                const double t = lv<AR_R, DIST>(F, sx, sy) - a;
-                s += in ? (d == 0 ? 1.0 : 0.5) * t : 0.0;
-            }
-        }
-        C.r[lv_idx(C, Ix, Iy)] = s;
+        for (int k = 1; k < 7; ++k) a = fma(F.st[k * int64_t(F.n) + p], xw[MG_DY[d] + MG_DY[k] + 2][MG_DX[d] + MG_DX[k] + 2], a);
+        const double t = __ldcg(F.r + p) - a;
+        s += in ? (d == 0 ? 1.0 : 0.5) * t : 0.0;
     }
+    return s;
 }
-
-// up: t_F = x1 + omega Dinv (r - A x1); fine rows [fy0, fy1)
-template <bool DF, bool DC> __device__ void mg_stage_up(const LvDev& F, const LvDev& C, int fy0, int fy1, int tid, int T) {
-    const int cnt = (fy1 - fy0) * F.px;
-    for (int i = tid; i < cnt; i += T) {
-        const int y = fy0 + i / F.px, x = i - (y - fy0) * F.px;
-        double xq[7];
+// up: t_F = x1 + omega Dinv (r - A x1)
+__device__ __forceinline__ double mg_up_point(const LvDev& F, const LvDev& C, int x, int y) {
+    double xq[7];
 #pragma unroll
-        for (int k = 0; k < 7; ++k) xq[k] = mg_x1<DF, DC>(F, C, x + MG_DX[k], y + MG_DY[k], x, y);
-        double s = lv_st<DF>(F, 0, x, y) * xq[0];
+    for (int k = 0; k < 7; ++k) xq[k] = mg_x1(F, C, x + MG_DX[k], y + MG_DY[k], x, y);
+    const int p = lv_idx(F, x, y);
+    double s = F.st[p] * xq[0];
 #pragma unroll
-        for (int k = 1; k < 7; ++k) s = fma(lv_st<DF>(F, k, x, y), xq[k], s);
-        F.t[lv_idx(F, x, y)] = fma(MG_OMEGA * F.dinv[lv_idx(F, x, y)], lv<AR_R, DF>(F, x, y) - s, xq[0]);
-    }
+    for (int k = 1; k < 7; ++k) s = fma(F.st[k * int64_t(F.n) + p], xq[k], s);
+    return fma(MG_OMEGA * F.dinv[p], __ldcg(F.r + p) - s, xq[0]);
 }
 
 // ---- vertex <-> trace adjacency ---------------------------------------------------------------------------------------------
@@ -241,13 +218,14 @@ __global__ void mg_fix_flags(int64_t cnt, const double* __restrict__ flag, const
     if (v < cnt) fx[v] = (flag[v] > 0.0 || count[v] == 0.0) ? 1.0 : 0.0;
 }
 
-// every rank copies the rows of a replicated array it does not own from their owners: narr arrays of stride n each
+// set-up, replicated levels: every rank copies the rows it does not own from their owners: narr arrays of stride n each
 struct GatherArgs {
     const double* src[MAXR];      // the same array on every rank (replicated levels share one layout)
     int ry0[MAXR + 1];            // owned rows of rank q: [ry0[q], ry0[q+1])
     int nranks, rank;
 };
-__device__ void mg_gather_rows_dev(const GatherArgs& g, double* dst, int64_t n, int narr, int px, int64_t tid, int64_t T) {
+__global__ void mg_gather_rows(const GatherArgs g, double* dst, int64_t n, int narr, int px) {
+    const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x, T = int64_t(gridDim.x) * blockDim.x;
     for (int q = 0; q < g.nranks; ++q) {
         if (q == g.rank) continue;
         const int64_t o = int64_t(g.ry0[q]) * px, cnt = int64_t(g.ry0[q + 1] - g.ry0[q]) * px;
@@ -255,20 +233,24 @@ __device__ void mg_gather_rows_dev(const GatherArgs& g, double* dst, int64_t n, 
             for (int64_t i = tid; i < cnt; i += T) dst[k * n + o + i] = __ldcg(g.src[q] + k * n + o + i);
     }
 }
-__global__ void mg_gather_rows(const GatherArgs g, double* dst, int64_t n, int narr, int px) {
-    mg_gather_rows_dev(g, dst, n, narr, px, int64_t(blockIdx.x) * blockDim.x + threadIdx.x, int64_t(gridDim.x) * blockDim.x);
+// set-up, distributed levels: the ghost rows of narr arrays (stride n) from the owners' copies (stride bn / an, row base brb / arb)
+__global__ void mg_pull_ghost_rows(double* dst, int64_t n, int rb, int oy0, int oy1, int rows, int narr, int px,
+                                   const double* below, int64_t bn, int brb, const double* above, int64_t an, int arb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nb = (oy0 - rb) * px, na = (rb + rows - oy1) * px;      // ghost points below / above
+    if (i < nb && below) {
+        const int y = rb + i / px, x = i % px;
+        for (int k = 0; k < narr; ++k) dst[k * n + (y - rb) * px + x] = __ldcg(below + k * bn + (y - brb) * px + x);
+    } else if (i >= nb && i < nb + na && above) {
+        const int y = oy1 + (i - nb) / px, x = (i - nb) % px;
+        for (int k = 0; k < narr; ++k) dst[k * n + (y - rb) * px + x] = __ldcg(above + k * an + (y - arb) * px + x);
+    }
 }
 
 // ---- A_c = P'AP on the vertex grid: partial rows from the owned faces of the local vertex rows ---------------------------
-// fixed flags in the level-0 layout; the rows from oy1 on are read from the rank above
-struct FxView {
-    const double* mine; const double* above;
-    int rb, oy1, a_rb, rep;
-};
-__device__ __forceinline__ bool mg_fixed(const FxView& f, int px, int x, int y) {
-    if (f.rep || y < f.oy1) return f.mine[int64_t(y - f.rb) * px + x] != 0.0;
-    return f.above[int64_t(y - f.a_rb) * px + x] != 0.0;
-}
+// fixed flags in the level-0 layout (ghost rows included)
+struct FxView { const double* fx; int rb; };
+__device__ __forceinline__ bool mg_fixed(const FxView& f, int px, int x, int y) { return f.fx[(y - f.rb) * px + x] != 0.0; }
 template <int NT>
 __global__ void mg_vertex_operator(const double* __restrict__ Kd, const double* __restrict__ Ko, const int32_t* __restrict__ kcol,
                                    const uint8_t* __restrict__ isbc, const int32_t* __restrict__ facenode, int node_row0,
@@ -325,18 +307,18 @@ __global__ void mg_rap(const LvDev F, const LvDev C, int cy0, int cy1) {
     const int Ix = int(i % C.px), Iy = cy0 + int(i / C.px);
     const int px = F.px, py = F.py, cx = C.px, cy = C.py;
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-    const bool free_twin = lv<AR_DINV, true>(F, 2 * Ix, 2 * Iy) != 0.0;
+    const bool free_twin = F.dinv[lv_idx(F, 2 * Ix, 2 * Iy)] != 0.0;
     if (free_twin) {
         for (int d = 0; d < 7; ++d) {
             const int fx = 2 * Ix + MG_DX[d], fy = 2 * Iy + MG_DY[d];
             if (fx < 0 || fy < 0 || fx >= px || fy >= py) continue;
-            if (lv<AR_DINV, true>(F, fx, fy) == 0.0) continue;
+            if (F.dinv[lv_idx(F, fx, fy)] == 0.0) continue;
             const double wr = d == 0 ? 1.0 : 0.5;
             for (int e = 0; e < 7; ++e) {
                 const int qx = fx + MG_DX[e], qy = fy + MG_DY[e];
                 if (qx < 0 || qy < 0 || qx >= px || qy >= py) continue;
-                if (lv<AR_DINV, true>(F, qx, qy) == 0.0) continue;
-                const double aw = wr * lv_st<true>(F, e, fx, fy);
+                if (F.dinv[lv_idx(F, qx, qy)] == 0.0) continue;
+                const double aw = wr * F.st[e * int64_t(F.n) + lv_idx(F, fx, fy)];
                 if (aw == 0.0) continue;
                 const int a2 = qx & 1, b2 = qy & 1, hx = qx >> 1, hy = qy >> 1;
                 int jx[2], jy[2], cn;
@@ -347,20 +329,20 @@ __global__ void mg_rap(const LvDev F, const LvDev C, int cy0, int cy1) {
                 else { jx[0] = hx + 1; jy[0] = hy; jx[1] = hx; jy[1] = hy + 1; cn = 2; wp = 0.5; }
                 for (int m = 0; m < cn; ++m) {
                     if (jx[m] >= cx || jy[m] >= cy) continue;
-                    if (lv<AR_DINV, true>(F, 2 * jx[m], 2 * jy[m]) == 0.0) continue;     // fixed coarse point
+                    if (F.dinv[lv_idx(F, 2 * jx[m], 2 * jy[m])] == 0.0) continue;     // fixed coarse point
                     const int sl = mg_slot(jx[m] - Ix, jy[m] - Iy);
                     if (sl >= 0) acc[sl] += aw * wp;
                 }
             }
         }
     }
-    const int64_t I = lv_idx(C, Ix, Iy);
+    const int I = lv_idx(C, Ix, Iy);
     if (free_twin && acc[0] > 0.0) {
-        for (int k = 0; k < 7; ++k) C.st[k * C.n + I] = acc[k];
+        for (int k = 0; k < 7; ++k) C.st[k * int64_t(C.n) + I] = acc[k];
         C.dinv[I] = 1.0 / acc[0];
     } else {
         C.st[I] = 1.0;
-        for (int k = 1; k < 7; ++k) C.st[k * C.n + I] = 0.0;
+        for (int k = 1; k < 7; ++k) C.st[k * int64_t(C.n) + I] = 0.0;
         C.dinv[I] = 0.0;
     }
 }
@@ -370,11 +352,11 @@ __global__ void mg_drop_fixed(const LvDev C, int cy0, int cy1) {
     int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= cnt) return;
     const int x = int(i % C.px), y = cy0 + int(i / C.px);
-    const int64_t p = lv_idx(C, x, y);
+    const int p = lv_idx(C, x, y);
     if (C.dinv[p] == 0.0) return;
     for (int k = 1; k < 7; ++k) {
         const int qx = x + MG_DX[k], qy = y + MG_DY[k];
-        if (qx < 0 || qy < 0 || qx >= C.px || qy >= C.py || lv<AR_DINV, true>(C, qx, qy) == 0.0) C.st[k * C.n + p] = 0.0;
+        if (qx < 0 || qy < 0 || qx >= C.px || qy >= C.py || C.dinv[lv_idx(C, qx, qy)] == 0.0) C.st[k * int64_t(C.n) + p] = 0.0;
     }
 }
 
@@ -429,11 +411,12 @@ struct VcArgs {
     int node_row0;     // global vertex row of local node row 0 (j0 of the strip) == first owned row of level 0
     int prows;         // local vertex rows with (partial) P'r: the owned rows + the row shared with the rank above
     const double* fx;  // level-0 fixed flags of the owned rows
+    double* above_x0;  // where the partial P'r of the row shared with the rank above goes: that row of its level-0 x vector
     // grid barrier + cross-GPU barrier
     unsigned* bar_count;
     volatile unsigned* bar_gen;
     XgComm xg;
-    GatherArgs gather;     // r of level lrep
+    double* rep_r[MAXR];   // r of the first replicated level on every rank (its owners store their rows into all copies)
     unsigned long long* trace;   // measurement: globaltimer (ns) of block 0 at every barrier of the last V-cycle, [0] = count
 };
 
@@ -560,20 +543,21 @@ __device__ void mg_tail(const VcArgs& A, double* sm) {
 
 template <int NT>
 __global__ void __launch_bounds__(MG_THREADS, 2) mg_vcycle_kernel(const VcArgs A) {
-    const int64_t T = int64_t(gridDim.x) * blockDim.x, tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int T = int(gridDim.x * blockDim.x), tid = int(blockIdx.x * blockDim.x + threadIdx.x);
     const bool multi = A.xg.nranks > 1;
     const LvDev& L0 = A.lev[0];
-    const int64_t o0 = int64_t(L0.oy0 - L0.rb) * L0.px;            // first owned row == local node row 0 inside the level-0 arrays
-    const int64_t nown = int64_t(L0.oy1 - L0.oy0) * L0.px;
+    const int o0 = (L0.oy0 - L0.rb) * L0.px;            // first owned row == local node row 0 inside the level-0 arrays
+    const int nown = (L0.oy1 - L0.oy0) * L0.px;
     extern __shared__ double mg_sm[];
     if (A.trace && tid == 0) { A.trace[0] = 1; A.trace[1] = mg_now(); }
     if (blockIdx.x == 0) mg_tail_load(A, mg_sm);
-    // ---- P'r at the local vertex rows: sums over the OWNED faces (partial in the row shared with the rank above); fixed vertices 0
+    // ---- P'r at the local vertex rows: sums over the OWNED faces, fixed vertices 0.  The row shared with the rank above holds
+    // a partial sum: it goes to the owner (into its x vector, unused on a level that is not in the tail)
     {
-        const int64_t cnt = int64_t(A.prows) * L0.px;
-        for (int64_t v = tid; v < cnt; v += T) {
+        const int cnt = A.prows * L0.px;
+        for (int v = tid; v < cnt; v += T) {
             const int c = A.vcnt[v];
-            const int4 e0 = *reinterpret_cast<const int4*>(A.vface + v * MG_MAXVAL), e1 = *reinterpret_cast<const int4*>(A.vface + v * MG_MAXVAL + 4);
+            const int4 e0 = *reinterpret_cast<const int4*>(A.vface + int64_t(v) * MG_MAXVAL), e1 = *reinterpret_cast<const int4*>(A.vface + int64_t(v) * MG_MAXVAL + 4);
             const int32_t e[MG_MAXVAL] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
             double r0[MG_MAXVAL], r1[MG_MAXVAL];
 #pragma unroll
@@ -585,36 +569,50 @@ __global__ void __launch_bounds__(MG_THREADS, 2) mg_vcycle_kernel(const VcArgs A
 #pragma unroll
             for (int k = 0; k < MG_MAXVAL; ++k)
                 if (k < c) s += 0.5 * r0[k] + ((e[k] < 0) ? MG_C1 : -MG_C1) * r1[k];
-            if (v < nown && A.fx[v] != 0.0) s = 0.0;
-            L0.r[o0 + v] = s;
+            if (v < nown) L0.r[o0 + v] = A.fx[v] != 0.0 ? 0.0 : s;
+            else A.above_x0[v - nown] = s;
         }
     }
     mg_grid_barrier(A, true);
     if (multi) {
-        // the owner of the shared row adds the partial sums of the rank below (its spare row)
-        const double* below = L0.rep ? A.gather.src[A.xg.rank > 0 ? A.xg.rank - 1 : 0] : L0.b_r;     // lrep == 0: gather.src = the ranks' level-0 r
-        if (A.xg.rank > 0 && below) {
-            const int64_t bo = int64_t(L0.oy0 - (L0.rep ? 0 : L0.b_rb)) * L0.px;
-            for (int64_t i = tid; i < L0.px; i += T)
-                if (A.fx[i] == 0.0) L0.r[o0 + i] += __ldcg(below + bo + i);
+        // the owner of a shared row adds the partial sums of the rank below; then the boundary rows of the completed vector go
+        // to the neighbours' ghost rows (distributed level 0) or all owned rows to every rank (replicated level 0)
+        const bool add = A.xg.rank > 0;      // row oy0 is shared with the rank below
+        if (L0.rep) {
+            for (int i = tid; i < nown; i += T) {
+                double v = L0.r[o0 + i];
+                if (add && i < L0.px) { v = A.fx[i] != 0.0 ? 0.0 : v + __ldcg(L0.x + o0 + i); L0.r[o0 + i] = v; }
+                for (int q = 0; q < A.xg.nranks; ++q)
+                    if (q != A.xg.rank) A.rep_r[q][o0 + i] = v;
+            }
+        } else {
+            const int nb = min(MG_GHOST, L0.oy1 - L0.oy0) * L0.px;
+            for (int i = tid; i < 2 * nb; i += T) {
+                const int k = i < nb ? i : nown - 2 * nb + i;          // the first / the last MG_GHOST owned rows
+                if (i >= nb && k < nb) continue;                        // fewer than 2 MG_GHOST owned rows: each row once
+                const int y = L0.oy0 + k / L0.px, x = k % L0.px;
+                double v = L0.r[o0 + k];
+                if (add && k < L0.px) v = A.fx[k] != 0.0 ? 0.0 : v + __ldcg(L0.x + o0 + k);
+                lv_store<AR_R>(L0, x, y, v);
+            }
         }
         mg_grid_barrier(A, true);
-        if (A.lrep == 0) {      // the whole hierarchy is replicated: collect the rows of the other ranks
-            mg_gather_rows_dev(A.gather, L0.r, L0.n, 1, L0.px, tid, T);
-            mg_grid_barrier(A, false);
-        }
     }
     // ---- down
     for (int l = 0; l < A.lt; ++l) {
         const LvDev &F = A.lev[l], &C = A.lev[l + 1];
         const bool own_rows = multi && l + 1 <= A.lrep;            // coarse level distributed, or the first replicated one
-        if (F.rep) mg_stage_down<false>(F, C, own_rows ? C.oy0 : 0, own_rows ? C.oy1 : C.py, int(tid), int(T));
-        else mg_stage_down<true>(F, C, own_rows ? C.oy0 : 0, own_rows ? C.oy1 : C.py, int(tid), int(T));
-        mg_grid_barrier(A, own_rows);
-        if (multi && l + 1 == A.lrep) {
-            mg_gather_rows_dev(A.gather, C.r, C.n, 1, C.px, tid, T);
-            mg_grid_barrier(A, false);
+        const bool to_all = multi && l + 1 == A.lrep;
+        const int cy0 = own_rows ? C.oy0 : 0, cy1 = own_rows ? C.oy1 : C.py;
+        const int cnt = (cy1 - cy0) * C.px;
+        for (int i = tid; i < cnt; i += T) {
+            const int Iy = cy0 + i / C.px, Ix = i - (Iy - cy0) * C.px;
+            const double s = C.dinv[lv_idx(C, Ix, Iy)] != 0.0 ? mg_down_point(F, Ix, Iy) : 0.0;
+            if (to_all) {
+                for (int q = 0; q < A.xg.nranks; ++q) A.rep_r[q][lv_idx(C, Ix, Iy)] = s;
+            } else lv_store<AR_R>(C, Ix, Iy, s);
         }
+        mg_grid_barrier(A, own_rows);
     }
     // ---- tail (block 0; the others wait at the barrier)
     if (blockIdx.x == 0) mg_tail(A, mg_sm);
@@ -623,39 +621,42 @@ __global__ void __launch_bounds__(MG_THREADS, 2) mg_vcycle_kernel(const VcArgs A
     for (int l = A.lt - 1; l >= 0; --l) {
         const LvDev &F = A.lev[l], &C = A.lev[l + 1];
         const bool dist = multi && l < A.lrep;
-        if (F.rep) mg_stage_up<false, false>(F, C, 0, F.py, int(tid), int(T));
-        else if (C.rep) mg_stage_up<true, false>(F, C, F.oy0, F.oy1, int(tid), int(T));
-        else mg_stage_up<true, true>(F, C, F.oy0, F.oy1, int(tid), int(T));
+        const int fy0 = dist ? F.oy0 : 0, fy1 = dist ? F.oy1 : F.py;
+        const int cnt = (fy1 - fy0) * F.px;
+        for (int i = tid; i < cnt; i += T) {
+            const int y = fy0 + i / F.px, x = i - (y - fy0) * F.px;
+            lv_store<AR_T>(F, x, y, mg_up_point(F, C, x, y));
+        }
         mg_grid_barrier(A, dist);
     }
     // ---- (P'r).V(P'r) over the owned rows, z += P t on the owned faces
     {
         double s = 0.0;
-        for (int64_t i = tid; i < nown; i += T) s = fma(__ldcg(L0.r + o0 + i), __ldcg(L0.t + o0 + i), s);
+        for (int i = tid; i < nown; i += T) s = fma(__ldcg(L0.r + o0 + i), __ldcg(L0.t + o0 + i), s);
         const double tot = block_sum(s);
         if (threadIdx.x == 0) A.part[blockIdx.x] = tot;
         if (blockIdx.x == 0)
             for (int i = gridDim.x + threadIdx.x; i < A.np; i += blockDim.x) A.part[i] = 0.0;
         constexpr int U = 4;      // faces per trip: the vertex loads of all of them are issued before the first update of z
-        for (int64_t f0 = tid; f0 < A.nface; f0 += T * U) {
+        for (int64_t f0 = tid; f0 < A.nface; f0 += int64_t(T) * U) {
             double a[U], b[U], z0[U], z1[U];
             bool ok[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int64_t f = f0 + u * T;
+                const int64_t f = f0 + int64_t(u) * T;
                 ok[u] = f < A.nface;
                 const int64_t fs = ok[u] ? f : 0;
                 const int2 vv = *reinterpret_cast<const int2*>(A.facenode + 2 * fs);
                 const int lo = min(vv.x, vv.y), hi = max(vv.x, vv.y);
-                a[u] = lv<AR_T, true>(L0, lo % L0.px, lo / L0.px + A.node_row0);
-                b[u] = lv<AR_T, true>(L0, hi % L0.px, hi / L0.px + A.node_row0);
+                a[u] = __ldcg(L0.t + o0 + lo);          // local node ids index the level-0 arrays from the first owned row on
+                b[u] = __ldcg(L0.t + o0 + hi);
                 z0[u] = A.z[fs * NT]; z1[u] = A.z[fs * NT + 1];
                 ok[u] = ok[u] && !A.isbc[fs];
             }
 #pragma unroll
             for (int u = 0; u < U; ++u)
                 if (ok[u]) {
-                    const int64_t f = f0 + u * T;
+                    const int64_t f = f0 + int64_t(u) * T;
                     A.z[f * NT] = z0[u] + 0.5 * (a[u] + b[u]);
                     A.z[f * NT + 1] = z1[u] + MG_C1 * (b[u] - a[u]);
                 }
@@ -669,6 +670,7 @@ struct MgLevelHost {
     int px = 0, py = 0;
     bool rep = false;
     int oy0[MAXR + 1] = {};          // owned rows of rank q: [oy0[q], oy0[q+1])
+    int rb[MAXR] = {};               // first stored row on rank q
     int64_t off[MAXR] = {};          // offset of the level's arrays in rank q's pool (doubles)
     int64_t n[MAXR] = {};            // stored points on rank q
 };
@@ -697,8 +699,8 @@ struct MgData {
 static inline unsigned nblk(int64_t n, int b = 256) { return (unsigned)std::max<int64_t>(1, ceil_div(n, b)); }
 
 // arrays of one level inside a pool: st (7 n) | dinv | r | t | x
-static void level_pointers(double* base, int64_t n, double*& st, double*& dinv, double*& r, double*& t, double*& x) {
-    st = base; dinv = base + 7 * n; r = base + 8 * n; t = base + 9 * n; x = base + 10 * n;
+static double* level_array(const MgData* m, int q, int l, int which) {
+    return static_cast<double*>(m->peer_pool[q]) + m->lev[l].off[q] + which * m->lev[l].n[q];
 }
 
 static LvDev level_dev(const MgData* m, int l) {
@@ -707,31 +709,15 @@ static LvDev level_dev(const MgData* m, int l) {
     LvDev L{};
     L.px = H.px; L.py = H.py; L.rep = H.rep ? 1 : 0;
     L.oy0 = H.oy0[q]; L.oy1 = H.oy0[q + 1];
-    L.rb = H.rep ? 0 : L.oy0;
-    L.n = H.n[q];
-    level_pointers(m->pool + H.off[q], L.n, L.st, L.dinv, L.r, L.t, L.x);
+    L.rb = H.rb[q];
+    L.n = int(H.n[q]);
+    L.st = level_array(m, q, l, 0); L.dinv = level_array(m, q, l, 7); L.r = level_array(m, q, l, 8);
+    L.t = level_array(m, q, l, 9); L.x = level_array(m, q, l, 10);
     if (!H.rep && m->R > 1) {
-        double *st, *dinv, *r, *t, *x;
-        if (q > 0) {
-            level_pointers(static_cast<double*>(m->peer_pool[q - 1]) + H.off[q - 1], H.n[q - 1], st, dinv, r, t, x);
-            L.b_st = st; L.b_dinv = dinv; L.b_r = r; L.b_t = t; L.b_rb = H.oy0[q - 1]; L.b_n = H.n[q - 1];
-        }
-        if (q + 1 < m->R) {
-            level_pointers(static_cast<double*>(m->peer_pool[q + 1]) + H.off[q + 1], H.n[q + 1], st, dinv, r, t, x);
-            L.a_st = st; L.a_dinv = dinv; L.a_r = r; L.a_t = t; L.a_rb = H.oy0[q + 1]; L.a_n = H.n[q + 1];
-        }
+        if (q > 0) { L.b_r = level_array(m, q - 1, l, 8); L.b_t = level_array(m, q - 1, l, 9); L.b_x = level_array(m, q - 1, l, 10); L.b_rb = H.rb[q - 1]; }
+        if (q + 1 < m->R) { L.a_r = level_array(m, q + 1, l, 8); L.a_t = level_array(m, q + 1, l, 9); L.a_x = level_array(m, q + 1, l, 10); L.a_rb = H.rb[q + 1]; }
     }
     return L;
-}
-
-// the array at offset `which` x n of a REPLICATED level on every rank (0: st followed by dinv, 8: r)
-static GatherArgs gather_args(const MgData* m, int l, int which) {
-    GatherArgs g{};
-    g.nranks = m->R; g.rank = m->rank;
-    const MgLevelHost& H = m->lev[l];
-    for (int q = 0; q <= m->R; ++q) g.ry0[q] = H.oy0[q];
-    for (int q = 0; q < m->R; ++q) g.src[q] = static_cast<const double*>(m->peer_pool[q]) + H.off[q] + which * H.n[q];
-    return g;
 }
 
 void mg_free(hdg_context* c) {
@@ -769,6 +755,7 @@ template <int NT> static hdg_status mg_setup_t(hdg_context* c) {
     mgx_free(c);
     if (multi && !comm_p2p(c))
         return set_err(c, HDG_ERR_INVALID, "the distributed multigrid preconditioner needs peer access between the GPUs (CUDA IPC)");
+    if (c->grid_px * c->grid_py >= (int64_t(1) << 31)) return set_err(c, HDG_ERR_INVALID, "vertex grid too large for 32-bit level indices");
     const int R = multi ? c->comm->nranks : 1, rank = multi ? c->comm->rank : 0;
     MgData* m = static_cast<MgData*>(c->mg);
     if (m && (m->nnode_local != c->nnode || m->nface != c->nface || m->nx != c->grid_px - 1 || m->ny != c->grid_py - 1 || m->R != R)) { mg_free(c); m = nullptr; }
@@ -799,7 +786,8 @@ template <int NT> static hdg_status mg_setup_t(hdg_context* c) {
                 else H.oy0[q] = q == R ? H.py : (m->lev[l - 1].oy0[q] + 1) / 2;
                 if (q > 0) minrows = std::min(minrows, H.oy0[q] - H.oy0[q - 1]);
             }
-            if (R > 1 && m->lrep == m->nlev && (int64_t(H.px) * H.py <= rep_max || minrows < 2)) m->lrep = l;
+            // a distributed level needs MG_GHOST owned rows on every rank: ghost rows come from the immediate neighbours only
+            if (R > 1 && m->lrep == m->nlev && (int64_t(H.px) * H.py <= rep_max || minrows < MG_GHOST)) m->lrep = l;
         }
         // tail: the levels with at most MG_TAIL_MAX points (always includes the dense one)
         m->lt = m->nlev - 1;
@@ -815,7 +803,9 @@ template <int NT> static hdg_status mg_setup_t(hdg_context* c) {
                     MgLevelHost& H = m->lev[l];
                     H.rep = R == 1 || l >= m->lrep;
                     if ((pass == 0) != H.rep) continue;
-                    H.n[q] = H.rep ? int64_t(H.px) * H.py : int64_t(H.oy0[q + 1] - H.oy0[q] + 1) * H.px;
+                    H.rb[q] = H.rep ? 0 : std::max(0, H.oy0[q] - MG_GHOST);
+                    const int re = H.rep ? H.py : std::min(H.py, H.oy0[q + 1] + MG_GHOST);
+                    H.n[q] = int64_t(re - H.rb[q]) * H.px;
                     H.off[q] = o;
                     o += 11 * H.n[q];
                 }
@@ -834,7 +824,7 @@ template <int NT> static hdg_status mg_setup_t(hdg_context* c) {
             HDG_CUDA(c, cudaMemsetAsync(m->trace, 0, sizeof(unsigned long long) * 64, c->stream));
         }
         m->peer_pool[rank] = m->pool;
-        if (R > 1) {     // neighbours for the distributed levels, everybody for the gather of the first replicated one (collective)
+        if (R > 1) {     // the neighbours' pools for the ghost rows, everybody's for the first replicated level (collective)
             HDG_CUDA(c, cudaStreamSynchronize(c->stream));
             hdg_status st = comm_share_buffer(c, m->pool, (1u << R) - 1u, m->peer_pool);
             if (st) return st;
@@ -858,16 +848,35 @@ template <int NT> static hdg_status mg_setup_t(hdg_context* c) {
     const int64_t lo = int64_t(j0 - L0.rb) * L0.px;         // local node 0 inside the level-0 arrays
     const int64_t pcount = int64_t(prows) * L0.px, ocount = int64_t(own_rows) * L0.px;
     if (multi && j0 != int(c->comm->j0)) return set_err(c, HDG_ERR_INVALID, "internal: strip rows of the multigrid hierarchy and of the mesh differ");
-    // the same row of the rank below: its spare row (distributed layout) or its copy of the row (replicated layout)
-    const int64_t bo = q > 0 ? int64_t(j0 - (H0.rep ? 0 : H0.oy0[q - 1])) * H0.px : 0;
-    const double* below0 = q > 0 ? static_cast<const double*>(m->peer_pool[q - 1]) + H0.off[q - 1] : nullptr;
-    FxView fxv{};
-    fxv.mine = fx; fxv.rb = L0.rb; fxv.oy1 = H0.oy0[q + 1]; fxv.rep = H0.rep ? 1 : 0;
-    if (!H0.rep && q + 1 < R) {
-        fxv.above = static_cast<const double*>(m->peer_pool[q + 1]) + m->fx_off[q + 1];
-        fxv.a_rb = H0.oy0[q + 1];
-    }
+    // row j0 in the arrays of the rank below: its copy of the shared row, holding its partial sums
+    const int64_t bo = q > 0 ? int64_t(j0 - H0.rb[q - 1]) * H0.px : 0;
     hdg_status st = HDG_OK;
+    // ghost rows of a distributed level (or all foreign rows of the first replicated one) of narr adjacent arrays starting at
+    // array index `which`, after their owners have written them
+    auto complete = [&](int l, int which, int narr) -> hdg_status {
+        if (!multi) return HDG_OK;
+        const MgLevelHost& H = m->lev[l];
+        if (H.rep && l != m->lrep) return HDG_OK;            // computed redundantly by every rank
+        hdg_status s2 = xbarrier(c);
+        if (s2) return s2;
+        double* dst = level_array(m, q, l, which);
+        if (H.rep) {
+            GatherArgs g{};
+            g.nranks = R; g.rank = q;
+            for (int k = 0; k <= R; ++k) g.ry0[k] = H.oy0[k];
+            for (int k = 0; k < R; ++k) g.src[k] = level_array(m, k, l, which);
+            mg_gather_rows<<<nblk(H.n[q]), 256, 0, c->stream>>>(g, dst, H.n[q], narr, H.px);
+        } else {
+            const int rows = int(H.n[q] / H.px);
+            const int ghosts = (H.oy0[q] - H.rb[q]) + (H.rb[q] + rows - H.oy0[q + 1]);
+            mg_pull_ghost_rows<<<nblk(int64_t(ghosts) * H.px), 256, 0, c->stream>>>(
+                dst, H.n[q], H.rb[q], H.oy0[q], H.oy0[q + 1], rows, narr, H.px,
+                q > 0 ? level_array(m, q - 1, l, which) : nullptr, q > 0 ? H.n[q - 1] : 0, q > 0 ? H.rb[q - 1] : 0,
+                q + 1 < R ? level_array(m, q + 1, l, which) : nullptr, q + 1 < R ? H.n[q + 1] : 0, q + 1 < R ? H.rb[q + 1] : 0);
+        }
+        c->launches += 1;
+        return xbarrier(c);                                    // nobody overwrites a row another rank is still copying
+    };
     if (!m->adjacency_ok) {
         HDG_CUDA(c, cudaMemsetAsync(m->vcnt, 0, sizeof(int32_t) * c->nnode, c->stream));
         HDG_CUDA(c, cudaMemsetAsync(c->d_flags + FLAG_MG, 0, sizeof(int32_t), c->stream));
@@ -878,23 +887,30 @@ template <int NT> static hdg_status mg_setup_t(hdg_context* c) {
         if (multi) {
             if ((st = xbarrier(c))) return st;
             if (q > 0) {
-                mg_add_shared_row<<<nblk(H0.px), 256, 0, c->stream>>>(L0.t + lo, L0.n, below0 + 9 * H0.n[q - 1] + bo, H0.n[q - 1], 2, H0.px);
+                mg_add_shared_row<<<nblk(H0.px), 256, 0, c->stream>>>(L0.t + lo, L0.n, level_array(m, q - 1, 0, 9) + bo, H0.n[q - 1], 2, H0.px);
                 c->launches += 1;
             }
         }
         mg_fix_flags<<<nblk(ocount), 256, 0, c->stream>>>(ocount, L0.t + lo, L0.x + lo, fx + lo);
         c->launches += 1;
-        if (multi) {
+        if (multi) {      // the flags of the ghost rows (all rows on a replicated level 0): the array behind the levels, same layout
             if ((st = xbarrier(c))) return st;
-            if (H0.rep) {    // replicated level 0: every rank needs all flags
+            if (H0.rep) {
                 GatherArgs g{};
                 g.nranks = R; g.rank = q;
                 for (int k = 0; k <= R; ++k) g.ry0[k] = H0.oy0[k];
                 for (int k = 0; k < R; ++k) g.src[k] = static_cast<const double*>(m->peer_pool[k]) + m->fx_off[k];
                 mg_gather_rows<<<nblk(H0.n[q]), 256, 0, c->stream>>>(g, fx, H0.n[q], 1, H0.px);
-                c->launches += 1;
-                if ((st = xbarrier(c))) return st;
+            } else {
+                const int rows = int(H0.n[q] / H0.px);
+                const int ghosts = (H0.oy0[q] - H0.rb[q]) + (H0.rb[q] + rows - H0.oy0[q + 1]);
+                mg_pull_ghost_rows<<<nblk(int64_t(ghosts) * H0.px), 256, 0, c->stream>>>(
+                    fx, H0.n[q], H0.rb[q], H0.oy0[q], H0.oy0[q + 1], rows, 1, H0.px,
+                    q > 0 ? static_cast<const double*>(m->peer_pool[q - 1]) + m->fx_off[q - 1] : nullptr, 0, q > 0 ? H0.rb[q - 1] : 0,
+                    q + 1 < R ? static_cast<const double*>(m->peer_pool[q + 1]) + m->fx_off[q + 1] : nullptr, 0, q + 1 < R ? H0.rb[q + 1] : 0);
             }
+            c->launches += 1;
+            if ((st = xbarrier(c))) return st;
         }
         HDG_CUDA(c, cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int32_t) * NFLAGS, cudaMemcpyDeviceToHost, c->stream));
         HDG_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -902,32 +918,20 @@ template <int NT> static hdg_status mg_setup_t(hdg_context* c) {
         m->adjacency_ok = true;
     }
     // ---- operators (every solve: the matrix may have changed)
+    const FxView fxv{fx, L0.rb};
     mg_vertex_operator<NT><<<nblk(pcount), 256, 0, c->stream>>>(c->d_Kd, c->d_Ko, c->d_kcol, c->d_isbc, c->d_facenode, j0, m->vcnt, m->vface,
                                                                 fxv, L0.px, pcount, L0.st + lo, L0.n);
     c->launches += 1;
     if (multi) {
         if ((st = xbarrier(c))) return st;
         if (q > 0) {
-            mg_add_shared_row<<<nblk(H0.px), 256, 0, c->stream>>>(L0.st + lo, L0.n, below0 + bo, H0.n[q - 1], 7, H0.px);
+            mg_add_shared_row<<<nblk(H0.px), 256, 0, c->stream>>>(L0.st + lo, L0.n, level_array(m, q - 1, 0, 0) + bo, H0.n[q - 1], 7, H0.px);
             c->launches += 1;
         }
     }
     mg_finalize_rows<<<nblk(ocount), 256, 0, c->stream>>>(fx + lo, ocount, L0.st + lo, L0.n, L0.dinv + lo);
     c->launches += 1;
-    auto complete_level = [&](int l) -> hdg_status {      // operators of level l written by their owners: make them readable everywhere
-        if (!multi) return HDG_OK;
-        hdg_status s2 = xbarrier(c);
-        if (s2) return s2;
-        if (m->lev[l].rep && l == m->lrep) {               // first replicated level: collect the other ranks' rows (st + dinv)
-            const LvDev L = level_dev(m, l);
-            const GatherArgs g = gather_args(m, l, 0);
-            mg_gather_rows<<<nblk(L.n), 256, 0, c->stream>>>(g, L.st, L.n, 8, L.px);
-            c->launches += 1;
-            s2 = xbarrier(c);
-        }
-        return s2;
-    };
-    if ((st = complete_level(0))) return st;
+    if ((st = complete(0, 0, 8))) return st;
     for (int l = 0; l + 1 < m->nlev; ++l) {
         const LvDev F = level_dev(m, l), C = level_dev(m, l + 1);
         const bool own = multi && l + 1 <= m->lrep;          // coarse rows computed by their owners
@@ -935,13 +939,13 @@ template <int NT> static hdg_status mg_setup_t(hdg_context* c) {
         const int64_t cnt = int64_t(cy1 - cy0) * C.px;
         mg_rap<<<nblk(cnt), 256, 0, c->stream>>>(F, C, cy0, cy1);
         c->launches += 1;
-        if (own && m->lev[l + 1].rep) {                      // first replicated level: gather, then drop on all rows
-            if ((st = complete_level(l + 1))) return st;
+        if (own && m->lev[l + 1].rep) {                      // first replicated level: collect all rows, then drop everywhere
+            if ((st = complete(l + 1, 0, 8))) return st;
             mg_drop_fixed<<<nblk(C.n), 256, 0, c->stream>>>(C, 0, C.py);
         } else {
-            if (own && (st = xbarrier(c))) return st;        // drop_fixed reads the neighbours' dinv
+            if (own && (st = complete(l + 1, 7, 1))) return st;     // drop_fixed reads Dinv of the ghost rows
             mg_drop_fixed<<<nblk(cnt), 256, 0, c->stream>>>(C, cy0, cy1);
-            if (own && (st = xbarrier(c))) return st;
+            if (own && (st = complete(l + 1, 0, 7))) return st;     // the stencils after the drop
         }
         c->launches += 1;
     }
@@ -959,9 +963,11 @@ template <int NT> static hdg_status mg_setup_t(hdg_context* c) {
     A.vcnt = m->vcnt; A.vface = m->vface; A.facenode = c->d_facenode; A.isbc = c->d_isbc;
     A.node_row0 = j0; A.prows = prows;
     A.fx = fx + lo;
+    if (q + 1 < R) A.above_x0 = level_array(m, q + 1, 0, 10) + int64_t(H0.oy0[q + 1] - H0.rb[q + 1]) * H0.px;      // its first owned row
     A.bar_count = m->bar; A.bar_gen = m->bar + 1;
     comm_xg(c, &A.xg);
-    if (multi) A.gather = gather_args(m, m->lrep, 8);       // r of the first replicated level
+    if (multi)
+        for (int k = 0; k < R; ++k) A.rep_r[k] = level_array(m, k, m->lrep, 8);      // r of the first replicated level, everywhere
     A.trace = m->trace;
     return HDG_OK;
 }
