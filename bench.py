@@ -400,8 +400,8 @@ def parity_leg(env):
         own = x1[pm["face_begin"] * nt: pm["face_end"] * nt]
         rel = env.maxf(np.abs(xm - own).max()) / env.maxf(np.abs(x1).max())
         worst = max(worst, rel)
-        iters_ok = iters_ok and abs(itm - it1) <= 1
-        err_ok = err_ok and abs(em - e1) <= 1e-9 * e1 + 1e-20
+        iters_ok = iters_ok and abs(itm - it1) <= max(1, it1 // 200)      # the dot products are summed in another order: +-0.5 % of a few thousand Jacobi iterations
+        err_ok = err_ok and abs(em - e1) <= 1e-9 * abs(e1) + 1e-20
         cases.append({"order": order, "precond": precond, "max_rel": rel, "iters": [itm, it1], "err2": [em, e1]})
     return {"max_rel": worst, "iters_equal": bool(iters_ok), "err2_equal": bool(err_ok), "cases": cases,
             "what": f"256 x {128*world} mesh on {world} GPUs vs the same mesh on one GPU; Jacobi and multigrid PCG, k=1 and k=3, rtol 1e-13"}

@@ -137,7 +137,7 @@ void hdg_destroy(hdg_context* c) {
     if (c->d_partials) cudaFree(c->d_partials);
     if (c->h_flags) cudaFreeHost(c->h_flags);
     if (c->h_scal) cudaFreeHost(c->h_scal);
-    for (Timer* t : {&c->t_assemble, &c->t_apply, &c->t_solve, &c->t_recover, &c->t_err, &c->t_elem}) {
+    for (Timer* t : {&c->t_assemble, &c->t_apply, &c->t_solve, &c->t_recover, &c->t_err, &c->t_elem, &c->t_mgsetup, &c->t_loop}) {
         if (t->a) cudaEventDestroy(t->a);
         if (t->b) cudaEventDestroy(t->b);
     }
@@ -467,6 +467,8 @@ hdg_status hdg_last_phase_ms(const hdg_context* cc, const char* phase, double* m
     else if (s == "recover") t = &c->t_recover;
     else if (s == "errornorm") t = &c->t_err;
     else if (s == "element_kernel") t = &c->t_elem;
+    else if (s == "mg_setup") t = &c->t_mgsetup;       // operators of the vertex hierarchy (inside "solve")
+    else if (s == "solve_loop") t = &c->t_loop;        // the PCG iterations alone (inside "solve")
     else return set_err(c, HDG_ERR_INVALID, "unknown phase");
     if (!t->a) { *ms = 0.0; return HDG_OK; }
     *ms = double(timer_ms(*t));

@@ -167,7 +167,7 @@ struct hdg_context {
     double *d_sigma = nullptr, *d_u = nullptr, *d_uhat_h = nullptr;
     bool recovered = false;
 
-    hdg::Timer t_assemble, t_apply, t_solve, t_recover, t_err, t_elem;
+    hdg::Timer t_assemble, t_apply, t_solve, t_recover, t_err, t_elem, t_mgsetup, t_loop;
     hdg::Comm* comm = nullptr;
 };
 

@@ -541,8 +541,11 @@ __device__ void mg_tail(const VcArgs& A, double* sm) {
     }
 }
 
+#ifndef MG_BLOCKS_PER_SM
+#define MG_BLOCKS_PER_SM 2
+#endif
 template <int NT>
-__global__ void __launch_bounds__(MG_THREADS, 2) mg_vcycle_kernel(const VcArgs A) {
+__global__ void __launch_bounds__(MG_THREADS, MG_BLOCKS_PER_SM) mg_vcycle_kernel(const VcArgs A) {
     const int T = int(gridDim.x * blockDim.x), tid = int(blockIdx.x * blockDim.x + threadIdx.x);
     const bool multi = A.xg.nranks > 1;
     const LvDev& L0 = A.lev[0];
@@ -836,7 +839,7 @@ template <int NT> static hdg_status mg_setup_t(hdg_context* c) {
         if (m->tail_smem > 48 * 1024)
             HDG_CUDA(c, cudaFuncSetAttribute(mg_vcycle_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(m->tail_smem)));
         HDG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mg_vcycle_kernel<NT>, MG_THREADS, m->tail_smem));
-        m->grid_blocks = sms * std::max(1, std::min(occ, 2));
+        m->grid_blocks = sms * std::max(1, std::min(occ, MG_BLOCKS_PER_SM));
     }
     const int q = rank;
     const MgLevelHost& H0 = m->lev[0];

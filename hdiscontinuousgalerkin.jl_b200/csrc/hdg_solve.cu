@@ -635,7 +635,9 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
     timer_start(c, c->t_solve);
     HDG_CUDA(c, cudaMemsetAsync(c->d_flags, 0, sizeof(int32_t) * NFLAGS, c->stream));
     if (mg) {
+        timer_start(c, c->t_mgsetup);
         hdg_status st = mg_setup(c);
+        timer_stop(c, c->t_mgsetup);
         if (st) { timer_stop(c, c->t_solve); return st; }
     }
     hdg_status cst = HDG_OK;
@@ -677,6 +679,7 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
     };
     int it = 0;
     bool done = false;
+    timer_start(c, c->t_loop);
     while (it < maxit && !done) {
         int chunk = std::min(CHUNK, maxit - it);
         if (chunk == CHUNK && use_graph) {
@@ -707,6 +710,7 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
         if (done) it += c->h_flags[FLAG_ITERS];
         else it += chunk;
     }
+    timer_stop(c, c->t_loop);
     if (multi) {   // recovery reads the trace on the ghost faces below the strip
         if (p2p) {   // publish x through the shared p array, barrier, pull the ghost values over NVLink, barrier
             const int64_t nghost = c->nface - c->nface_own;

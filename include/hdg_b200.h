@@ -236,7 +236,7 @@ hdg_status hdg_comm_pingpong(hdg_context* ctx, int32_t iters, double* usec_per_e
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* Device time (ms, CUDA events on the context stream) of the kernels of the last call of the
  * named phase: "assemble" (memsets + element kernel), "element_kernel", "apply", "solve",
- * "recover", "errornorm". */
+ * "recover", "errornorm"; inside "solve": "mg_setup" (operators of the vertex hierarchy) and "solve_loop" (the PCG iterations). */
 hdg_status hdg_last_phase_ms(const hdg_context* ctx, const char* phase, double* ms);
 /* FP64 FMA throughput of the context's device (TFLOP/s, best of 3 launches of a register-only DFMA kernel, CUDA events):
  * the denominator for the FP64 roofline of the k >= 2 element kernels - MEASURED_PEAKS.json holds no FP64 figure. */

@@ -71,7 +71,7 @@ def main():
             ref.close()
             xg = np.concatenate([p[1] for p in sorted(xs, key=lambda p: p[0])])
             ex = np.abs(xg - xr).max() / np.abs(xr).max()
-            good = ex < 1e-10 and abs(err2 - e1) <= 1e-9 * e1 + 1e-20 and abs(iters - it1) <= 1 and iters <= 60      # err2 of k=4 is at roundoff (1e-16)
+            good = ex < 1e-10 and abs(err2 - e1) <= 1e-9 * abs(e1) + 1e-20 and abs(iters - it1) <= 1      # err2 of k=4 is at roundoff (1e-16); anisotropic strips take > 60 iterations on one GPU as well
             ok &= good
             print(f"multigrid k={order} {nx}x{ny} rep_max={rep_max} on {world} GPUs: iters {iters} (1 GPU: {it1})  relerr(uhat)={ex:.2e} "
                   f"err2 {err2:.12e} vs {e1:.12e}  {'OK' if good else 'FAIL'}", flush=True)

@@ -32,6 +32,11 @@ info = hdg.api.SolveInfo()
 for _ in range(2):
     hdg.check(lib.hdg_solve(ctx.h, 1e-12, 1000, C.byref(info)), ctx.h)
 full_ms, its = info.solve_ms, info.iterations
+ph = {}
+for name in ("mg_setup", "solve_loop"):
+    v = C.c_double()
+    lib.hdg_last_phase_ms(ctx.h, name.encode(), C.byref(v))
+    ph[name] = v.value
 lib.hdg_solve(ctx.h, 1e-12, 4, C.byref(info))        # set-up + one graph chunk of 4 iterations (status 7: not converged)
 short_ms = info.solve_ms
 per_it = (full_ms - short_ms) / max(its - 4, 1)
@@ -41,6 +46,8 @@ t = us[:n]
 if rank == 0:
     print(f"k={order} {nx}x{ny} on {world} GPU(s): {its} iterations, {full_ms:.3f} ms; 4 iterations + set-up {short_ms:.3f} ms -> "
           f"{per_it * 1e3:.1f} us / iteration, set-up ~{short_ms - 4 * per_it:.3f} ms")
+    print(f"phases of the full solve: mg_setup {ph['mg_setup']:.3f} ms, iteration loop {ph['solve_loop']:.3f} ms "
+          f"({ph['solve_loop'] / its * 1e3:.1f} us / iteration incl. graph capture and the host round trips), rest {full_ms - ph['mg_setup'] - ph['solve_loop']:.3f} ms")
     print("timestamps (us):", np.round(t, 1).tolist())
     # entries alternate: [start, b1_in, b1_out, b2_in, b2_out, ..., end]
     work = [t[1] - t[0]] + [t[i + 1] - t[i] for i in range(2, n - 1, 2)]
