@@ -610,15 +610,121 @@ hdg_status alloc_system(hdg_context* c) {
 }
 
 // ------------------------------------------------------------------------------------------
-// hdg_set_mesh on several GPUs: every rank receives the whole mesh and keeps a contiguous range of cell ids.
-// With the reference's first-encounter numbering the faces a rank's cells create also form a contiguous id range
-// (= the trace rows it owns).  Like for the strips of hdg_set_rectangle_mesh, the cells of other ranks that touch an
-// owned face are recomputed as ghost cells, and the faces they (or the owned cells) reference beyond the owned range
-// become ghost columns whose p values are read from the owner's memory during the SpMV.
+// hdg_set_mesh on several GPUs: every rank is handed the whole mesh (the Julia process of a GPU holds it) but UPLOADS ONLY ITS
+// PART: a contiguous range of cell ids, the rows of the face table those cells create - with the reference's first-encounter
+// numbering (src/generate_mesh.jl:20-46) they are a contiguous id range too, = the trace rows the rank owns - and the node
+// coordinates.  Everything else happens on the device: the cells of other ranks that touch an owned face (recomputed as ghost
+// cells, like the ghost layer of the strips) are found from the owned face rows, the faces local cells reference beyond the
+// owned range become ghost columns whose p values the SpMV reads from the owner's memory, local numbering / adjacency / tile
+// pairing / Dirichlet flags are built by kernels.  The host only sorts the two small interface lists (ghost cells, ghost faces)
+// and gathers the ghost cells' rows; there is no pass over the mesh on the host (the partition boundaries come from R binary
+// searches in the face table's first-cell column).
 // ------------------------------------------------------------------------------------------
-__global__ void mark_isbc_list(const int32_t* __restrict__ bfaces, int64_t nb, uint8_t* __restrict__ isbc) {
-    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i < nb) isbc[bfaces[i]] = 1;
+__device__ __forceinline__ int64_t lower_bound_i64(const int64_t* __restrict__ a, int64_t n, int64_t key) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+// owned face rows: ids in range, first cells inside the owned cell range and ascending; ghost-cell candidates = second cells
+// outside the owned range (appended in any order, duplicates possible)
+__global__ void part_check_faces(const int64_t* __restrict__ fv1, const int64_t* __restrict__ fv2, const int64_t* __restrict__ fc1,
+                                 const int64_t* __restrict__ fc2, int64_t nown, int64_t cb, int64_t ce, int64_t ncell, int64_t nnode,
+                                 int64_t* __restrict__ cand, unsigned long long* __restrict__ ncand, int32_t* __restrict__ flag) {
+    const int64_t f = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (f >= nown) return;
+    const int64_t c1 = fc1[f] - 1, c2 = fc2[f] - 1;
+    if (fv1[f] < 1 || fv1[f] > nnode || fv2[f] < 1 || fv2[f] > nnode) atomicCAS(flag, 0, 3);
+    if (c1 < cb || c1 >= ce || c2 < -1 || c2 >= ncell) atomicCAS(flag, 0, 4);
+    if (f > 0 && fc1[f] < fc1[f - 1]) atomicCAS(flag, 0, 5);
+    if (c2 >= 0 && (c2 < cb || c2 >= ce)) cand[atomicAdd(ncand, 1ull)] = c2;
+}
+// faces of the local cells (owned + ghost) beyond the owned face range (any order, duplicates possible); id range check
+__global__ void part_ghost_face_candidates(const int64_t* __restrict__ cells, int64_t ncloc, int64_t fb, int64_t fe, int64_t nface,
+                                           int64_t nnode, int64_t* __restrict__ cand, unsigned long long* __restrict__ ncand,
+                                           int32_t* __restrict__ flag) {
+    const int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= ncloc) return;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int64_t v = cells[6 * c + k], f = cells[6 * c + 3 + k] - 1;
+        if (v < 1 || v > nnode) atomicCAS(flag, 0, 1);
+        if (f < 0 || f >= nface) { atomicCAS(flag, 0, 2); continue; }
+        if (f < fb || f >= fe) cand[atomicAdd(ncand, 1ull)] = f;
+    }
+}
+// device records of the local cells: global node ids, LOCAL face ids (owned: f - fb, ghost: nown + position in the sorted ghost
+// list), bit 31 = this cell is the face's second cell (owned face: the face row says so; ghost face of an owned cell: its first
+// cell lives on another rank, so always)
+__global__ void part_convert_cells(const int64_t* __restrict__ cells, int64_t ncloc, int64_t ncown, int64_t cb, const int64_t* __restrict__ gcells,
+                                   int64_t fb, int64_t fe, const int64_t* __restrict__ fc2, const int64_t* __restrict__ gfaces, int64_t ngf,
+                                   int32_t* __restrict__ cellinfo) {
+    const int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= ncloc) return;
+    const int64_t cg = c < ncown ? cb + c : gcells[c - ncown];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cellinfo[CI * c + k] = int32_t(cells[6 * c + k] - 1);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int64_t f = cells[6 * c + 3 + k] - 1;
+        int64_t fl;
+        uint32_t sec;
+        if (f >= fb && f < fe) { fl = f - fb; sec = (fc2[fl] - 1 == cg) ? 0x80000000u : 0u; }
+        else { fl = (fe - fb) + lower_bound_i64(gfaces, ngf, f); sec = c < ncown ? 0x80000000u : 0u; }
+        cellinfo[CI * c + 3 + k] = int32_t(uint32_t(fl) | sec);
+    }
+}
+// face -> (first, second) LOCAL cell of the owned faces from their rows (-1: no second cell, -2: a cell this rank does not hold)
+__global__ void part_owned_facecell(const int64_t* __restrict__ fv1, const int64_t* __restrict__ fv2, const int64_t* __restrict__ fc1,
+                                    const int64_t* __restrict__ fc2, int64_t nown, int64_t cb, int64_t ce, int64_t ncown,
+                                    const int64_t* __restrict__ gcells, int64_t ngc, int32_t* __restrict__ facecell, int32_t* __restrict__ facenode) {
+    const int64_t f = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (f >= nown) return;
+    facenode[2 * f] = int32_t(fv1[f] - 1);
+    facenode[2 * f + 1] = int32_t(fv2[f] - 1);
+    facecell[2 * f] = int32_t(fc1[f] - 1 - cb);
+    const int64_t c2 = fc2[f] - 1;
+    int32_t l2 = -1;
+    if (c2 >= 0) {
+        if (c2 >= cb && c2 < ce) l2 = int32_t(c2 - cb);
+        else {
+            const int64_t p = lower_bound_i64(gcells, ngc, c2);
+            l2 = (p < ngc && gcells[p] == c2) ? int32_t(ncown + p) : -2;
+        }
+    }
+    facecell[2 * f + 1] = l2;
+}
+// ghost faces: the local cells that hold them (min / max local id; a single holder leaves the second entry at -1) and the end
+// nodes from one holder's edge - enough for the tile pairing hints, these rows are never used as rows of K
+__global__ void part_ghost_facecell(const int32_t* __restrict__ cellinfo, int64_t ncloc, int64_t nown, int32_t* __restrict__ facecell,
+                                    int32_t* __restrict__ facenode) {
+    const int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= ncloc) return;
+    const int k1[3] = {1, 2, 0}, k2[3] = {2, 0, 1};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int64_t f = uint32_t(cellinfo[CI * c + 3 + k]) & 0x7fffffffu;
+        if (f < nown) continue;
+        atomicMin(&facecell[2 * f], int32_t(c));
+        atomicMax(&facecell[2 * f + 1], int32_t(c));
+        facenode[2 * f] = cellinfo[CI * c + k1[k]];        // any holder's edge (both holders write the same two nodes, possibly swapped)
+        facenode[2 * f + 1] = cellinfo[CI * c + k2[k]];
+    }
+}
+// Dirichlet set (global 1-based ids, any order) -> flags of the local faces; an owned face with two cells raises the assertion
+__global__ void part_mark_dirichlet(const int64_t* __restrict__ bfaces, int64_t nb, int64_t nface, int64_t fb, int64_t fe,
+                                    const int64_t* __restrict__ fc2, const int64_t* __restrict__ gfaces, int64_t ngf, int32_t* __restrict__ dflag,
+                                    int32_t* __restrict__ flags) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    const int64_t f = bfaces[i] - 1;
+    if (f < 0 || f >= nface) { atomicCAS(&flags[FLAG_BAD_ID], 0, 6); return; }
+    if (f >= fb && f < fe) {
+        if (fc2[f - fb] != 0) atomicExch(&flags[FLAG_NOT_BOUNDARY], int32_t(f + 1));      // src/boundary.jl:22
+        dflag[f - fb] = 1;
+    } else {
+        const int64_t p = lower_bound_i64(gfaces, ngf, f);
+        if (p < ngf && gfaces[p] == f) dflag[(fe - fb) + p] = 1;
+    }
 }
 
 static hdg_status mesh_from_host_partitioned(hdg_context* c, const int64_t* cells, int64_t ncell, const double* nodes,
@@ -628,102 +734,127 @@ static hdg_status mesh_from_host_partitioned(hdg_context* c, const int64_t* cell
     const int R = m->nranks, r = m->rank;
     if (!faces) return set_err(c, HDG_ERR_INVALID, "hdg_set_mesh on several GPUs needs the faces array");
     if (ncell < R) return set_err(c, HDG_ERR_INVALID, "need at least one cell per rank");
-    auto FC = [&](int64_t f, int col) { return faces[f + col * nface]; };   // column-major nface x 4, 1-based
-    for (int64_t f = 1; f < nface; ++f)
-        if (FC(f, 2) < FC(f - 1, 2))
-            return set_err(c, HDG_ERR_INVALID, "hdg_set_mesh on several GPUs needs first-encounter face numbering (faces ordered by their first cell)");
+    const int64_t* fcol[4] = {faces, faces + nface, faces + 2 * nface, faces + 3 * nface};      // column-major nface x 4, 1-based
+    // partition: equal cell-id ranges; the faces whose first cell lies in the range (the first-cell column is ascending with
+    // first-encounter numbering - checked on the device for the rows a rank owns, which together are all rows)
     std::vector<int64_t> c0(R + 1), F0(R + 1);
     for (int q = 0; q <= R; ++q) c0[q] = ncell * q / R;
-    for (int q = 0; q <= R; ++q) {   // first face whose first cell is >= c0[q]
+    for (int q = 0; q <= R; ++q) {
         int64_t lo = 0, hi = nface;
-        while (lo < hi) { int64_t mid = (lo + hi) / 2; if (FC(mid, 2) - 1 < c0[q]) lo = mid + 1; else hi = mid; }
+        while (lo < hi) { const int64_t mid = (lo + hi) / 2; if (fcol[2][mid] - 1 < c0[q]) lo = mid + 1; else hi = mid; }
         F0[q] = lo;
     }
     const int64_t cb = c0[r], ce = c0[r + 1], fb = F0[r], fe = F0[r + 1];
     const int64_t ncown = ce - cb, nown = fe - fb;
-    // ghost cells: second cells of owned faces that live on another rank
-    std::vector<int64_t> gcells;
-    for (int64_t f = fb; f < fe; ++f) {
-        int64_t c2 = FC(f, 3) - 1;
-        if (c2 >= 0 && (c2 < cb || c2 >= ce)) gcells.push_back(c2);
-    }
+    if (nown <= 0) return set_err(c, HDG_ERR_INVALID, "hdg_set_mesh on several GPUs needs first-encounter face numbering (faces ordered by their first cell)");
+    const int B = 256;
+    hdg_status st = HDG_OK;
+    // ---- upload the owned face rows; ghost cells
+    int64_t *d_f = nullptr, *d_cand = nullptr;
+    unsigned long long* d_n = nullptr;
+    HDG_CUDA(c, cudaMalloc(&d_f, sizeof(int64_t) * 4 * nown));
+    HDG_CUDA(c, cudaMalloc(&d_cand, sizeof(int64_t) * std::max<int64_t>(nown, 1)));
+    HDG_CUDA(c, cudaMalloc(&d_n, sizeof(unsigned long long)));
+    auto cleanup = [&](hdg_status s2) { cudaStreamSynchronize(c->stream); cudaFree(d_f); cudaFree(d_cand); cudaFree(d_n); return s2; };
+    for (int k = 0; k < 4; ++k)
+        if (cudaMemcpyAsync(d_f + k * nown, fcol[k] + fb, sizeof(int64_t) * nown, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+            return cleanup(set_err(c, HDG_ERR_CUDA, "cudaMemcpyAsync(faces)"));
+    cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), c->stream);
+    cudaMemsetAsync(c->d_flags, 0, sizeof(int32_t) * NFLAGS, c->stream);
+    part_check_faces<<<(unsigned)ceil_div(nown, B), B, 0, c->stream>>>(d_f, d_f + nown, d_f + 2 * nown, d_f + 3 * nown, nown, cb, ce, ncell, nnode,
+                                                                        d_cand, d_n, c->d_flags + FLAG_BAD_ID);
+    c->launches += 1;
+    unsigned long long ncand = 0;
+    cudaMemcpyAsync(&ncand, d_n, sizeof(ncand), cudaMemcpyDeviceToHost, c->stream);
+    cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int32_t) * NFLAGS, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return cleanup(set_err(c, HDG_ERR_CUDA, "partition: face check failed"));
+    if (c->h_flags[FLAG_BAD_ID] == 5 || c->h_flags[FLAG_BAD_ID] == 4)
+        return cleanup(set_err(c, HDG_ERR_INVALID, "hdg_set_mesh on several GPUs needs first-encounter face numbering (faces ordered by their first cell) and cell ids in range"));
+    if (c->h_flags[FLAG_BAD_ID]) return cleanup(set_err(c, HDG_ERR_INVALID, "mesh arrays: node id of a face out of range (ids are 1-based)"));
+    std::vector<int64_t> gcells(ncand);
+    if (ncand) HDG_CUDA(c, cudaMemcpy(gcells.data(), d_cand, sizeof(int64_t) * ncand, cudaMemcpyDeviceToHost));
     std::sort(gcells.begin(), gcells.end());
     gcells.erase(std::unique(gcells.begin(), gcells.end()), gcells.end());
-    const int64_t ncloc = ncown + int64_t(gcells.size());
-    auto local_cell = [&](int64_t cg) -> int32_t {   // global 0-based cell -> local id, -2 if not held here
-        if (cg >= cb && cg < ce) return int32_t(cg - cb);
-        auto it = std::lower_bound(gcells.begin(), gcells.end(), cg);
-        if (it != gcells.end() && *it == cg) return int32_t(ncown + (it - gcells.begin()));
-        return -2;
+    const int64_t ngc = int64_t(gcells.size()), ncloc = ncown + ngc;
+    // ---- local cell rows: the owned slice straight from the caller's array, the ghost rows gathered
+    int64_t *d_cells = nullptr, *d_gcells = nullptr, *d_fcand = nullptr, *d_gfaces = nullptr, *d_bf = nullptr;
+    int32_t* d_dflag = nullptr;
+    int64_t* d_offs = nullptr;
+    auto cleanup2 = [&](hdg_status s2) {
+        cudaStreamSynchronize(c->stream);
+        cudaFree(d_cells); cudaFree(d_gcells); cudaFree(d_fcand); cudaFree(d_gfaces); cudaFree(d_bf); cudaFree(d_dflag); cudaFree(d_offs);
+        return cleanup(s2);
     };
-    auto global_cell = [&](int64_t cl) { return cl < ncown ? cb + cl : gcells[cl - ncown]; };
-    // ghost faces: faces of local cells outside the owned range
-    std::vector<int64_t> gfaces;
-    for (int64_t cl = 0; cl < ncloc; ++cl) {
-        const int64_t cg = global_cell(cl);
-        for (int k = 0; k < 3; ++k) {
-            int64_t f = cells[6 * cg + 3 + k] - 1;
-            if (f < fb || f >= fe) gfaces.push_back(f);
-        }
+    if (cudaMalloc(&d_cells, sizeof(int64_t) * 6 * ncloc) != cudaSuccess || cudaMalloc(&d_gcells, sizeof(int64_t) * std::max<int64_t>(ngc, 1)) != cudaSuccess ||
+        cudaMalloc(&d_fcand, sizeof(int64_t) * 3 * ncloc) != cudaSuccess)
+        return cleanup2(set_err(c, HDG_ERR_CUDA, "cudaMalloc(partition)"));
+    cudaMemcpyAsync(d_cells, cells + 6 * cb, sizeof(int64_t) * 6 * ncown, cudaMemcpyHostToDevice, c->stream);
+    std::vector<int64_t> grows(size_t(ngc) * 6);
+    for (int64_t g = 0; g < ngc; ++g) std::copy(cells + 6 * gcells[g], cells + 6 * gcells[g] + 6, grows.begin() + 6 * g);
+    if (ngc) {
+        cudaMemcpyAsync(d_cells + 6 * ncown, grows.data(), sizeof(int64_t) * 6 * ngc, cudaMemcpyHostToDevice, c->stream);
+        cudaMemcpyAsync(d_gcells, gcells.data(), sizeof(int64_t) * ngc, cudaMemcpyHostToDevice, c->stream);
     }
+    cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), c->stream);
+    part_ghost_face_candidates<<<(unsigned)ceil_div(ncloc, B), B, 0, c->stream>>>(d_cells, ncloc, fb, fe, nface, nnode, d_fcand, d_n, c->d_flags + FLAG_BAD_ID);
+    c->launches += 1;
+    cudaMemcpyAsync(&ncand, d_n, sizeof(ncand), cudaMemcpyDeviceToHost, c->stream);
+    cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int32_t) * NFLAGS, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return cleanup2(set_err(c, HDG_ERR_CUDA, "partition: cell pass failed"));
+    if (c->h_flags[FLAG_BAD_ID]) return cleanup2(set_err(c, HDG_ERR_INVALID, "mesh arrays: node / face id of a cell out of range (ids are 1-based: nodes 1..nnode, faces 1..nface)"));
+    std::vector<int64_t> gfaces(ncand);
+    if (ncand) HDG_CUDA(c, cudaMemcpy(gfaces.data(), d_fcand, sizeof(int64_t) * ncand, cudaMemcpyDeviceToHost));
     std::sort(gfaces.begin(), gfaces.end());
     gfaces.erase(std::unique(gfaces.begin(), gfaces.end()), gfaces.end());
-    const int64_t nfloc = nown + int64_t(gfaces.size());
-    auto local_face = [&](int64_t f) -> int64_t {
-        if (f >= fb && f < fe) return f - fb;
-        return nown + (std::lower_bound(gfaces.begin(), gfaces.end(), f) - gfaces.begin());
-    };
-    auto global_face = [&](int64_t fl) { return fl < nown ? fb + fl : gfaces[fl - nown]; };
-    // device-format arrays
-    std::vector<int32_t> cellinfo(size_t(ncloc) * CI, 0), facecell(size_t(nfloc) * 2), facenode(size_t(nfloc) * 2), bf;
-    for (int64_t cl = 0; cl < ncloc; ++cl) {
-        const int64_t cg = global_cell(cl);
-        for (int k = 0; k < 3; ++k) cellinfo[CI * cl + k] = int32_t(cells[6 * cg + k] - 1);   // node ids stay global
-        for (int k = 0; k < 3; ++k) {
-            const int64_t f = cells[6 * cg + 3 + k] - 1;
-            const uint32_t sec = (FC(f, 3) - 1 == cg) ? 0x80000000u : 0u;
-            cellinfo[CI * cl + 3 + k] = int32_t(uint32_t(local_face(f)) | sec);
-        }
-    }
-    std::vector<uint8_t> isdir(size_t(nface), 0);
-    for (int64_t i = 0; i < nbface; ++i) {
-        if (bfaces[i] < 1 || bfaces[i] > nface) return set_err(c, HDG_ERR_INVALID, "boundary face id out of range");
-        if (FC(bfaces[i] - 1, 3) != 0) return set_err(c, HDG_ERR_NOT_BOUNDARY, "Face " + std::to_string(bfaces[i]) + " is not in boundary");
-        isdir[bfaces[i] - 1] = 1;
-    }
-    for (int64_t fl = 0; fl < nfloc; ++fl) {
-        const int64_t f = global_face(fl);
-        facenode[2 * fl] = int32_t(FC(f, 0) - 1);
-        facenode[2 * fl + 1] = int32_t(FC(f, 1) - 1);
-        facecell[2 * fl] = local_cell(FC(f, 2) - 1);
-        facecell[2 * fl + 1] = FC(f, 3) == 0 ? -1 : local_cell(FC(f, 3) - 1);
-        if (isdir[f]) bf.push_back(int32_t(fl));
-    }
+    const int64_t ngf = int64_t(gfaces.size()), nfloc = nown + ngf;
     // ghost face -> (owner rank, local index there)
     std::vector<int32_t> ridx, owner;
     for (int64_t f : gfaces) {
-        int q = int(std::upper_bound(F0.begin(), F0.end(), f) - F0.begin()) - 1;
+        const int q = int(std::upper_bound(F0.begin(), F0.end(), f) - F0.begin()) - 1;
         owner.push_back(q);
         ridx.push_back(int32_t(f - F0[q]));
     }
+    // ---- device mesh
     c->ncell = ncloc; c->ncell_own = ncown; c->nnode = nnode; c->nface = nfloc; c->nface_own = nown;
-    c->nbface = int64_t(bf.size()); c->nx = c->ny = 0; c->grid_px = c->grid_py = 0;
-    hdg_status st = alloc_mesh(c);
-    if (st) return st;
-    HDG_CUDA(c, cudaMemcpyAsync(c->d_cellinfo, cellinfo.data(), sizeof(int32_t) * cellinfo.size(), cudaMemcpyHostToDevice, c->stream));
-    HDG_CUDA(c, cudaMemcpyAsync(c->d_facecell, facecell.data(), sizeof(int32_t) * facecell.size(), cudaMemcpyHostToDevice, c->stream));
-    HDG_CUDA(c, cudaMemcpyAsync(c->d_facenode, facenode.data(), sizeof(int32_t) * facenode.size(), cudaMemcpyHostToDevice, c->stream));
-    HDG_CUDA(c, cudaMemcpyAsync(c->d_nodes, nodes, sizeof(double) * 2 * nnode, cudaMemcpyHostToDevice, c->stream));
-    const int B = 256;
+    c->nbface = std::min<int64_t>(nbface, nfloc); c->nx = c->ny = 0; c->grid_px = c->grid_py = 0;
+    st = alloc_mesh(c);
+    if (st) return cleanup2(st);
+    if (cudaMalloc(&d_gfaces, sizeof(int64_t) * std::max<int64_t>(ngf, 1)) != cudaSuccess || cudaMalloc(&d_bf, sizeof(int64_t) * std::max<int64_t>(nbface, 1)) != cudaSuccess ||
+        cudaMalloc(&d_dflag, sizeof(int32_t) * nfloc) != cudaSuccess || cudaMalloc(&d_offs, sizeof(int64_t) * (nfloc + 1)) != cudaSuccess)
+        return cleanup2(set_err(c, HDG_ERR_CUDA, "cudaMalloc(partition)"));
+    if (ngf) cudaMemcpyAsync(d_gfaces, gfaces.data(), sizeof(int64_t) * ngf, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(c->d_nodes, nodes, sizeof(double) * 2 * nnode, cudaMemcpyHostToDevice, c->stream);
+    part_convert_cells<<<(unsigned)ceil_div(ncloc, B), B, 0, c->stream>>>(d_cells, ncloc, ncown, cb, d_gcells, fb, fe, d_f + 3 * nown, d_gfaces, ngf, c->d_cellinfo);
+    part_owned_facecell<<<(unsigned)ceil_div(nown, B), B, 0, c->stream>>>(d_f, d_f + nown, d_f + 2 * nown, d_f + 3 * nown, nown, cb, ce, ncown, d_gcells, ngc,
+                                                                           c->d_facecell, c->d_facenode);
+    if (ngf) {
+        init_facecell<<<(unsigned)ceil_div(ngf, B), B, 0, c->stream>>>(c->d_facecell + 2 * nown, ngf);
+        part_ghost_facecell<<<(unsigned)ceil_div(ncloc, B), B, 0, c->stream>>>(c->d_cellinfo, ncloc, nown, c->d_facecell, c->d_facenode);
+        finish_facecell<<<(unsigned)ceil_div(ngf, B), B, 0, c->stream>>>(c->d_facecell + 2 * nown, ngf);
+    }
     build_kcol<<<(unsigned)ceil_div(ncloc, B), B, 0, c->stream>>>(c->d_cellinfo, ncloc, c->d_kcol);
     build_partner<<<(unsigned)ceil_div(ncloc, B), B, 0, c->stream>>>(c->d_cellinfo, ncloc, c->d_facecell);
-    c->launches += 2;
-    if (!bf.empty()) {
-        HDG_CUDA(c, cudaMemcpyAsync(c->d_bfaces, bf.data(), sizeof(int32_t) * bf.size(), cudaMemcpyHostToDevice, c->stream));
-        mark_isbc_list<<<(unsigned)ceil_div(int64_t(bf.size()), B), B, 0, c->stream>>>(c->d_bfaces, int64_t(bf.size()), c->d_isbc);
+    c->launches += 7;
+    // Dirichlet set: flags of the local faces, compacted ascending (the dof order of Dirichlet, src/boundary.jl:19-21)
+    cudaMemsetAsync(d_dflag, 0, sizeof(int32_t) * nfloc, c->stream);
+    int64_t nbloc = 0;
+    if (nbface) {
+        cudaMemcpyAsync(d_bf, bfaces, sizeof(int64_t) * nbface, cudaMemcpyHostToDevice, c->stream);
+        part_mark_dirichlet<<<(unsigned)ceil_div(nbface, B), B, 0, c->stream>>>(d_bf, nbface, nface, fb, fe, d_f + 3 * nown, d_gfaces, ngf, d_dflag, c->d_flags);
         c->launches += 1;
     }
-    HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+    int64_t* d_tot = d_offs + nfloc;
+    st = exclusive_scan(c, d_dflag, nfloc, d_offs, d_tot);
+    if (st) return cleanup2(st);
+    cudaMemcpyAsync(&nbloc, d_tot, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream);
+    cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int32_t) * NFLAGS, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return cleanup2(set_err(c, HDG_ERR_CUDA, "partition: Dirichlet pass failed"));
+    if (c->h_flags[FLAG_BAD_ID]) return cleanup2(set_err(c, HDG_ERR_INVALID, "boundary face id out of range"));
+    if (c->h_flags[FLAG_NOT_BOUNDARY]) return cleanup2(set_err(c, HDG_ERR_NOT_BOUNDARY, "Face " + std::to_string(c->h_flags[FLAG_NOT_BOUNDARY]) + " is not in boundary"));
+    compact_boundary<<<(unsigned)ceil_div(nfloc, B), B, 0, c->stream>>>(d_dflag, d_offs, nfloc, c->d_bfaces, c->d_isbc);
+    c->launches += 1;
+    c->nbface = nbloc;
+    cleanup2(HDG_OK);
     m->j0 = m->j1 = m->ny_global = 0;
     m->cell_begin = cb; m->face_begin = fb; m->ncell_global = ncell; m->nface_global = nface;
     m->nbelow = m->nabove = 0;

@@ -78,7 +78,7 @@ struct LvDev {
     int px, py;
     int rb, oy0, oy1;
     int rep;
-    int n;                      // stored points: the stride between the 7 stencil slots (levels have < 2^31 points)
+    int n;                      // stride between the arrays of the level (>= the stored points; levels have < 2^31 points)
     double *st, *dinv, *r, *t, *x;
     double *b_r, *b_t, *b_x;  int b_rb;
     double *a_r, *a_t, *a_x;  int a_rb;
@@ -87,10 +87,14 @@ struct LvDev {
 enum MgArr : int { AR_R = 1, AR_T = 2, AR_X = 3 };
 
 __device__ __forceinline__ int lv_idx(const LvDev& L, int x, int y) { return (y - L.rb) * L.px + x; }
-// Dynamic vectors (r, t) are written by other SMs / GPUs inside the same launch: L2-coherent loads (ld.global.cg) for them,
-// plain loads for the operators (constant during a solve).
-__device__ __forceinline__ double lv_r(const LvDev& L, int x, int y) { return __ldcg(L.r + lv_idx(L, x, y)); }
-__device__ __forceinline__ double lv_t(const LvDev& L, int x, int y) { return __ldcg(L.t + lv_idx(L, x, y)); }
+// The dynamic vectors (r, t) are written by other SMs / GPUs inside the same launch, yet the stage loads are PLAIN (L1-cached)
+// loads - the 7-point stencils of neighbouring threads re-read the same values, and served from L2 (ld.global.cg) those gathers
+// were what bounded the big levels.  That is safe because every vector is written exactly once per launch (own rows by this
+// GPU, ghost rows by the neighbours, all in the producing stage) and first read after the grid barrier that follows, so no SM
+// can hold a stale line of it; L1 is invalidated between launches.  The one stage that reads a vector while the neighbours are
+// still pushing its ghost rows (the shared-row addition at level 0) uses ld.global.cg.
+__device__ __forceinline__ double lv_r(const LvDev& L, int x, int y) { return L.r[lv_idx(L, x, y)]; }
+__device__ __forceinline__ double lv_t(const LvDev& L, int x, int y) { return L.t[lv_idx(L, x, y)]; }
 // store into the own array and, for the first / last MG_GHOST owned rows of a distributed level, into the ghost rows of the neighbours
 template <int W> __device__ __forceinline__ void lv_store(const LvDev& L, int x, int y, double v) {
     double* own = W == AR_R ? L.r : (W == AR_T ? L.t : L.x);
@@ -152,7 +156,7 @@ __device__ __forceinline__ double mg_down_point(const LvDev& F, int Ix, int Iy) 
         double a = F.st[p] * xw[MG_DY[d] + 2][MG_DX[d] + 2];
 #pragma unroll
         for (int k = 1; k < 7; ++k) a = fma(F.st[k * int64_t(F.n) + p], xw[MG_DY[d] + MG_DY[k] + 2][MG_DX[d] + MG_DX[k] + 2], a);
-        const double t = __ldcg(F.r + p) - a;
+        const double t = F.r[p] - a;
         s += in ? (d == 0 ? 1.0 : 0.5) * t : 0.0;
     }
     return s;
@@ -166,7 +170,7 @@ __device__ __forceinline__ double mg_up_point(const LvDev& F, const LvDev& C, in
     double s = F.st[p] * xq[0];
 #pragma unroll
     for (int k = 1; k < 7; ++k) s = fma(F.st[k * int64_t(F.n) + p], xq[k], s);
-    return fma(MG_OMEGA * F.dinv[p], __ldcg(F.r + p) - s, xq[0]);
+    return fma(MG_OMEGA * F.dinv[p], F.r[p] - s, xq[0]);
 }
 
 // ---- vertex <-> trace adjacency ---------------------------------------------------------------------------------------------
@@ -361,7 +365,7 @@ __global__ void mg_drop_fixed(const LvDev C, int cy0, int cy1) {
 }
 
 // coarsest grid: dense inverse by Gauss-Jordan without pivoting (SPD + identity rows), one block
-__global__ void mg_dense_inverse(const double* __restrict__ st, int px, int py, double* __restrict__ ainv) {
+__global__ void mg_dense_inverse(const double* __restrict__ st, int64_t stride, int px, int py, double* __restrict__ ainv) {
     extern __shared__ double A[];      // n x n
     const int n = px * py;
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) A[e] = 0.0;
@@ -371,7 +375,7 @@ __global__ void mg_dense_inverse(const double* __restrict__ st, int px, int py, 
         for (int k = 0; k < 7; ++k) {
             const int qx = ix + MG_DX[k], qy = iy + MG_DY[k];
             if (qx < 0 || qy < 0 || qx >= px || qy >= py) continue;
-            A[p * n + qy * px + qx] = st[k * n + p];
+            A[p * n + qy * px + qx] = st[k * stride + p];
         }
     }
     __syncthreads();
@@ -451,21 +455,22 @@ __device__ __forceinline__ void mg_grid_barrier(const VcArgs& A, bool cross) {
 struct TailLv { int px, py, n; double *st, *dinv, *r, *t, *x; };
 __device__ __forceinline__ TailLv mg_tail_level(const VcArgs& A, double* sm, int l) {
     int o = 0;
-    for (int k = A.lt; k < l; ++k) o += 11 * int(A.lev[k].n);
-    const int n = int(A.lev[l].n);
+    for (int k = A.lt; k < l; ++k) o += 11 * A.lev[k].px * A.lev[k].py;
+    const int n = A.lev[l].px * A.lev[l].py;
     return TailLv{A.lev[l].px, A.lev[l].py, n, sm + o, sm + o + 7 * n, sm + o + 8 * n, sm + o + 9 * n, sm + o + 10 * n};
 }
-__device__ void mg_tail_load(const VcArgs& A, double* sm) {      // st | dinv of every tail level (adjacent in the pool as well)
+__device__ void mg_tail_load(const VcArgs& A, double* sm) {      // st (7 arrays) and dinv of every tail level
     for (int l = A.lt; l < A.nlev; ++l) {
         const TailLv L = mg_tail_level(A, sm, l);
         const double* __restrict__ src = A.lev[l].st;
+        const int stride = A.lev[l].n, cnt = 8 * L.n;
         constexpr int U = 8;      // independent loads in flight per thread: one block fetches ~60 kB here
-        for (int i0 = threadIdx.x; i0 < 8 * L.n; i0 += blockDim.x * U) {
+        for (int i0 = threadIdx.x; i0 < cnt; i0 += blockDim.x * U) {
             double v[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) { const int i = i0 + u * blockDim.x; v[u] = i < 8 * L.n ? src[i] : 0.0; }
+            for (int u = 0; u < U; ++u) { const int i = i0 + u * blockDim.x; v[u] = i < cnt ? src[(i / L.n) * int64_t(stride) + i % L.n] : 0.0; }
 #pragma unroll
-            for (int u = 0; u < U; ++u) { const int i = i0 + u * blockDim.x; if (i < 8 * L.n) L.st[i] = v[u]; }
+            for (int u = 0; u < U; ++u) { const int i = i0 + u * blockDim.x; if (i < cnt) L.st[i] = v[u]; }
         }
     }
 }
@@ -583,7 +588,7 @@ __global__ void __launch_bounds__(MG_THREADS, MG_BLOCKS_PER_SM) mg_vcycle_kernel
         const bool add = A.xg.rank > 0;      // row oy0 is shared with the rank below
         if (L0.rep) {
             for (int i = tid; i < nown; i += T) {
-                double v = L0.r[o0 + i];
+                double v = __ldcg(L0.r + o0 + i);
                 if (add && i < L0.px) { v = A.fx[i] != 0.0 ? 0.0 : v + __ldcg(L0.x + o0 + i); L0.r[o0 + i] = v; }
                 for (int q = 0; q < A.xg.nranks; ++q)
                     if (q != A.xg.rank) A.rep_r[q][o0 + i] = v;
@@ -594,7 +599,7 @@ __global__ void __launch_bounds__(MG_THREADS, MG_BLOCKS_PER_SM) mg_vcycle_kernel
                 const int k = i < nb ? i : nown - 2 * nb + i;          // the first / the last MG_GHOST owned rows
                 if (i >= nb && k < nb) continue;                        // fewer than 2 MG_GHOST owned rows: each row once
                 const int y = L0.oy0 + k / L0.px, x = k % L0.px;
-                double v = L0.r[o0 + k];
+                double v = __ldcg(L0.r + o0 + k);
                 if (add && k < L0.px) v = A.fx[k] != 0.0 ? 0.0 : v + __ldcg(L0.x + o0 + k);
                 lv_store<AR_R>(L0, x, y, v);
             }
@@ -675,7 +680,7 @@ struct MgLevelHost {
     int oy0[MAXR + 1] = {};          // owned rows of rank q: [oy0[q], oy0[q+1])
     int rb[MAXR] = {};               // first stored row on rank q
     int64_t off[MAXR] = {};          // offset of the level's arrays in rank q's pool (doubles)
-    int64_t n[MAXR] = {};            // stored points on rank q
+    int64_t n[MAXR] = {};            // array stride on rank q: the stored points rounded up to a multiple of 16
 };
 
 struct MgData {
@@ -808,7 +813,7 @@ template <int NT> static hdg_status mg_setup_t(hdg_context* c) {
                     if ((pass == 0) != H.rep) continue;
                     H.rb[q] = H.rep ? 0 : std::max(0, H.oy0[q] - MG_GHOST);
                     const int re = H.rep ? H.py : std::min(H.py, H.oy0[q + 1] + MG_GHOST);
-                    H.n[q] = int64_t(re - H.rb[q]) * H.px;
+                    H.n[q] = (int64_t(re - H.rb[q]) * H.px + 15) / 16 * 16;      // array stride: every array starts on its own 128-byte line
                     H.off[q] = o;
                     o += 11 * H.n[q];
                 }
@@ -870,7 +875,7 @@ template <int NT> static hdg_status mg_setup_t(hdg_context* c) {
             for (int k = 0; k < R; ++k) g.src[k] = level_array(m, k, l, which);
             mg_gather_rows<<<nblk(H.n[q]), 256, 0, c->stream>>>(g, dst, H.n[q], narr, H.px);
         } else {
-            const int rows = int(H.n[q] / H.px);
+            const int rows = (H.rep ? H.py : std::min(H.py, H.oy0[q + 1] + MG_GHOST)) - H.rb[q];
             const int ghosts = (H.oy0[q] - H.rb[q]) + (H.rb[q] + rows - H.oy0[q + 1]);
             mg_pull_ghost_rows<<<nblk(int64_t(ghosts) * H.px), 256, 0, c->stream>>>(
                 dst, H.n[q], H.rb[q], H.oy0[q], H.oy0[q + 1], rows, narr, H.px,
@@ -905,7 +910,7 @@ template <int NT> static hdg_status mg_setup_t(hdg_context* c) {
                 for (int k = 0; k < R; ++k) g.src[k] = static_cast<const double*>(m->peer_pool[k]) + m->fx_off[k];
                 mg_gather_rows<<<nblk(H0.n[q]), 256, 0, c->stream>>>(g, fx, H0.n[q], 1, H0.px);
             } else {
-                const int rows = int(H0.n[q] / H0.px);
+                const int rows = std::min(H0.py, H0.oy0[q + 1] + MG_GHOST) - H0.rb[q];
                 const int ghosts = (H0.oy0[q] - H0.rb[q]) + (H0.rb[q] + rows - H0.oy0[q + 1]);
                 mg_pull_ghost_rows<<<nblk(int64_t(ghosts) * H0.px), 256, 0, c->stream>>>(
                     fx, H0.n[q], H0.rb[q], H0.oy0[q], H0.oy0[q + 1], rows, 1, H0.px,
@@ -953,7 +958,7 @@ template <int NT> static hdg_status mg_setup_t(hdg_context* c) {
         c->launches += 1;
     }
     const LvDev last = level_dev(m, m->nlev - 1);
-    mg_dense_inverse<<<1, 256, sizeof(double) * last.n * last.n, c->stream>>>(last.st, last.px, last.py, m->ainv);
+    mg_dense_inverse<<<1, 256, sizeof(double) * last.px * last.py * last.px * last.py, c->stream>>>(last.st, last.n, last.px, last.py, m->ainv);
     c->launches += 1;
     HDG_CUDA(c, cudaGetLastError());
     // ---- arguments of the V-cycle kernel
