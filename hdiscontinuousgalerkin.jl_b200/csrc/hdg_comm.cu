@@ -211,7 +211,7 @@ hdg_status comm_share_vectors(hdg_context* c, void* region, int64_t ndof_own) {
     hdg_status st = allgather_records(c, mine, all);
     if (st) return st;
     for (int q = 0; q < m->nranks && q < MAXR; ++q) {
-        if (q == m->rank || !((m->need_rank >> q) & 1u)) continue;
+        if (q == m->rank) continue;      // every rank's region: a later mesh of the same sizes may have other neighbours
         void* p = nullptr;
         cudaError_t e = cudaIpcOpenMemHandle(&p, all[q].handle, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) {

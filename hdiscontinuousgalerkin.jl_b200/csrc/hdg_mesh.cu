@@ -561,9 +561,6 @@ void free_mesh(hdg_context* c) {
 // Device buffers are kept across hdg_set_mesh / hdg_set_rectangle_mesh calls with unchanged sizes
 // (cudaMalloc / cudaFree of ~1 GB costs far more than re-uploading the mesh).
 static bool same_capacity(const hdg_context* c, int64_t ncell, int64_t nnode, int64_t nface, int64_t nbface) {
-    // several GPUs: the decision would have to be collective (a neighbour whose sizes did change frees the vector region this
-    // rank has mapped and re-shares it in its next solve) - every mesh change goes through free_mesh / re-share there
-    if (comm_active(c)) return false;
     return c->d_cellinfo && c->d_Ke && c->cap_ncell == ncell && c->cap_nnode == nnode && c->cap_nface == nface &&
            c->cap_nbface >= nbface;
 }
@@ -572,7 +569,19 @@ static hdg_status alloc_mesh(hdg_context* c) {
     if (c->ncell <= 0 || c->nface <= 0 || c->nnode <= 0) return set_err(c, HDG_ERR_INVALID, "empty mesh");
     if (c->nface >= (int64_t(1) << 31) || c->ncell >= (int64_t(1) << 31) || c->nnode >= (int64_t(1) << 31))
         return set_err(c, HDG_ERR_INVALID, "mesh too large for 32-bit device ids");
-    if (same_capacity(c, c->ncell, c->nnode, c->nface, c->nbface)) {
+    bool same = same_capacity(c, c->ncell, c->nnode, c->nface, c->nbface);
+    if (comm_active(c)) {
+        // several GPUs: the decision is COLLECTIVE - a rank whose sizes did change frees the vector region its neighbours have
+        // mapped and re-shares it in its next solve, so either every rank keeps its buffers or none does
+        double flag = same ? 0.0 : 1.0;
+        HDG_CUDA(c, cudaMemcpyAsync(c->comm->d_gscal, &flag, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        hdg_status st = comm_allreduce_sum(c, c->comm->d_gscal, 1);
+        if (st) return st;
+        HDG_CUDA(c, cudaMemcpyAsync(&flag, c->comm->d_gscal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        HDG_CUDA(c, cudaStreamSynchronize(c->stream));
+        same = flag == 0.0;
+    }
+    if (same) {
         c->have_mesh = c->assembled = c->applied = c->solved = c->recovered = false;
         HDG_CUDA(c, cudaMemsetAsync(c->d_isbc, 0, c->nface, c->stream));
         HDG_CUDA(c, cudaMemsetAsync(c->d_kcol, 0xFF, sizeof(int32_t) * 4 * c->nface, c->stream));
