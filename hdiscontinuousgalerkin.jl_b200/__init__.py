@@ -11,4 +11,4 @@ from .api import *  # noqa: F401,F403
 from .api import _Context  # noqa: F401
 from . import cg  # noqa: F401  (CG side of the exported API: DofHandler, create_sparsity_pattern, ...)
 from .cg import (ContinuousLagrange, LagrangeField, DofHandler, DirichletCG, create_sparsity_pattern, ndofs,  # noqa: F401
-                 ndofs_per_cell, dof_range, reconstruct_, get_vertices_matrix, getcells_matrix)
+                 ndofs_per_cell, dof_range, reconstruct_, get_vertices_matrix, getcells_matrix, CGDevice, poisson2D_CG)

@@ -118,6 +118,15 @@ SIGNATURES = {
     "hdg_last_phase_ms": (C.c_int, [_P, C.c_char_p, _F64P]),
     "hdg_measure_fp64_peak": (C.c_int, [_P, _F64P]),
     "hdg_mg_trace": (C.c_int32, [_P, _F64P, C.c_int32]),
+    "hdg_cg_setup": (C.c_int, [_P, C.c_int32, _I64P]),
+    "hdg_cg_get_sizes": (C.c_int, [_P, _I64P]),
+    "hdg_cg_get_dofhandler": (C.c_int, [_P, _I64P, _I64P, _I64P]),
+    "hdg_cg_assemble": (C.c_int, [_P]),
+    "hdg_cg_apply_dirichlet": (C.c_int, [_P]),
+    "hdg_cg_solve": (C.c_int, [_P, C.c_double, C.c_int32, C.POINTER(SolveInfo)]),
+    "hdg_cg_get_system": (C.c_int, [_P, _F64P, _F64P, _F64P]),
+    "hdg_cg_errornorm": (C.c_int, [_P, _F64P]),
+    "hdg_cg_get_meandiag": (C.c_int, [_P, _F64P]),
     "hdg_launch_count": (C.c_int64, [_P]),
 }
 

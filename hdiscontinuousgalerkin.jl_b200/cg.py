@@ -1,15 +1,20 @@
 """Continuous-Galerkin side of the reference's exported API: DofHandler, sparsity pattern,
 Dirichlet conditions on a DofHandler, reconstruct!, and the mesh matrix helpers used for plotting.
 
-Host-side INTEGER logic only (dof numbering and patterns, like `number_faces`); there is no CG assembly kernel in
-libhdg_b200 - the CG example (examples/poisson2D_CG.jl) is outside the HDG hot path.  The sequential dictionary walk of
-the reference (src/dofhandler.jl:84-152) is replaced by a sort-based first-encounter ranking; results are identical to
-the reference's goldens (test/test_handlers.jl:13-19) and to the loop-faithful oracle (tests/test_host_logic.py)."""
+Two layers.  (1) Host-side integer logic (`DofHandler`, `create_sparsity_pattern`, `DirichletCG`, `reconstruct_`): the
+sequential dictionary walk of the reference (src/dofhandler.jl:84-152) as a sort-based first-encounter ranking; identical to
+the reference's goldens (test/test_handlers.jl:13-19) and to the loop-faithful oracle (tests/test_host_logic.py).
+(2) The device path (`poisson2D_CG`, `CGDevice`): examples/poisson2D_CG.jl through the C ABI (hdg_cg_* in
+include/hdg_b200.h, csrc/hdg_cg.cu) - dof numbering, sparsity pattern, element matrices + assemble!, Dirichlet + apply!, the
+solve and errornorm all run on the GPU; there is no CPU fallback for it."""
 from __future__ import annotations
 
 import numpy as np
 
-from .api import PolygonalMesh, RefTetrahedron
+import ctypes as C
+
+from ._lib import SolveInfo, check, f64p, i64p
+from .api import PolygonalMesh, RefTetrahedron, _Context
 
 
 class ContinuousLagrange:
@@ -167,3 +172,76 @@ def get_vertices_matrix(mesh: PolygonalMesh):
 def getcells_matrix(mesh: PolygonalMesh):
     """getcells_matrix(mesh), src/mesh.jl:63-69: ncell x 3 node ids (1-based)."""
     return np.array(mesh.cells[:, :3], dtype=np.int64, copy=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# device path: examples/poisson2D_CG.jl through the C ABI
+# ----------------------------------------------------------------------------------------------
+class CGDevice:
+    """DofHandler + create_sparsity_pattern + doassemble + apply! + K \\ b + errornorm of examples/poisson2D_CG.jl on the GPU
+    (hdg_cg_*).  `mesh` is handed over like in the HDG driver; `order` is that of ContinuousLagrange{2,RefTetrahedron,order}."""
+
+    def __init__(self, mesh: PolygonalMesh, order=1, device=-1):
+        self.ctx = _Context(1, 2, 1.0, 1, device)        # the HDG tables of the context are not used by the CG side
+        self.ctx.set_mesh(mesh)
+        self.mesh, self.order = mesh, order
+        n = C.c_int64()
+        check(self.ctx.lib.hdg_cg_setup(self.ctx.h, int(order), C.byref(n)), self.ctx.h)
+        sz = np.zeros(4, np.int64)
+        check(self.ctx.lib.hdg_cg_get_sizes(self.ctx.h, i64p(sz)), self.ctx.h)
+        self.ndofs, self.nnz, self.ndofs_per_cell, self.ncell = (int(v) for v in sz)
+
+    def dofhandler(self):
+        """(cell_dofs (ncell, ndofs_per_cell), colptr, rowval) - 1-based Int64 like dh.cell_dofs and the SparseMatrixCSC."""
+        cd = np.empty((self.ncell, self.ndofs_per_cell), np.int64)
+        cp = np.empty(self.ndofs + 1, np.int64)
+        rv = np.empty(self.nnz, np.int64)
+        check(self.ctx.lib.hdg_cg_get_dofhandler(self.ctx.h, i64p(cd), i64p(cp), i64p(rv)), self.ctx.h)
+        return cd, cp, rv
+
+    def doassemble(self):
+        check(self.ctx.lib.hdg_cg_assemble(self.ctx.h), self.ctx.h)
+        return self.system()
+
+    def system(self):
+        import scipy.sparse as sp
+        cd, cp, rv = self.dofhandler()
+        nz, b = np.empty(self.nnz), np.empty(self.ndofs)
+        check(self.ctx.lib.hdg_cg_get_system(self.ctx.h, f64p(nz), f64p(b), None), self.ctx.h)
+        return sp.csc_matrix((nz, rv - 1, cp - 1), shape=(self.ndofs, self.ndofs)), b
+
+    def apply_(self):
+        check(self.ctx.lib.hdg_cg_apply_dirichlet(self.ctx.h), self.ctx.h)
+        m = C.c_double()
+        check(self.ctx.lib.hdg_cg_get_meandiag(self.ctx.h, C.byref(m)), self.ctx.h)
+        return m.value
+
+    def solve(self, rtol=1e-13, maxit=100000):
+        info = SolveInfo()
+        check(self.ctx.lib.hdg_cg_solve(self.ctx.h, float(rtol), int(maxit), C.byref(info)), self.ctx.h)
+        u = np.empty(self.ndofs)
+        check(self.ctx.lib.hdg_cg_get_system(self.ctx.h, None, None, f64p(u)), self.ctx.h)
+        return u, dict(iterations=info.iterations, converged=bool(info.converged), relres=info.relres, solve_ms=info.solve_ms)
+
+    def errornorm(self):
+        e = C.c_double()
+        check(self.ctx.lib.hdg_cg_errornorm(self.ctx.h, C.byref(e)), self.ctx.h)
+        return e.value
+
+    def close(self):
+        self.ctx.close()
+
+
+def poisson2D_CG(mesh=None, order=1, rtol=1e-13):
+    """examples/poisson2D_CG.jl end to end on the device.  Returns a dict (K and b before apply!, u, err2, info)."""
+    from .api import TriangleCell, rectangle_mesh
+    if mesh is None:
+        mesh = rectangle_mesh(TriangleCell, (10, 10), (0.0, 0.0), (1.0, 1.0))
+    dev = CGDevice(mesh, order)
+    try:
+        K, b = dev.doassemble()
+        m = dev.apply_()
+        u, info = dev.solve(rtol)
+        return dict(K=K, b=b, u=u, err2=dev.errornorm(), info=info, meandiag=m, ndofs=dev.ndofs, dofhandler=dev.dofhandler())
+    finally:
+        dev.close()

@@ -506,6 +506,53 @@ hdg_status hdg_measure_fp64_peak(hdg_context* c, double* tflops) {
     return HDG_OK;
 }
 
+// ---- CG side of the exported API (examples/poisson2D_CG.jl), hdg_cg.cu ----------------------------------------------------
+hdg_status hdg_cg_setup(hdg_context* c, int32_t order, int64_t* ndofs) {
+    if (!c) return HDG_ERR_INVALID;
+    if (!c->have_mesh) return set_err(c, HDG_ERR_INVALID, "hdg_cg_setup before a mesh is set");
+    cudaSetDevice(c->device);
+    return cg_setup(c, order, ndofs);
+}
+hdg_status hdg_cg_get_sizes(hdg_context* c, int64_t out[4]) {
+    if (!c || !out) return HDG_ERR_INVALID;
+    return cg_sizes(c, out);
+}
+hdg_status hdg_cg_get_dofhandler(hdg_context* c, int64_t* cell_dofs, int64_t* colptr, int64_t* rowval) {
+    if (!c) return HDG_ERR_INVALID;
+    cudaSetDevice(c->device);
+    return cg_download(c, cell_dofs, colptr, rowval, nullptr, nullptr, nullptr);
+}
+hdg_status hdg_cg_assemble(hdg_context* c) {
+    if (!c) return HDG_ERR_INVALID;
+    cudaSetDevice(c->device);
+    return cg_assemble(c);
+}
+hdg_status hdg_cg_apply_dirichlet(hdg_context* c) {
+    if (!c) return HDG_ERR_INVALID;
+    cudaSetDevice(c->device);
+    return cg_apply_dirichlet(c);
+}
+hdg_status hdg_cg_solve(hdg_context* c, double rtol, int32_t maxit, hdg_solve_info* info) {
+    if (!c) return HDG_ERR_INVALID;
+    cudaSetDevice(c->device);
+    return cg_solve(c, rtol, maxit, info);
+}
+hdg_status hdg_cg_get_system(hdg_context* c, double* nzval, double* rhs, double* u) {
+    if (!c) return HDG_ERR_INVALID;
+    cudaSetDevice(c->device);
+    return cg_download(c, nullptr, nullptr, nullptr, nzval, rhs, u);
+}
+hdg_status hdg_cg_errornorm(hdg_context* c, double* err2) {
+    if (!c || !err2) return HDG_ERR_INVALID;
+    cudaSetDevice(c->device);
+    return cg_errornorm(c, err2);
+}
+hdg_status hdg_cg_get_meandiag(const hdg_context* c, double* m) {
+    if (!c || !m) return HDG_ERR_INVALID;
+    *m = cg_meandiag(c);
+    return HDG_OK;
+}
+
 int32_t hdg_mg_trace(hdg_context* c, double* usec, int32_t capacity) {
     if (!c || !usec) return 0;
     cudaSetDevice(c->device);

@@ -155,7 +155,8 @@ struct hdg_context {
     double* d_binv = nullptr;        // block-Jacobi: inverted face-diagonal blocks
     int precond = 0;                 // 0 Jacobi, 1 block-Jacobi, 2 block-Jacobi + P1-vertex multigrid (hdg_mg.cu)
     void* mg = nullptr;              // hdg::MgData
-    void* mg_general = nullptr;      // MgGeneral (round-2 candidate, hdg_mg.cu)
+    void* mg_general = nullptr;      // MgGeneral: vertex term on meshes without grid structure (hdg_mgx.cu)
+    void* cg = nullptr;              // CgData: CG side of the exported API (hdg_cg.cu)
     double* d_partials = nullptr;    // reduction partials
     double* d_scal = nullptr;        // device scalars
     int32_t* d_flags = nullptr;      // error / convergence flags
@@ -229,6 +230,18 @@ hdg_status recover(hdg_context* c);                             // hdg_recover.c
 hdg_status errornorm(hdg_context* c, int exact_id, const double* uex_host, double* err2);
 hdg_status local_download(hdg_context* c, int64_t cell, double* Ke, double* be);
 hdg_status nodal_average(hdg_context* c, double* out);
+
+// hdg_cg.cu: CG side (examples/poisson2D_CG.jl) on the mesh of the context
+hdg_status cg_setup(hdg_context* c, int order, int64_t* ndofs_out);
+hdg_status cg_sizes(hdg_context* c, int64_t out[4]);
+hdg_status cg_download(hdg_context* c, int64_t* cell_dofs, int64_t* colptr, int64_t* rowval, double* nzval, double* rhs, double* u);
+hdg_status cg_assemble(hdg_context* c);
+hdg_status cg_apply_dirichlet(hdg_context* c);
+hdg_status cg_solve(hdg_context* c, double rtol, int maxit, hdg_solve_info* info);
+hdg_status cg_errornorm(hdg_context* c, double* err2);
+double cg_meandiag(const hdg_context* c);
+void cg_release(hdg_context* c);
+hdg_status exclusive_scan_i32(hdg_context* c, const int32_t* in, int64_t n, int64_t* out, int64_t* d_total);   // hdg_mesh.cu
 
 // hdg_comm.cu
 bool comm_active(const hdg_context* c);

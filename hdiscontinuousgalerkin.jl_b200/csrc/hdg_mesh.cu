@@ -107,6 +107,8 @@ static hdg_status exclusive_scan(hdg_context* c, const int32_t* in, int64_t n, i
     return HDG_OK;
 }
 
+hdg_status exclusive_scan_i32(hdg_context* c, const int32_t* in, int64_t n, int64_t* out, int64_t* d_total) { return exclusive_scan(c, in, n, out, d_total); }
+
 // ------------------------------------------------------------------------------------------
 // mesh from host arrays (Julia layouts, 1-based int64)
 // ------------------------------------------------------------------------------------------
@@ -545,6 +547,7 @@ hdg_status number_faces_host(hdg_context* c, const int64_t* tri, int64_t ncell, 
 // ------------------------------------------------------------------------------------------
 void free_mesh(hdg_context* c) {
     mg_free(c);
+    cg_release(c);
     auto F = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     F(c->d_cellinfo); F(c->d_nodes); F(c->d_facecell); F(c->d_facenode); F(c->d_bfaces); F(c->d_isbc);
     F(c->d_kcol); F(c->d_fq); F(c->d_Kd); F(c->d_Ko); F(c->d_Ke); F(c->d_bcval);
@@ -902,6 +905,7 @@ __global__ void grid_check(const int32_t* __restrict__ facenode, int64_t nface, 
 hdg_status mesh_from_host(hdg_context* c, const int64_t* cells, int64_t ncell, const double* nodes, int64_t nnode,
                           const int64_t* faces, int64_t nface, const int64_t* bfaces, int64_t nbface) {
     mg_invalidate(c);   // vertex adjacency of the previous mesh (buffers are kept while the sizes fit)
+    cg_release(c);      // the DofHandler of the previous mesh
 
     if (comm_active(c)) return mesh_from_host_partitioned(c, cells, ncell, nodes, nnode, faces, nface, bfaces, nbface);
     c->ncell = c->ncell_own = ncell; c->nnode = nnode; c->nface = c->nface_own = nface; c->nbface = nbface; c->nx = c->ny = 0;
@@ -1025,6 +1029,7 @@ hdg_status mesh_set_dirichlet(hdg_context* c, const int64_t* bfaces, int64_t nbf
 
 hdg_status mesh_rectangle(hdg_context* c, int64_t nx, int64_t ny, double llx, double lly, double urx, double ury) {
     mg_invalidate(c);   // vertex adjacency of the previous mesh (buffers are kept while the sizes fit)
+    cg_release(c);      // the DofHandler of the previous mesh
 
     if (nx < 1 || ny < 1 || !(urx > llx) || !(ury > lly)) return set_err(c, HDG_ERR_INVALID, "rectangle_mesh: need nx,ny >= 1 and UR > LL");
     // strip of quad rows owned by this rank (whole mesh on one GPU)

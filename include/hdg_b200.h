@@ -216,6 +216,31 @@ hdg_status hdg_get_mvalues(hdg_context* ctx, double* sigma, double* u, double* u
  * (value(u_h,node,cell), :70-79) and averaged over the cells sharing a node; nnode doubles.  Plotting helper. */
 hdg_status hdg_nodal_avg(hdg_context* ctx, double* out);
 
+/* ---- CG side of the exported API -------------------------------------------
+ * examples/poisson2D_CG.jl on the mesh of the context: ContinuousLagrange{2,RefTetrahedron,order} (order 1 or 2), one scalar
+ * field, quad_degree = order + 1 (the default of ScalarFunctionSpace), f = 2 pi^2 sin(pi x) sin(pi y).  One GPU.
+ * hdg_cg_setup == DofHandler([u_h], mesh) (_distribute_dofs, src/dofhandler.jl:80-152) + create_sparsity_pattern(dh)
+ * (:181-220) on the device; *ndofs receives ndofs(dh). */
+hdg_status hdg_cg_setup(hdg_context* ctx, int32_t order, int64_t* ndofs);
+/* out = {ndofs, nnz of the pattern, ndofs_per_cell, ncell} */
+hdg_status hdg_cg_get_sizes(hdg_context* ctx, int64_t out[4]);
+/* dh.cell_dofs (ncell x ndofs_per_cell, 1-based, cell-major == the reference's flat vector) and the CSC pattern of
+ * create_sparsity_pattern (colptr ndofs+1, rowval nnz; Int64, 1-based).  Any pointer may be NULL. */
+hdg_status hdg_cg_get_dofhandler(hdg_context* ctx, int64_t* cell_dofs, int64_t* colptr, int64_t* rowval);
+/* doassemble(Wh, K, dh) of examples/poisson2D_CG.jl:72-126: start_assemble, element matrices, assemble!(assembler, dofs, fe, Ke)
+ * (src/assembler.jl:62-137). */
+hdg_status hdg_cg_assemble(hdg_context* ctx);
+/* dbc = Dirichlet(u_h, dh, "boundary", [0.0]) (src/boundary.jl:48-96) on the context's Dirichlet face set + apply!(K, b, dbc)
+ * (:121-158). */
+hdg_status hdg_cg_apply_dirichlet(hdg_context* ctx);
+/* u = K \ b (examples/poisson2D_CG.jl:134) by Jacobi-PCG. */
+hdg_status hdg_cg_solve(hdg_context* ctx, double rtol, int32_t maxit, hdg_solve_info* info);
+/* K.nzval (pattern order), b, u (ndofs each).  Any pointer may be NULL. */
+hdg_status hdg_cg_get_system(hdg_context* ctx, double* nzval, double* rhs, double* u);
+/* reconstruct!(u_h, u, dh) + errornorm(u_h, u_ex) with u_ex = sin(pi x) sin(pi y) (squared L2, test/test_CGExample.jl:92-93). */
+hdg_status hdg_cg_errornorm(hdg_context* ctx, double* err2);
+hdg_status hdg_cg_get_meandiag(const hdg_context* ctx, double* m);
+
 /* ---- multi-GPU (one process per GPU) ------------------------------------------------------
  * The caller (torch.distributed / MPI / Julia Distributed) creates a 128-byte ncclUniqueId on
  * rank 0 with hdg_comm_unique_id, broadcasts it, and every rank calls hdg_comm_init.  After

@@ -770,3 +770,101 @@ def dirichlet_dofhandler(mesh, cell_dofs, offsets, order=1, faceset="boundary"):
             if d not in prescribed:
                 prescribed.append(d)
     return np.array(sorted(prescribed), dtype=np.int64)
+
+
+# --------------------------------------------------------------------------
+# CG side: examples/poisson2D_CG.jl (ContinuousLagrange{2,RefTetrahedron,order}, one scalar field)
+# --------------------------------------------------------------------------
+def lagrange_nodal_points(order):
+    """get_nodal_points(RefTetrahedron, Val{2}, order), src/shapes.jl:46-57 for order 1, 2: the vertices, then the interior
+    points of the reference edges ((1,0)-(0,1), (0,1)-(0,0), (0,0)-(1,0), src/shapes.jl:19-23)."""
+    v = [np.array([0.0, 0.0]), np.array([1.0, 0.0]), np.array([0.0, 1.0])]
+    pts = list(v)
+    edges = [(v[1], v[2]), (v[2], v[0]), (v[0], v[1])]
+    for a, b in edges:
+        for i in range(1, order):
+            pts.append(a + i * (b - a) / order)
+    assert order <= 2
+    return np.array(pts)
+
+
+def lagrange_tables(order, quad_degree=None):
+    """Lagrange{2,RefTetrahedron,order} as the reference builds it (src/basis.jl:264-293): nodal_base_coefs = inv(V),
+    V[i,j] = Dubiner_j(nodal point i); value(ip,k,xi) = nodal_base_coefs[:,k] . Dubiner(xi).  Tables of
+    ScalarFunctionSpace(mesh, ContinuousLagrange; quad_degree = order + 1) (src/ScalarFunctionSpaces.jl:24-99)."""
+    qd = quad_degree or order + 1
+    pts, w = default_quad_2d(qd)
+    n = (order + 1) * (order + 2) // 2
+    nodal = lagrange_nodal_points(order)
+    V = np.array([[dubiner_value(j + 1, p[0], p[1]) for j in range(n)] for p in nodal])
+    coefs = np.linalg.inv(V)
+    nq = len(w)
+    N = np.empty((n, nq)); dN = np.empty((n, nq, 2))
+    for q in range(nq):
+        d = np.array([dubiner_value(j + 1, pts[q][0], pts[q][1]) for j in range(n)])
+        g = np.array([dubiner_grad(j + 1, pts[q][0], pts[q][1]) for j in range(n)])      # (n, 2)
+        for k in range(n):
+            N[k, q] = coefs[:, k] @ d
+            dN[k, q] = coefs[:, k] @ g
+    M = np.array([[1 - p[0] - p[1], p[0], p[1]] for p in pts]).T      # geometry, (3, nq)
+    return dict(order=order, n=n, nq=nq, N=N, dN=dN, qw=np.asarray(w, float), M=M, qp=np.asarray(pts, float))
+
+
+def cg_doassemble(mesh, order=1, f=source_poisson):
+    """doassemble(Wh, K, dh) of examples/poisson2D_CG.jl:72-126 with assemble!(assembler, dofs, fe, Ke)
+    (src/assembler.jl:62-137): returns (K csc with the pattern of create_sparsity_pattern, b, cell_dofs, offsets, tables)."""
+    tab = lagrange_tables(order)
+    n, nq = tab["n"], tab["nq"]
+    cell_dofs, offsets = distribute_dofs(mesh, order)
+    colptr, rowval = create_sparsity_pattern(cell_dofs, offsets)
+    ndofs = colptr.size - 1
+    K = sp.csc_matrix((np.zeros(rowval.size), rowval - 1, colptr - 1), shape=(ndofs, ndofs))
+    b = np.zeros(ndofs)
+    for c in range(mesh.ncells):
+        x = mesh.nodes[mesh.cells[c] - 1]
+        J = np.array([x[1] - x[0], x[2] - x[0]])            # rows: d x / d xi_r   (reinit!, src/ScalarFunctionSpaces.jl:101-132)
+        detJ = J[0, 0] * J[1, 1] - J[0, 1] * J[1, 0]
+        Jinv = np.linalg.inv(J)
+        Ke = np.zeros((n, n)); fe = np.zeros(n)
+        for q in range(nq):
+            dO = detJ * tab["qw"][q]
+            xq = tab["M"][:, q] @ x
+            fh = f(xq)
+            grads = tab["dN"][:, q, :] @ Jinv.T                 # dNdx = dNdxi . Jinv
+            for i in range(n):
+                fe[i] += fh * tab["N"][i, q] * dO
+                for j in range(n):
+                    Ke[i, j] += (grads[i] @ grads[j]) * dO
+        g = cell_dofs[offsets[c] - 1: offsets[c] - 1 + n] - 1
+        for j in range(n):
+            for i in range(n):
+                # _assemble!: the stored entry (row g[i], column g[j])
+                lo, hi = K.indptr[g[j]], K.indptr[g[j] + 1]
+                p = lo + np.searchsorted(K.indices[lo:hi], g[i])
+                K.data[p] += Ke[i, j]
+            b[g[j]] += fe[j]
+    return K, b, cell_dofs, offsets, tab
+
+
+def cg_errornorm(mesh, tab, cell_dofs, offsets, u, u_ex=exact_poisson):
+    """reconstruct!(u_h, u, dh) (src/dofhandler.jl:218-228) + errornorm(u_h, u_ex) (src/DiscreteFunctions.jl:97-120)."""
+    n, nq = tab["n"], tab["nq"]
+    tot = 0.0
+    for c in range(mesh.ncells):
+        x = mesh.nodes[mesh.cells[c] - 1]
+        detJ = (x[1, 0] - x[0, 0]) * (x[2, 1] - x[0, 1]) - (x[2, 0] - x[0, 0]) * (x[1, 1] - x[0, 1])
+        uc = u[cell_dofs[offsets[c] - 1: offsets[c] - 1 + n] - 1]
+        for q in range(nq):
+            uq = uc @ tab["N"][:, q]
+            tot += (uq - u_ex(tab["M"][:, q] @ x)) ** 2 * detJ * tab["qw"][q]
+    return tot
+
+
+def run_poisson_cg(mesh, order=1):
+    """examples/poisson2D_CG.jl end to end: assemble, Dirichlet(u_h, dh, "boundary", [0.0]), apply!, K \\ b, errornorm."""
+    K, b, cell_dofs, offsets, tab = cg_doassemble(mesh, order)
+    dofs = dirichlet_dofhandler(mesh, cell_dofs, offsets, order, "boundary")
+    K2, b2, m = apply_dirichlet(K, b, dofs, np.zeros(dofs.size))
+    u = spla.spsolve(K2.tocsc(), b2)
+    return dict(K=K, b=b, cell_dofs=cell_dofs, offsets=offsets, dofs=dofs, K_bc=K2, b_bc=b2, meandiag=m, u=u,
+                err2=cg_errornorm(mesh, tab, cell_dofs, offsets, u), tab=tab)

@@ -689,3 +689,64 @@ def test_malformed_mesh_ids_are_rejected(what):
     ctx.set_mesh(host_mesh_from_oracle(mo))           # still usable
     hdg.check(ctx.lib.hdg_assemble(ctx.h), ctx.h)
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------- CG side on the device
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("case", ["rect10", "rect7x5", "figure.1", "permuted"])
+def test_cg_side_on_the_device(order, case):
+    """examples/poisson2D_CG.jl through hdg_cg_*: dh.cell_dofs and the sparsity pattern bit-identical to the reference's
+    sequential walk (oracle restatement, pinned on test/test_handlers.jl:13-19), K / b / meandiag / u within 1e-10 of the oracle's
+    doassemble + apply! + direct solve, err2 <= 0.0002 on the shipped 10 x 10 P1 case (test/test_CGExample.jl:92-93)."""
+    if case == "rect10":
+        mo = orc.rectangle_mesh(10, 10)
+    elif case == "rect7x5":
+        mo = orc.rectangle_mesh(7, 5, (0.0, 0.0), (2.0, 1.0))
+    elif case == "figure.1":
+        mo = orc.parse_mesh_triangle(triangle_root("figure.1"))
+    else:
+        base = orc.rectangle_mesh(6, 4)
+        perm = np.random.default_rng(2).permutation(base.ncells)
+        cf, faces = hdg.number_faces(base.cells[perm])
+        mo = orc.Mesh(base.cells[perm], cf, base.nodes, faces, {"boundary": set((np.flatnonzero(faces[:, 3] == 0) + 1).tolist())})
+    ro = orc.run_poisson_cg(mo, order)
+    dev = hdg.CGDevice(host_mesh_from_oracle(mo), order)
+    cd, cp, rv = dev.dofhandler()
+    n = 3 if order == 1 else 6
+    assert np.array_equal(cd.ravel(), ro["cell_dofs"]) and dev.ndofs == ro["cell_dofs"].max() and dev.ndofs_per_cell == n
+    cpo, rvo = orc.create_sparsity_pattern(ro["cell_dofs"], ro["offsets"])
+    assert np.array_equal(cp, cpo) and np.array_equal(rv, rvo)
+    K, b = dev.doassemble()
+    assert relerr(K.data, ro["K"].data) < RTOL and relerr(b, ro["b"]) < RTOL
+    m = dev.apply_()
+    assert abs(m - ro["meandiag"]) < 1e-13 * ro["meandiag"]
+    K2, b2 = dev.system()
+    assert relerr(K2.data, ro["K_bc"].data) < RTOL and relerr(b2, ro["b_bc"]) < RTOL
+    u, info = dev.solve(1e-14)
+    assert info["converged"] and relerr(u, ro["u"]) < RTOL
+    e2 = dev.errornorm()
+    assert abs(e2 - ro["err2"]) < 1e-9 * ro["err2"] + 1e-20
+    if case == "rect10" and order == 1:
+        assert e2 <= 0.0002                      # test/test_CGExample.jl:93
+    dev.close()
+
+
+def test_cg_driver_and_state_machine():
+    r = hdg.poisson2D_CG()                       # the shipped 10 x 10 P1 example
+    assert r["ndofs"] == 121 and r["err2"] <= 0.0002 and r["info"]["converged"]
+    dev = hdg.CGDevice(hdg.rectangle_mesh(hdg.TriangleCell, (4, 4), (0.0, 0.0), (1.0, 1.0)), 2)
+    with pytest.raises(hdg.HDGError):
+        dev.apply_()                             # doassemble first
+    dev.doassemble()
+    with pytest.raises(hdg.HDGError):
+        dev.solve()                              # apply! first
+    dev.apply_()
+    with pytest.raises(hdg.HDGError):
+        dev.apply_()                             # the system is already modified
+    u, info = dev.solve()
+    assert info["converged"] and np.isfinite(u).all()
+    dev.close()
+    ctx = hdg._Context(1, 2)
+    with pytest.raises(hdg.HDGError):
+        hdg.check(ctx.lib.hdg_cg_setup(ctx.h, 1, None), ctx.h)      # no mesh yet
+    ctx.close()
