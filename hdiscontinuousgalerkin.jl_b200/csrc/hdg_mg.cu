@@ -270,23 +270,38 @@ __global__ void mg_vertex_operator(const double* __restrict__ Kd, const double* 
         const int32_t e = vface[v * MG_MAXVAL + k];
         const int64_t f = e & 0x7fffffff;
         const double pf0 = 0.5, pf1 = (e < 0) ? MG_C1 : -MG_C1;       // coefficients of this vertex in face f
-        for (int s = -1; s < 4; ++s) {
-            const int64_t g = s < 0 ? f : kcol[4 * f + s];
-            if (g < 0 || isbc[g]) continue;
-            const double* blk = s < 0 ? Kd + f * NT2 : Ko + (f * 4 + s) * NT2;    // column-major: blk[b*NT + a] = K[a][b]
+        // the 5 block columns of row f (diagonal + 4 neighbours): all loads of all of them issued before the first use
+        // (absent / Dirichlet columns read the diagonal block's addresses and are masked out)
+        const int4 kc = *reinterpret_cast<const int4*>(kcol + 4 * f);
+        const int cols[5] = {int(f), kc.x, kc.y, kc.z, kc.w};
+        double t0[5], t1[5];
+        int lox[5], loy[5], hix[5], hiy[5];
+        bool ok[5], flo[5], fhi[5];
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            const int64_t g = cols[s] < 0 ? f : cols[s];
+            ok[s] = cols[s] >= 0 && !isbc[g];
+            const double* blk = s == 0 ? Kd + f * NT2 : Ko + (f * 4 + (s - 1)) * NT2;    // column-major: blk[b*NT + a] = K[a][b]
+            const double b00 = blk[0], b10 = blk[1], b01 = blk[NT], b11 = blk[NT + 1];
             // t_b = - sum_a pf_a K[a][b]   (A = -K on free rows), b = 0, 1
-            const double t0 = -(pf0 * blk[0] + pf1 * blk[1]);
-            const double t1 = -(pf0 * blk[NT] + pf1 * blk[NT + 1]);
-            const int64_t g1 = facenode[2 * g], g2 = facenode[2 * g + 1];
-            const int64_t lo = min(g1, g2), hi = max(g1, g2);
-            const int lox = int(lo % px), loy = int(lo / px) + node_row0, hix = int(hi % px), hiy = int(hi / px) + node_row0;
-            if (!mg_fixed(fxv, px, lox, loy)) {
-                const int sl = mg_slot(lox - vx, loy - vy);
-                if (sl >= 0) acc[sl] += 0.5 * t0 - MG_C1 * t1;
+            t0[s] = -(pf0 * b00 + pf1 * b10);
+            t1[s] = -(pf0 * b01 + pf1 * b11);
+            const int2 gn = *reinterpret_cast<const int2*>(facenode + 2 * g);
+            const int lo = min(gn.x, gn.y), hi = max(gn.x, gn.y);
+            lox[s] = lo % px; loy[s] = lo / px + node_row0; hix[s] = hi % px; hiy[s] = hi / px + node_row0;
+            flo[s] = mg_fixed(fxv, px, lox[s], loy[s]);
+            fhi[s] = mg_fixed(fxv, px, hix[s], hiy[s]);
+        }
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            if (!ok[s]) continue;
+            if (!flo[s]) {
+                const int sl = mg_slot(lox[s] - vx, loy[s] - vy);
+                if (sl >= 0) acc[sl] += 0.5 * t0[s] - MG_C1 * t1[s];
             }
-            if (!mg_fixed(fxv, px, hix, hiy)) {
-                const int sl = mg_slot(hix - vx, hiy - vy);
-                if (sl >= 0) acc[sl] += 0.5 * t0 + MG_C1 * t1;
+            if (!fhi[s]) {
+                const int sl = mg_slot(hix[s] - vx, hiy[s] - vy);
+                if (sl >= 0) acc[sl] += 0.5 * t0[s] + MG_C1 * t1[s];
             }
         }
     }
@@ -303,40 +318,60 @@ __global__ void mg_finalize_rows(const double* __restrict__ fx, int64_t cnt, dou
     dinv[v] = 0.0;
 }
 
-// ---- Galerkin coarse operator: A_c[I][J] = sum_p sum_q R[I,p] A[p,q] P[q,J], gathered per coarse point; coarse rows [cy0, cy1)
+// ---- Galerkin coarse operator: A_c[I][J] = sum_p sum_q R[I,p] A[p,q] P[q,J], gathered per coarse point; coarse rows [cy0, cy1).
+// Like the stages of the V-cycle this is written for memory-level parallelism: the "is this point free" flags of the 2-ring
+// around the fine twin come from ONE 5 x 5 window of Dinv (they also answer "is the coarse neighbour fixed": its twin lies in the
+// window), and the 49 stencil coefficients are loaded unconditionally from clamped addresses, so nothing waits behind a branch
+// (the first version took ~35 us per level whatever its size).  Same sums in the same order.
 __global__ void mg_rap(const LvDev F, const LvDev C, int cy0, int cy1) {
-    const int64_t cnt = int64_t(cy1 - cy0) * C.px;
-    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int cnt = (cy1 - cy0) * C.px;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cnt) return;
-    const int Ix = int(i % C.px), Iy = cy0 + int(i / C.px);
+    const int Iy = cy0 + i / C.px, Ix = i - (Iy - cy0) * C.px;
     const int px = F.px, py = F.py, cx = C.px, cy = C.py;
+    const int fx0 = 2 * Ix, fy0 = 2 * Iy;
+    bool fr[5][5];      // free fine point (in the grid and Dinv != 0)
+#pragma unroll
+    for (int dy = -2; dy <= 2; ++dy)
+#pragma unroll
+        for (int dx = -2; dx <= 2; ++dx) {
+            fr[dy + 2][dx + 2] = false;
+            if (dx + dy >= -2 && dx + dy <= 2) {
+                const int qx = fx0 + dx, qy = fy0 + dy;
+                const bool in = (qx >= 0) & (qy >= 0) & (qx < px) & (qy < py);
+                const double dv = F.dinv[in ? lv_idx(F, qx, qy) : lv_idx(F, fx0, fy0)];
+                fr[dy + 2][dx + 2] = in & (dv != 0.0);
+            }
+        }
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-    const bool free_twin = F.dinv[lv_idx(F, 2 * Ix, 2 * Iy)] != 0.0;
-    if (free_twin) {
-        for (int d = 0; d < 7; ++d) {
-            const int fx = 2 * Ix + MG_DX[d], fy = 2 * Iy + MG_DY[d];
-            if (fx < 0 || fy < 0 || fx >= px || fy >= py) continue;
-            if (F.dinv[lv_idx(F, fx, fy)] == 0.0) continue;
-            const double wr = d == 0 ? 1.0 : 0.5;
-            for (int e = 0; e < 7; ++e) {
-                const int qx = fx + MG_DX[e], qy = fy + MG_DY[e];
-                if (qx < 0 || qy < 0 || qx >= px || qy >= py) continue;
-                if (F.dinv[lv_idx(F, qx, qy)] == 0.0) continue;
-                const double aw = wr * F.st[e * int64_t(F.n) + lv_idx(F, fx, fy)];
-                if (aw == 0.0) continue;
-                const int a2 = qx & 1, b2 = qy & 1, hx = qx >> 1, hy = qy >> 1;
-                int jx[2], jy[2], cn;
-                double wp;
-                if (!a2 && !b2) { jx[0] = hx; jy[0] = hy; cn = 1; wp = 1.0; }
-                else if (a2 && !b2) { jx[0] = hx; jy[0] = hy; jx[1] = hx + 1; jy[1] = hy; cn = 2; wp = 0.5; }
-                else if (!a2 && b2) { jx[0] = hx; jy[0] = hy; jx[1] = hx; jy[1] = hy + 1; cn = 2; wp = 0.5; }
-                else { jx[0] = hx + 1; jy[0] = hy; jx[1] = hx; jy[1] = hy + 1; cn = 2; wp = 0.5; }
-                for (int m = 0; m < cn; ++m) {
-                    if (jx[m] >= cx || jy[m] >= cy) continue;
-                    if (F.dinv[lv_idx(F, 2 * jx[m], 2 * jy[m])] == 0.0) continue;     // fixed coarse point
-                    const int sl = mg_slot(jx[m] - Ix, jy[m] - Iy);
-                    if (sl >= 0) acc[sl] += aw * wp;
-                }
+    const bool free_twin = fr[2][2];
+#pragma unroll
+    for (int d = 0; d < 7; ++d) {
+        const bool pfree = fr[MG_DY[d] + 2][MG_DX[d] + 2];
+        const int p = pfree ? lv_idx(F, fx0 + MG_DX[d], fy0 + MG_DY[d]) : lv_idx(F, fx0, fy0);
+        const double wr = d == 0 ? 1.0 : 0.5;
+#pragma unroll
+        for (int e = 0; e < 7; ++e) {
+            const int ddx = MG_DX[d] + MG_DX[e], ddy = MG_DY[d] + MG_DY[e];      // q relative to the twin (compile time)
+            const double aw = wr * F.st[e * int64_t(F.n) + p];
+            if (!(free_twin && pfree && fr[ddy + 2][ddx + 2]) || aw == 0.0) continue;
+            // P[q, J]: the coarse points q interpolates from, by the parity of q - the twin is even, so the parity of (ddx, ddy)
+            const int a2 = ddx & 1, b2 = ddy & 1;
+            const int hx = (ddx - a2) / 2, hy = (ddy - b2) / 2;                  // floor(dd / 2): coarse offset of q's lower-left twin
+            int jx[2], jy[2], cn;
+            double wp;
+            if (!a2 && !b2) { jx[0] = hx; jy[0] = hy; cn = 1; wp = 1.0; }
+            else if (a2 && !b2) { jx[0] = hx; jy[0] = hy; jx[1] = hx + 1; jy[1] = hy; cn = 2; wp = 0.5; }
+            else if (!a2 && b2) { jx[0] = hx; jy[0] = hy; jx[1] = hx; jy[1] = hy + 1; cn = 2; wp = 0.5; }
+            else { jx[0] = hx + 1; jy[0] = hy; jx[1] = hx; jy[1] = hy + 1; cn = 2; wp = 0.5; }
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                if (m >= cn) continue;
+                if (jx[m] < -1 || jx[m] > 1 || jy[m] < -1 || jy[m] > 1) continue;           // not a stencil neighbour of I
+                if (Ix + jx[m] >= cx || Iy + jy[m] >= cy) continue;                          // (negative ones are not free: outside the grid)
+                if (!fr[2 * jy[m] + 2][2 * jx[m] + 2]) continue;                             // fixed coarse point: its twin is not free
+                const int sl = mg_slot(jx[m], jy[m]);
+                if (sl >= 0) acc[sl] += aw * wp;
             }
         }
     }
