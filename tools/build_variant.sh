@@ -5,5 +5,6 @@ cd "$(dirname "$0")/../hdiscontinuousgalerkin.jl_b200/csrc"
 mkdir -p ../variants
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v $2 -c hdg_element.cu -o ../variants/elem_$1.o 2> ../variants/elem_$1.log
 grep -A2 "element_quad_kernel" ../variants/elem_$1.log | grep -E "registers|spill" || true
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../variants/lib_$1.so ../build/hdg_api.o ../build/hdg_mesh.o ../variants/elem_$1.o ../build/hdg_solve.o ../build/hdg_mg.o ../build/hdg_recover.o ../build/hdg_comm.o ../build/hdg_tables.o
+OBJS=$(ls ../build/*.o | grep -v hdg_element.o)
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../variants/lib_$1.so $OBJS ../variants/elem_$1.o
 rm -f ../variants/elem_$1.o
