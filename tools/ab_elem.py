@@ -101,7 +101,12 @@ def main():
             if nm in res and "quad" in res:
                 A, B = np.load(f"/tmp/ab_{k}_quad.npz"), np.load(f"/tmp/ab_{k}_{nm}.npz")
                 d = max(np.abs(A[name] - B[name]).max() / max(np.abs(A[name]).max(), 1e-300) for name in ("rhs", "nz", "loc"))
-                print(f"    {nm}: max rel diff vs default {d:.3e}; default/{nm} time {res['quad']['ms_med'] / res[nm]['ms_med']:.3f}", flush=True)
+                print(f"    {nm}: max rel diff vs default {d:.3e}{' (bit-identical)' if d == 0.0 else ''}; default/{nm} time {res['quad']['ms_med'] / res[nm]['ms_med']:.3f}", flush=True)
+        for tag, _ in arms:                                     # the dumps are GBs at 4 M cells
+            try:
+                os.remove(f"/tmp/ab_{k}_{tag}.npz")
+            except OSError:
+                pass
 
 
 if __name__ == "__main__":
