@@ -303,9 +303,9 @@ __global__ void __launch_bounds__(SchurCfg<K>::threads, SchurCfg<K>::min_blocks)
                 const double cf = tau * dJf_l;
 #pragma unroll
                 for (int i = 0; i < n; ++i) {
-                    double r = cf * T.Fhat[i * t + col];
-                    r = fma(ca_l, T.Qr[i * t + col], r);
-                    u[i] = fma(cb_l, T.Qs[i * t + col], r);
+                    double r = cf * T.RT[(col * n + i) * 4];
+                    r = fma(ca_l, T.RT[(col * n + i) * 4 + 1], r);
+                    u[i] = fma(cb_l, T.RT[(col * n + i) * 4 + 2], r);
                 }
             }
             // S u = r  by L D L'
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(SchurCfg<K>::threads, SchurCfg<K>::min_blocks)
                     p = fma(T.Tr[i * n + k], u[k], p);
                     q = fma(T.Ts[i * n + k], u[k], q);
                 }
-                double mf = isb ? 0.0 : T.MF[i * t + col];
+                double mf = isb ? 0.0 : T.RT[(col * n + i) * 4 + 3];
                 sx[i] = fma(g.G00, p, fma(g.G10, q, -ex * mf));
                 sy[i] = fma(g.G01, p, fma(g.G11, q, -ey * mf));
             }
@@ -869,7 +869,12 @@ template <int K> static void fill_dev_tables(const RefTables& R, DevTables<K>& D
     cp(R.Tr, D.Tr, n * n); cp(R.Ts, D.Ts, n * n);
     cp(R.Prr, D.Prr, n * n); cp(R.Prs, D.Prs, n * n); cp(R.Pss, D.Pss, n * n);
     cp(R.Chat, D.Chat, 3 * n * n);
-    cp(R.Fhat, D.Fhat, n * t); cp(R.MF, D.MF, n * t); cp(R.Qr, D.Qr, n * t); cp(R.Qs, D.Qs, n * t);
+    cp(R.Fhat, D.Fhat, n * t);
+    for (int col = 0; col < t; ++col)
+        for (int i = 0; i < n; ++i) {
+            double* q = D.RT + (col * n + i) * 4;
+            q[0] = R.Fhat[i * t + col]; q[1] = R.Qr[i * t + col]; q[2] = R.Qs[i * t + col]; q[3] = R.MF[i * t + col];
+        }
     cp(R.Hhat, D.Hhat, nt * nt);
     cp(R.WN, D.WN, MAX_NQ * n);
     cp(R.Mgeo, D.Mgeo, MAX_NQ * 3);

@@ -319,9 +319,9 @@ __global__ void __launch_bounds__(QuadCfg<K>::threads, QuadCfg<K>::min_blocks) e
                 }
 #pragma unroll
                 for (int i = 0; i < n; ++i) {
-                    double r = cf * T.Fhat[i * t + col];
-                    r = fma(ca_l, T.Qr[i * t + col], r);
-                    u[cb][i] = fma(cb_l, T.Qs[i * t + col], r);
+                    double r = cf * T.RT[(col * n + i) * 4];
+                    r = fma(ca_l, T.RT[(col * n + i) * 4 + 1], r);
+                    u[cb][i] = fma(cb_l, T.RT[(col * n + i) * 4 + 2], r);
                 }
             } else if (col == t) {
 #pragma unroll
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(QuadCfg<K>::threads, QuadCfg<K>::min_blocks) e
                         if ((Sp::tr(i) >> k) & 1u) p = fma(T.Tr[i * n + k], uc[k], p);
                         if ((Sp::ts(i) >> k) & 1u) s = fma(T.Ts[i * n + k], uc[k], s);
                     }
-                    const double mf = T.MF[i * t + mcol];
+                    const double mf = T.RT[(mcol * n + i) * 4 + 3];
                     const double sx = fma(g.G00, p, fma(g.G10, s, -ex * mf));
                     const double sy = fma(g.G01, p, fma(g.G11, s, -ey * mf));
                     if (active && !dbg) {               // 256-byte row segments of the tile

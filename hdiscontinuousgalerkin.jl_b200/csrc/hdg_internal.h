@@ -30,8 +30,12 @@ template <int K> struct DevTables {
     double Tr[Ord<K>::n * Ord<K>::n], Ts[Ord<K>::n * Ord<K>::n];
     double Prr[Ord<K>::n * Ord<K>::n], Prs[Ord<K>::n * Ord<K>::n], Pss[Ord<K>::n * Ord<K>::n];
     double Chat[3 * Ord<K>::n * Ord<K>::n];
-    double Fhat[Ord<K>::n * Ord<K>::t], MF[Ord<K>::n * Ord<K>::t];
-    double Qr[Ord<K>::n * Ord<K>::t], Qs[Ord<K>::n * Ord<K>::t];
+    double Fhat[Ord<K>::n * Ord<K>::t];
+    // The four matrices that are read with a RUN-TIME column index (the right-hand side of a column and its MF term), packed per
+    // (column, row): RT[(col * n + i) * 4 + {0: Fhat, 1: Qr, 2: Qs, 3: MF}].  An indexed constant load goes through the small
+    // indexed-constant cache; row-major n x t matrices made the n loads of a column touch n different lines of each matrix
+    // (ncu, k = 3: hit rate 57 %, the GPC-level constant cache at 63 % of its peak) - packed, a column is n * 32 contiguous bytes.
+    double RT[Ord<K>::n * Ord<K>::t * 4];
     double Hhat[Ord<K>::nt * Ord<K>::nt];
     double WN[MAX_NQ * Ord<K>::n];        // w_q N[i,q] at [q*n + i]
     double Mgeo[MAX_NQ * 3];
