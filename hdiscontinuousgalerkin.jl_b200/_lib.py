@@ -82,6 +82,7 @@ SIGNATURES = {
     "hdg_set_mesh": (C.c_int, [_P, _I64P, C.c_int64, _F64P, C.c_int64, _I64P, C.c_int64, _I64P, C.c_int64]),
     "hdg_set_rectangle_mesh": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double]),
     "hdg_number_faces": (C.c_int, [_P, _I64P, C.c_int64, _F64P, C.c_int64, _I64P, _I64P, C.c_int64, _I64P]),
+    "hdg_order_cells": (C.c_int, [_P, _I64P, C.c_int64, _F64P, C.c_int64, _I64P]),
     "hdg_perturb_nodes": (C.c_int, [_P, C.c_double, C.c_uint64]),
     "hdg_get_sizes": (C.c_int, [_P, C.POINTER(Sizes)]),
     "hdg_get_mesh": (C.c_int, [_P, _I64P, _F64P, _I64P, _I64P]),

@@ -299,6 +299,61 @@ def number_faces_gpu(tri_nodes, nodes):
     return cells, faces
 
 
+def order_cells_gpu(tri_nodes, nodes):
+    """Morton (Z-order) permutation of the cells by centroid, computed and sorted on the device (hdg_order_cells).
+    Returns perm (0-based): the cell that comes i-th along the curve is input cell perm[i]."""
+    tri = np.ascontiguousarray(np.asarray(tri_nodes)[:, :3], dtype=np.int64)
+    xy = np.ascontiguousarray(nodes, dtype=np.float64)
+    perm = np.empty(tri.shape[0], np.int64)
+    ctx = _Context(order=1)
+    try:
+        check(ctx.lib.hdg_order_cells(ctx.h, i64p(tri), tri.shape[0], f64p(xy), xy.shape[0], i64p(perm)), ctx.h)
+    finally:
+        ctx.close()
+    return perm - 1
+
+
+class RenumberedMesh:
+    """A mesh with its cells reordered (and its faces renumbered by the reference's first-encounter rule for that cell order,
+    src/triangle_mesh.jl:66-101) plus the maps back to the caller's numbering.
+
+    mesh      : the renumbered PolygonalMesh (hand this to doassemble / hdg_set_mesh)
+    cell_perm : new cell i (0-based) is the caller's cell cell_perm[i]
+    face_new  : the caller's face f (0-based) is face face_new[f] of `mesh`
+    Node ids are unchanged, so face orientations - and with them the sign conventions of the trace basis - are the same in both
+    numberings: trace coefficients and cell-wise coefficients only move, they never change."""
+
+    def __init__(self, mesh, cell_perm, face_new):
+        self.mesh, self.cell_perm, self.face_new = mesh, cell_perm, face_new
+
+    def trace_to_original(self, x, nt):
+        """trace vector of `mesh` (face-major, nt coefficients per face) -> the caller's face numbering"""
+        return np.asarray(x).reshape(-1, nt)[self.face_new].reshape(-1)
+
+    def cells_to_original(self, m_values):
+        """cell-wise values (ncell, ...) of `mesh` -> the caller's cell numbering"""
+        out = np.empty_like(m_values)
+        out[self.cell_perm] = m_values
+        return out
+
+
+def renumber_mesh(mesh, perm=None):
+    """Reorder the cells of `mesh` along the Morton curve (or by a given 0-based permutation) and renumber its faces the way
+    the reference would for that element order - the pre-processing step that makes the contiguous-range partition of
+    hdg_set_mesh on several GPUs local for any input order.  Both steps run on the device."""
+    if perm is None:
+        perm = order_cells_gpu(mesh.cells[:, :3], mesh.nodes)
+    perm = np.asarray(perm, dtype=np.int64)
+    old = mesh.cells[perm]
+    cells, faces = number_faces_gpu(old[:, :3], mesh.nodes)
+    if not np.array_equal(cells[:, :3], old[:, :3]):
+        raise ValueError("renumber_mesh expects counter-clockwise cells (a mesh built by this package or the reference)")
+    face_new = np.empty(mesh.faces.shape[0], np.int64)
+    face_new[old[:, 3:].reshape(-1) - 1] = cells[:, 3:].reshape(-1) - 1
+    facesets = {k: set((face_new[np.fromiter(v, np.int64, len(v)) - 1] + 1).tolist()) for k, v in mesh.facesets.items()}
+    return RenumberedMesh(PolygonalMesh(cells, mesh.nodes, faces, facesets), perm, face_new)
+
+
 def parse_mesh_triangle(root_file):
     """parse_mesh_triangle(root_file), src/triangle_mesh.jl:115-126 (.node/.edge/.ele reader)."""
     nodes = np.array([[float(r[1]), float(r[2])] for r in _triangle_rows(root_file + ".node")])

@@ -173,6 +173,13 @@ hdg_status hdg_number_faces(hdg_context* c, const int64_t* tri, int64_t ncell, c
     return number_faces_host(c, tri, ncell, nodes, nnode, cells_out, faces_out, faces_capacity, nface_out);
 }
 
+hdg_status hdg_order_cells(hdg_context* c, const int64_t* tri, int64_t ncell, const double* nodes, int64_t nnode, int64_t* perm_out) {
+    if (!c || !tri || !nodes || !perm_out) return HDG_ERR_INVALID;
+    if (ncell < 1 || nnode < 3) return set_err(c, HDG_ERR_INVALID, "empty mesh");
+    cudaSetDevice(c->device);
+    return order_cells_host(c, tri, ncell, nodes, nnode, perm_out);
+}
+
 hdg_status hdg_perturb_nodes(hdg_context* c, double fraction, uint64_t seed) {
     if (!c) return HDG_ERR_INVALID;
     cudaSetDevice(c->device);

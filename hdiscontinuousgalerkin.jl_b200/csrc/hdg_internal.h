@@ -213,6 +213,7 @@ hdg_status mesh_download(hdg_context* c, int64_t* cells, double* nodes, int64_t*
 hdg_status pattern_download(hdg_context* c, int64_t* colptr, int64_t* rowval);
 hdg_status values_download(hdg_context* c, double* nzval);
 int64_t pattern_nnz(hdg_context* c);
+hdg_status order_cells_host(hdg_context* c, const int64_t* tri, int64_t ncell, const double* nodes, int64_t nnode, int64_t* perm);   // hdg_order.cu
 hdg_status number_faces_host(hdg_context* c, const int64_t* tri, int64_t ncell, const double* nodes, int64_t nnode,
                              int64_t* cells_out, int64_t* faces_out, int64_t faces_capacity, int64_t* nface_out);
 hdg_status alloc_system(hdg_context* c);                        // hdg_mesh.cu (after mesh known)

@@ -126,6 +126,14 @@ hdg_status hdg_set_dirichlet_faces(hdg_context* ctx, const int64_t* bfaces, int6
 hdg_status hdg_number_faces(hdg_context* ctx, const int64_t* tri, int64_t ncell, const double* nodes, int64_t nnode,
                             int64_t* cells_out, int64_t* faces_out, int64_t faces_capacity, int64_t* nface_out);
 
+/* Locality-preserving cell order for hdg_set_mesh on several GPUs: perm_out[i] (1-based) = the input cell that comes i-th along
+ * the Morton curve through the cell centroids (computed and sorted on the device; cells with equal keys keep their input
+ * order).  hdg_set_mesh partitions by contiguous cell-id ranges, so a mesh whose cells are renumbered in this order - cells
+ * permuted, faces renumbered by hdg_number_faces, which is what the reference's parse_cells! (src/triangle_mesh.jl:48-108)
+ * would produce for the permuted element list - splits into compact patches whatever the order of the generator's output. */
+hdg_status hdg_order_cells(hdg_context* ctx, const int64_t* tri, int64_t ncell, const double* nodes, int64_t nnode,
+                           int64_t* perm_out);
+
 /* Deterministic interior-node jitter (fraction of h) to defeat translation invariance in
  * benchmarks (SURVEY Appendix A integrity note).  Applies to the device mesh in place. */
 hdg_status hdg_perturb_nodes(hdg_context* ctx, double fraction, uint64_t seed);

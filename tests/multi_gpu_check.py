@@ -120,9 +120,13 @@ def main():
     interior = np.ones(nodes.shape[0], bool)
     interior[bnodes] = False
     nodes[interior] += rng.uniform(-0.012, 0.012, size=(interior.sum(), 2))
-    for label, perm in (("natural", np.arange(base.cells.shape[0])), ("permuted", rng.permutation(base.cells.shape[0]))):
+    scatter = rng.permutation(base.cells.shape[0])
+    for label, perm in (("natural", np.arange(base.cells.shape[0])), ("permuted", scatter), ("permuted + Morton order", scatter)):
         cf, faces = hdg.number_faces(base.cells[perm, :3])
         cells = np.ascontiguousarray(np.hstack([base.cells[perm, :3], cf]))
+        if label.endswith("Morton order"):      # hdg_order_cells + hdg_number_faces on every rank's device: same renumbered mesh everywhere
+            rm = hdg.renumber_mesh(hdg.PolygonalMesh(cells, nodes, faces, {"boundary": set()}))
+            cells, faces = rm.mesh.cells, np.asarray(rm.mesh.faces)
         faces = np.asfortranarray(faces)
         bf = np.flatnonzero(faces[:, 3] == 0).astype(np.int64) + 1
         for order, qd in ((1, 2), (3, 6)):

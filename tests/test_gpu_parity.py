@@ -209,6 +209,67 @@ def test_randomly_permuted_unstructured_mesh(seed, order, qd):
     # err2 ~ 1e-13 for k=4 is a sum of squares of differences at the 1e-7 level: 1e-16 perturbations of u move it by ~1e-8 relative
     assert abs(res["err2"] - ro["err2"]) <= 1e-9 * ro["err2"] + 1e-20
 
+def _host_morton_perm(tri, nodes):
+    """The order hdg_order_cells defines, restated with numpy (same arithmetic, stable sort)."""
+    lo, hi = nodes.min(axis=0), nodes.max(axis=0)
+    scale = 2147483647.0 / max(hi[0] - lo[0], hi[1] - lo[1])
+    p = nodes[tri - 1]
+    cen = ((p[:, 0] + p[:, 1]) + p[:, 2]) * (1.0 / 3.0)
+    q = np.clip((cen - lo) * scale, 0.0, 2147483647.0).astype(np.uint64)
+
+    def spread(v):
+        v = (v | (v << np.uint64(16))) & np.uint64(0x0000ffff0000ffff)
+        v = (v | (v << np.uint64(8))) & np.uint64(0x00ff00ff00ff00ff)
+        v = (v | (v << np.uint64(4))) & np.uint64(0x0f0f0f0f0f0f0f0f)
+        v = (v | (v << np.uint64(2))) & np.uint64(0x3333333333333333)
+        v = (v | (v << np.uint64(1))) & np.uint64(0x5555555555555555)
+        return v
+    key = spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1))
+    return np.argsort(key, kind="stable")
+
+
+def _cut_faces(cells, faces, parts):
+    """faces whose two cells fall into different pieces when the cell ids are cut into `parts` contiguous ranges"""
+    nc = cells.shape[0]
+    piece = (np.arange(nc) * parts) // nc
+    inner = faces[:, 3] > 0
+    return int(np.count_nonzero(piece[faces[inner, 2] - 1] != piece[faces[inner, 3] - 1]))
+
+
+@pytest.mark.parametrize("order,qd", [(1, 2), (3, 6)])
+def test_morton_renumbering(order, qd):
+    """hdg_order_cells / renumber_mesh (the partitioner's pre-processing): a jittered mesh whose cells arrive in random
+    order is renumbered along the Morton curve on the device - bit-identical to the numpy restatement of the same keys -, the
+    contiguous 8-way cut of the new numbering is local, and the solution in the new numbering maps back onto the solution in the
+    caller's numbering."""
+    rng = np.random.default_rng(11)
+    base = hdg.rectangle_mesh(hdg.TriangleCell, (24, 20), (0.0, 0.0), (2.0, 1.0))
+    nodes = base.nodes.copy()
+    interior = np.ones(nodes.shape[0], bool)
+    interior[np.unique(base.faces[base.faces[:, 3] == 0, :2]) - 1] = False
+    nodes[interior] += rng.uniform(-0.012, 0.012, size=(int(interior.sum()), 2))
+    tri = base.cells[rng.permutation(base.cells.shape[0]), :3]
+    cf, faces = hdg.number_faces(tri)
+    bnd = set((np.flatnonzero(faces[:, 3] == 0) + 1).tolist())
+    scattered = hdg.PolygonalMesh(np.hstack([tri, cf]), nodes, faces, {"boundary": bnd})
+
+    rm = hdg.renumber_mesh(scattered)
+    assert np.array_equal(np.sort(rm.cell_perm), np.arange(tri.shape[0]))
+    assert np.array_equal(rm.cell_perm, _host_morton_perm(tri, nodes))                  # the device order, bit for bit
+    cf2, faces2 = hdg.number_faces(tri[rm.cell_perm])                                   # the reference's numbering of that element order
+    assert np.array_equal(rm.mesh.cells[:, 3:], cf2) and np.array_equal(np.asarray(rm.mesh.faces), faces2)
+    assert rm.mesh.facesets["boundary"] == set((np.flatnonzero(faces2[:, 3] == 0) + 1).tolist())
+    cut_scattered, cut_morton = _cut_faces(scattered.cells, np.asarray(scattered.faces), 8), _cut_faces(rm.mesh.cells, faces2, 8)
+    assert cut_morton * 5 < cut_scattered and cut_morton < 0.15 * faces2.shape[0], (cut_scattered, cut_morton)
+
+    a = hdg.poisson2D_HDG(scattered, order, qd, rtol=1e-14)
+    b = hdg.poisson2D_HDG(rm.mesh, order, qd, rtol=1e-14)
+    nt = order + 1
+    assert relerr(rm.trace_to_original(b["uhat"].to_numpy(), nt), a["uhat"].to_numpy()) < RTOL
+    assert relerr(rm.cells_to_original(b["u_h"].m_values), a["u_h"].m_values) < RTOL
+    assert relerr(rm.cells_to_original(b["sigma_h"].m_values), a["sigma_h"].m_values) < RTOL
+    assert abs(a["err2"] - b["err2"]) <= 1e-9 * a["err2"]
+
 
 @pytest.mark.parametrize("seed,order,qd", [(0, 1, 2), (1, 2, 4), (2, 3, 6)])
 def test_random_delaunay_mesh(seed, order, qd):
