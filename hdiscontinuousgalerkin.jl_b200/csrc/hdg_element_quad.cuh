@@ -270,16 +270,17 @@ __global__ void __launch_bounds__(QuadCfg<K>::threads, QuadCfg<K>::min_blocks) e
             __syncwarp();
         }
         }
-        // be = sum of the 4 partial vectors (fixed order)
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int i = q + 4 * r;
-            if (i < n) {
-                const double* pp = sp + (Q::o_diag + i) * CS;
-                sp[(Q::o_be + i) * CS] = ((pp[0] + pp[n * CS]) + pp[2 * n * CS]) + pp[3 * n * CS];
-            }
-        }
         if (q == 0) sp[Q::o_status * CS] = spd ? 1.0 : -1.0;
+    }
+    // be = sum of the 4 partial vectors (fixed order), lane = cell again, warp w takes rows w, w+4, ...: with the 4-lanes-per-cell
+    // mapping of the factorisation these loads were 4-way bank conflicts (ncu: 45 M of the kernel's 66 M excess wavefronts at k = 3)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = w + 4 * r;
+        if (i < n) {
+            const double* pp = sm + (Q::o_diag + i) * CS;
+            sm[(Q::o_be + i) * CS] = ((pp[0] + pp[n * CS]) + pp[2 * n * CS]) + pp[3 * n * CS];
+        }
     }
     __syncthreads();
 
