@@ -90,10 +90,13 @@ template <int K> struct QuadCfg {
     // shared-memory record per cell, stored [entry][cell]
     static constexpr int o_L = 0;                     // strict lower triangle of S, overwritten by L
     static constexpr int o_dinv = o_L + nL;           // diagonal of S, overwritten by D^-1
-    static constexpr int o_be = o_dinv + n;
-    static constexpr int o_status = o_be + n;
+    static constexpr int o_status = o_dinv + n;
     static constexpr int o_diag = o_status + 1;       // staging of the face-diagonal blocks (phases 2-3); partial be sums (phases 0-1)
     static constexpr int o_rhs = o_diag + 3 * nt * nt;
+    // the load vector be shares the rhs staging entries: the warp that solves the load-vector column reads be into registers at
+    // the start of that column and stages bte (3 nt >= n entries) at its end, lane = cell both times
+    static constexpr int o_be = o_rhs;
+    static_assert(3 * nt >= n && 3 * nt * nt >= 4 * n && !SPLITB, "be aliases the rhs staging entries, behind the four partial load vectors");
     static constexpr int o_scr = o_rhs + (SPLITB ? 4 : 1) * 3 * nt;      // phase 2: solutions of the 2nd ... CB-th column of a batch, per warp
     static constexpr bool STAGE_OFF = (K == 2 && QSTAGE2) || (K == 4 && QSTAGE4);
     static constexpr bool INV = ((QINV >> (K - 2)) & 1) != 0;          // bit 0: k = 2, bit 1: k = 3, bit 2: k = 4

@@ -1,2 +1,2 @@
-python tools/ab_elem.py --orders 3,2,4 --libs base --reps 15
-timeout 400 python -m pytest tests -m gpu -x -q -k "assembly or driver or permuted or delaunay or lu_path or tau" 2>&1 | tail -3
+python tools/ab_elem.py --orders 4 --libs base,k4m4 --reps 15
+python tools/ab_elem.py --orders 3,2 --libs base --reps 10
