@@ -70,6 +70,21 @@ namespace hdg {
 #define QFOLD 4
 #endif
 
+// QPFk: tiles ahead whose cell records are prefetched into L2 by warp 0 of a block (0 = off).  The blocks of a launch start in index
+// order, so the tile that some SM picks up next is about (resident blocks = 148 x 4) ahead of this one; the block that gets it then
+// finds its first load in L2 (the cell records -> vertices -> geometry chain at block start is 8 % of the warp time, ncu).
+// Measured (4 M / 1 M cells, 296 / 592 / 1184 tiles ahead): k=2 2.101 -> 2.013 / 2.013 / 2.049 ms; k=3 4.670 -> 4.685 / 4.745 / 4.629;
+// k=4 3.285 -> 3.323 / 3.331 / 3.318  ->  on for k = 2 only.
+#ifndef QPF2
+#define QPF2 592
+#endif
+#ifndef QPF3
+#define QPF3 0
+#endif
+#ifndef QPF4
+#define QPF4 0
+#endif
+
 template <int K> struct QuadCfg {
     static constexpr int n = Ord<K>::n, nt = Ord<K>::nt, t = Ord<K>::t;
     static constexpr int G = 4;                       // threads per element
@@ -107,6 +122,7 @@ template <int K> struct QuadCfg {
     static constexpr size_t smem = smem_rec + (STAGE_OFF ? sizeof(uint32_t) * 3 * cells : 0);   // + face words of the tile
     static constexpr int min_blocks = K == 2 ? QMINB2 : (K == 3 ? QMINB3 : QMINB4);
     static constexpr bool col_sweep = K <= 3;         // ordering of the triangular sweeps, see phase 2
+    static constexpr int PF = K == 2 ? QPF2 : (K == 3 ? QPF3 : QPF4);
     static constexpr bool FOLD = ((QFOLD >> (K - 2)) & 1) != 0;
 };
 
@@ -150,6 +166,10 @@ __global__ void __launch_bounds__(QuadCfg<K>::threads, QuadCfg<K>::min_blocks) e
     const double tau = a.tau;
 
     // =========================== phase 0: lane = cell, warp w = rows / quadrature points w, w+4, ... ========
+    if constexpr (Q::PF > 0) {
+        const int64_t cn = c + int64_t(Q::PF) * Q::cells;
+        if (w == 0 && cn < a.cell_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.cellinfo + CI * cn));
+    }
     CellGeom g;
     load_geometry(a, cl, g);
     const double cf0 = tau * g.dJf[0], cf1 = tau * g.dJf[1], cf2 = tau * g.dJf[2];
