@@ -337,15 +337,16 @@ class RenumberedMesh:
         return out
 
 
-def renumber_mesh(mesh, perm=None):
+def renumber_mesh(mesh, perm=None, number=None):
     """Reorder the cells of `mesh` along the Morton curve (or by a given 0-based permutation) and renumber its faces the way
     the reference would for that element order - the pre-processing step that makes the contiguous-range partition of
-    hdg_set_mesh on several GPUs local for any input order.  Both steps run on the device."""
+    hdg_set_mesh on several GPUs local for any input order.  Both steps run on the device (`number`: another implementation of
+    the first-encounter numbering with the signature of number_faces_gpu, e.g. the numpy mirror in tests)."""
     if perm is None:
         perm = order_cells_gpu(mesh.cells[:, :3], mesh.nodes)
     perm = np.asarray(perm, dtype=np.int64)
     old = mesh.cells[perm]
-    cells, faces = number_faces_gpu(old[:, :3], mesh.nodes)
+    cells, faces = (number or number_faces_gpu)(old[:, :3], mesh.nodes)
     if not np.array_equal(cells[:, :3], old[:, :3]):
         raise ValueError("renumber_mesh expects counter-clockwise cells (a mesh built by this package or the reference)")
     face_new = np.empty(mesh.faces.shape[0], np.int64)

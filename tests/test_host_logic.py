@@ -276,3 +276,33 @@ def test_c_recover_errornorm_apply_match_numpy_oracle(order, qd):
     assert np.array_equal(K2.indptr, r["K_bc"].indptr) and np.array_equal(K2.indices, r["K_bc"].indices)
     assert np.array_equal(K2.data, r["K_bc"].data) and np.array_equal(f2, r["rhs_bc"])
     assert dset.sum() == len(r["dofs"])
+
+
+def test_renumbered_mesh_maps_back():
+    """renumber_mesh (host mirror of the partitioner's pre-processing): with a given permutation and the numpy first-encounter
+    numbering, faces keep their vertex pairs, face sets follow, and the maps bring trace / cell data back to the caller's ids."""
+    rng = np.random.default_rng(3)
+    mo = orc.rectangle_mesh(7, 5)
+    bnd = set((np.flatnonzero(mo.faces[:, 3] == 0) + 1).tolist())
+    mesh = hdg.PolygonalMesh(np.hstack([mo.cells, mo.cell_faces]), mo.nodes, mo.faces, {"boundary": bnd, "some": {3, 17, 40}})
+
+    def number(tri, nodes):
+        cf, faces = hdg.number_faces(tri)
+        return np.hstack([tri, cf]), faces
+    perm = rng.permutation(mesh.cells.shape[0])
+    rm = hdg.renumber_mesh(mesh, perm, number=number)
+    new = rm.mesh
+    assert np.array_equal(new.cells[:, :3], mesh.cells[perm, :3])
+    old_pairs = np.sort(np.asarray(mesh.faces)[:, :2], axis=1)
+    new_pairs = np.sort(np.asarray(new.faces)[:, :2], axis=1)
+    assert np.array_equal(new_pairs[rm.face_new], old_pairs)                      # a face keeps its two vertices
+    assert new.facesets["boundary"] == set((np.flatnonzero(np.asarray(new.faces)[:, 3] == 0) + 1).tolist())
+    assert new.facesets["some"] == {int(rm.face_new[f - 1]) + 1 for f in (3, 17, 40)}
+    nt = 3
+    x_new = rng.random(new.faces.shape[0] * nt)
+    x_old = rm.trace_to_original(x_new, nt).reshape(-1, nt)
+    for f in (0, 5, old_pairs.shape[0] - 1):
+        assert np.array_equal(x_old[f], x_new.reshape(-1, nt)[rm.face_new[f]])
+    u_new = rng.random((new.cells.shape[0], 6))
+    u_old = rm.cells_to_original(u_new)
+    assert np.array_equal(u_old[perm], u_new)
