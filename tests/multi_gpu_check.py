@@ -77,41 +77,7 @@ def main():
                   f"err2 {err2:.12e} vs {e1:.12e}  {'OK' if good else 'FAIL'}", flush=True)
     os.environ.pop("HDG_MG_REP_MAX", None)
     if "--mg-only" in sys.argv:
-        # ---- documented limits fail with a clean status and message, on every rank, without hanging the others
-    ctx = hdg._Context(1, 2, 1.0, 1, lr)
-    ctx.comm_init(dist, device=torch.device("cuda", lr))
-    hdg.check(ctx.lib.hdg_set_rectangle_mesh(ctx.h, 16, 8 * world, 0.0, 0.0, 2.0, 1.0), ctx.h)
-    one = np.array([1], dtype=np.int64)
-    limits = []
-    for name, call in (("hdg_set_dirichlet_faces", lambda: ctx.lib.hdg_set_dirichlet_faces(ctx.h, hdg.api.i64p(one), 1)),
-                       ("hdg_get_pattern", lambda: ctx.lib.hdg_get_pattern(ctx.h, None, None)),
-                       ("hdg_get_mesh", lambda: ctx.lib.hdg_get_mesh(ctx.h, None, None, None, None))):
-        st = call()
-        msg = ctx.lib.hdg_last_error(ctx.h).decode()
-        limits.append((name, st, msg))
-        ok &= st == 1 and "single-GPU" in msg
-    ctx.close()
-    os.environ["HDG_NO_P2P"] = "1"      # no peer mappings: a partitioned hdg_set_mesh mesh must refuse to solve, with NCCL still usable afterwards
-    ctx = hdg._Context(1, 2, 1.0, 1, lr)
-    ctx.comm_init(dist, device=torch.device("cuda", lr))
-    del os.environ["HDG_NO_P2P"]
-    hdg.check(ctx.lib.hdg_set_mesh(ctx.h, hdg.api.i64p(cells), cells.shape[0], hdg.api.f64p(nodes), nodes.shape[0],
-                                   hdg.api.i64p(faces), faces.shape[0], hdg.api.i64p(bf), bf.size), ctx.h)
-    hdg.check(ctx.lib.hdg_assemble(ctx.h), ctx.h)
-    hdg.check(ctx.lib.hdg_apply_dirichlet(ctx.h, None), ctx.h)
-    info = hdg.api.SolveInfo()
-    st = ctx.lib.hdg_solve(ctx.h, 1e-10, 100, C.byref(info))
-    msg = ctx.lib.hdg_last_error(ctx.h).decode()
-    limits.append(("hdg_solve without peer memory on a partitioned mesh", st, msg))
-    ok &= st != 0 and "peer-memory" in msg
-    hdg.check(ctx.lib.hdg_set_rectangle_mesh(ctx.h, 16, 8 * world, 0.0, 0.0, 2.0, 1.0), ctx.h)      # strips still solve over NCCL send/recv
-    xs_, us_, e_, it_, md_ = solve(ctx, 16, 8 * world, 1e-12)
-    ctx.close()
-    if rank == 0:
-        for name, st, msg in limits:
-            print(f"limit: {name}: status {st}, \"{msg}\"", flush=True)
-        print(f"NCCL fallback (HDG_NO_P2P=1) strips: {it_} iterations, err2 {e_:.6e}", flush=True)
-    flag = torch.tensor([1 if ok else 0], device="cuda")
+        flag = torch.tensor([1 if ok else 0], device="cuda")
         dist.broadcast(flag, src=0)
         dist.barrier()
         dist.destroy_process_group()
@@ -186,6 +152,40 @@ def main():
                 ok &= good
                 print(f"hdg_set_mesh {label} k={order} on {world} GPUs: iters {iters} (1 GPU: {it1}) ghosts/rank {ghosts}  "
                       f"relerr(uhat)={ex:.2e} relerr(u)={eu:.2e} err2 {err2:.6e} vs {e1:.6e}  {'OK' if good else 'FAIL'}", flush=True)
+    # ---- documented limits fail with a clean status and message, on every rank, without hanging the others
+    ctx = hdg._Context(1, 2, 1.0, 1, lr)
+    ctx.comm_init(dist, device=torch.device("cuda", lr))
+    hdg.check(ctx.lib.hdg_set_rectangle_mesh(ctx.h, 16, 8 * world, 0.0, 0.0, 2.0, 1.0), ctx.h)
+    one = np.array([1], dtype=np.int64)
+    limits = []
+    for name, call in (("hdg_set_dirichlet_faces", lambda: ctx.lib.hdg_set_dirichlet_faces(ctx.h, hdg.api.i64p(one), 1)),
+                       ("hdg_get_pattern", lambda: ctx.lib.hdg_get_pattern(ctx.h, None, None)),
+                       ("hdg_get_mesh", lambda: ctx.lib.hdg_get_mesh(ctx.h, None, None, None, None))):
+        st = call()
+        msg = ctx.lib.hdg_last_error(ctx.h).decode()
+        limits.append((name, st, msg))
+        ok &= st == 1 and "single-GPU" in msg
+    ctx.close()
+    os.environ["HDG_NO_P2P"] = "1"      # no peer mappings: a partitioned hdg_set_mesh mesh must refuse to solve, with NCCL still usable afterwards
+    ctx = hdg._Context(1, 2, 1.0, 1, lr)
+    ctx.comm_init(dist, device=torch.device("cuda", lr))
+    del os.environ["HDG_NO_P2P"]
+    hdg.check(ctx.lib.hdg_set_mesh(ctx.h, hdg.api.i64p(cells), cells.shape[0], hdg.api.f64p(nodes), nodes.shape[0],
+                                   hdg.api.i64p(faces), faces.shape[0], hdg.api.i64p(bf), bf.size), ctx.h)
+    hdg.check(ctx.lib.hdg_assemble(ctx.h), ctx.h)
+    hdg.check(ctx.lib.hdg_apply_dirichlet(ctx.h, None), ctx.h)
+    info = hdg.api.SolveInfo()
+    st = ctx.lib.hdg_solve(ctx.h, 1e-10, 100, C.byref(info))
+    msg = ctx.lib.hdg_last_error(ctx.h).decode()
+    limits.append(("hdg_solve without peer memory on a partitioned mesh", st, msg))
+    ok &= st != 0 and "peer-memory" in msg
+    hdg.check(ctx.lib.hdg_set_rectangle_mesh(ctx.h, 16, 8 * world, 0.0, 0.0, 2.0, 1.0), ctx.h)      # strips still solve over NCCL send/recv
+    xs_, us_, e_, it_, md_ = solve(ctx, 16, 8 * world, 1e-12)
+    ctx.close()
+    if rank == 0:
+        for name, st, msg in limits:
+            print(f"limit: {name}: status {st}, \"{msg}\"", flush=True)
+        print(f"NCCL fallback (HDG_NO_P2P=1) strips: {it_} iterations, err2 {e_:.6e}", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.barrier()

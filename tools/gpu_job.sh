@@ -1,7 +1,3 @@
-for v in "" s370 s740 s1480; do
-  echo "variant '$v'"
-  if [ -n "$v" ]; then export HDG_B200_LIB=$PWD/hdiscontinuousgalerkin.jl_b200/variants/lib_$v.so; fi
-  python bench.py --steps 50 --warmup 5 --no-pcg --no-cpu --no-e2e 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('  ms_per_step', d['ms_per_step'], 'kernel_ms', d['roofline']['kernel_ms'], 'frac', d['roofline']['frac'])"
-done
-unset HDG_B200_LIB
-python tools/ab_elem.py --orders 2 --reps 10 | grep -v "max |v1"
+mkdir -p gpurun_out
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517"
+timeout 600 $TR tests/multi_gpu_check.py > gpurun_out/r2_mgcheck_n2c.log 2>&1; echo "multi_gpu_check exit $?"; grep -i "limit\|fallback\|parity\|FAIL\|Error" gpurun_out/r2_mgcheck_n2c.log | tail -12
