@@ -224,7 +224,11 @@ hdg_status pcg_solve(hdg_context* c, double rtol, int maxit, hdg_solve_info* inf
 
 // hdg_mg.cu: P1-vertex multigrid term of the preconditioner (one GPU, rectangle_mesh)
 hdg_status mg_setup(hdg_context* c);                                              // operators of the current trace matrix
-hdg_status mg_apply(hdg_context* c, const double* r, double* z, double* part, int np);   // z += P V(P'r); part = partials of (P'r).V(P'r)
+hdg_status mg_apply(hdg_context* c, const double* r, double* z, double* part, int np, bool fuse = false);   // z += P V(P'r); part = partials of (P'r).V(P'r)
+// fuse: the V-cycle leaves its result t on the vertices and the caller's direction update adds P t itself (pcg_dir_mg); the
+// pointers it needs, false when the general-mesh term (hdg_mgx.cu) is active - that one always updates z itself
+bool mg_fused_ptrs(const hdg_context* c, const int32_t** facenode, const double** t0);
+constexpr double MG_C1 = 0.28867513459481287;   // 1 / (2 sqrt 3): trace mode 1 of a P1 function with vertex values (a, b) is C1 (b - a)
 void mg_free(hdg_context* c);
 void mg_invalidate(hdg_context* c);                             // keep the buffers, rebuild adjacency / flags at the next solve
 int mg_levels(const hdg_context* c);

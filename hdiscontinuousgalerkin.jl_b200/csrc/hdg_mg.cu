@@ -55,7 +55,6 @@ constexpr int MG_MAXLEV = 16;       // 2^16 vertices per direction
 constexpr int MG_TAIL_MAX = 640;    // levels with at most this many points run inside ONE block (block barriers)
 constexpr int MG_REP_MAX = 32768;   // several GPUs: levels with at most this many points are replicated on every rank
 constexpr double MG_OMEGA = 0.8;    // damped Jacobi on the vertex grids
-constexpr double MG_C1 = 0.28867513459481287;   // 1 / (2 sqrt 3)
 constexpr int MG_THREADS = 256;
 
 // stencil slots: centre, E, W, N, S, SE, NW  (the neighbours of a vertex in the triangulation)
@@ -457,6 +456,7 @@ struct VcArgs {
     XgComm xg;
     double* rep_r[MAXR];   // r of the first replicated level on every rank (its owners store their rows into all copies)
     unsigned long long* trace;   // measurement: globaltimer (ns) of block 0 at every barrier of the last V-cycle, [0] = count
+    int fuse;          // 1: stop after the level-0 result t; the caller's direction update adds P t to z (pcg_dir_mg, hdg_solve.cu)
 };
 
 // all blocks of the grid; with `cross` the last block to arrive also runs the barrier across the GPUs before releasing
@@ -660,28 +660,36 @@ __global__ void __launch_bounds__(MG_THREADS, MG_BLOCKS_PER_SM) mg_vcycle_kernel
     // ---- tail (block 0; the others wait at the barrier)
     if (blockIdx.x == 0) mg_tail(A, mg_sm);
     mg_grid_barrier(A, false);
-    // ---- up
+    // ---- up.  The level-0 stage also accumulates (P'r).V(P'r) = sum r t over the owned rows: the thread that forms t(i) adds
+    // r(i) t(i), in the order i = tid, tid + T, ... of the separate pass that used to follow the last barrier
+    double dot = 0.0;
+    const bool dot_in_up = A.lt > 0;
     for (int l = A.lt - 1; l >= 0; --l) {
         const LvDev &F = A.lev[l], &C = A.lev[l + 1];
         const bool dist = multi && l < A.lrep;
         const int fy0 = dist ? F.oy0 : 0, fy1 = dist ? F.oy1 : F.py;
         const int cnt = (fy1 - fy0) * F.px;
+        const bool last = l == 0;
         for (int i = tid; i < cnt; i += T) {
             const int y = fy0 + i / F.px, x = i - (y - fy0) * F.px;
-            lv_store<AR_T>(F, x, y, mg_up_point(F, C, x, y));
+            const double tv = mg_up_point(F, C, x, y);
+            lv_store<AR_T>(F, x, y, tv);
+            if (last && y >= F.oy0 && y < F.oy1) dot = fma(F.r[lv_idx(F, x, y)], tv, dot);
         }
-        mg_grid_barrier(A, dist);
+        // fused with the caller's direction update on one GPU: nothing in this launch reads t any more, the kernel boundary orders it
+        if (!(last && A.fuse && !multi)) mg_grid_barrier(A, dist);
     }
     // ---- (P'r).V(P'r) over the owned rows, z += P t on the owned faces
     {
-        double s = 0.0;
-        for (int i = tid; i < nown; i += T) s = fma(__ldcg(L0.r + o0 + i), __ldcg(L0.t + o0 + i), s);
+        double s = dot;
+        if (!dot_in_up)
+            for (int i = tid; i < nown; i += T) s = fma(__ldcg(L0.r + o0 + i), __ldcg(L0.t + o0 + i), s);
         const double tot = block_sum(s);
         if (threadIdx.x == 0) A.part[blockIdx.x] = tot;
         if (blockIdx.x == 0)
             for (int i = gridDim.x + threadIdx.x; i < A.np; i += blockDim.x) A.part[i] = 0.0;
         constexpr int U = 4;      // faces per trip: the vertex loads of all of them are issued before the first update of z
-        for (int64_t f0 = tid; f0 < A.nface; f0 += int64_t(T) * U) {
+        for (int64_t f0 = tid; f0 < (A.fuse ? 0 : A.nface); f0 += int64_t(T) * U) {
             double a[U], b[U], z0[U], z1[U];
             bool ok[U];
 #pragma unroll
@@ -700,8 +708,8 @@ __global__ void __launch_bounds__(MG_THREADS, MG_BLOCKS_PER_SM) mg_vcycle_kernel
             for (int u = 0; u < U; ++u)
                 if (ok[u]) {
                     const int64_t f = f0 + int64_t(u) * T;
-                    A.z[f * NT] = z0[u] + 0.5 * (a[u] + b[u]);
-                    A.z[f * NT + 1] = z1[u] + MG_C1 * (b[u] - a[u]);
+                    A.z[f * NT] = fma(0.5, a[u] + b[u], z0[u]);
+                    A.z[f * NT + 1] = fma(MG_C1, b[u] - a[u], z1[u]);
                 }
         }
         if (A.trace && tid == 0) { const unsigned long long k = A.trace[0] + 1; if (k < 62) { A.trace[k] = mg_now(); A.trace[0] = k; } }
@@ -1026,25 +1034,34 @@ hdg_status mg_setup(hdg_context* c) {
 }
 
 // z += P V(P' r);  part[0..np) = partial sums of (P' r) . V(P' r).  One cooperative launch on c->stream (capturable).
-template <int NT> static hdg_status mg_apply_t(hdg_context* c, const double* r, double* z, double* part, int np) {
+template <int NT> static hdg_status mg_apply_t(hdg_context* c, const double* r, double* z, double* part, int np, bool fuse) {
     MgData* m = static_cast<MgData*>(c->mg);
     VcArgs A = m->args;
-    A.r = r; A.z = z; A.part = part; A.np = np;
+    A.r = r; A.z = z; A.part = part; A.np = np; A.fuse = fuse ? 1 : 0;
     const int grid = std::max(1, std::min(m->grid_blocks, np));
     void* args[] = {&A};
     HDG_CUDA(c, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(mg_vcycle_kernel<NT>), dim3(grid), dim3(MG_THREADS), args, m->tail_smem, c->stream));
     return HDG_OK;
 }
 
-hdg_status mg_apply(hdg_context* c, const double* r, double* z, double* part, int np) {
+hdg_status mg_apply(hdg_context* c, const double* r, double* z, double* part, int np, bool fuse) {
     if (mgx_active(c)) return mgx_apply(c, r, z, part, np);
     switch (c->tab.nt) {
-        case 2: return mg_apply_t<2>(c, r, z, part, np);
-        case 3: return mg_apply_t<3>(c, r, z, part, np);
-        case 4: return mg_apply_t<4>(c, r, z, part, np);
-        case 5: return mg_apply_t<5>(c, r, z, part, np);
+        case 2: return mg_apply_t<2>(c, r, z, part, np, fuse);
+        case 3: return mg_apply_t<3>(c, r, z, part, np, fuse);
+        case 4: return mg_apply_t<4>(c, r, z, part, np, fuse);
+        case 5: return mg_apply_t<5>(c, r, z, part, np, fuse);
     }
     return HDG_OK;
+}
+
+bool mg_fused_ptrs(const hdg_context* c, const int32_t** facenode, const double** t0) {
+    const MgData* m = static_cast<const MgData*>(c->mg);
+    if (!m || mgx_active(c) || getenv("HDG_MG_NOFUSE")) return false;
+    const LvDev& L0 = m->args.lev[0];
+    *facenode = m->args.facenode;
+    *t0 = L0.t + int64_t(L0.oy0 - L0.rb) * L0.px;      // local node ids index the level-0 arrays from the first owned row on
+    return true;
 }
 
 // measurement (HDG_MG_TRACE=1): microseconds since the kernel start at every barrier entry / exit of the last V-cycle

@@ -452,6 +452,47 @@ __global__ void __launch_bounds__(RB) pcg_dir(const PcgArgs a, int64_t N, int pa
     }
 }
 
+// Direction update of the multigrid-PCG with the last stage of the V-cycle folded in: z = (block-Jacobi part, in Ap) + P t, where t is
+// the vertex-space result the V-cycle kernel left on level 0, then p = z + beta p.  Thread per owned face.  The V-cycle used to
+// end with a grid barrier and a pass that read and rewrote z for every face (12 us + barrier of a 128 us V-cycle at k = 1, 1 M
+// elements; 74 of 343 us at k = 3, 4 M); here the two vertex values are gathered while z and p stream through anyway.  Same
+// operations on the same values as the separate pass (fma(0.5, a + b, z0), fma(C1, b - a, z1), then fma(beta, p, z)): same bits.
+template <int NT>
+__global__ void __launch_bounds__(RB) pcg_dir_mg(const PcgArgs a, int parity, int iter, const int32_t* __restrict__ facenode,
+                                                const double* __restrict__ t0) {
+    if (*reinterpret_cast<volatile int32_t*>(a.flags + FLAG_DONE)) return;
+    const double rz_old = get_rz(a, parity ? P_RZ1 : P_RZ0);
+    const double rz_new = get_rz(a, parity ? P_RZ0 : P_RZ1);
+    const double rr = get_sum(a, P_RR);
+    const double bb = a.scal[S_BNORM2];
+    const bool conv = rr <= a.rtol * a.rtol * bb;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.scal[S_RELRES] = sqrt(rr / bb);
+        a.flags[FLAG_ITERS] = iter;
+    }
+    if (conv) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.flags[FLAG_DONE] = 1;
+        return;
+    }
+    const double beta = rz_new / rz_old;
+    for (int64_t f = int64_t(blockIdx.x) * RB + threadIdx.x; f < a.nface; f += int64_t(gridDim.x) * RB) {
+        const int2 vv = *reinterpret_cast<const int2*>(facenode + 2 * f);
+        const int lo = min(vv.x, vv.y), hi = max(vv.x, vv.y);
+        const double ta = t0[lo], tb = t0[hi];
+        const bool bc = a.isbc[f] != 0;
+        double z[NT], p[NT];
+        load_vec<NT>(a.Ap + f * NT, z);
+        load_vec<NT>(a.p + f * NT, p);
+        if (!bc) {
+            z[0] = fma(0.5, ta + tb, z[0]);
+            z[1] = fma(MG_C1, tb - ta, z[1]);
+        }
+#pragma unroll
+        for (int e = 0; e < NT; ++e) p[e] = fma(beta, p[e], z[e]);
+        store_vec<NT>(a.pnext + f * NT, p);
+    }
+}
+
 template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit, hdg_solve_info* info);
 
 // ---- block-Jacobi variant: M = blockdiag(D K_ff), the nt x nt face-diagonal blocks --------------
@@ -640,6 +681,9 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
         timer_stop(c, c->t_mgsetup);
         if (st) { timer_stop(c, c->t_solve); return st; }
     }
+    const int32_t* mg_facenode = nullptr;
+    const double* mg_t0 = nullptr;
+    const bool mg_fused = mg && mg_fused_ptrs(c, &mg_facenode, &mg_t0);      // after mg_setup: the level arrays exist
     hdg_status cst = HDG_OK;
     auto note = [&](hdg_status s2) { if (s2) cst = s2; };
     auto global_sums = [&](unsigned mask) {   // several GPUs: selected partial arrays -> sums over all ranks (+ inter-GPU barrier)
@@ -672,9 +716,10 @@ template <int NT> static hdg_status pcg_t(hdg_context* c, double rtol, int maxit
         global_sums(1u << P_PAP);      // p.Ap; every rank has finished reading the neighbours' vectors
         if (blockjac) pcg_update_blk<NT><<<G, RB, 0, c->stream>>>(ak, c->d_binv, parity);
         else pcg_update<<<G, RB, 0, c->stream>>>(ak, N, parity);
-        if (mg) note(mg_apply(c, ak.r, ak.Ap, c->d_partials + (parity ? P_RZC0 : P_RZC1) * MAX_PARTIALS, G));   // z (in Ap) += P V(P'r)
+        if (mg) note(mg_apply(c, ak.r, ak.Ap, c->d_partials + (parity ? P_RZC0 : P_RZC1) * MAX_PARTIALS, G, mg_fused));   // z (in Ap) += P V(P'r); fused: P t is added by pcg_dir_mg
         global_sums((1u << (parity ? P_RZ0 : P_RZ1)) | (1u << P_RR) | (mg ? 1u << (parity ? P_RZC0 : P_RZC1) : 0u));   // r.z (+ its vertex-space part), r.r; r complete on every rank
-        pcg_dir<<<G, RB, 0, c->stream>>>(ak, N, parity, it + 1, blockjac ? 1 : 0);
+        if (mg_fused) pcg_dir_mg<NT><<<G, RB, 0, c->stream>>>(ak, parity, it + 1, mg_facenode, mg_t0);
+        else pcg_dir<<<G, RB, 0, c->stream>>>(ak, N, parity, it + 1, blockjac ? 1 : 0);
         if (ghost_mode == 1) global_sums(0);  // barrier: p complete on every rank before the next SpMV reads it
     };
     int it = 0;

@@ -1,3 +1,5 @@
-mkdir -p gpurun_out
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517"
-timeout 600 $TR tests/multi_gpu_check.py > gpurun_out/r2_mgcheck_n2c.log 2>&1; echo "multi_gpu_check exit $?"; grep -i "limit\|fallback\|parity\|FAIL\|Error" gpurun_out/r2_mgcheck_n2c.log | tail -12
+timeout 500 python -m pytest tests -m gpu -x -q -k "multigrid or mg or driver or size" 2>&1 | tail -4
+HDG_MG_TRACE=1 python tools/mg_trace.py 1 1000 500
+HDG_MG_NOFUSE=1 HDG_MG_TRACE=1 python tools/mg_trace.py 1 1000 500 | head -2
+HDG_MG_TRACE=1 python tools/mg_trace.py 3 2000 1000 | head -2
+HDG_MG_NOFUSE=1 HDG_MG_TRACE=1 python tools/mg_trace.py 3 2000 1000 | head -2
