@@ -164,4 +164,26 @@ function errornorm_b200(ctx::Context, Wh, mesh, u_ex::Function)
     e[]
 end
 
-end # module
+# ---- mesh pre-processing for several GPUs: Morton-curve order of the cells (hdg_order_cells), then the reference's own
+# first-encounter numbering of the permuted element list, on the device (hdg_number_faces == parse_cells!, src/triangle_mesh.jl:48-108)
+function order_cells(ctx::Context, tri::Matrix{Int64}, nodes::Matrix{Float64})     # tri: 3 x ncell, nodes: 2 x nnode (Julia column-major)
+    perm = Vector{Int64}(undef, size(tri, 2))
+    check(ccall((:hdg_order_cells, lib), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Float64}, Int64, Ptr{Int64}),
+                ctx.h, tri, size(tri, 2), nodes, size(nodes, 2), perm), ctx.h)
+    return perm                                                                   # 1-based: new cell i is old cell perm[i]
+end
+
+# ---- CG side (examples/poisson2D_CG.jl): DofHandler numbering + sparsity pattern, assembly, apply!, solve, errornorm
+function cg_poisson(ctx::Context, order::Int; rtol = 1e-12, maxit = 100_000)
+    nd = Ref{Int64}(0)
+    check(ccall((:hdg_cg_setup, lib), Cint, (Ptr{Cvoid}, Int32, Ref{Int64}), ctx.h, order, nd), ctx.h)
+    check(ccall((:hdg_cg_assemble, lib), Cint, (Ptr{Cvoid},), ctx.h), ctx.h)
+    check(ccall((:hdg_cg_apply_dirichlet, lib), Cint, (Ptr{Cvoid},), ctx.h), ctx.h)
+    info = Ref(SolveInfo())
+    check(ccall((:hdg_cg_solve, lib), Cint, (Ptr{Cvoid}, Float64, Int32, Ref{SolveInfo}), ctx.h, rtol, maxit, info), ctx.h)
+    e = Ref{Float64}(0.0)
+    check(ccall((:hdg_cg_errornorm, lib), Cint, (Ptr{Cvoid}, Ref{Float64}), ctx.h, e), ctx.h)
+    return nd[], info[], e[]
+end
+
+end
