@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517"
-timeout 700 $TR tests/multi_gpu_check.py > gpurun_out/r2_mgcheck_n8_final.log 2>&1; echo "multi_gpu_check exit $?"; grep -i "GPUs:\|limit\|fallback\|parity\|FAIL" gpurun_out/r2_mgcheck_n8_final.log | tail -30
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests -m gpu -x -q -k "not size and not c2 and not c3" > gpurun_out/r2_memcheck.log 2>&1; echo "memcheck exit $?"
+grep -E "ERROR SUMMARY|passed|failed" gpurun_out/r2_memcheck.log | tail -4
+timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests -m gpu -x -q -k "assembly_rectangle or assembly_unstructured or morton or multigrid_preconditioner or lu_path or tau_not_one" > gpurun_out/r2_racecheck.log 2>&1; echo "racecheck exit $?"
+grep -E "RACECHECK SUMMARY|passed|failed|hazard" gpurun_out/r2_racecheck.log | tail -6
