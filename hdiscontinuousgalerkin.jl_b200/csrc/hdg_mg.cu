@@ -598,22 +598,41 @@ __global__ void __launch_bounds__(MG_THREADS, MG_BLOCKS_PER_SM) mg_vcycle_kernel
     // a partial sum: it goes to the owner (into its x vector, unused on a level that is not in the tail)
     {
         const int cnt = A.prows * L0.px;
-        for (int v = tid; v < cnt; v += T) {
-            const int c = A.vcnt[v];
-            const int4 e0 = *reinterpret_cast<const int4*>(A.vface + int64_t(v) * MG_MAXVAL), e1 = *reinterpret_cast<const int4*>(A.vface + int64_t(v) * MG_MAXVAL + 4);
-            const int32_t e[MG_MAXVAL] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-            double r0[MG_MAXVAL], r1[MG_MAXVAL];
+        constexpr int UV = 2;      // vertices per trip: the adjacency rows of both are loaded first, then all 2 x 16 gathers are in flight together
+        for (int v0 = tid; v0 < cnt; v0 += UV * T) {
+            int c[UV];
+            int32_t e[UV][MG_MAXVAL];
+            double r0[UV][MG_MAXVAL], r1[UV][MG_MAXVAL];
 #pragma unroll
-            for (int k = 0; k < MG_MAXVAL; ++k) {      // all gathers in flight together; slots beyond the count read face 0
-                const int64_t f = k < c ? (e[k] & 0x7fffffff) : 0;
-                r0[k] = A.r[f * NT]; r1[k] = A.r[f * NT + 1];
+            for (int u = 0; u < UV; ++u) {
+                const int v = v0 + u * T < cnt ? v0 + u * T : v0;
+                c[u] = A.vcnt[v];
+                const int4 e0 = *reinterpret_cast<const int4*>(A.vface + int64_t(v) * MG_MAXVAL), e1 = *reinterpret_cast<const int4*>(A.vface + int64_t(v) * MG_MAXVAL + 4);
+                e[u][0] = e0.x; e[u][1] = e0.y; e[u][2] = e0.z; e[u][3] = e0.w; e[u][4] = e1.x; e[u][5] = e1.y; e[u][6] = e1.z; e[u][7] = e1.w;
             }
-            double s = 0.0;
 #pragma unroll
-            for (int k = 0; k < MG_MAXVAL; ++k)
-                if (k < c) s += 0.5 * r0[k] + ((e[k] < 0) ? MG_C1 : -MG_C1) * r1[k];
-            if (v < nown) L0.r[o0 + v] = A.fx[v] != 0.0 ? 0.0 : s;
-            else A.above_x0[v - nown] = s;
+            for (int u = 0; u < UV; ++u)
+#pragma unroll
+                for (int k = 0; k < MG_MAXVAL; ++k) {      // slots beyond the count read face 0
+                    const int64_t f = k < c[u] ? (e[u][k] & 0x7fffffff) : 0;
+                    if constexpr (NT % 2 == 0) {
+                        const double2 q = *reinterpret_cast<const double2*>(A.r + f * NT);
+                        r0[u][k] = q.x; r1[u][k] = q.y;
+                    } else {
+                        r0[u][k] = A.r[f * NT]; r1[u][k] = A.r[f * NT + 1];
+                    }
+                }
+#pragma unroll
+            for (int u = 0; u < UV; ++u) {
+                const int v = v0 + u * T;
+                if (v >= cnt) continue;
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < MG_MAXVAL; ++k)
+                    if (k < c[u]) s += 0.5 * r0[u][k] + ((e[u][k] < 0) ? MG_C1 : -MG_C1) * r1[u][k];
+                if (v < nown) L0.r[o0 + v] = A.fx[v] != 0.0 ? 0.0 : s;
+                else A.above_x0[v - nown] = s;
+            }
         }
     }
     mg_grid_barrier(A, true);
